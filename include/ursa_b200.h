@@ -1,0 +1,171 @@
+/*
+ * ursa_b200.h -- C ABI of the B200-native URSABench hot path.
+ *
+ * The reference (reml-lab/URSABench) is pure Python on PyTorch and has no FFI:
+ * its "plugin interface" for this path is the Python class API
+ * (inference/inference_base.py:12-56, tasks/task_base.py:4-20).  This header is
+ * the boundary *below* that API: each entry point replaces the implicit ATen
+ * launch sequence of one reference function (cited per function, paths relative
+ * to /root/reference/URSABench/).  `ursabench_b200/_C.py` binds it with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers + sizes, no torch / C++ types;
+ *  - the caller owns all memory; nothing here allocates device memory
+ *    (workspaces are sized by the *_workspace() helpers and passed in);
+ *  - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 = URSA_OK, negative = error; ursa_last_error() returns a
+ *    thread-local message for the last failing call on this thread;
+ *  - no global mutable state besides that message: thread-compatible;
+ *  - all arithmetic is fp32 unless stated; "n" counts elements, "ld" strides
+ *    are in elements.
+ */
+#ifndef URSA_B200_H
+#define URSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URSA_OK               0
+#define URSA_ERR_INVALID     -1   /* bad argument (null pointer, bad size, misalignment) */
+#define URSA_ERR_CUDA        -2   /* CUDA runtime error; message carries cudaGetErrorString */
+#define URSA_ERR_UNSUPPORTED -3   /* shape / architecture not covered by this build */
+
+#define URSA_ABI_VERSION 1
+
+int ursa_abi_version(void);
+const char *ursa_last_error(void);
+/* SM count and compute capability of the current device. */
+int ursa_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------
+ * K1  fused SG-MCMC update  (replaces optimSGHMC.step, inference/optim_sghmc.py:30-68:
+ *     7-8 ATen launches per parameter tensor -> ONE launch over the flat buffer)
+ *
+ *   d = g + wd_over_n * p                                   (:47-48; skipped when wd_over_n == 0)
+ *   momentum != 0:  if FIRST: v = d                         (:51-52)
+ *                   v = momentum * v - lr * d ; u = v       (:53/:56, :60)
+ *   momentum == 0:  u = -lr * d                             (:62)
+ *   NOISE:          u = u + (z * noise_mul) / noise_div     (:63-64; z ~ N(0,1))
+ *   p = p + u                                               (:65)
+ *   momentum != 0:  v = u                                   (:66-67; the noise is stored in the momentum)
+ *   snapshot != NULL: snapshot[i] = p[i]                    (replaces deepcopy(model.cpu()), sghmc.py:99)
+ *   ZERO_GRAD:      g = 0                                   (fused optimizer.zero_grad(), sghmc.py:79)
+ *
+ * `noise` != NULL : z is read from `noise` (parity mode; bit-exact vs. the reference's CPU arithmetic).
+ * `noise` == NULL : z is drawn in-register: Philox4x32-10, key = seed, counter =
+ *                   ((elem_offset+i)/4, step); Box-Muller; lane (elem_offset+i)%4.  The scale is applied
+ *                   as one multiply by noise_mul/noise_div.
+ * A [chains, D] buffer is just n = chains*D elements (the update is elementwise and the schedule is
+ * shared); ranks pass their global element base in `elem_offset` so chains never share a noise stream.
+ * p, g, v, snapshot, noise must be 16-byte aligned.  v may be NULL iff momentum == 0.
+ * ---------------------------------------------------------------------- */
+#define URSA_STEP_FIRST     1u
+#define URSA_STEP_NOISE     2u
+#define URSA_STEP_ZERO_GRAD 4u
+
+int ursa_sgmcmc_step(float *p, float *g, float *v, float *snapshot, const float *noise,
+                     int64_t n, float lr, float momentum, float wd_over_n,
+                     float noise_mul, float noise_div, uint32_t flags,
+                     uint64_t seed, uint64_t step, uint64_t elem_offset, void *stream);
+
+/* Fill `out[n]` with the N(0,1) stream ursa_sgmcmc_step would consume (test / diagnostics hook). */
+int ursa_philox_normal(float *out, int64_t n, uint64_t seed, uint64_t step, uint64_t elem_offset, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K2a SWAG moment + deviation-row update  (replaces SWA._collect_model, inference/swa.py:79-90 and
+ *     CovarianceSpace.collect_vector, inference/subspaces.py:85-89: T D2H copies + 7 CPU passes + a
+ *     K x D torch.cat -> one pass, 24 B/param, ring row written in place)
+ *   mean = mean * keep + w / denom ; sq = sq * keep + (w*w) / denom ; dev_row = w - mean
+ *   keep = n/(n+1), denom = n+1 computed by the caller in double (swa.py:83-88).
+ * ---------------------------------------------------------------------- */
+int ursa_swag_collect(const float *w, float *mean, float *sq_mean, float *dev_row,
+                      int64_t n, float keep, float denom, void *stream);
+
+/* var = max(sq_mean - mean^2, clamp)     (SWA._get_mean_and_variance, inference/swa.py:106-108) */
+int ursa_swag_variance(const float *mean, const float *sq_mean, float *var, int64_t n, float clamp,
+                       void *stream);
+
+/* ------------------------------------------------------------------------
+ * K2b batched SWAG draw  (the formula of inference/swag.py:85-97; the reference discards its draw at :98 and
+ *     its low-rank branch raises -- see DESIGN.md "reference quirks")
+ *   out[s, :] = mean + sqrt(var) * z1[s, :] + (ring^T z2[s, :]) / rank_div        s = 0..S-1
+ * ring: [K, ld_ring] deviation rows (K == 0 -> diagonal draw); z2: [S, K] device, row-major;
+ * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox (key = seed, counter =
+ * (s*D + d)/4 .. as in K1 with elem index s*D+d, step).  All S draws are produced in ONE pass over the
+ * ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  Rows (ring, out, z1) must be 16-byte aligned:
+ * ld_* % 4 == 0.  S <= URSA_DRAW_MAX_S, K <= URSA_DRAW_MAX_K.
+ * ---------------------------------------------------------------------- */
+#define URSA_DRAW_MAX_S 32
+#define URSA_DRAW_MAX_K 24
+
+int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, const float *var,
+                   const float *ring, int64_t ld_ring, int K, const float *z2,
+                   const float *z1, int64_t ld_z1, int S, int64_t D, float rank_div,
+                   uint64_t seed, uint64_t step, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K3  BMA accumulation  (replaces the inner loop of Prediction.update_statistics,
+ *     tasks/prediction.py:52-75: per sample softmax twice + 2 D2H + CPU accumulate)
+ *   for s in order: p = softmax(logits[s, i, :]) ; proba_sum[i, :] += p ;
+ *                   entropy_sum[i] += -sum_c q log q,  q = (1-gamma) p + gamma/C   (util.py:126-144)
+ * logits: [S, N, C] with sample stride ld_sample (elements).  Accumulation order over s is sequential,
+ * as in the reference, so results do not depend on the launch shape.
+ * ---------------------------------------------------------------------- */
+int ursa_bma_accumulate(const float *logits, int64_t S, int64_t N, int C, int64_t ld_sample,
+                        float *proba_sum, float *entropy_sum, double gamma, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K4  BMA metric counters  (replaces Prediction.get_performance_metrics + _get_ece + _get_brier,
+ *     tasks/prediction.py:79-102,152-194: numpy on [N, C] -> counters the host turns into metrics)
+ *   pbar = proba_sum / num_samples (fp32 division) ; pred = first argmax ; conf = max
+ *   out_i64 = [correct, bin_count[n_bins], bin_correct[n_bins]]            (exact)
+ *   out_f64 = [nll_sum, brier_sum, bin_conf_sum[n_bins]]                   (fp64, fixed reduction order)
+ *   bins are (b/n_bins, (b+1)/n_bins] compared in fp64 (np.linspace(0,1,n_bins+1), :160-170)
+ *   nll_sum = sum_i -log((1-gamma) pbar[i, y_i] + gamma/C) ; brier_sum = sum_i sum_c (pbar - onehot)^2
+ *   pred_out / conf_out ([N], nullable) receive the per-row argmax / confidence.
+ * Deterministic: per-block partials in `workspace`, reduced in block order by a second launch.
+ * ---------------------------------------------------------------------- */
+size_t ursa_bma_metrics_workspace(int64_t N, int n_bins);
+int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples, const int64_t *targets,
+                     double gamma, int n_bins, int64_t *out_i64, double *out_f64,
+                     int32_t *pred_out, float *conf_out, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ------------------------------------------------------------------------
+ * K3  sample-batched BMA forward, MLP  (replaces S x ceil(N/B) calls of model(x) + the accumulation above
+ *     for models/mlp.py:8-23).  bank: [S, ld_bank] flat weight vectors in model.parameters() order
+ *     (fc1.weight[h,in], fc1.bias[h], fc2.weight[h,h], fc2.bias[h], fc3.weight[C,h], fc3.bias[C]).
+ *     x: [N, in_dim].  Accumulates into proba_sum [N, C] / entropy_sum [N] in sample order.
+ *     logits_out (nullable): [S, N, C].
+ *     algo: URSA_ALGO_FFMA (fp32 CUDA cores) or URSA_ALGO_TCGEN05 (3xTF32 on tcgen05 + TMA).
+ * ---------------------------------------------------------------------- */
+#define URSA_ALGO_FFMA    0
+#define URSA_ALGO_TCGEN05 1
+
+size_t ursa_bma_mlp_workspace(int S, int64_t N, int in_dim, int hidden, int C, int algo);
+int ursa_bma_mlp_forward(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N,
+                         int in_dim, int hidden, int C, float *proba_sum, float *entropy_sum,
+                         float *logits_out, double gamma, void *workspace, size_t workspace_bytes,
+                         int algo, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K3  sample-batched BMA forward, PreResNet (BasicBlock, depth = 6n+2 < 44; models/preresnet.py:90-151)
+ *     bank: [S, ld_bank] parameters; bufbank: [S, ld_buf] BatchNorm running stats in named_buffers()
+ *     order with the int64 num_batches_tracked entries dropped (mean, var per BN layer);
+ *     x: [N, 3, 32, 32] NCHW.  Eval-mode BN (eps 1e-5) + ReLU are folded into the consuming conv.
+ * ---------------------------------------------------------------------- */
+size_t ursa_bma_preresnet_workspace(int S, int64_t N, int depth, int C, int algo);
+int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf,
+                               int S, const float *x, int64_t N, int depth, int C,
+                               float *proba_sum, float *entropy_sum, float *logits_out, double gamma,
+                               void *workspace, size_t workspace_bytes, int algo, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URSA_B200_H */

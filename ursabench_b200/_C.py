@@ -1,0 +1,208 @@
+"""ctypes binding of ``libursa_b200.so`` (C ABI in ``include/ursa_b200.h``).
+
+There is NO fallback: if the library is missing or a call fails, this module
+raises.  Device pointers come from ``tensor.data_ptr()`` and the stream from
+``torch.cuda.current_stream()``; torch is used here only as the owner of
+device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libursa_b200.so")
+
+STEP_FIRST, STEP_NOISE, STEP_ZERO_GRAD = 1, 2, 4
+ALGO_FFMA, ALGO_TCGEN05 = 0, 1
+DRAW_MAX_S, DRAW_MAX_K = 32, 24
+
+_c = ctypes
+_vp, _i64, _i32, _u32, _u64, _f32, _f64, _sz = (_c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32, _c.c_uint64,
+                                                _c.c_float, _c.c_double, _c.c_size_t)
+
+# name -> (restype, argtypes); mirrors include/ursa_b200.h one to one
+SIGNATURES = {
+    "ursa_abi_version": (_i32, []),
+    "ursa_last_error": (_c.c_char_p, []),
+    "ursa_device_info": (_i32, [_c.POINTER(_i32)] * 3),
+    "ursa_sgmcmc_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _u32, _u64, _u64, _u64, _vp]),
+    "ursa_philox_normal": (_i32, [_vp, _i64, _u64, _u64, _u64, _vp]),
+    "ursa_swag_collect": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp]),
+    "ursa_swag_variance": (_i32, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "ursa_swag_draw": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _i64, _f32, _u64, _u64, _vp]),
+    "ursa_bma_accumulate": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _f64, _vp]),
+    "ursa_bma_metrics_workspace": (_sz, [_i64, _i32]),
+    "ursa_bma_metrics": (_i32, [_vp, _i64, _i32, _f32, _vp, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ursa_bma_mlp_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
+    "ursa_bma_mlp_forward": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp, _sz, _i32, _vp]),
+    "ursa_bma_preresnet_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
+    "ursa_bma_preresnet_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
+                                          _sz, _i32, _vp]),
+}
+
+_lib = None
+
+
+class UrsaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once; raise if it is absent (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UrsaError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "or `make -C ursabench_b200/csrc`; there is no fallback path" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.ursa_abi_version() != 1:
+            raise UrsaError("libursa_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().ursa_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError("%s: %s" % (what, msg))
+        raise UrsaError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dev_f32(t, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return
+        raise ValueError("%s is required" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor: this engine has no CPU path" % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("%s must be contiguous float32" % name)
+
+
+def sgmcmc_step(p, g, v=None, snapshot=None, noise=None, *, lr, momentum, wd_over_n, noise_mul=0.0, noise_div=1.0,
+                first_step=False, add_noise=True, zero_grad=False, seed=0, step=0, elem_offset=0):
+    """Fused optimSGHMC update over flat buffers (see ursa_sgmcmc_step in the header)."""
+    for t, nm, opt in ((p, "p", False), (g, "g", False), (v, "v", True), (snapshot, "snapshot", True), (noise, "noise", True)):
+        _dev_f32(t, nm, opt)
+    n = p.numel()
+    for t, nm in ((g, "g"), (v, "v"), (snapshot, "snapshot"), (noise, "noise")):
+        if t is not None and t.numel() < n:
+            raise ValueError("%s has fewer elements than p" % nm)
+    flags = (STEP_FIRST if first_step else 0) | (STEP_NOISE if add_noise else 0) | (STEP_ZERO_GRAD if zero_grad else 0)
+    rc = lib().ursa_sgmcmc_step(_ptr(p), _ptr(g), _ptr(v), _ptr(snapshot), _ptr(noise), n, lr, momentum, wd_over_n,
+                                noise_mul, noise_div, flags, seed, step, elem_offset, _stream(p))
+    _check(rc, "ursa_sgmcmc_step")
+
+
+def philox_normal(out, seed, step, elem_offset=0):
+    _dev_f32(out, "out")
+    _check(lib().ursa_philox_normal(_ptr(out), out.numel(), seed, step, elem_offset, _stream(out)), "ursa_philox_normal")
+    return out
+
+
+def swag_collect(w, mean, sq_mean, dev_row, n_collected):
+    for t, nm in ((w, "w"), (mean, "mean"), (sq_mean, "sq_mean"), (dev_row, "dev_row")):
+        _dev_f32(t, nm)
+    n = w.numel()
+    keep = n_collected / (n_collected + 1.0)
+    rc = lib().ursa_swag_collect(_ptr(w), _ptr(mean), _ptr(sq_mean), _ptr(dev_row), n, keep, n_collected + 1.0, _stream(w))
+    _check(rc, "ursa_swag_collect")
+
+
+def swag_variance(mean, sq_mean, var, clamp=1e-30):
+    for t, nm in ((mean, "mean"), (sq_mean, "sq_mean"), (var, "var")):
+        _dev_f32(t, nm)
+    _check(lib().ursa_swag_variance(_ptr(mean), _ptr(sq_mean), _ptr(var), mean.numel(), clamp, _stream(mean)),
+           "ursa_swag_variance")
+    return var
+
+
+def swag_draw(out, mean, var, D, ring=None, z2=None, z1=None, rank_div=1.0, seed=0, step=0):
+    """out: [S, ld]; ring: [K, ld] or None; z2: [S, K]; z1: [S, ld] or None (Philox)."""
+    _dev_f32(out, "out"), _dev_f32(mean, "mean"), _dev_f32(var, "var")
+    _dev_f32(ring, "ring", True), _dev_f32(z2, "z2", True), _dev_f32(z1, "z1", True)
+    S = out.shape[0]
+    K = 0 if ring is None else ring.shape[0]
+    rc = lib().ursa_swag_draw(_ptr(out), out.stride(0), _ptr(mean), _ptr(var), _ptr(ring),
+                              0 if ring is None else ring.stride(0), K, _ptr(z2), _ptr(z1),
+                              0 if z1 is None else z1.stride(0), S, D, rank_div, seed, step, _stream(out))
+    _check(rc, "ursa_swag_draw")
+    return out
+
+
+def bma_accumulate(logits, proba_sum, entropy_sum, gamma=1e-4):
+    """logits: [S, N, C] contiguous."""
+    _dev_f32(logits, "logits"), _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum")
+    S, N, C = logits.shape
+    rc = lib().ursa_bma_accumulate(_ptr(logits), S, N, C, N * C, _ptr(proba_sum), _ptr(entropy_sum), gamma,
+                                   _stream(logits))
+    _check(rc, "ursa_bma_accumulate")
+
+
+def bma_metrics(proba_sum, num_samples, targets, gamma=1e-4, n_bins=15, want_rows=False):
+    """Returns (i64[1+2*nb], f64[2+nb], pred|None, conf|None) as device tensors."""
+    _dev_f32(proba_sum, "proba_sum")
+    if targets.dtype != torch.int64 or not targets.is_cuda:
+        raise ValueError("targets must be a CUDA int64 tensor")
+    N, C = proba_sum.shape
+    dev = proba_sum.device
+    out_i = torch.empty(1 + 2 * n_bins, dtype=torch.int64, device=dev)
+    out_f = torch.empty(2 + n_bins, dtype=torch.float64, device=dev)
+    pred = torch.empty(N, dtype=torch.int32, device=dev) if want_rows else None
+    conf = torch.empty(N, dtype=torch.float32, device=dev) if want_rows else None
+    wsb = lib().ursa_bma_metrics_workspace(N, n_bins)
+    ws = torch.empty((wsb + 7) // 8, dtype=torch.int64, device=dev)
+    rc = lib().ursa_bma_metrics(_ptr(proba_sum), N, C, float(num_samples), _ptr(targets), gamma, n_bins, _ptr(out_i),
+                                _ptr(out_f), _ptr(pred), _ptr(conf), _ptr(ws), ws.numel() * 8, _stream(proba_sum))
+    _check(rc, "ursa_bma_metrics")
+    return out_i, out_f, pred, conf
+
+
+def bma_mlp_forward(bank, S, x, in_dim, hidden, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
+                    algo=ALGO_FFMA, workspace=None):
+    _dev_f32(bank, "bank"), _dev_f32(x, "x"), _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum")
+    _dev_f32(logits_out, "logits_out", True)
+    N = x.shape[0]
+    need = lib().ursa_bma_mlp_workspace(S, N, in_dim, hidden, C, algo)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_bma_mlp_forward(_ptr(bank), bank.stride(0), S, _ptr(x), N, in_dim, hidden, C, _ptr(proba_sum),
+                                    _ptr(entropy_sum), _ptr(logits_out), gamma, _ptr(workspace),
+                                    workspace.numel() * workspace.element_size(), algo, _stream(x))
+    _check(rc, "ursa_bma_mlp_forward")
+    return workspace
+
+
+def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
+                          algo=ALGO_FFMA, workspace=None):
+    _dev_f32(bank, "bank"), _dev_f32(bufbank, "bufbank"), _dev_f32(x, "x")
+    _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum"), _dev_f32(logits_out, "logits_out", True)
+    N = x.shape[0]
+    need = lib().ursa_bma_preresnet_workspace(S, N, depth, C, algo)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_bma_preresnet_forward(_ptr(bank), bank.stride(0), _ptr(bufbank), bufbank.stride(0), S, _ptr(x), N,
+                                          depth, C, _ptr(proba_sum), _ptr(entropy_sum), _ptr(logits_out), gamma,
+                                          _ptr(workspace), workspace.numel() * workspace.element_size(), algo,
+                                          _stream(x))
+    _check(rc, "ursa_bma_preresnet_forward")
+    return workspace
+
+
+def device_info():
+    sm, major, minor = _i32(), _i32(), _i32()
+    _check(lib().ursa_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "ursa_device_info")
+    return sm.value, major.value, minor.value

@@ -1,0 +1,85 @@
+// Shared device/host helpers for the ursa_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ursa_b200.h"
+
+namespace ursa {
+
+// ---- error plumbing (thread-local message; see include/ursa_b200.h) -------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+int sm_count();
+
+#define URSA_REQUIRE(cond, ...)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::ursa::set_error(__VA_ARGS__);    \
+            return URSA_ERR_INVALID;           \
+        }                                      \
+    } while (0)
+
+#define URSA_CUDA(call)                                          \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return ::ursa::cuda_fail(e__, #call); \
+    } while (0)
+
+#define URSA_LAUNCH_CHECK(name)                                  \
+    do {                                                         \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return ::ursa::cuda_fail(e__, name); \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based ---------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1,
+                       (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Box-Muller on one Philox block: (r.x, r.y) -> (z0, z1), (r.z, r.w) -> (z2, z3).
+// u1 = r*2^-32 + 2^-33 in (0, 1]; theta = 2*pi*u2.  MUFU lg2 / sqrt / sin / cos.
+__device__ __forceinline__ float4 box_muller4(uint4 r) {
+    const float k2m32 = 2.3283064365386963e-10f, k2m33 = 1.1641532182693481e-10f;
+    const float kTwoPi2m32 = 1.4629180792671596e-9f;          // 2*pi * 2^-32
+    const float u1a = fmaf(__uint2float_rn(r.x), k2m32, k2m33);
+    const float u1b = fmaf(__uint2float_rn(r.z), k2m32, k2m33);
+    const float ra = fast_sqrt(-1.3862943611198906f * __log2f(u1a));   // sqrt(-2 ln u)
+    const float rb = fast_sqrt(-1.3862943611198906f * __log2f(u1b));
+    const float ta = fmaf(__uint2float_rn(r.y), kTwoPi2m32, 0.5f * kTwoPi2m32);
+    const float tb = fmaf(__uint2float_rn(r.w), kTwoPi2m32, 0.5f * kTwoPi2m32);
+    float sa, ca, sb, cb;
+    __sincosf(ta, &sa, &ca);
+    __sincosf(tb, &sb, &cb);
+    return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+// The 4 normals of Philox block `blk` (= element index / 4) at stream position `step`.
+__device__ __forceinline__ float4 philox_normal4(uint64_t blk, uint64_t step, uint2 key) {
+    const uint4 ctr = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)step, (uint32_t)(step >> 32));
+    return box_muller4(philox4x32_10(ctr, key));
+}
+
+__device__ __forceinline__ float f4_get(const float4 &v, int i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+}  // namespace ursa
