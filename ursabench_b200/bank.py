@@ -1,0 +1,209 @@
+"""Device-resident posterior-sample bank.
+
+The reference hands samples around as a Python list of deep-copied CPU modules
+(``deepcopy(self.model.cpu())``, inference/sghmc.py:99) and ``Prediction`` moves
+every one of them to the device and back for every test batch
+(tasks/prediction.py:57,64).  Here a sample is one row of a ``[S, ld]`` fp32
+matrix in HBM (+ one row of BatchNorm running statistics); ``BankedSample`` is
+the ``nn.Module`` handle returned to callers: tasks of this package read the
+rows in place, anything else sees an ordinary CPU module materialised on first
+use.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from .flat import _round_up
+
+
+class SampleBank:
+    def __init__(self, D, nb, device, capacity=16, skeleton=None):
+        self.D, self.nb = D, nb
+        self.ld = _round_up(D, 4)
+        self.ldb = _round_up(max(nb, 1), 4)
+        self.device = torch.device(device)
+        self.w = torch.zeros(max(capacity, 1), self.ld, dtype=torch.float32, device=self.device)
+        self.b = torch.zeros(max(capacity, 1), self.ldb, dtype=torch.float32, device=self.device)
+        self.count = 0
+        self.skeleton = skeleton          # CPU module used to materialise samples lazily
+
+    @property
+    def capacity(self):
+        return self.w.shape[0]
+
+    def reserve(self, n):
+        if n <= self.capacity:
+            return
+        cap = max(n, 2 * self.capacity)
+        w = torch.zeros(cap, self.ld, dtype=torch.float32, device=self.device)
+        b = torch.zeros(cap, self.ldb, dtype=torch.float32, device=self.device)
+        w[:self.count].copy_(self.w[:self.count])
+        b[:self.count].copy_(self.b[:self.count])
+        self.w, self.b = w, b
+
+    def next_row(self):
+        """Reserve the next row and return (index, weight row view [ld]) -- the K1 launch writes it (snapshot)."""
+        self.reserve(self.count + 1)
+        i = self.count
+        self.count += 1
+        return i, self.w[i]
+
+    def append(self, flat_p, flat_b=None):
+        i, row = self.next_row()
+        row[:self.D].copy_(flat_p[:self.D])
+        if flat_b is not None and self.nb:
+            self.b[i, :self.nb].copy_(flat_b[:self.nb])
+        return i
+
+    def set_buffers(self, i, flat_b):
+        if self.nb:
+            self.b[i, :self.nb].copy_(flat_b[:self.nb])
+
+    def handle(self, i):
+        return BankedSample(self, i)
+
+    def rows(self, idx):
+        """(w [n, ld], b [n, ldb]) for a list of row indices; a view when the indices are one contiguous run."""
+        if len(idx) and idx == list(range(idx[0], idx[0] + len(idx))):
+            return self.w[idx[0]:idx[0] + len(idx)], self.b[idx[0]:idx[0] + len(idx)]
+        sel = torch.as_tensor(idx, dtype=torch.long, device=self.device)
+        return self.w.index_select(0, sel), self.b.index_select(0, sel)
+
+    @classmethod
+    def from_modules(cls, models, device):
+        """Pack ordinary modules (e.g. CPU samples from the reference) into a bank: one H2D copy per sample."""
+        first = models[0]
+        D = sum(p.numel() for p in first.parameters())
+        bufs = [b for b in first.buffers() if b.dtype == torch.float32]
+        nb = sum(b.numel() for b in bufs)
+        bank = cls(D, nb, device, capacity=len(models), skeleton=None)
+        stage_w = torch.empty(len(models), bank.ld, dtype=torch.float32).pin_memory() if torch.cuda.is_available() \
+            else torch.empty(len(models), bank.ld, dtype=torch.float32)
+        stage_b = torch.zeros(len(models), bank.ldb, dtype=torch.float32)
+        for i, m in enumerate(models):
+            off = 0
+            for p in m.parameters():
+                n = p.numel()
+                stage_w[i, off:off + n].copy_(p.detach().reshape(-1))
+                off += n
+            if off != D:
+                raise ValueError("models in one ensemble must share an architecture")
+            off = 0
+            for b in m.buffers():
+                if b.dtype == torch.float32:
+                    stage_b[i, off:off + b.numel()].copy_(b.detach().reshape(-1))
+                    off += b.numel()
+        bank.w[:len(models)].copy_(stage_w, non_blocking=True)
+        bank.b[:len(models)].copy_(stage_b)
+        bank.count = len(models)
+        return bank
+
+
+def _load_row_into(module, w_row, b_row):
+    off = 0
+    for p in module.parameters():
+        n = p.numel()
+        p.data.copy_(w_row[off:off + n].view(p.shape))
+        off += n
+    off = 0
+    for b in module.buffers():
+        if b.dtype == torch.float32:
+            n = b.numel()
+            b.copy_(b_row[off:off + n].view(b.shape))
+            off += n
+
+
+class BankedSample(nn.Module):
+    """``nn.Module`` handle of one bank row.  Behaves like the deep-copied CPU module the reference returns
+    (materialised lazily on the CPU); ``ursabench_b200.tasks`` recognise it and use the device row directly."""
+
+    def __init__(self, bank, row):
+        super().__init__()
+        object.__setattr__(self, "_ursa_bank", bank)
+        object.__setattr__(self, "_ursa_row", row)
+        object.__setattr__(self, "_ursa_inner", None)
+
+    def materialize(self):
+        inner = self._ursa_inner
+        if inner is None:
+            bank = self._ursa_bank
+            if bank.skeleton is None:
+                raise RuntimeError("this bank has no module skeleton to materialise samples from")
+            inner = copy.deepcopy(bank.skeleton)
+            _load_row_into(inner, bank.w[self._ursa_row].cpu(), bank.b[self._ursa_row].cpu())
+            object.__setattr__(self, "_ursa_inner", inner)
+        return inner
+
+    def is_pristine(self):
+        """True while nobody has touched the materialised copy (so the bank row is still the sample)."""
+        return self._ursa_inner is None
+
+    def forward(self, *args, **kwargs):
+        return self.materialize()(*args, **kwargs)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name.startswith("_ursa"):
+                raise
+            return getattr(self.materialize(), name)
+
+    # -- nn.Module surface that must act on the materialised module, not on this empty shell
+    def parameters(self, recurse=True):
+        return self.materialize().parameters(recurse)
+
+    def named_parameters(self, *a, **k):
+        return self.materialize().named_parameters(*a, **k)
+
+    def buffers(self, recurse=True):
+        return self.materialize().buffers(recurse)
+
+    def named_buffers(self, *a, **k):
+        return self.materialize().named_buffers(*a, **k)
+
+    def children(self):
+        return self.materialize().children()
+
+    def named_children(self):
+        return self.materialize().named_children()
+
+    def modules(self):
+        return self.materialize().modules()
+
+    def named_modules(self, *a, **k):
+        return self.materialize().named_modules(*a, **k)
+
+    def state_dict(self, *a, **k):
+        return self.materialize().state_dict(*a, **k)
+
+    def load_state_dict(self, *a, **k):
+        return self.materialize().load_state_dict(*a, **k)
+
+    def apply(self, fn):
+        self.materialize().apply(fn)
+        return self
+
+    def to(self, *a, **k):
+        self.materialize().to(*a, **k)
+        return self
+
+    def cpu(self):
+        self.materialize().cpu()
+        return self
+
+    def cuda(self, device=None):
+        self.materialize().cuda(device)
+        return self
+
+    def train(self, mode=True):
+        if self._ursa_inner is not None:
+            self._ursa_inner.train(mode)
+        return super().train(mode)
+
+    def eval(self):
+        return self.train(False)
+
+    def __deepcopy__(self, memo):
+        return copy.deepcopy(self.materialize(), memo)
