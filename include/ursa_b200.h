@@ -73,6 +73,18 @@ int ursa_sgmcmc_step(float *p, float *g, float *v, float *snapshot, const float 
                      float noise_mul, float noise_div, uint32_t flags,
                      uint64_t seed, uint64_t step, uint64_t elem_offset, void *stream);
 
+/* Same update with the per-step scalars read from DEVICE memory, so the launch can sit inside a captured CUDA graph
+ * whose replays see new values: dyn = [lr, momentum, wd_over_n, noise_scale (= noise_mul/noise_div; 0 gates the
+ * noise off), step_lo, step_hi] (six 32-bit words; the step counter words are raw bit patterns).  The momentum
+ * branch is taken iff v != NULL.  In external-noise mode the noise term is z * noise_scale. */
+int ursa_sgmcmc_step_dyn(float *p, float *g, float *v, float *snapshot, const float *noise, int64_t n,
+                         const float *dyn, uint32_t flags, uint64_t seed, uint64_t elem_offset, void *stream);
+
+/* Write the six dyn words from by-value arguments (a 1-thread launch: the values are captured at launch time, so
+ * the host may run ahead of the device without racing on a staging buffer). */
+int ursa_sgmcmc_set_dyn(float *dyn, float lr, float momentum, float wd_over_n, float noise_scale, uint64_t step,
+                        void *stream);
+
 /* Fill `out[n]` with the N(0,1) stream ursa_sgmcmc_step would consume (test / diagnostics hook). */
 int ursa_philox_normal(float *out, int64_t n, uint64_t seed, uint64_t step, uint64_t elem_offset, void *stream);
 

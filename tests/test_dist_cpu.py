@@ -1,0 +1,77 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: sharding of independent units and the single BMA
+all-reduce.  The device kernels are not involved; this covers ursabench_b200/dist.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ursabench_b200 import dist as udist
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 100, 1000, 1024):
+        for world in (1, 2, 3, 4, 8):
+            spans = [udist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_chain_elem_offsets_disjoint_and_aligned():
+    D = 272_282
+    offs = [udist.chain_elem_offset(c, D) for c in range(8)]
+    assert all(o % 4 == 0 for o in offs)
+    assert all(b - a >= D for a, b in zip(offs, offs[1:]))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert udist.is_distributed() and udist.rank_world() == (rank, world)
+        S, N, C = 10, 37, 5
+        rng = np.random.RandomState(0)                         # same data on every rank
+        p = rng.dirichlet(np.ones(C), size=(S, N)).astype(np.float32)
+        e = rng.rand(S, N).astype(np.float32)
+        lo, hi = udist.shard_range(S)                          # samples sharded across ranks
+        local_p = torch.from_numpy(p[lo:hi].sum(0))
+        local_e = torch.from_numpy(e[lo:hi].sum(0))
+        before = local_p.clone()
+        P, E, cnt = udist.allreduce_bma(local_p, local_e, hi - lo)
+        assert torch.equal(local_p, before)                    # inputs untouched
+        assert cnt == S
+        np.testing.assert_allclose(P.numpy(), p.sum(0), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(E.numpy(), e.sum(0), rtol=1e-6, atol=1e-6)
+        # every rank ends with the same reduced tensors -> identical metrics everywhere
+        gathered = [torch.zeros_like(P) for _ in range(world)]
+        dist.all_gather(gathered, P.contiguous())
+        assert all(torch.equal(gathered[0], g) for g in gathered)
+        assert udist.allreduce_max_scalar(float(rank + 1), torch.device("cpu")) == float(world)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bma_allreduce_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def test_single_process_is_identity():
+    P, E = torch.rand(4, 3), torch.rand(4)
+    P2, E2, n = udist.allreduce_bma(P, E, 7)
+    assert P2 is P and E2 is E and n == 7

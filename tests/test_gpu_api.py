@@ -1,0 +1,390 @@
+"""GPU tests of the drop-in class API (inference/*, tasks/Prediction) against the reference's golden fixtures, the
+torch-CPU port (oracle/port_torch.py) and the call shapes of the reference's drivers
+(hyperopt/hyper_optimization.py:51-73, experiment.py:172-179, time_script.py:100-113)."""
+import copy
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port_torch as PT
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = torch.device("cuda")
+
+
+def _npz(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _json(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+@pytest.fixture(scope="module")
+def U():
+    import ursabench_b200
+    return ursabench_b200
+
+
+def _flat(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def _toy(n=256, d=20, c=3, bs=32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 1, 4, 5, generator=g)
+    w = torch.randn(d, c, generator=g)
+    y = (x.view(n, -1) @ w).argmax(1)
+    ds = torch.utils.data.TensorDataset(x, y)
+    return ds, torch.utils.data.DataLoader(ds, batch_size=bs, shuffle=False)
+
+
+# ------------------------------------------------------------------------------------------ optimizer class
+CASES = ["sgld_wd_noise", "sgld_nowd_nonoise", "sghmc_wd_noise", "sghmc_nowd_noise", "sghmc_wd_nonoise"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_optimizer_class_matches_reference_golden(U, case):
+    """the reference protocol verbatim: ragged parameter tensors, ``p.grad`` assigned directly, lr moved through
+    ``param_groups`` between steps, identical noise -> bit-identical parameters and momentum buffers."""
+    g = _npz("sgmcmc_step.npz")
+    lr0, mom, wd, n_train, noise = g[case + "/hyper"]
+    shapes = [(7,), (13, 5), (64,), (3, 3, 3, 4), (1,), (257,), (31, 33)]
+    sizes = [int(s) for s in g["sizes"]]
+    init = torch.from_numpy(g[case + "/init"].copy())
+    params = [torch.nn.Parameter(t.clone().view(s).to(DEV)) for t, s in zip(torch.split(init, sizes), shapes)]
+    opt = U.inference.optimSGHMC(params, lr=lr0, momentum=mom, num_training_samples=int(n_train), weight_decay=wd)
+    for t in range(4):
+        for grp in opt.param_groups:
+            grp["lr"] = float(g["%s/lr%d" % (case, t)])
+        gt = torch.from_numpy(g["%s/g%d" % (case, t)].copy())
+        for p, gg in zip(params, torch.split(gt, sizes)):
+            p.grad = gg.clone().view_as(p).to(DEV)
+        z = torch.zeros(opt.flat.ld, device=DEV)
+        z[:opt.flat.D] = torch.from_numpy(g["%s/z%d" % (case, t)].copy()).to(DEV)
+        opt.step(add_langevin_noise=bool(noise), noise=z if noise else None)
+        got = torch.cat([p.detach().reshape(-1) for p in params]).cpu().numpy()
+        assert np.array_equal(got, g["%s/p%d" % (case, t)])
+        if mom != 0:
+            v = torch.cat([opt.state[p]["momentum_buffer"].reshape(-1) for p in params]).cpu().numpy()
+            assert np.array_equal(v, g["%s/v%d" % (case, t)])
+    assert opt.launches == 4                       # ONE kernel launch per step for all 7 tensors
+
+
+def test_optimizer_argument_errors(U):
+    p = [torch.nn.Parameter(torch.zeros(4, device=DEV))]
+    with pytest.raises(ValueError, match="Invalid learning rate"):
+        U.inference.optimSGHMC(p, lr=-1.0)
+    with pytest.raises(ValueError, match="Invalid momentum"):
+        U.inference.optimSGHMC(p, lr=0.1, momentum=-0.1)
+    with pytest.raises(ValueError, match="Invalid weight_decay"):
+        U.inference.optimSGHMC(p, lr=0.1, weight_decay=-1.0)
+    with pytest.raises(ValueError):
+        U.inference.optimSGHMC([torch.nn.Parameter(torch.zeros(4))], lr=0.1)       # CPU parameter: no CPU path
+
+
+# ------------------------------------------------------------------------------------------ samplers
+def _deterministic_trajectory(U, cls_name, hyp, epochs_to_run):
+    """GPU sampler vs. the torch-CPU port with the Langevin noise gated off: weights after the same number of
+    steps must agree (fp32 fwd/bwd on different hardware -> 1e-4)."""
+    ds, loader = _toy()
+    torch.manual_seed(1)
+    model = U.models.MLP(16, 20, 3)
+    ref_model = copy.deepcopy(model)
+    inf = getattr(U.inference, cls_name)(dict(hyp), model.to(DEV), loader, device=DEV)
+    return inf, ref_model, loader, ds
+
+
+def test_csghmc_schedule_and_trajectory_vs_port(U, capsys):
+    hyp = {"lr_0": 0.3, "prior_std": 1.0, "num_samples_per_cycle": 2, "cycle_length": 5, "burn_in_epochs": 1,
+           "num_cycles": 2, "alpha": 0.3}
+    inf, ref_model, loader, ds = _deterministic_trajectory(U, "cSGHMC", hyp, 2)
+    # epochs 0,1 of the cycle are noise-free: (e % 5) + 1 > 5 - 1 - 2 = 2  is False for e = 0, 1
+    noise_flags = []
+    orig_step = inf.optimizer.step
+
+    def spy(add_langevin_noise=True, **kw):
+        noise_flags.append(add_langevin_noise)
+        return orig_step(add_langevin_noise=add_langevin_noise, **kw)
+    inf.optimizer.step = spy
+    inf._run_epoch(lambda b: inf._noise_gate(), lr_for_batch=lambda b: inf._adjust_learning_rate(inf.optimizer, inf.epochs_run, b))
+    inf.epochs_run += 1
+    inf._run_epoch(lambda b: inf._noise_gate(), lr_for_batch=lambda b: inf._adjust_learning_rate(inf.optimizer, inf.epochs_run, b))
+    inf.epochs_run += 1
+    assert not any(noise_flags)
+    batches = [(x, y) for x, y in loader]
+    nb = R.csghmc_num_batch(len(ds), 32)
+    opt = PT.PortOptimSGHMC(ref_model.parameters(), hyp["lr_0"], 1 - hyp["alpha"], 1.0, len(ds))
+    ref = PT.port_sgmcmc_epochs(ref_model, batches, opt, 2, noise_fn=lambda e, b: False,
+                                lr_fn=lambda e, b: PT.port_csghmc_lr(hyp["lr_0"], e, b, nb, 5, 2))
+    got = _flat(inf.model).cpu()
+    assert (got - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    # schedule: host float64, identical to the reference formula
+    assert inf.num_batch == nb
+    assert inf._adjust_learning_rate(inf.optimizer, 3, 4) == R.csghmc_lr(hyp["lr_0"], 3, 4, nb, 5, 2)
+
+
+def test_csghmc_sample_gates_and_bank(U, capsys):
+    hyp = {"lr_0": 0.05, "prior_std": 1.0, "num_samples_per_cycle": 2, "cycle_length": 4, "burn_in_epochs": 1,
+           "num_cycles": 2, "alpha": 0.5}
+    ds, loader = _toy()
+    torch.manual_seed(2)
+    inf = U.inference.cSGHMC(hyp, U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+    samples = inf.sample()
+    assert len(samples) == 4 and inf.epochs_run == 8           # samples at epochs 3,4 of each 4-epoch cycle
+    out = capsys.readouterr().out
+    assert out.count("Epoch: ") == 8
+    assert inf.optimizer.launches == 8 * len(loader)           # exactly one K1 launch per step
+    # the last handle equals the live weights; handles are CPU modules like the reference's deep copies
+    last = samples[-1]
+    assert isinstance(last, torch.nn.Module)
+    assert torch.equal(_flat(last), _flat(inf.model).cpu())
+    assert next(last.parameters()).device.type == "cpu"
+    assert not torch.equal(_flat(samples[0]), _flat(samples[1]))
+    x = torch.randn(5, 1, 4, 5)
+    live = inf.model.eval()(x.to(DEV)).cpu()
+    assert torch.allclose(last.eval()(x), live, atol=1e-5)
+    with pytest.raises(AssertionError):
+        U.inference.cSGHMC({**hyp, "cycle_length": 3}, U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+
+
+@pytest.mark.parametrize("cls_name", ["SGLD", "SGHMC"])
+def test_sghmc_sgld_api_and_scheduler(U, cls_name):
+    hyp = {"lr": 0.05, "prior_std": 1.0, "num_samples": 3, "alpha": 0.4, "burn_in_epochs": 2}
+    ds, loader = _toy()
+    torch.manual_seed(3)
+    inf = getattr(U.inference, cls_name)(hyp, U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+    if cls_name == "SGLD":
+        assert hyp["alpha"] == 1.0 and inf.optimizer.param_groups[0]["momentum"] == 0      # sgld.py:22
+    samples = inf.sample()
+    assert len(samples) == 3 and inf.burnt_in is True
+    assert inf.optimizer.launches == (2 + 1 + 2) * len(loader)       # burn-in + 1, then 1 epoch per sample
+    # CosineAnnealingLR(T_max = burn_in + num_samples) stepped once per epoch (sghmc.py:44-45,87)
+    ref_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=hyp["lr"])
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(ref_opt, T_max=5)
+    for _ in range(5):
+        ref_opt.step()
+        sch.step()
+    assert inf.optimizer.param_groups[0]["lr"] == pytest.approx(ref_opt.param_groups[0]["lr"], rel=1e-9, abs=1e-12)
+    # update_hyp re-initialises the model in place and keeps the flat views attached (hyper_optimization.py:55)
+    before = _flat(inf.model).clone()
+    inf.update_hyp({"lr": 0.01, "prior_std": 2.0, "num_samples": 2, "alpha": 0.4, "burn_in_epochs": 0})
+    assert not torch.equal(before, _flat(inf.model)) and inf.flat.is_attached(inf.model)
+    assert inf.burnt_in is False and len(inf.sample()) == 2
+
+
+def test_sgld_learns_and_noise_has_reference_scale(U):
+    """SGLD on a separable toy problem: the loss goes down, and the per-step noise std is sqrt(2 lr)/N (Q4)."""
+    ds, loader = _toy(n=512)
+    torch.manual_seed(4)
+    model = U.models.MLP(16, 20, 3).to(DEV)
+    hyp = {"lr": 0.5, "prior_std": 10.0, "num_samples": 1, "alpha": 1.0, "burn_in_epochs": 15}
+    inf = U.inference.SGLD(hyp, model, loader, device=DEV)
+    l0 = inf.compute_val_loss(loader)
+    inf.sample()
+    assert inf.compute_val_loss(loader) < 0.6 * l0
+    opt = inf.optimizer
+    p0 = opt.flat.p.clone()
+    opt.flat.g.zero_()
+    opt.param_groups[0]["weight_decay"] = 0.0
+    opt.param_groups[0]["lr"] = 0.1                            # the cosine schedule has annealed lr to ~0 by now
+    opt.step(add_langevin_noise=True)
+    delta = (opt.flat.p - p0)[:opt.flat.D]
+    expect = math.sqrt(2 * opt.param_groups[0]["lr"]) / len(ds)
+    assert abs(delta.std().item() / expect - 1) < 0.1
+
+
+# ------------------------------------------------------------------------------------------ SWAG
+def _swag_hyp(**kw):
+    h = {"swag_lr": 0.02, "swag_wd": 0.0, "lr_init": 0.05, "num_samples": 6, "momentum": 0.5, "burn_in_epochs": 2,
+         "num_iterates": 5, "subspace_type": "covariance"}
+    h.update(kw)
+    return h
+
+
+def test_swag_reference_compat_reproduces_quirks(U):
+    facts = _json("swag_compat_facts.json")
+    ds, loader = _toy(n=64, bs=16)
+    torch.manual_seed(0)
+    swag = U.inference.SWAG(_swag_hyp(reference_compat=True, num_samples=3), U.models.MLP(8, 20, 3).to(DEV), loader,
+                            device=DEV)
+    samples = swag.sample()
+    flats = [_flat(m) for m in samples]
+    assert len(samples) == facts["num_returned"]
+    assert int(swag.num_models_collected.item()) == facts["num_models_collected"] == 0
+    assert all(torch.equal(flats[0], f) for f in flats) == facts["all_samples_identical"]
+    assert torch.equal(flats[0], _flat(swag.model).cpu()) == facts["sample_equals_last_iterate"]
+    assert bool((swag.weight_variance == 1e-30).all()) == facts["variance_all_clamp"]
+    assert bool((swag.subspace.cov_mat_sqrt == 0).all()) == facts["ring_all_zero"]
+    with pytest.raises(AttributeError, match="subspace"):
+        swag.sample_iterative(full_cov=True)
+
+
+def test_swag_textbook_moments_and_draws(U):
+    ds, loader = _toy(n=128, bs=32)
+    torch.manual_seed(5)
+    swag = U.inference.SWAG(_swag_hyp(num_samples=32), U.models.MLP(8, 20, 3).to(DEV), loader, device=DEV, max_rank=4)
+    iterates = []
+    orig = swag._collect_model
+
+    def spy():
+        iterates.append(_flat(swag.model).clone())
+        orig()
+    swag._collect_model = spy
+    from ursabench_b200 import _C
+    seen = {}
+    orig_draw = _C.swag_draw
+
+    def draw_spy(out, mean_, var_, D_, **kw):
+        seen.update(kw, ld=out.shape[1])
+        return orig_draw(out, mean_, var_, D_, **kw)
+    _C.swag_draw = draw_spy
+    try:
+        samples = swag.sample(full_cov=True)
+    finally:
+        _C.swag_draw = orig_draw
+    W = torch.stack(iterates)                                   # [5, D]
+    assert int(swag.num_models_collected.item()) == 5 and len(samples) == 32
+    # moments == CPU port run on the same iterates (bit-exact: same op order)
+    mean, sq = torch.zeros(W.shape[1]), torch.zeros(W.shape[1])
+    devs = []
+    for k in range(5):
+        devs.append(PT.port_swa_collect(W[k].cpu(), mean, sq, k).clone())
+    assert torch.equal(swag.weight_mean.cpu(), mean) and torch.equal(swag.sq_mean.cpu(), sq)
+    assert torch.equal(swag.subspace.cov_mat_sqrt.cpu(), torch.stack(devs[-4:]))       # ring: last max_rank rows
+    assert int(swag.subspace.rank.item()) == 4
+    var = torch.clamp(sq - mean ** 2, 1e-30)
+    assert torch.equal(swag.weight_variance.cpu(), var)
+    # draws == mean + sqrt(var) z1 + D^T z2 / sqrt(max_rank - 1) with the z2 the class drew and the documented
+    # Philox z1 stream (swag.py:88-97 without the :98 overwrite)
+    draws = torch.stack([_flat(m) for m in samples])            # [32, D] (CPU handles)
+    D = W.shape[1]
+    z1 = torch.empty(32 * seen["ld"], device=DEV)
+    _C.philox_normal(z1, seen["seed"], seen["step"])
+    z1 = z1.view(32, seen["ld"])[:, :D].cpu().numpy()
+    expect = R.swag_draw(mean.numpy(), var.numpy(), z1, seen["ring"][:, :D].cpu().numpy(), seen["z2"].cpu().numpy(),
+                         max_rank=4)
+    np.testing.assert_allclose(draws.numpy(), expect, rtol=2e-5, atol=2e-6)
+    assert len({tuple(d[:8].tolist()) for d in draws}) == 32    # all distinct
+
+
+def test_swag_batched_draw_uses_one_pass(U, monkeypatch):
+    ds, loader = _toy(n=64, bs=32)
+    swag = U.inference.SWAG(_swag_hyp(num_samples=30, burn_in_epochs=1, num_iterates=2), U.models.MLP(8, 20, 3).to(DEV),
+                            loader, device=DEV)
+    calls = []
+    from ursabench_b200 import _C
+    orig = _C.swag_draw
+    monkeypatch.setattr(_C, "swag_draw", lambda *a, **k: (calls.append(a[0].shape[0]), orig(*a, **k))[1])
+    swag.sample(full_cov=True)
+    assert calls == [30]                                        # 30 draws, ONE kernel launch over the ring
+
+
+# ------------------------------------------------------------------------------------------ Prediction
+def _mlp_models_from_golden(U, name):
+    g = _npz("prediction.npz")
+    hidden, in_dim, C = (int(v) for v in g[name + "/arch"])
+    ms = []
+    for row in g[name + "/bank"]:
+        m = U.models.MLP(hidden, in_dim, C)
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(row.copy()), m.parameters())
+        ms.append(m)
+    x, y = torch.from_numpy(g[name + "/x"]), torch.from_numpy(g[name + "/y"])
+    return g, ms, x, y, C
+
+
+@pytest.mark.parametrize("engine", ["auto", "generic"])
+def test_prediction_matches_reference_golden_mlp(U, engine):
+    g, ms, x, y, C = _mlp_models_from_golden(U, "mlp")
+    ref = _json("prediction_metrics.json")["mlp"]
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=128, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, C, DEV, "ALL", engine=engine)
+    assert torch.equal(task.targets, y)
+    task.update_statistics(ms[:3], output_performance=False)            # accumulates across calls (:38-48)
+    task.update_statistics(ms[3:], output_performance=False)
+    assert task.num_samples_collected == 5
+    assert task.last_engine == ("fused_mlp" if engine == "auto" else "generic")
+    np.testing.assert_allclose(task.ensemble_proba.numpy(), g["mlp/ensemble_proba"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(task.expected_data_uncertainty.numpy(), g["mlp/entropy"], atol=1e-5, rtol=1e-5)
+    m = task.get_performance_metrics()
+    assert set(m) == set(ref)
+    for k, v in ref.items():
+        tol = 1e-9 if k == "error_rate" else 2e-5
+        assert m[k] == pytest.approx(v, abs=tol, rel=2e-5), k
+    assert all(next(mm.parameters()).device.type == "cpu" for mm in ms)   # callers' modules end where they started
+
+
+def test_prediction_single_module_and_output_performance(U):
+    g, ms, x, y, C = _mlp_models_from_golden(U, "mlp")
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=128, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, C, DEV, ["ll"])
+    ll = task.update_statistics(ms[0], output_performance=True)
+    assert isinstance(ll, float)
+    assert ll == pytest.approx(_json("prediction_metrics.json")["mlp_single_ll"], rel=2e-5)
+    task2 = U.tasks.Prediction({"in_distribution_test": loader}, C, DEV, ["ll", "ece"])
+    with pytest.raises(RuntimeError, match="Multiple metrics"):
+        task2.update_statistics(ms[0], output_performance=True)
+    with pytest.raises(NotImplementedError):
+        task2.update_statistics([1, 2, 3])
+    with pytest.raises(AssertionError):
+        U.tasks.Prediction({"in_distribution_test": loader}, C, DEV, ["accuracy"])
+    task.reset()
+    assert task.num_samples_collected == 0 and not task.ensemble_proba.any()
+    assert task.expected_data_uncertainty.any()                            # reference reset() keeps it (Q10)
+
+
+def test_prediction_preresnet8_generic_matches_reference_golden(U):
+    g = _npz("prediction.npz")
+    ref = _json("prediction_metrics.json")["preresnet8"]
+    ms = []
+    for s in range(2):
+        m = U.models.PreResNet(num_classes=10, depth=8)
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(g["preresnet8/bank"][s].copy()), m.parameters())
+        off, buf = 0, torch.from_numpy(g["preresnet8/buffers"][s].copy())
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.copy_(buf[off:off + b.numel()].view(b.shape))
+                off += b.numel()
+        ms.append(m)
+    x, y = torch.from_numpy(g["preresnet8/x"].astype(np.float32)), torch.from_numpy(g["preresnet8/y"])
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate", "nll", "brier_score", "ece"])
+    task.update_statistics(ms, output_performance=False)
+    np.testing.assert_allclose(task.ensemble_proba.numpy(), g["preresnet8/ensemble_proba"], atol=1e-5, rtol=0)
+    m = task.get_performance_metrics()
+    for k in m:
+        assert m[k] == pytest.approx(ref[k], abs=2e-5, rel=2e-5), k
+
+
+def test_hyperopt_shaped_call_sequence(U, capsys):
+    """hyperopt/hyper_optimization.py:51-73: update_hyp -> reset -> sample -> update_statistics(output_performance)."""
+    ds, loader = _toy(n=256)
+    tds, tloader = _toy(n=100, seed=9)
+    torch.manual_seed(6)
+    inf = U.inference.cSGLD(None, U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+    task = U.tasks.Prediction({"in_distribution_test": tloader}, 3, DEV, ["ll"])
+    objs = []
+    for lr in (0.2, 0.4):
+        hyp = {"lr_0": lr, "prior_std": 5.0, "num_samples_per_cycle": 2, "cycle_length": 4, "burn_in_epochs": 1,
+               "num_cycles": 1}
+        inf.update_hyp(hyp)
+        task.reset()
+        samples = U.util.silent(inf.sample)()
+        obj = task.update_statistics(samples, output_performance=True)
+        assert isinstance(obj, float) and obj < 0 and task.last_engine == "fused_mlp"
+        assert task.num_samples_collected == 2
+        objs.append(obj)
+    assert capsys.readouterr().out.count("Epoch") == 0              # util.silent swallowed the per-epoch prints
+    # the bank fast path and the reference-style path (materialised CPU modules) agree
+    task.reset()
+    a = task.update_statistics(samples, output_performance=True)
+    plain = [copy.deepcopy(s.materialize()) for s in samples]
+    task.reset()
+    b = task.update_statistics(plain, output_performance=True)
+    assert a == pytest.approx(b, rel=1e-6)

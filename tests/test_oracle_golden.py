@@ -182,3 +182,98 @@ def test_philox_normals_moments():
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
     z2, _ = R.philox_normals(1000, seed=1234, step=7, elem_offset=500)
     assert np.array_equal(z2[:100], z[500:600])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/port_torch.py (the timed CPU baseline) pinned to the same fixtures
+@pytest.mark.parametrize("case", CASES)
+def test_port_optimizer_matches_reference(case):
+    import torch
+    from oracle.port_torch import PortOptimSGHMC
+    g = _npz("sgmcmc_step.npz")
+    lr0, mom, wd, n_train, noise = g[case + "/hyper"]
+    sizes = [int(s) for s in g["sizes"]]
+    flat = torch.from_numpy(g[case + "/init"].copy())
+    params = [t.clone().requires_grad_(True) for t in torch.split(flat, sizes)]
+    opt = PortOptimSGHMC(params, lr0, mom, wd, int(n_train))
+    for t in range(4):
+        opt.lr = float(g["%s/lr%d" % (case, t)])
+        gs = torch.split(torch.from_numpy(g["%s/g%d" % (case, t)].copy()), sizes)
+        zs = list(torch.split(torch.from_numpy(g["%s/z%d" % (case, t)].copy()), sizes))
+        for p, gg in zip(params, gs):
+            p.grad = gg.clone()
+        opt.step(add_langevin_noise=bool(noise), noise=zs)
+        got = torch.cat([p.detach() for p in params]).numpy()
+        assert np.array_equal(got, g["%s/p%d" % (case, t)])
+
+
+def test_port_prediction_matches_reference():
+    import torch
+    from oracle.port_torch import port_metrics, port_prediction_update
+    from ursabench_b200.models import MLP
+    g = _npz("prediction.npz")
+    ref = _json("prediction_metrics.json")["mlp"]
+    hidden, in_dim, C = (int(v) for v in g["mlp/arch"])
+    ms = []
+    for row in g["mlp/bank"]:
+        m = MLP(hidden, in_dim, C)
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(row.copy()), m.parameters())
+        ms.append(m)
+    x, y = torch.from_numpy(g["mlp/x"]), torch.from_numpy(g["mlp/y"])
+    batches = [(x[i:i + 128], y[i:i + 128]) for i in range(0, len(x), 128)]
+    P, E = port_prediction_update(ms, batches, C)
+    assert np.array_equal(P.numpy(), g["mlp/ensemble_proba"])
+    np.testing.assert_allclose(E.numpy(), g["mlp/entropy"], rtol=1e-6)
+    m = port_metrics(P, len(ms), y)
+    for k in ("error_rate", "nll", "brier_score", "ece"):
+        assert m[k] == pytest.approx(ref[k], rel=1e-7, abs=1e-9)
+
+
+def test_port_swa_collect_matches_reference():
+    import torch
+    from oracle.port_torch import port_swa_collect
+    g = _npz("swa_collect.npz")
+    ws = g["textbook/w"]
+    mean, sq = torch.zeros(ws.shape[1]), torch.zeros(ws.shape[1])
+    for k in range(ws.shape[0]):
+        port_swa_collect(torch.from_numpy(ws[k].copy()), mean, sq, k)
+        assert np.array_equal(mean.numpy(), g["textbook/mean%d" % k])
+        assert np.array_equal(sq.numpy(), g["textbook/sq%d" % k])
+
+
+def test_model_layouts_match_reference():
+    """our models.py keeps the reference's parameter order / shapes / buffer order (flat layout = util.flatten)."""
+    import warnings
+    from ursabench_b200 import models
+    lay = _json("layouts.json")
+    mk = {"MLP400_c10": lambda: models.MLP(400, 784, 10),
+          "PreResNet20_c10": lambda: models.PreResNet(num_classes=10, depth=20),
+          "PreResNet8_c10": lambda: models.PreResNet(num_classes=10, depth=8),
+          "WRN28x10_c100": lambda: models.WideResNet(num_classes=100, depth=28, widen_factor=10)}
+    for k, f in mk.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = f()
+        assert [[n, list(p.shape)] for n, p in m.named_parameters()] == lay[k]["params"], k
+        assert [[n, list(b.shape), str(b.dtype)] for n, b in m.named_buffers()] == lay[k]["buffers"], k
+        assert sum(p.numel() for p in m.parameters()) == lay[k]["D"]
+
+
+def test_model_forward_matches_reference_golden():
+    """same weights -> same logits as the reference's PreResNet / MLP (pins models.py and the flat layout)."""
+    import torch
+    from ursabench_b200 import models
+    g = _npz("prediction.npz")
+    m = models.PreResNet(num_classes=10, depth=8).eval()
+    x = torch.from_numpy(g["preresnet8/x"].astype(np.float32))
+    for s in range(2):
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(g["preresnet8/bank"][s].copy()), m.parameters())
+        off = 0
+        buf = torch.from_numpy(g["preresnet8/buffers"][s].copy())
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.copy_(buf[off:off + b.numel()].view(b.shape))
+                off += b.numel()
+        with torch.no_grad():
+            out = m(x).numpy()
+        np.testing.assert_allclose(out, g["preresnet8/logits"][s], rtol=1e-5, atol=1e-5)

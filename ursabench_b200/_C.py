@@ -27,6 +27,8 @@ SIGNATURES = {
     "ursa_last_error": (_c.c_char_p, []),
     "ursa_device_info": (_i32, [_c.POINTER(_i32)] * 3),
     "ursa_sgmcmc_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _u32, _u64, _u64, _u64, _vp]),
+    "ursa_sgmcmc_step_dyn": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _u32, _u64, _u64, _vp]),
+    "ursa_sgmcmc_set_dyn": (_i32, [_vp, _f32, _f32, _f32, _f32, _u64, _vp]),
     "ursa_philox_normal": (_i32, [_vp, _i64, _u64, _u64, _u64, _vp]),
     "ursa_swag_collect": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp]),
     "ursa_swag_variance": (_i32, [_vp, _vp, _vp, _i64, _f32, _vp]),
@@ -102,9 +104,31 @@ def sgmcmc_step(p, g, v=None, snapshot=None, noise=None, *, lr, momentum, wd_ove
         if t is not None and t.numel() < n:
             raise ValueError("%s has fewer elements than p" % nm)
     flags = (STEP_FIRST if first_step else 0) | (STEP_NOISE if add_noise else 0) | (STEP_ZERO_GRAD if zero_grad else 0)
-    rc = lib().ursa_sgmcmc_step(_ptr(p), _ptr(g), _ptr(v), _ptr(snapshot), _ptr(noise), n, lr, momentum, wd_over_n,
-                                noise_mul, noise_div, flags, seed, step, elem_offset, _stream(p))
+    rc = lib().ursa_sgmcmc_step(_ptr(p), _ptr(g), _ptr(v), _ptr(snapshot), _ptr(noise), n, float(lr), float(momentum),
+                                float(wd_over_n), float(noise_mul), float(noise_div), flags, int(seed), int(step),
+                                int(elem_offset), _stream(p))
     _check(rc, "ursa_sgmcmc_step")
+
+
+def sgmcmc_step_dyn(p, g, v, snapshot, noise, dyn, *, first_step=False, add_noise=True, zero_grad=False, seed=0,
+                    elem_offset=0):
+    """K1 with [lr, momentum, wd_over_n, noise_scale, step_lo, step_hi] read from the device tensor ``dyn``
+    (graph-capturable: replays pick up new scalars)."""
+    for t, nm, opt in ((p, "p", False), (g, "g", False), (v, "v", True), (snapshot, "snapshot", True),
+                       (noise, "noise", True), (dyn, "dyn", False)):
+        _dev_f32(t, nm, opt)
+    flags = (STEP_FIRST if first_step else 0) | (STEP_NOISE if add_noise else 0) | (STEP_ZERO_GRAD if zero_grad else 0)
+    rc = lib().ursa_sgmcmc_step_dyn(_ptr(p), _ptr(g), _ptr(v), _ptr(snapshot), _ptr(noise), p.numel(), _ptr(dyn),
+                                    flags, int(seed), int(elem_offset), _stream(p))
+    _check(rc, "ursa_sgmcmc_step_dyn")
+
+
+def sgmcmc_set_dyn(dyn, lr, momentum, wd_over_n, noise_scale, step):
+    _dev_f32(dyn, "dyn")
+    if dyn.numel() < 6:
+        raise ValueError("dyn needs 6 words")
+    _check(lib().ursa_sgmcmc_set_dyn(_ptr(dyn), float(lr), float(momentum), float(wd_over_n), float(noise_scale),
+                                     int(step), _stream(dyn)), "ursa_sgmcmc_set_dyn")
 
 
 def philox_normal(out, seed, step, elem_offset=0):

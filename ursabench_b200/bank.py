@@ -132,6 +132,7 @@ class BankedSample(nn.Module):
                 raise RuntimeError("this bank has no module skeleton to materialise samples from")
             inner = copy.deepcopy(bank.skeleton)
             _load_row_into(inner, bank.w[self._ursa_row].cpu(), bank.b[self._ursa_row].cpu())
+            inner.train(self.training)
             object.__setattr__(self, "_ursa_inner", inner)
         return inner
 

@@ -19,6 +19,7 @@ struct StepArgs {
     uint32_t flags;
     uint2 key;
     uint64_t step, elem_offset;
+    const float *dyn;   // optional device-resident [lr, momentum, wd_over_n, noise_scale, step_lo, step_hi] (CUDA-graph replay)
 };
 
 // The arithmetic of one element, in the reference's operation order.  __fmul_rn / __fadd_rn pin the
@@ -54,7 +55,17 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 2;
 
 template <bool HAS_MOM, int NOISE>
-__global__ void __launch_bounds__(kThreads, 4) sgmcmc_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) sgmcmc_step_kernel(const StepArgs a_in) {
+    StepArgs a = a_in;
+    if (a.dyn) {        // scalars that change between replays of a captured graph live in device memory
+        a.lr = __ldg(a.dyn + 0);
+        a.momentum = __ldg(a.dyn + 1);
+        a.wd_over_n = __ldg(a.dyn + 2);
+        a.noise_scale = __ldg(a.dyn + 3);
+        a.noise_mul = a.noise_scale;
+        a.noise_div = 1.f;
+        a.step = ((uint64_t)__float_as_uint(__ldg(a.dyn + 5)) << 32) | (uint64_t)__float_as_uint(__ldg(a.dyn + 4));
+    }
     const bool first = (a.flags & URSA_STEP_FIRST) != 0;
     const bool zero_g = (a.flags & URSA_STEP_ZERO_GRAD) != 0;
     const int64_t nvec = a.n >> 2;
@@ -129,6 +140,17 @@ __global__ void __launch_bounds__(kThreads) philox_normal_kernel(float *out, int
     }
 }
 
+__global__ void set_dyn_kernel(float *dyn, float lr, float momentum, float wd_over_n, float noise_scale, uint64_t step) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        dyn[0] = lr;
+        dyn[1] = momentum;
+        dyn[2] = wd_over_n;
+        dyn[3] = noise_scale;
+        dyn[4] = __uint_as_float((uint32_t)step);
+        dyn[5] = __uint_as_float((uint32_t)(step >> 32));
+    }
+}
+
 static int grid_for(int64_t nvec, int ctas_per_sm) {
     const int64_t want = (nvec + (int64_t)kThreads * kUnroll - 1) / ((int64_t)kThreads * kUnroll);
     const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
@@ -160,7 +182,7 @@ extern "C" int ursa_sgmcmc_step(float *p, float *g, float *v, float *snapshot, c
     a.noise_scale = add_noise ? (float)((double)noise_mul / (double)noise_div) : 0.f;
     a.flags = flags;
     a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    a.step = step; a.elem_offset = elem_offset;
+    a.step = step; a.elem_offset = elem_offset; a.dyn = nullptr;
     const int mode = !add_noise ? NOISE_NONE : (noise ? NOISE_EXTERNAL : NOISE_PHILOX);
     const bool mom = momentum != 0.f;
     cudaStream_t st = (cudaStream_t)stream;
@@ -189,5 +211,47 @@ extern "C" int ursa_philox_normal(float *out, int64_t n, uint64_t seed, uint64_t
     philox_normal_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
         out, n, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), step, elem_offset);
     URSA_LAUNCH_CHECK("philox_normal_kernel");
+    return URSA_OK;
+}
+
+extern "C" int ursa_sgmcmc_step_dyn(float *p, float *g, float *v, float *snapshot, const float *noise, int64_t n,
+                                    const float *dyn, uint32_t flags, uint64_t seed, uint64_t elem_offset,
+                                    void *stream) {
+    URSA_REQUIRE(n >= 0 && dyn, "ursa_sgmcmc_step_dyn: bad arguments");
+    URSA_REQUIRE(n == 0 || (p && g), "ursa_sgmcmc_step_dyn: p and g must be non-null");
+    URSA_REQUIRE(aligned16(p) && aligned16(g) && aligned16(v) && aligned16(snapshot) && aligned16(noise),
+                 "ursa_sgmcmc_step_dyn: buffers must be 16-byte aligned");
+    URSA_REQUIRE((elem_offset & 3u) == 0, "ursa_sgmcmc_step_dyn: elem_offset must be a multiple of 4");
+    if (n == 0) return URSA_OK;
+    StepArgs a;
+    a.p = p; a.g = g; a.v = v; a.snap = snapshot; a.noise = noise; a.n = n;
+    a.lr = a.momentum = a.wd_over_n = a.noise_mul = a.noise_scale = 0.f; a.noise_div = 1.f;
+    a.flags = flags;
+    a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.step = 0; a.elem_offset = elem_offset; a.dyn = dyn;
+    const bool add_noise = (flags & URSA_STEP_NOISE) != 0;
+    const int mode = !add_noise ? NOISE_NONE : (noise ? NOISE_EXTERNAL : NOISE_PHILOX);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n >> 2, 8);
+#define URSA_K1(M, Z) sgmcmc_step_kernel<M, Z><<<grid, kThreads, 0, st>>>(a)
+    if (v) {                       // momentum buffer present <=> momentum != 0 (the value itself is dynamic)
+        if (mode == NOISE_NONE) URSA_K1(true, NOISE_NONE);
+        else if (mode == NOISE_EXTERNAL) URSA_K1(true, NOISE_EXTERNAL);
+        else URSA_K1(true, NOISE_PHILOX);
+    } else {
+        if (mode == NOISE_NONE) URSA_K1(false, NOISE_NONE);
+        else if (mode == NOISE_EXTERNAL) URSA_K1(false, NOISE_EXTERNAL);
+        else URSA_K1(false, NOISE_PHILOX);
+    }
+#undef URSA_K1
+    URSA_LAUNCH_CHECK("sgmcmc_step_kernel(dyn)");
+    return URSA_OK;
+}
+
+extern "C" int ursa_sgmcmc_set_dyn(float *dyn, float lr, float momentum, float wd_over_n, float noise_scale,
+                                   uint64_t step, void *stream) {
+    URSA_REQUIRE(dyn, "ursa_sgmcmc_set_dyn: dyn is null");
+    set_dyn_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dyn, lr, momentum, wd_over_n, noise_scale, step);
+    URSA_LAUNCH_CHECK("set_dyn_kernel");
     return URSA_OK;
 }

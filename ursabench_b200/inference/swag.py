@@ -1,0 +1,101 @@
+"""SWAG: SWA moments + batched diagonal / low-rank posterior draws (reference inference/swag.py:12-147).
+
+Reference quirks (verified on the live reference, tests/golden/swag_compat_facts.json):
+  Q5  every draw is overwritten by the mean (``weight_sample = self.weight_mean``, :98/:118);
+  Q6  ``num_models_collected`` is never incremented, so the "mean" is the last iterate and the variance 1e-30;
+  Q7  ``full_cov=True`` raises AttributeError (``self.swag_model.subspace``, :90).
+``hyperparameters['reference_compat'] = True`` reproduces Q5/Q6 bit for bit (Q7 raises the same AttributeError).
+The default is the algorithm the code was written to be (Maddox et al. 2019): n increments after each collect and
+the draw of swag.py:85-97 is returned -- all S draws produced by ONE pass over the deviation ring (K2b).
+"""
+import torch
+
+from .. import _C
+from ..util import bn_update, check_bn
+from .swa import SWA
+
+
+class SWAG(SWA):
+    def __init__(self, hyperparameters, model=None, train_loader=None, model_loss="multi_class_linear_output",
+                 device=torch.device("cpu"), **subspace_kwargs):
+        if hyperparameters is None:
+            hyperparameters = dict(self._defaults)
+        super().__init__(hyperparameters, model=model, train_loader=train_loader, model_loss=model_loss,
+                         device=device, **subspace_kwargs)
+        self.num_samples = hyperparameters["num_samples"]
+        self.reference_compat = bool(hyperparameters.get("reference_compat", False))
+        self.weight_variance = None
+        self._draw_calls = 0
+
+    def update_hyp(self, hyperparameters, **subspace_kwargs):
+        super().update_hyp(hyperparameters, **subspace_kwargs)
+        self.num_samples = hyperparameters["num_samples"]
+        self.reference_compat = bool(hyperparameters.get("reference_compat", False))
+        self.weight_variance = None
+
+    # -- training + collection (first call only), reference :54-83 ---------------------------------------------
+    def _fit_moments(self, val_loader, debug_val_loss, wandb_debug):
+        epochs = self.burn_in_epochs + self.num_iterates
+        for epoch in range(epochs):
+            total = self._sgd_epoch(track_loss=debug_val_loss)
+            if debug_val_loss:
+                self._debug(total, val_loader, wandb_debug)
+            if epoch >= self.burn_in_epochs:
+                self._collect_model()
+                if not self.reference_compat:
+                    self.num_models_collected += 1           # the increment the reference forgot (Q6)
+        self.burnt_in = True
+        _, self.weight_variance = self._get_mean_and_variance()
+
+    # -- K2b -----------------------------------------------------------------------------------------------------
+    def _draw_into_bank(self, num, full_cov):
+        """Draw ``num`` weight vectors into fresh bank rows with one kernel launch per <= 32 draws."""
+        if full_cov and self.reference_compat:
+            # reference :90 dereferences self.swag_model.subspace, which does not exist (Q7)
+            raise AttributeError("'%s' object has no attribute 'subspace'" % type(self.swag_model).__name__)
+        first = self.bank.count
+        self.bank.reserve(first + num)
+        D = self.num_parameters
+        var_full = torch.empty_like(self._mean)
+        _C.swag_variance(self._mean, self._sq, var_full, self.var_clamp)
+        rows = self.subspace.rows() if full_cov else None
+        K = 0 if rows is None else rows.shape[0]
+        done = 0
+        while done < num:
+            s = min(_C.DRAW_MAX_S, num - done)
+            out = self.bank.w[first + done:first + done + s]
+            if self.reference_compat:
+                out[:, :D] = self._mean[:D]                    # Q5: the draw is discarded, the mean is returned
+            else:
+                z2 = torch.randn(s, K, device=self.device) if K else None
+                _C.swag_draw(out, self._mean, var_full, D, ring=rows if K else None, z2=z2,
+                             rank_div=float((self.subspace.max_rank - 1) ** 0.5),          # reference :95
+                             seed=int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, step=self._draw_calls)
+                self._draw_calls += 1
+            done += s
+        self.bank.count = first + num
+        return list(range(first, first + num))
+
+    def _finish_sample(self, row, update_bn):
+        """Load the draw into ``swag_model``, re-estimate BatchNorm statistics (reference :99-102,:123-124 -- one full
+        pass over the train set per sample) and store them with the row."""
+        if update_bn and check_bn(self.swag_model):
+            self.swag_flat.load_vector(self.bank.w[row])
+            bn_update(self.train_loader, self.swag_model, device=self.device)
+        self.bank.set_buffers(row, self.swag_flat.b)
+        return self.bank.handle(row)
+
+    def sample_iterative(self, update_bn=True, val_loader=None, debug_val_loss=False, wandb_debug=False,
+                         full_cov=False):
+        if self.burnt_in is False:
+            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+        row = self._draw_into_bank(1, full_cov)[0]
+        return self._finish_sample(row, update_bn)
+
+    def sample(self, num_samples=None, val_loader=None, debug_val_loss=False, wandb_debug=False, full_cov=False):
+        if num_samples is None:
+            num_samples = self.num_samples
+        if self.burnt_in is False:
+            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+        rows = self._draw_into_bank(num_samples, full_cov)     # all draws: one pass over the ring
+        return [self._finish_sample(r, True) for r in rows]
