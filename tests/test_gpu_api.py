@@ -388,3 +388,63 @@ def test_hyperopt_shaped_call_sequence(U, capsys):
     task.reset()
     b = task.update_statistics(plain, output_performance=True)
     assert a == pytest.approx(b, rel=1e-6)
+
+
+def test_prediction_preresnet8_fused_matches_reference_golden(U):
+    g = _npz("prediction.npz")
+    ref = _json("prediction_metrics.json")["preresnet8"]
+    ms = []
+    for s in range(2):
+        m = U.models.PreResNet(num_classes=10, depth=8)
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(g["preresnet8/bank"][s].copy()), m.parameters())
+        off, buf = 0, torch.from_numpy(g["preresnet8/buffers"][s].copy())
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.copy_(buf[off:off + b.numel()].view(b.shape))
+                off += b.numel()
+        ms.append(m)
+    x, y = torch.from_numpy(g["preresnet8/x"].astype(np.float32)), torch.from_numpy(g["preresnet8/y"])
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate", "nll", "brier_score", "ece"])
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_engine == "fused_preresnet"
+    np.testing.assert_allclose(task.ensemble_proba.numpy(), g["preresnet8/ensemble_proba"], atol=1e-5, rtol=0)
+    m = task.get_performance_metrics()
+    for k in m:
+        assert m[k] == pytest.approx(ref[k], abs=2e-5, rel=2e-5), k
+
+
+def test_cuda_graph_step_matches_eager(U, capsys):
+    """forward + backward + K1 captured in one CUDA graph follows the same trajectory as eager launches
+    (noise gated off through the device-resident scalars; lr changes every step)."""
+    hyp = {"lr_0": 0.3, "prior_std": 1.0, "num_samples_per_cycle": 1, "cycle_length": 6, "burn_in_epochs": 0,
+           "num_cycles": 1, "alpha": 0.3}
+    ds, loader = _toy(n=256, bs=32)
+    flats = []
+    for graphed in (False, True):
+        torch.manual_seed(11)
+        inf = U.inference.cSGHMC(dict(hyp), U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+        if graphed:
+            x0, y0 = next(iter(loader))
+            g = inf.enable_cuda_graph(x0, y0)
+        for e in range(2):
+            for b, (x, y) in enumerate(loader):
+                inf._adjust_learning_rate(inf.optimizer, e, b)
+                inf.train_step(x, y, add_langevin_noise=False)
+        flats.append(_flat(inf.model).clone())
+        if graphed:
+            assert g.replays == 2 * len(loader) - 1            # all but the momentum-initialising first step
+    assert (flats[0] - flats[1]).abs().max().item() < 1e-6
+    # with noise on, the graphed sampler draws the same Philox stream as the eager one (same seed / step counter)
+    outs = []
+    for graphed in (False, True):
+        torch.manual_seed(12)
+        inf = U.inference.cSGHMC(dict(hyp), U.models.MLP(16, 20, 3).to(DEV), loader, device=DEV)
+        if graphed:
+            x0, y0 = next(iter(loader))
+            inf.enable_cuda_graph(x0, y0)
+        for b, (x, y) in enumerate(loader):
+            inf._adjust_learning_rate(inf.optimizer, 0, b)
+            inf.train_step(x, y, add_langevin_noise=True)
+        outs.append(_flat(inf.model).clone())
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-5

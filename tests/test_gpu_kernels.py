@@ -312,3 +312,50 @@ def test_k3_mlp_forward_config1_shape_vs_torch(C):
     assert (logits - ref).abs().max().item() < 2e-5
     pref = torch.softmax(ref.double(), -1).sum(0)
     assert (P.double() - pref).abs().max().item() < 1e-5
+
+
+# ----------------------------------------------------------------------------- K3 forward, PreResNet
+def test_k3_preresnet8_forward_matches_reference_golden(C):
+    g = _npz("prediction.npz")
+    bank, bufs = dev(g["preresnet8/bank"]), dev(g["preresnet8/buffers"])
+    x = dev(g["preresnet8/x"].astype(np.float32))
+    S, N, Cc = 2, x.shape[0], 10
+    P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
+    logits = torch.empty(S, N, Cc, device="cuda")
+    C.bma_preresnet_forward(bank, bufs, S, x, 8, Cc, P, E, logits_out=logits)
+    ref = g["preresnet8/logits"]
+    err = np.abs(logits.cpu().numpy() - ref).max()
+    assert err < 1e-4 * max(1.0, np.abs(ref).max()), err
+    np.testing.assert_allclose(P.cpu().numpy(), g["preresnet8/ensemble_proba"], atol=1e-5, rtol=0)   # north star
+    np.testing.assert_allclose(E.cpu().numpy(), g["preresnet8/entropy"], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("depth,S,N,Cc", [(20, 3, 70, 10), (14, 9, 5, 100), (20, 1, 513, 10)])
+def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc):
+    """PreResNet-20 (config 2/5) with random BN statistics against a plain PyTorch fp32 forward (TF32 off);
+    N not a multiple of the per-CTA image group, S crossing the sample-chunk size, image chunking (N > 512)."""
+    from ursabench_b200.models import PreResNet
+    torch.manual_seed(depth + S)
+    ms = []
+    for s in range(S):
+        m = PreResNet(num_classes=Cc, depth=depth).cuda().eval()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.data.uniform_(0.5, 1.5)
+                mod.bias.data.normal_(0, 0.2)
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 2.0)
+        m.fc.weight.data.mul_(4.0)
+        ms.append(m)
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
+    bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms])
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
+    logits = torch.empty(S, N, Cc, device="cuda")
+    C.bma_preresnet_forward(bank, bufs, S, x, depth, Cc, P, E, logits_out=logits)
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        ref = torch.stack([m(x) for m in ms])
+    scale = max(1.0, ref.abs().max().item())
+    assert (logits - ref).abs().max().item() < 1e-4 * scale
+    pref = torch.softmax(ref.double(), -1).sum(0)
+    assert (P.double() - pref).abs().max().item() < 2e-5

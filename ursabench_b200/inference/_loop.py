@@ -102,21 +102,27 @@ class _GraphedStep:
                 list(opt._first), opt.launches)
         owner.model.train()
         opt.zero_grad()
-        if opt.param_groups[0]["momentum"] != 0 and opt._first[0]:
-            # the momentum-initialising first step (optim_sghmc.py:51-52) is a different kernel variant: run it
-            # eagerly once so that the captured variant is the steady-state one (state is restored below)
-            loss = owner.loss_criterion(owner.model(self.x), self.y)
-            loss.backward()
-            opt.step(add_langevin_noise=False, zero_grad=True)
+        # Autograd caches one AccumulateGrad node per parameter for as long as any graph that references it is alive,
+        # and the node remembers the stream it was created on.  Every loss below is therefore deleted before the next
+        # forward, so the capture creates fresh nodes on the capture stream.
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            if opt.param_groups[0]["momentum"] != 0 and opt._first[0]:
+                # the momentum-initialising first step (optim_sghmc.py:51-52) is a different kernel variant: run it
+                # once so that the captured variant is the steady-state one (state is restored below)
+                loss = owner.loss_criterion(owner.model(self.x), self.y)
+                loss.backward()
+                opt.step(add_langevin_noise=False, zero_grad=True)
+                del loss
             for _ in range(3):                                   # warm-up on a side stream (cuDNN / cuBLAS handles)
                 opt.refresh_device_scalars(False)
                 loss = owner.loss_criterion(owner.model(self.x), self.y)
                 loss.backward()
                 opt.step_captured(zero_grad=True)
+                del loss
         torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         opt.refresh_device_scalars(False)
         with torch.cuda.graph(self.graph):
@@ -124,6 +130,7 @@ class _GraphedStep:
             loss.backward()
             opt.step_captured(zero_grad=True)
             self.loss = loss.detach()
+        del loss
         # capture does not execute; undo the warm-up updates so the sampler state is exactly what it was
         flat.p.copy_(keep[0])
         flat.b.copy_(keep[1])
