@@ -194,7 +194,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _C.lib()
-    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- the chain of this rank --------------------------------------------------------------------------------
@@ -323,7 +323,7 @@ def run_ours(args):
         "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "chains": world, "parallelism": "chains x%d, no collective" % world,
-                   "cuda_graph": not args.no_graph, "l2": "inputs cycle through a %d-batch pool (%d MB > 126 MB L2)" % (POOL_BATCHES, POOL_BATCHES * h2d >> 20),
+                   "cuda_graph": not args.no_graph, "cudnn_benchmark": bool(args.cudnn_benchmark), "l2": "inputs cycle through a %d-batch pool (%d MB > 126 MB L2)" % (POOL_BATCHES, POOL_BATCHES * h2d >> 20),
                    "hyper": HYP},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -332,16 +332,16 @@ def run_ours(args):
         "roofline": roofline,
     }
 
-    if rank == 0 and world == 1:
-        sps, n, dt, cores = cpu_reference_steps_per_s(budget_s=15.0, max_steps=40)
-        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d cSGHMC steps (PreResNet-20 fwd+bwd+optimSGHMC.step op sequence), batch 128, %.1f s"
-                                          % (n, dt)}
     if not args.skip_extras:
         try:
             line["extras"] = run_extras(dev, rank, world, peak)
         except Exception as e:  # noqa: BLE001  (extras never invalidate the headline line)
             line["extras"] = {"error": repr(e)}
+    if rank == 0 and world == 1:
+        sps, n, dt, cores = cpu_reference_steps_per_s(budget_s=15.0, max_steps=60)
+        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                                "sample": "%d cSGHMC steps (PreResNet-20 fwd+bwd+optimSGHMC.step op sequence), batch 128, %.1f s"
+                                          % (n, dt)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -383,8 +383,9 @@ def run_extras(dev, rank, world, peak):
     bank = torch.empty(S, ld, device=dev)
     z2 = torch.randn(S, K, device=dev)
     fn = lambda: _C.swag_draw(bank, mean, var, D, ring=ring, z2=z2, rank_div=math.sqrt(K - 1.0), seed=5, step=1)  # noqa: E731
-    fn()
-    ms, _ = _event_time_ms(fn, 5)
+    for _ in range(3):
+        fn()
+    ms, _ = _event_time_ms(fn, 10)
     out["k2_draw_S30_K20_wrn28x10"] = {"ms": ms, "GBps": (K + 2 + S) * 4 * D / ms / 1e6,
                                        "frac": (K + 2 + S) * 4 * D / ms / 1e6 / peak, "us_per_draw": ms * 1e3 / S}
     del p, g, v, mean, sq, ring, var, bank
@@ -415,6 +416,44 @@ def run_extras(dev, rank, world, peak):
     out["bma_mlp400_S100_N10k"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
                                    "img_samples_per_s": N * S_all / ms * 1e3,
                                    "TFLOPs": 955_200 * N * S_all / ms / 1e9, "n_gpus": world}
+    del bankm, x, P, E
+    ws[0] = None
+    torch.cuda.empty_cache()
+    # BMA: PreResNet-20 (BASELINE.json configs[4]), S = 100 samples sharded over ranks, N = 10 000 test images
+    m = models.PreResNet(num_classes=10, depth=20)
+    Dp = sum(q.numel() for q in m.parameters())
+    nbuf = sum(b.numel() for b in m.buffers() if b.dtype == torch.float32)
+    ns = hi - lo
+    flat = torch.cat([q.detach().reshape(-1) for q in m.parameters()]).to(dev)
+    bankp = (flat[None, :] + 0.01 * torch.randn(ns, Dp, device=dev)).contiguous()
+    bufp = torch.zeros(ns, (nbuf + 3) // 4 * 4, device=dev)
+    # running_mean = 0, running_var = 1 per BN layer: buffers are [mean(C), var(C)] per layer in order
+    off = 0
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            c = mod.num_features
+            bufp[:, off:off + c] = 0.0
+            bufp[:, off + c:off + 2 * c] = 1.0
+            off += 2 * c
+    xi = torch.randn(N, 3, 32, 32, device=dev)
+    P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
+
+    def bma_conv():
+        P.zero_()
+        E.zero_()
+        ws[0] = _C.bma_preresnet_forward(bankp, bufp, ns, xi, 20, 10, P, E, workspace=ws[0])
+        Pr, Er, n = udist.allreduce_bma(P, E, ns)
+        return _C.bma_metrics(Pr, n, y)
+    ws[0] = _C.bma_preresnet_forward(bankp[:1], bufp[:1], 1, xi[:512], 20, 10, P[:512], E[:512], workspace=None)
+    ws[0] = None
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms, _ = _event_time_ms(bma_conv, 2)
+    ms = udist.allreduce_max_scalar(ms, dev)
+    out["bma_preresnet20_S100_N10k"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                        "img_samples_per_s": N * S_all / ms * 1e3,
+                                        "TFLOPs": 81.63e6 * N * S_all / ms / 1e9, "n_gpus": world, "algo": "ffma"}
     return out
 
 
@@ -426,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--cudnn-benchmark", type=int, default=0, help="torch.backends.cudnn.benchmark for fwd/bwd")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
