@@ -359,3 +359,51 @@ def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc):
     assert (logits - ref).abs().max().item() < 1e-4 * scale
     pref = torch.softmax(ref.double(), -1).sum(0)
     assert (P.double() - pref).abs().max().item() < 2e-5
+
+
+# ----------------------------------------------------------------------------- K3 forward, MLP on tcgen05 (3xTF32)
+@pytest.mark.parametrize("name,S", [("mlp", 5), ("mlp_c100", 3)])
+def test_k3_mlp_tcgen05_matches_reference_golden(C, name, S):
+    g = _npz("prediction.npz")
+    hidden, in_dim, Cc = (int(v) for v in g[name + "/arch"])
+    bank = dev(g[name + "/bank"])
+    x = dev(g[name + "/x"].reshape(g[name + "/x"].shape[0], -1))
+    N = x.shape[0]
+    P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
+    logits = torch.empty(S, N, Cc, device="cuda")
+    C.bma_mlp_forward(bank, S, x, in_dim, hidden, Cc, P, E, logits_out=logits, algo=C.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    if name + "/logits" in g:
+        np.testing.assert_allclose(logits.cpu().numpy(), g[name + "/logits"], atol=3e-5, rtol=1e-5)
+    np.testing.assert_allclose(P.cpu().numpy(), g[name + "/ensemble_proba"], atol=1e-5, rtol=0)   # north star
+    np.testing.assert_allclose(E.cpu().numpy(), g[name + "/entropy"], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("hidden,S,N", [(400, 6, 1000), (200, 3, 333), (600, 2, 129)])
+def test_k3_mlp_tcgen05_vs_ffma_config1_shapes(C, hidden, S, N):
+    """MLP 784-h-h-10 (config 1 and its siblings): the tensor-core path against the fp32 CUDA-core path and a
+    float64 forward -- 3xTF32 must stay at fp32-level accuracy (single-pass TF32 would be ~1e-3)."""
+    from ursabench_b200.models import MLP
+    torch.manual_seed(hidden)
+    ms = [MLP(hidden, 784, 10).cuda() for _ in range(S)]
+    for m in ms:
+        for p in m.parameters():
+            p.data.mul_(2.0)
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
+    x = torch.randn(N, 784, device="cuda")
+    outs = {}
+    for algo in (C.ALGO_FFMA, C.ALGO_TCGEN05):
+        P, E = torch.zeros(N, 10, device="cuda"), torch.zeros(N, device="cuda")
+        logits = torch.empty(S, N, 10, device="cuda")
+        C.bma_mlp_forward(bank, S, x, 784, hidden, 10, P, E, logits_out=logits, algo=algo)
+        torch.cuda.synchronize()
+        outs[algo] = (logits, P)
+    with torch.no_grad():
+        ref = torch.stack([m.double()(x.double()) for m in ms])
+    scale = max(1.0, ref.abs().max().item())
+    e_ffma = (outs[C.ALGO_FFMA][0].double() - ref).abs().max().item()
+    e_tc = (outs[C.ALGO_TCGEN05][0].double() - ref).abs().max().item()
+    assert e_ffma < 2e-5 * scale
+    assert e_tc < 4e-5 * scale, (e_tc, e_ffma)
+    pref = torch.softmax(ref, -1).sum(0)
+    assert (outs[C.ALGO_TCGEN05][1].double() - pref).abs().max().item() < 1e-5

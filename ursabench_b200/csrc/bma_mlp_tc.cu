@@ -1,14 +1,461 @@
-// K3 (MLP) on tcgen05: placeholder until the 3xTF32 UMMA path lands.
+// K3 (MLP) on 5th-generation tensor cores: sample-batched 3xTF32 GEMM, TMA-fed, accumulators in TMEM.
+//
+// Why 3xTF32: BMA probabilities must match the reference's fp32 forward to 1e-5; one TF32 pass has ~1e-3 relative
+// logit error.  Every operand is split a = hi + lo with hi = rn_tf32(a), lo = rn_tf32(a - hi) (exact residual), and
+//     D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (fp32 accumulation in TMEM; the lo*lo term ~2^-22 is dropped)
+// which restores ~fp32 accuracy for 3x the MMA work -- still far above the CUDA-core roofline.
+//
+// Kernel anatomy (one 128 x BN output tile of one sample per CTA, 192 threads):
+//   warp 0      TMA producer: per k-block (32 fp32 = one 128-byte swizzle row) four 3-D tiled loads
+//               (A_hi, A_lo: 128 x 32; B_hi, B_lo: BN x 32) into a 4-stage shared-memory ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues 4 (UMMA_K = 8) x 3 tcgen05.mma.kind::tf32 per
+//               stage; tcgen05.commit frees the stage / signals the epilogue
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 16 columns) -> + bias -> ReLU -> split hi/lo -> global (the next
+//               layer's TMA source), or plain fp32 logits for the last layer
+// Operand layout: K-major rows of 128 bytes, SWIZZLE_128B in both the tensor maps and the UMMA descriptors.
+#include <cuda.h>
+
+#include "async.cuh"
 #include "common.cuh"
 
 namespace ursa {
 
-size_t mlp_workspace_tcgen05(int, int64_t, int, int, int) { return 0; }
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB per A tile
 
-int mlp_forward_tcgen05(const float *, int64_t, int, const float *, int64_t, int, int, int, float *, float *, float *,
-                        double, void *, size_t, cudaStream_t) {
-    set_error("ursa_bma_mlp_forward: URSA_ALGO_TCGEN05 is not built in this revision");
-    return URSA_ERR_UNSUPPORTED;
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier receives one arrival once all tcgen05.mma previously issued by this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// raw-address mbarrier / TMA helpers (the tile ring is addressed by 32-bit shared-window offsets)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait_a(bar, parity); ++spin)
+        if (spin > (1u << 27)) __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *tmap, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO = 1 (unused for
+// swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TcGemmArgs {
+    const float *bias;            // per-sample bias vector: bias + s * bias_stride
+    int64_t bias_stride;
+    float *out_hi, *out_lo;       // split outputs [S][M][ld_out]; out_lo == nullptr: plain fp32 output in out_hi
+    int64_t out_batch_stride;
+    int ld_out;
+    int64_t M;
+    int n_valid;                  // real output features (bias guard / plain-store guard)
+    int BN;                       // N tile (multiple of 16, <= 256)
+    int k_blocks;                 // Kp / 32
+    int a_batched;                // 0: A shared by all samples (layer 1 input)
+    int relu;
+    int stages;                   // smem ring depth (<= TC_STAGES)
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const TcGemmArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, n_blk = blockIdx.y, s = blockIdx.z;
+    const uint32_t b_bytes = (uint32_t)a.BN * TC_BK * 4;
+    const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle-128B tiles need 1024-byte alignment
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi);
+        tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane) =====
+        if (elect_one()) {
+            const int a_b = a.a_batched ? s : 0;
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int st = kb % a.stages;
+                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+                mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);              // slot free (first pass: passes at once)
+                const uint32_t fb = smem_u32(&full_bar[st]);
+                mbar_expect_tx_a(fb, stage_bytes);
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const int k0 = kb * TC_BK;
+                tma_load_3d_a(base, &tm_a_hi, k0, m_blk * TC_BM, a_b, fb);
+                tma_load_3d_a(base + TC_A_BYTES, &tm_a_lo, k0, m_blk * TC_BM, a_b, fb);
+                tma_load_3d_a(base + 2 * TC_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, s, fb);
+                tma_load_3d_a(base + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, s, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (elect_one()) {
+            // cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both,
+            // N >> 3 at bits 17-22, M >> 4 at bits 24-28
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t acc = 0;
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+                const int st = kb % a.stages;
+                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+                mbar_wait_a(smem_u32(&full_bar[st]), ph);                    // TMA bytes have landed
+                tc_fence_after();
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const uint64_t d_ahi = make_sw128_desc(base), d_alo = make_sw128_desc(base + TC_A_BYTES);
+                const uint64_t d_bhi = make_sw128_desc(base + 2 * TC_A_BYTES);
+                const uint64_t d_blo = make_sw128_desc(base + 2 * TC_A_BYTES + b_bytes);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t koff = (uint64_t)((k * 32) >> 4);         // advance 32 bytes inside the swizzle row
+                    umma_tf32(tmem_base, d_alo + koff, d_bhi + koff, idesc, acc);
+                    acc = 1;
+                    umma_tf32(tmem_base, d_ahi + koff, d_blo + koff, idesc, 1);
+                    umma_tf32(tmem_base, d_ahi + koff, d_bhi + koff, idesc, 1);
+                }
+                umma_commit(smem_u32(&empty_bar[st]));                       // frees the smem slot when the MMAs retire
+            }
+            umma_commit(smem_u32(&tmem_full_bar));                           // accumulator complete -> epilogue
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        mbar_wait_a(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
+        const float *bias = a.bias + (int64_t)s * a.bias_stride;
+        const bool split = a.out_lo != nullptr;
+        float *ohi = a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out;
+        float *olo = split ? a.out_lo + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+        for (int c0 = 0; c0 < a.BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            const int col0 = n_blk * a.BN + c0;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int col = col0 + i;
+                float x = __uint_as_float(r[i]) + (col < a.n_valid ? __ldg(bias + col) : 0.f);
+                if (a.relu) x = fmaxf(x, 0.f);
+                v[i] = x;
+            }
+            if (row < a.M) {
+                if (split) {
+                    if (col0 + 16 <= a.ld_out) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 h, l;
+                            h.x = rn_tf32(v[i]); h.y = rn_tf32(v[i + 1]); h.z = rn_tf32(v[i + 2]); h.w = rn_tf32(v[i + 3]);
+                            l.x = rn_tf32(v[i] - h.x); l.y = rn_tf32(v[i + 1] - h.y);
+                            l.z = rn_tf32(v[i + 2] - h.z); l.w = rn_tf32(v[i + 3] - h.w);
+                            *reinterpret_cast<float4 *>(ohi + col0 + i) = h;
+                            *reinterpret_cast<float4 *>(olo + col0 + i) = l;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (col0 + i < a.n_valid) ohi[col0 + i] = v[i];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// fp32 [rows, cols] (ld, per-batch stride) -> zero-padded hi / lo planes [batch][rows_p][cols_p]
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, int64_t ld_src, int64_t src_batch_stride,
+                                                         int rows, int cols, float *__restrict__ hi, float *__restrict__ lo,
+                                                         int rows_p, int cols_p) {
+    const int b = blockIdx.y;
+    const int64_t total = (int64_t)rows_p * cols_p;
+    const float *sb = src + (int64_t)b * src_batch_stride;
+    float *hb = hi + (int64_t)b * total, *lb = lo + (int64_t)b * total;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % cols_p);
+        const int64_t r = i / cols_p;
+        float x = 0.f;
+        if (r < rows && c < cols) x = __ldg(sb + r * ld_src + c);
+        const float h = rn_tf32(x);
+        hb[i] = h;
+        lb[i] = rn_tf32(x - h);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D fp32 tensor [batch][rows][cols_p] (cols innermost), box = [1][box_rows][32], 128-byte swizzle
+static int make_tmap(CUtensorMap *tm, const float *base, int64_t cols_p, int64_t rows, int64_t batch, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return URSA_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols_p, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)cols_p * 4, (cuuint64_t)cols_p * 4 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for tensor [%lld][%lld][%lld] box_rows %d", (int)r, (long long)batch,
+                  (long long)rows, (long long)cols_p, box_rows);
+        return URSA_ERR_CUDA;
+    }
+    return URSA_OK;
+}
+
+static int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
+
+// N tile: multiple of 16, <= 128, minimal padding (ties -> larger tile)
+static int pick_bn(int n_out) {
+    const int nr = round_up_i(n_out, 16);
+    if (nr <= 128) return nr;
+    int best = 128, best_waste = round_up_i(nr, 128) - nr;
+    for (int bn = 112; bn >= 64; bn -= 16) {
+        const int w = round_up_i(nr, bn) - nr;
+        if (w < best_waste) { best = bn; best_waste = w; }
+    }
+    return best;
+}
+
+struct TcPlan {
+    int K1p, K2p, BN1, BN3, Np1, Np3, sc;
+    size_t x_plane, w1_plane, w2_plane, w3_plane, h_plane, logit_plane;   // floats per (sample) plane
+    size_t total_bytes;
+};
+
+static TcPlan tc_plan(int S, int64_t N, int in_dim, int hidden, int C) {
+    TcPlan p;
+    p.K1p = round_up_i(in_dim, TC_BK);
+    p.K2p = round_up_i(hidden, TC_BK);
+    p.BN1 = pick_bn(hidden);
+    p.BN3 = pick_bn(C);
+    p.Np1 = round_up_i(round_up_i(hidden, 16), p.BN1);
+    p.Np3 = round_up_i(round_up_i(C, 16), p.BN3);
+    p.x_plane = (size_t)N * p.K1p;
+    p.w1_plane = (size_t)p.Np1 * p.K1p;
+    p.w2_plane = (size_t)p.Np1 * p.K2p;
+    p.w3_plane = (size_t)p.Np3 * p.K2p;
+    p.h_plane = (size_t)N * p.K2p;
+    p.logit_plane = ((size_t)N * C + 3) & ~(size_t)3;
+    const size_t per_sample = 2 * (p.w1_plane + p.w2_plane + p.w3_plane) + 4 * p.h_plane + p.logit_plane;
+    size_t sc = (size_t)(768ull << 20) / (per_sample * 4 + 1);
+    if (sc < 1) sc = 1;
+    if (sc > (size_t)S) sc = S;
+    if (sc > 16) sc = 16;
+    p.sc = (int)sc;
+    p.total_bytes = (2 * p.x_plane + (size_t)p.sc * per_sample) * sizeof(float) + 1024;
+    return p;
+}
+
+static int launch_tc_gemm(const float *a_hi, const float *a_lo, int64_t a_rows, int64_t a_batch, int Kp, const float *b_hi,
+                          const float *b_lo, int Np, int BN, int batch, TcGemmArgs g, cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (int rc = make_tmap(&ta_hi, a_hi, Kp, a_rows, a_batch, TC_BM)) return rc;
+    if (int rc = make_tmap(&ta_lo, a_lo, Kp, a_rows, a_batch, TC_BM)) return rc;
+    if (int rc = make_tmap(&tb_hi, b_hi, Kp, Np, batch, BN)) return rc;
+    if (int rc = make_tmap(&tb_lo, b_lo, Kp, Np, batch, BN)) return rc;
+    g.BN = BN;
+    g.k_blocks = Kp / TC_BK;
+    g.a_batched = a_batch > 1 ? 1 : 0;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)BN) cols <<= 1;
+    g.tmem_cols = cols;
+    const size_t stage_bytes = 2 * TC_A_BYTES + 2 * (size_t)BN * TC_BK * 4;
+    int stages = (int)((size_t)(226 << 10) / stage_bytes);
+    if (stages > TC_STAGES) stages = TC_STAGES;
+    if (stages > g.k_blocks) stages = g.k_blocks;
+    URSA_REQUIRE(stages >= 1, "mlp_tc_gemm: tile does not fit in shared memory");
+    g.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    URSA_CUDA(cudaFuncSetAttribute(mlp_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((g.M + TC_BM - 1) / TC_BM), (unsigned)(Np / BN), (unsigned)batch);
+    mlp_tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    URSA_LAUNCH_CHECK("mlp_tc_gemm_kernel");
+    return URSA_OK;
+}
+
+size_t mlp_workspace_tcgen05(int S, int64_t N, int in_dim, int hidden, int C) {
+    if (in_dim % 4 != 0 || hidden % 4 != 0) return 0;      // TMA needs 16-byte row pitches (covers MLP200/400/600)
+    return tc_plan(S, N, in_dim, hidden, C).total_bytes;
+}
+
+int mlp_forward_tcgen05(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N, int in_dim, int hidden,
+                        int C, float *proba_sum, float *entropy_sum, float *logits_out, double gamma, void *workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+    if (in_dim % 4 != 0 || hidden % 4 != 0) {
+        set_error("URSA_ALGO_TCGEN05 needs in_dim %% 4 == 0 and hidden %% 4 == 0 (TMA 16-byte pitch); use URSA_ALGO_FFMA");
+        return URSA_ERR_UNSUPPORTED;
+    }
+    const TcPlan p = tc_plan(S, N, in_dim, hidden, C);
+    URSA_REQUIRE(workspace_bytes >= p.total_bytes, "ursa_bma_mlp_forward: workspace too small");
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    float *x_hi = ws, *x_lo = x_hi + p.x_plane;
+    float *w1_hi = x_lo + p.x_plane, *w1_lo = w1_hi + p.sc * p.w1_plane;
+    float *w2_hi = w1_lo + p.sc * p.w1_plane, *w2_lo = w2_hi + p.sc * p.w2_plane;
+    float *w3_hi = w2_lo + p.sc * p.w2_plane, *w3_lo = w3_hi + p.sc * p.w3_plane;
+    float *h1_hi = w3_lo + p.sc * p.w3_plane, *h1_lo = h1_hi + p.sc * p.h_plane;
+    float *h2_hi = h1_lo + p.sc * p.h_plane, *h2_lo = h2_hi + p.sc * p.h_plane;
+    float *lg = h2_lo + p.sc * p.h_plane;
+
+    const int64_t oW1 = 0, ob1 = oW1 + (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)hidden * hidden,
+                  oW3 = ob2 + hidden, ob3 = oW3 + (int64_t)C * hidden;
+    auto split = [&](const float *src, int64_t ld, int64_t bstride, int rows, int cols, float *hi, float *lo, int rows_p,
+                     int cols_p, int batch) -> int {
+        const int64_t total = (int64_t)rows_p * cols_p;
+        int gx = (int)((total + 255) / 256);
+        if (gx > 148 * 8) gx = 148 * 8;
+        split_tf32_kernel<<<dim3(gx, batch), 256, 0, st>>>(src, ld, bstride, rows, cols, hi, lo, rows_p, cols_p);
+        URSA_LAUNCH_CHECK("split_tf32_kernel");
+        return URSA_OK;
+    };
+    if (int rc = split(x, in_dim, 0, (int)N, in_dim, x_hi, x_lo, (int)N, p.K1p, 1)) return rc;
+    // hidden-activation padding columns (hidden..K2p) are never written by a tile: zero them once
+    URSA_CUDA(cudaMemsetAsync(h1_hi, 0, 4 * (size_t)p.sc * p.h_plane * sizeof(float), st));
+
+    for (int s0 = 0; s0 < S; s0 += p.sc) {
+        const int nb = (S - s0 < p.sc) ? (S - s0) : p.sc;
+        const float *bk = bank + (int64_t)s0 * ld_bank;
+        if (int rc = split(bk + oW1, in_dim, ld_bank, hidden, in_dim, w1_hi, w1_lo, p.Np1, p.K1p, nb)) return rc;
+        if (int rc = split(bk + oW2, hidden, ld_bank, hidden, hidden, w2_hi, w2_lo, p.Np1, p.K2p, nb)) return rc;
+        if (int rc = split(bk + oW3, hidden, ld_bank, C, hidden, w3_hi, w3_lo, p.Np3, p.K2p, nb)) return rc;
+        TcGemmArgs g;
+        g.M = N; g.bias_stride = ld_bank;
+        // layer 1: relu(x W1^T + b1) -> h1 (split)
+        g.bias = bk + ob1; g.out_hi = h1_hi; g.out_lo = h1_lo; g.out_batch_stride = (int64_t)p.h_plane; g.ld_out = p.K2p;
+        g.n_valid = hidden; g.relu = 1;
+        if (int rc = launch_tc_gemm(x_hi, x_lo, N, 1, p.K1p, w1_hi, w1_lo, p.Np1, p.BN1, nb, g, st)) return rc;
+        // layer 2: relu(h1 W2^T + b2) -> h2 (split)
+        g.bias = bk + ob2; g.out_hi = h2_hi; g.out_lo = h2_lo;
+        if (int rc = launch_tc_gemm(h1_hi, h1_lo, N, nb, p.K2p, w2_hi, w2_lo, p.Np1, p.BN1, nb, g, st)) return rc;
+        // layer 3: logits = h2 W3^T + b3 (plain fp32)
+        g.bias = bk + ob3; g.out_hi = lg; g.out_lo = nullptr; g.out_batch_stride = (int64_t)p.logit_plane; g.ld_out = C;
+        g.n_valid = C; g.relu = 0;
+        if (int rc = launch_tc_gemm(h2_hi, h2_lo, N, nb, p.K2p, w3_hi, w3_lo, p.Np3, p.BN3, nb, g, st)) return rc;
+        if (int rc = ursa_bma_accumulate(lg, nb, N, C, (int64_t)p.logit_plane, proba_sum, entropy_sum, gamma, (void *)st))
+            return rc;
+        if (logits_out)
+            URSA_CUDA(cudaMemcpy2DAsync(logits_out + (size_t)s0 * N * C, (size_t)N * C * sizeof(float), lg,
+                                        p.logit_plane * sizeof(float), (size_t)N * C * sizeof(float), nb,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    return URSA_OK;
 }
 
 }  // namespace ursa

@@ -75,20 +75,26 @@ struct DrawArgs {
     uint64_t step;
 };
 
-template <int SP>
-__global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawArgs a) {
+// SP = padded number of draws, NG = sample groups: thread (tid % 256) owns 4 columns, group (tid / 256) owns the
+// draws [g*SP/NG, (g+1)*SP/NG): more resident warps and fewer accumulator registers per thread for large S.
+template <int SP, int NG>
+__global__ void __launch_bounds__(kDrawThreads * NG, 1) swag_draw_kernel(const DrawArgs a) {
+    constexpr int SPG = SP / NG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *ring_s = reinterpret_cast<float *>(smem_raw);                       // [kStages][K][kTileCols]
     __shared__ __align__(16) float z2s[URSA_DRAW_MAX_K * SP];                  // [K][SP], zero padded
     __shared__ __align__(8) uint64_t full_bar[kStages];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % kDrawThreads;          // column owner
+    const int grp = threadIdx.x / kDrawThreads;          // sample group (warp-uniform)
+    const int s_lo = grp * SPG;
     const int K = a.K, S = a.S;
-    for (int i = tid; i < K * SP; i += kDrawThreads) {
+    const float inv_div = (K > 0) ? 1.0f / a.rank_div : 0.f;
+    for (int i = threadIdx.x; i < K * SP; i += kDrawThreads * NG) {
         const int k = i / SP, s = i - k * SP;
-        z2s[i] = (s < S) ? a.z2[(int64_t)s * K + k] : 0.f;
+        z2s[i] = (s < S) ? a.z2[(int64_t)s * K + k] * inv_div : 0.f;      // 1/sqrt(max_rank-1) folded in (swag.py:95)
     }
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
     }
@@ -107,27 +113,27 @@ __global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawAr
             bulk_g2s(dst + (size_t)k * kTileCols, a.ring + (int64_t)k * a.ld_ring + c0, bytes, &full_bar[stage]);
     };
 
-    if (K > 0 && tid == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    if (K > 0 && threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int stage = it & 1;
         const uint32_t parity = (uint32_t)(it >> 1) & 1u;
         const int64_t next = tile + gridDim.x;
-        if (K > 0 && tid == 0 && next < ntiles) issue(next, stage ^ 1);
+        if (K > 0 && threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);
 
-        float acc[SP][4];
+        float acc[SPG][4];
 #pragma unroll
-        for (int s = 0; s < SP; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+        for (int s = 0; s < SPG; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
 
         if (K > 0) {
             mbar_wait(&full_bar[stage], parity);
             const float4 *rs = reinterpret_cast<const float4 *>(ring_s + (size_t)stage * K * kTileCols) + tid;
             for (int k = 0; k < K; ++k) {
                 const float4 r = rs[(size_t)k * (kTileCols / 4)];
-                const float4 *zk = reinterpret_cast<const float4 *>(z2s + k * SP);
+                const float4 *zk = reinterpret_cast<const float4 *>(z2s + k * SP + s_lo);
 #pragma unroll
-                for (int q = 0; q < SP / 4; ++q) {
+                for (int q = 0; q < SPG / 4; ++q) {
                     const float4 z = zk[q];
                     const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -159,7 +165,8 @@ __global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawAr
                 }
             }
 #pragma unroll
-            for (int s = 0; s < SP; ++s) {
+            for (int sl = 0; sl < SPG; ++sl) {
+                const int s = s_lo + sl;
                 if (s < S) {
                     float z[4];
                     if (a.z1) {
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawAr
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float r = __fmul_rn(sd[j], z[j]);                                  // swag.py:88-89
-                        if (K > 0) r = __fadd_rn(r, __fdiv_rn(acc[s][j], a.rank_div));     // swag.py:95-96
+                        if (K > 0) r = __fadd_rn(r, acc[sl][j]);                           // swag.py:95-96 (scale folded)
                         o[j] = __fadd_rn(m[j], r);                                         // swag.py:97
                     }
                     float *orow = a.out + (int64_t)s * a.ld_out + c0;
@@ -203,13 +210,13 @@ static int ew_grid(int64_t work_items) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-template <int SP>
+template <int SP, int NG>
 static int launch_draw(const DrawArgs &a, cudaStream_t st) {
     const size_t smem = (size_t)kStages * (a.K > 0 ? a.K : 0) * kTileCols * sizeof(float);
-    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<SP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    swag_draw_kernel<SP><<<grid, kDrawThreads, smem, st>>>(a);
+    swag_draw_kernel<SP, NG><<<grid, kDrawThreads * NG, smem, st>>>(a);
     URSA_LAUNCH_CHECK("swag_draw_kernel");
     return URSA_OK;
 }
@@ -260,7 +267,7 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
     a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     a.step = step;
     cudaStream_t st = (cudaStream_t)stream;
-    if (S <= 8) return launch_draw<8>(a, st);
-    if (S <= 16) return launch_draw<16>(a, st);
-    return launch_draw<32>(a, st);
+    if (S <= 8) return launch_draw<8, 1>(a, st);
+    if (S <= 16) return launch_draw<16, 2>(a, st);
+    return launch_draw<32, 4>(a, st);
 }

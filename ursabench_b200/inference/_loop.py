@@ -93,8 +93,8 @@ class _GraphedStep:
         dev = owner.device
         if opt._dyn is None:
             opt.use_device_scalars(True)
-        self.x = torch.zeros(example_data.shape, dtype=example_data.dtype, device=dev)
-        self.y = torch.zeros(example_labels.shape, dtype=example_labels.dtype, device=dev)
+        self.x = torch.empty_like(example_data, device=dev)       # keeps the memory format (e.g. channels_last)
+        self.y = torch.empty_like(example_labels, device=dev)
         self.x.copy_(example_data)
         self.y.copy_(example_labels)
         flat = owner.flat
