@@ -202,14 +202,11 @@ def run_ours(args):
     g = torch.Generator().manual_seed(100 + rank)
     host_x = torch.randn(POOL_BATCHES, BATCH, 3, 32, 32, generator=g).pin_memory()
     host_y = torch.randint(0, NUM_CLASSES, (POOL_BATCHES, BATCH), generator=g).pin_memory()
-    if args.channels_last:       # experiment: NHWC activations for cuDNN (weights stay in the flat NCHW layout)
-        model = model.to(memory_format=torch.channels_last)
-        host_x = host_x.view(-1, 3, 32, 32).contiguous(memory_format=torch.channels_last).view(
-            POOL_BATCHES, BATCH, 3, 32, 32).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
     loader = _ListLoader([(host_x[i], host_y[i]) for i in range(POOL_BATCHES)], N_TRAIN, BATCH)
     torch.manual_seed(1234 + rank)                         # Philox key of this chain
     inf = inference.cSGHMC(dict(HYP), model, loader, device=dev)
+    inf._channels_last = bool(args.channels_last)          # default on: NHWC activations for cuDNN
     inf.optimizer.elem_offset = udist.chain_elem_offset(rank, inf.flat.D)
     inf.model.train()
     if not args.no_graph:
@@ -469,7 +466,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-extras", action="store_true")
-    ap.add_argument("--channels-last", type=int, default=0, help="NHWC activations in fwd/bwd (experiment)")
+    ap.add_argument("--channels-last", type=int, default=1, help="NHWC activations in fwd/bwd (engine default)")
     ap.add_argument("--cudnn-benchmark", type=int, default=0, help="torch.backends.cudnn.benchmark for fwd/bwd")
     args = ap.parse_args()
     if args.impl == "reference":
