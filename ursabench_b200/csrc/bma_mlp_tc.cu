@@ -13,104 +13,12 @@
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 16 columns) -> + bias -> ReLU -> split hi/lo -> global (the next
 //               layer's TMA source), or plain fp32 logits for the last layer
 // Operand layout: K-major rows of 128 bytes, SWIZZLE_128B in both the tensor maps and the UMMA descriptors.
-#include <cuda.h>
-
-#include "async.cuh"
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ursa {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 192;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB per A tile
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// the mbarrier receives one arrival once all tcgen05.mma previously issued by this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar_addr) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// raw-address mbarrier / TMA helpers (the tile ring is addressed by 32-bit shared-window offsets)
-__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait_a(bar, parity); ++spin)
-        if (spin > (1u << 27)) __trap();
-}
-__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *tmap, int x, int y, int z, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
-        : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO = 1 (unused for
-// swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 struct TcGemmArgs {
     const float *bias;            // per-sample bias vector: bias + s * bias_stride
@@ -185,10 +93,7 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (elect_one()) {
-            // cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both,
-            // N >> 3 at bits 17-22, M >> 4 at bits 24-28
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc = make_tf32_idesc(TC_BM, a.BN);
             uint32_t acc = 0;
             for (int kb = 0; kb < a.k_blocks; ++kb) {
                 const int st = kb % a.stages;
@@ -196,9 +101,9 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 mbar_wait_a(smem_u32(&full_bar[st]), ph);                    // TMA bytes have landed
                 tc_fence_after();
                 const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
-                const uint64_t d_ahi = make_sw128_desc(base), d_alo = make_sw128_desc(base + TC_A_BYTES);
-                const uint64_t d_bhi = make_sw128_desc(base + 2 * TC_A_BYTES);
-                const uint64_t d_blo = make_sw128_desc(base + 2 * TC_A_BYTES + b_bytes);
+                const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + TC_A_BYTES);
+                const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * TC_A_BYTES);
+                const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t koff = (uint64_t)((k * 32) >> 4);         // advance 32 bytes inside the swizzle row
@@ -282,42 +187,12 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // 3-D fp32 tensor [batch][rows][cols_p] (cols innermost), box = [1][box_rows][32], 128-byte swizzle
 static int make_tmap(CUtensorMap *tm, const float *base, int64_t cols_p, int64_t rows, int64_t batch, int box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return URSA_ERR_CUDA;
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)cols_p, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)cols_p * 4, (cuuint64_t)cols_p * 4 * (cuuint64_t)rows};
-    cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) for tensor [%lld][%lld][%lld] box_rows %d", (int)r, (long long)batch,
-                  (long long)rows, (long long)cols_p, box_rows);
-        return URSA_ERR_CUDA;
-    }
-    return URSA_OK;
+    const uint64_t dims[3] = {(uint64_t)cols_p, (uint64_t)rows, (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)cols_p * 4, (uint64_t)cols_p * 4 * (uint64_t)rows};
+    const uint32_t box[3] = {TC_BK, (uint32_t)box_rows, 1};
+    return make_tensor_map(tm, base, 3, dims, strides, box, 128);
 }
 
 static int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
