@@ -134,6 +134,39 @@ def k3(res):
         ws[0] = None
 
 
+def k3conv(res):
+    from ursabench_b200.models import PreResNet
+    S, N = 16, 2048
+    torch.manual_seed(0)
+    m = PreResNet(num_classes=10, depth=20)
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cuda()
+    bank = (flat[None, :] + 0.01 * torch.randn(S, flat.numel(), device="cuda")).contiguous()
+    bufs = torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]).cuda()[None, :].repeat(S, 1).contiguous()
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    P, E = torch.zeros(N, 10, device="cuda"), torch.zeros(N, device="cuda")
+    ws = [None]
+    outs = {}
+    for algo, nm in ((_C.ALGO_FFMA, "ffma"), (_C.ALGO_TCGEN05, "tcgen05")):
+        try:
+            lg = torch.empty(S, N, 10, device="cuda")
+
+            def f():
+                ws[0] = _C.bma_preresnet_forward(bank, bufs, S, x, 20, 10, P, E, logits_out=lg, algo=algo, workspace=ws[0])
+            med, best = timeit(f, iters=3, warm=1)
+            outs[nm] = lg
+        except Exception as e:  # noqa: BLE001
+            print("K3 preresnet20 %s: %s" % (nm, e))
+            ws[0] = None
+            continue
+        flops = 81.63e6 * S * N
+        res["k3_preresnet20_" + nm] = dict(ms=med, TFLOPs=flops / med / 1e9, img_samples_per_s=S * N / med * 1e3)
+        print("K3 preresnet20 %-8s S=%d N=%d  %.2f ms  %.1f TFLOP/s  %.1f k img*samples/s" %
+              (nm, S, N, med, flops / med / 1e9, S * N / med), flush=True)
+        ws[0] = None
+    if len(outs) == 2:
+        print("max |logit diff| tcgen05 vs ffma: %.3e" % (outs["ffma"] - outs["tcgen05"]).abs().max().item())
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "all"
     res = {}
@@ -144,5 +177,7 @@ if __name__ == "__main__":
         k2(res)
     if which in ("k3", "all"):
         k3(res)
+    if which in ("k3conv", "all"):
+        k3conv(res)
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)

@@ -14,54 +14,14 @@
 // Activations are NCHW planes per (sample, image) in the workspace; the first conv reads the shared input x.
 // This is the fp32 reference-accuracy path (URSA_ALGO_FFMA); see DESIGN.md for the tcgen05 plan.
 #include "common.cuh"
+#include "preresnet_plan.cuh"
 
 namespace ursa {
 
-constexpr int kMaxLayers = 96;
-
-struct PrepEntry {
-    int type;          // 0 conv3x3, 1 conv1x1, 2 bn fold, 3 copy
-    int cin, cout;     // conv: channels; bn: cout = channels; copy: cout = count
-    int64_t src;       // offset in the bank row (conv weight / bn weight / copy source)
-    int64_t src2;      // bn: offset of bias in the bank row
-    int64_t buf;       // bn: offset of running_mean in the buffer row (running_var follows at +C)
-    int64_t dst;       // offset in the packed row
-};
-
-struct PrepTable {
-    int n;
-    PrepEntry e[kMaxLayers];
-};
-
-__global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTable t, const float *__restrict__ bank,
-                                                              int64_t ld_bank, const float *__restrict__ bufbank,
-                                                              int64_t ld_buf, float *__restrict__ packed,
-                                                              int64_t ld_packed) {
-    const int s = blockIdx.y;
-    const PrepEntry e = t.e[blockIdx.x];
-    const float *row = bank + (int64_t)s * ld_bank;
-    const float *brow = bufbank + (int64_t)s * ld_buf;
-    float *dst = packed + (int64_t)s * ld_packed + e.dst;
-    if (e.type == 0 || e.type == 1) {
-        const int taps = e.type == 0 ? 9 : 1;
-        const int total = e.cout * e.cin * taps;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {       // i over dst [ci][tap][co]
-            const int co = i % e.cout;
-            const int tap = (i / e.cout) % taps;
-            const int ci = i / (e.cout * taps);
-            dst[i] = row[e.src + ((int64_t)co * e.cin + ci) * taps + tap];   // PyTorch [co][ci][kh][kw]
-        }
-    } else if (e.type == 2) {
-        for (int c = threadIdx.x; c < e.cout; c += blockDim.x) {
-            const float mean = brow[e.buf + c], var = brow[e.buf + e.cout + c];
-            const float a = row[e.src + c] / sqrtf(var + 1e-5f);     // alpha = weight * invstd
-            dst[c] = a;
-            dst[e.cout + c] = row[e.src2 + c] - mean * a;            // beta = bias - mean * alpha
-        }
-    } else {
-        for (int i = threadIdx.x; i < e.cout; i += blockDim.x) dst[i] = row[e.src + i];
-    }
-}
+size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C);
+int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
+                              int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
+                              double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
 // -----------------------------------------------------------------------------------------------------------
 struct ConvArgs {
@@ -234,75 +194,6 @@ __global__ void __launch_bounds__(256) preresnet_head_kernel(const float *__rest
 }
 
 // -----------------------------------------------------------------------------------------------------------
-struct NetPlan {
-    int n_blocks;               // per stage
-    int C;
-    PrepTable table;
-    int64_t packed_floats;
-    int64_t conv1_w;
-    struct Block { int64_t bn1, w1, bn2, w2, ds; } blocks[3][8];
-    int64_t bn_final, fc;
-    int64_t D, NB;              // expected bank / buffer row lengths
-};
-
-static bool build_plan(int depth, int C, NetPlan &pl) {
-    if (depth >= 44 || depth < 8 || (depth - 2) % 6 != 0 || C < 1) return false;
-    const int n = (depth - 2) / 6;
-    if (n > 8) return false;
-    pl.n_blocks = n;
-    pl.C = C;
-    PrepTable &t = pl.table;
-    t.n = 0;
-    int64_t src = 0, buf = 0, dst = 0;
-    auto add_conv = [&](int type, int cin, int cout) {
-        PrepEntry &e = t.e[t.n++];
-        e.type = type; e.cin = cin; e.cout = cout; e.src = src; e.src2 = 0; e.buf = 0; e.dst = dst;
-        const int64_t cnt = (int64_t)cin * cout * (type == 0 ? 9 : 1);
-        src += cnt;
-        const int64_t d = dst;
-        dst += cnt;
-        return d;
-    };
-    auto add_bn = [&](int c) {
-        PrepEntry &e = t.e[t.n++];
-        e.type = 2; e.cin = 0; e.cout = c; e.src = src; e.src2 = src + c; e.buf = buf; e.dst = dst;
-        src += 2 * c;
-        buf += 2 * c;          // running_mean, running_var (num_batches_tracked is int64 and not in the float bank)
-        const int64_t d = dst;
-        dst += 2 * c;
-        return d;
-    };
-    // parameter order = model.parameters(): conv1, per block [bn1.w, bn1.b, conv1, bn2.w, bn2.b, conv2, (downsample)],
-    // bn.w, bn.b, fc.w, fc.b   (tests/golden/layouts.json)
-    pl.conv1_w = add_conv(0, 3, 16);
-    const int widths[3] = {16, 32, 64};
-    int inpl = 16;
-    for (int st = 0; st < 3; ++st) {
-        for (int b = 0; b < n; ++b) {
-            const int w = widths[st];
-            NetPlan::Block &B = pl.blocks[st][b];
-            B.bn1 = add_bn(inpl);
-            B.w1 = add_conv(0, inpl, w);
-            B.bn2 = add_bn(w);
-            B.w2 = add_conv(0, w, w);
-            B.ds = (b == 0 && st > 0) ? add_conv(1, inpl, w) : -1;
-            inpl = w;
-        }
-    }
-    pl.bn_final = add_bn(64);
-    {
-        PrepEntry &e = t.e[t.n++];
-        e.type = 3; e.cin = 0; e.cout = C * 64 + C; e.src = src; e.src2 = 0; e.buf = 0; e.dst = dst;
-        pl.fc = dst;
-        src += C * 64 + C;
-        dst += C * 64 + C;
-    }
-    pl.packed_floats = (dst + 3) & ~(int64_t)3;
-    pl.D = src;
-    pl.NB = buf;
-    return t.n <= kMaxLayers;
-}
-
 constexpr int kChunkSamples = 8, kChunkImages = 512;
 constexpr int64_t kActFloats = 16 * 32 * 32;      // largest activation per (sample, image): 64 KB
 
@@ -340,7 +231,9 @@ using namespace ursa;
 
 extern "C" size_t ursa_bma_preresnet_workspace(int S, int64_t N, int depth, int C, int algo) {
     NetPlan pl;
-    if (S < 1 || N < 1 || algo != URSA_ALGO_FFMA || !build_plan(depth, C, pl)) return 0;
+    if (S < 1 || N < 1) return 0;
+    if (algo == URSA_ALGO_TCGEN05) return preresnet_workspace_tcgen05(S, N, depth, C);
+    if (algo != URSA_ALGO_FFMA || !build_plan(depth, C, pl)) return 0;
     return chunking(S, N, pl).total;
 }
 
@@ -350,8 +243,11 @@ extern "C" int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, co
                                           size_t workspace_bytes, int algo, void *stream) {
     URSA_REQUIRE(bank && bufbank && x && proba_sum && entropy_sum && workspace, "ursa_bma_preresnet_forward: null pointer");
     URSA_REQUIRE(S >= 1 && N >= 1, "ursa_bma_preresnet_forward: bad shape");
+    if (algo == URSA_ALGO_TCGEN05)
+        return preresnet_forward_tcgen05(bank, ld_bank, bufbank, ld_buf, S, x, N, depth, C, proba_sum, entropy_sum,
+                                         logits_out, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
     if (algo != URSA_ALGO_FFMA) {
-        set_error("ursa_bma_preresnet_forward: only URSA_ALGO_FFMA is built in this revision");
+        set_error("ursa_bma_preresnet_forward: unknown algo %d", algo);
         return URSA_ERR_UNSUPPORTED;
     }
     static thread_local NetPlan pl;     // ~3 KB; rebuilt per call (cheap)

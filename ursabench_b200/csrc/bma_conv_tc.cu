@@ -1,0 +1,471 @@
+// K3 (PreResNet) on 5th-generation tensor cores: sample-batched implicit-GEMM 3x3 convolutions, 3xTF32,
+// TMA-fed, accumulators in TMEM (see bma_mlp_tc.cu for the 3xTF32 rationale).
+//
+// Data layout (per chunk of S_c samples x N_c images, pair p = s*N_c + n), NHWC:
+//   R   raw block outputs            fp32 [P][H][W][C]      (residual stream)
+//   A   pre-activated conv inputs    tf32 hi / lo planes [P][H][W][C] = split(relu(bn(R)))  -- written by the
+//       PRODUCER's epilogue, so the consumer's TMA can fetch the im2col slices directly and the zero padding
+//       (TMA out-of-bounds fill) is applied after the activation, exactly like PyTorch pads relu(bn(x)).
+// Implicit GEMM per CTA: M = 128 output pixels (4 rows x 32 | 8 rows x 16 | 2 images x 8 x 8), N = Cout,
+// K = 9 taps x Cin.  For each tap the [128 pixels x CW channels] A slice is ONE 5-D tiled TMA box at shifted
+// coordinates (c0, w0+kw-1, h0+kh-1, n0, s); stride-2 convs use four parity-split tensor maps (a space-to-depth
+// view) so that every tap is still a dense box.  B = filters packed K-major [Cout][tap*Cin + ci], split hi / lo.
+//   warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer (3 tcgen05.mma per UMMA_K) | warps 2-5: epilogue
+//   epilogue mode 0 (conv1 of a block): A' = split(relu(bn2(acc)))
+//   epilogue mode 1 (conv2 of a block): R' = acc + shortcut ; A'' = split(relu(bn_next(R')))
+// The 3->16 stem, the 1x1 stride-2 shortcuts and the head (1.6 % of the FLOPs) stay on CUDA cores.
+#include "preresnet_plan.cuh"
+#include "tc_common.cuh"
+
+namespace ursa {
+
+struct ConvTcMaps {
+    CUtensorMap a_hi[4], a_lo[4];      // index = h-parity * 2 + w-parity for stride 2; [0] only for stride 1
+    CUtensorMap b_hi, b_lo;
+};
+
+struct ConvTcArgs {
+    int cin, cout, hout, stride, n_images;
+    int kchunks;                       // cin / CW
+    int stages;
+    uint32_t tmem_cols;
+    int mode;                          // 0 / 1, see above
+    const float *packed;
+    int64_t ld_packed, bn_off;         // epilogue BN (a[cout], b[cout]) in the packed row; < 0: none
+    const float *res;                  // mode 1: shortcut [P][hout][hout][cout]
+    float *out_raw;                    // mode 1
+    float *out_hi, *out_lo;            // split outputs (may be null in mode 1 for the last block)
+};
+
+constexpr int CTC_THREADS = 192, CTC_MAX_STAGES = 8;
+
+template <int CW>      // channels per shared-memory row: 16 (64-byte swizzle) or 32 (128-byte swizzle)
+__global__ void __launch_bounds__(CTC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
+    constexpr int ROW_BYTES = CW * 4;
+    constexpr uint32_t A_BYTES = 128 * ROW_BYTES;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[CTC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[CTC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bn_s[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.y;
+    // tile geometry
+    const int WT = a.hout, HT = a.hout >= 16 ? 128 / a.hout : a.hout, NT = 128 / (WT * HT);
+    const int tpi = (a.hout * a.hout) / 128;                 // tiles per image (0 when one tile spans 2 images)
+    int n0, h0;
+    if (NT == 1) { n0 = blockIdx.x / tpi; h0 = (blockIdx.x % tpi) * HT; } else { n0 = blockIdx.x * NT; h0 = 0; }
+
+    const uint32_t b_bytes = (uint32_t)a.cout * ROW_BYTES;
+    const uint32_t stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int k_blocks = 9 * a.kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    if (warp >= 2 && a.bn_off >= 0) {
+        const float *bn = a.packed + (int64_t)s * a.ld_packed + a.bn_off;
+        for (int i = threadIdx.x - 64; i < 2 * a.cout; i += 128) bn_s[i] = __ldg(bn + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int st = kb % a.stages;
+                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+                const int tap = kb / a.kchunks, cc = kb - tap * a.kchunks;
+                const int kh = tap / 3, kw = tap - kh * 3;
+                mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[st]);
+                mbar_expect_tx_a(fb, stage_bytes);
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                int mi = 0, cw = kw - 1, ch = h0 + kh - 1;
+                if (a.stride == 2) {
+                    mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);        // parity of (kh-1, kw-1)
+                    cw = (kw - 1) >> 1;                                // floor((kw-1)/2)
+                    ch = h0 + ((kh - 1) >> 1);
+                }
+                tma_load_5d_a(base, &maps.a_hi[mi], cc * CW, cw, ch, n0, s, fb);
+                tma_load_5d_a(base + A_BYTES, &maps.a_lo[mi], cc * CW, cw, ch, n0, s, fb);
+                tma_load_3d_a(base + 2 * A_BYTES, &maps.b_hi, tap * a.cin + cc * CW, 0, s, fb);
+                tma_load_3d_a(base + 2 * A_BYTES + b_bytes, &maps.b_lo, tap * a.cin + cc * CW, 0, s, fb);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_tf32_idesc(128, a.cout);
+            uint32_t acc = 0;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                const int st = kb % a.stages;
+                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+                mbar_wait_a(smem_u32(&full_bar[st]), ph);
+                tc_fence_after();
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const uint64_t d_ahi = make_kmajor_desc<ROW_BYTES>(base), d_alo = make_kmajor_desc<ROW_BYTES>(base + A_BYTES);
+                const uint64_t d_bhi = make_kmajor_desc<ROW_BYTES>(base + 2 * A_BYTES);
+                const uint64_t d_blo = make_kmajor_desc<ROW_BYTES>(base + 2 * A_BYTES + b_bytes);
+#pragma unroll
+                for (int k = 0; k < CW / 8; ++k) {
+                    const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                    umma_tf32(tmem_base, d_alo + koff, d_bhi + koff, idesc, acc);
+                    acc = 1;
+                    umma_tf32(tmem_base, d_ahi + koff, d_blo + koff, idesc, 1);
+                    umma_tf32(tmem_base, d_ahi + koff, d_bhi + koff, idesc, 1);
+                }
+                umma_commit(smem_u32(&empty_bar[st]));
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        // ===== epilogue: thread = output pixel =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
+        const int n = n0 + nl;
+        const bool valid = n < a.n_images;
+        const int64_t off = ((((int64_t)s * a.n_images + n) * a.hout + (h0 + h)) * a.hout + w) * a.cout;
+        const bool has_bn = a.bn_off >= 0;
+        mbar_wait_a(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < a.cout; c0 += 16) {
+            uint32_t rr[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+            if (!valid) continue;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+            if (a.mode == 1) {
+                const float4 *rp = reinterpret_cast<const float4 *>(a.res + off + c0);
+                float4 *op = reinterpret_cast<float4 *>(a.out_raw + off + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 t = __ldg(rp + i);
+                    v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                    op[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+            if (a.out_hi) {
+                float4 *hp = reinterpret_cast<float4 *>(a.out_hi + off + c0);
+                float4 *lp = reinterpret_cast<float4 *>(a.out_lo + off + c0);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float y[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = v[i + j];
+                        if (has_bn) t = fmaxf(fmaf(bn_s[c0 + i + j], t, bn_s[a.cout + c0 + i + j]), 0.f);
+                        y[j] = t;
+                    }
+                    float4 hv, lv;
+                    hv.x = rn_tf32(y[0]); hv.y = rn_tf32(y[1]); hv.z = rn_tf32(y[2]); hv.w = rn_tf32(y[3]);
+                    lv.x = rn_tf32(y[0] - hv.x); lv.y = rn_tf32(y[1] - hv.y); lv.z = rn_tf32(y[2] - hv.z); lv.w = rn_tf32(y[3] - hv.w);
+                    hp[i >> 2] = hv;
+                    lp[i >> 2] = lv;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ---- CUDA-core helpers in NHWC -----------------------------------------------------------------------------
+// stem: R0 = conv3x3(x) (3 -> 16), A0 = split(relu(bn1_of_block0(R0)));  x is NCHW and shared by all samples
+__global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ packed,
+                                                         int64_t ld_packed, int64_t w_off, int64_t bn_off, int n_images,
+                                                         float *__restrict__ out_raw, float *__restrict__ out_hi,
+                                                         float *__restrict__ out_lo) {
+    __shared__ float xs[3][34][35];
+    __shared__ __align__(16) float ws[27 * 16];
+    __shared__ float bn[32];
+    const int n = blockIdx.x, s = blockIdx.y;
+    const float *pk = packed + (int64_t)s * ld_packed;
+    for (int i = threadIdx.x; i < 27 * 16; i += 256) ws[i] = __ldg(pk + w_off + i);     // [ci][tap][co]
+    for (int i = threadIdx.x; i < 32; i += 256) bn[i] = __ldg(pk + bn_off + i);
+    for (int i = threadIdx.x; i < 3 * 34 * 34; i += 256) {
+        const int ww = i % 34, hh = (i / 34) % 34, ci = i / (34 * 34);
+        const int hi = hh - 1, wi = ww - 1;
+        xs[ci][hh][ww] = (hi >= 0 && hi < 32 && wi >= 0 && wi < 32) ? __ldg(x + ((int64_t)n * 3 + ci) * 1024 + hi * 32 + wi) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int p = threadIdx.x + j * 256;
+        const int h = p >> 5, w = p & 31;
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float av = xs[ci][h + kh][w + kw];
+                    const float4 *wp = reinterpret_cast<const float4 *>(ws + (ci * 9 + kh * 3 + kw) * 16);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 w4 = wp[qd];
+                        acc[4 * qd + 0] = fmaf(av, w4.x, acc[4 * qd + 0]);
+                        acc[4 * qd + 1] = fmaf(av, w4.y, acc[4 * qd + 1]);
+                        acc[4 * qd + 2] = fmaf(av, w4.z, acc[4 * qd + 2]);
+                        acc[4 * qd + 3] = fmaf(av, w4.w, acc[4 * qd + 3]);
+                    }
+                }
+        const int64_t off = (((int64_t)s * n_images + n) * 1024 + p) * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            *reinterpret_cast<float4 *>(out_raw + off + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            float y[4], hv[4], lv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                y[k] = fmaxf(fmaf(bn[i + k], acc[i + k], bn[16 + i + k]), 0.f);
+                hv[k] = rn_tf32(y[k]);
+                lv[k] = rn_tf32(y[k] - hv[k]);
+            }
+            *reinterpret_cast<float4 *>(out_hi + off + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4 *>(out_lo + off + i) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+        }
+    }
+}
+
+// 1x1 stride-2 shortcut on the raw NHWC block input
+__global__ void __launch_bounds__(256) shortcut_nhwc_kernel(const float *__restrict__ in, const float *__restrict__ packed,
+                                                             int64_t ld_packed, int64_t w_off, int cin, int cout, int hout,
+                                                             int n_images, float *__restrict__ out) {
+    __shared__ float ws[32 * 64];
+    const int n = blockIdx.x, s = blockIdx.y;
+    const float *pk = packed + (int64_t)s * ld_packed + w_off;                    // [ci][co]
+    for (int i = threadIdx.x; i < cin * cout; i += 256) ws[i] = __ldg(pk + i);
+    __syncthreads();
+    const int hin = hout * 2;
+    const float *ib = in + ((int64_t)s * n_images + n) * hin * hin * cin;
+    float *ob = out + ((int64_t)s * n_images + n) * hout * hout * cout;
+    for (int i = threadIdx.x; i < hout * hout * cout; i += 256) {
+        const int co = i % cout, px = i / cout;
+        const int h = px / hout, w = px - h * hout;
+        const float *ip = ib + ((int64_t)(2 * h) * hin + 2 * w) * cin;
+        float acc = 0.f;
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(ip + ci), ws[ci * cout + co], acc);
+        ob[i] = acc;
+    }
+}
+
+// final BN + ReLU + AvgPool2d(8) + fc on NHWC raw [P][8][8][64]; one warp per pair
+__global__ void __launch_bounds__(256) head_nhwc_kernel(const float *__restrict__ act, const float *__restrict__ packed,
+                                                         int64_t ld_packed, int64_t bn_off, int64_t fc_off, int n_images,
+                                                         int n_pairs, int C, float *__restrict__ logits) {
+    __shared__ float feat_s[8][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 8 + warp;
+    if (pair >= n_pairs) return;
+    const int s = pair / n_images;
+    const float *pk = packed + (int64_t)s * ld_packed;
+    const float *x = act + (int64_t)pair * 64 * 64;
+    const float a0 = __ldg(pk + bn_off + lane), b0 = __ldg(pk + bn_off + 64 + lane);
+    const float a1 = __ldg(pk + bn_off + 32 + lane), b1 = __ldg(pk + bn_off + 96 + lane);
+    float f0 = 0.f, f1 = 0.f;
+    for (int px = 0; px < 64; ++px) {
+        f0 += fmaxf(fmaf(a0, __ldg(x + px * 64 + lane), b0), 0.f);
+        f1 += fmaxf(fmaf(a1, __ldg(x + px * 64 + 32 + lane), b1), 0.f);
+    }
+    feat_s[warp][lane] = f0 * (1.f / 64.f);
+    feat_s[warp][32 + lane] = f1 * (1.f / 64.f);
+    __syncwarp();
+    const float *fw = pk + fc_off, *fb = pk + fc_off + (int64_t)C * 64;
+    for (int c = lane; c < C; c += 32) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) acc = fmaf(feat_s[warp][k], __ldg(fw + c * 64 + k), acc);
+        logits[(int64_t)pair * C + c] = acc + __ldg(fb + c);
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+constexpr int kTcChunkSamples = 8, kTcChunkImages = 512;
+
+struct TcChunking {
+    int sc, nc;
+    size_t raw_bytes, packed_bytes, logit_bytes, total;
+};
+
+static TcChunking tc_chunking(int S, int64_t N, const NetPlan &pl) {
+    TcChunking c;
+    c.sc = S < kTcChunkSamples ? S : kTcChunkSamples;
+    c.nc = (int)(N < kTcChunkImages ? N : kTcChunkImages);
+    const size_t pairs = (size_t)c.sc * c.nc;
+    c.raw_bytes = pairs * 16 * 32 * 32 * sizeof(float);               // largest activation: 64 KB per pair
+    c.packed_bytes = (((size_t)c.sc * pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
+    c.logit_bytes = (((pairs * pl.C * sizeof(float)) + 1023) & ~(size_t)1023);
+    // R_a, R_b, R_shortcut, A1 hi/lo, A2 hi/lo = 7 planes
+    c.total = 7 * c.raw_bytes + c.packed_bytes + c.logit_bytes + 2048;
+    return c;
+}
+
+// activations plane [S_c][N_c][H][W][C]; parity >= 0 selects the (h, w) parity sub-lattice of a stride-2 conv input
+static int make_act_map(CUtensorMap *tm, const float *plane, int sc, int nc, int H, int C, int cw, int hout, int stride,
+                        int parity) {
+    const int WT = hout, HT = hout >= 16 ? 128 / hout : hout, NT = 128 / (WT * HT);
+    const uint32_t box[5] = {(uint32_t)cw, (uint32_t)WT, (uint32_t)HT, (uint32_t)NT, 1};
+    if (stride == 1) {
+        const uint64_t dims[5] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)nc, (uint64_t)sc};
+        const uint64_t st[4] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4, (uint64_t)nc * H * H * C * 4};
+        return make_tensor_map(tm, plane, 5, dims, st, box, cw * 4);
+    }
+    const int hp = parity >> 1, wp = parity & 1;
+    const float *base = plane + ((int64_t)hp * H + wp) * C;
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)(H / 2), (uint64_t)(H / 2), (uint64_t)nc, (uint64_t)sc};
+    const uint64_t st[4] = {(uint64_t)2 * C * 4, (uint64_t)2 * H * C * 4, (uint64_t)H * H * C * 4, (uint64_t)nc * H * H * C * 4};
+    return make_tensor_map(tm, base, 5, dims, st, box, cw * 4);
+}
+
+static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin, int cout, int stride, int sc, int nc,
+                          const float *packed, int64_t ld_packed, int64_t w_hi_off, int64_t w_lo_off, ConvTcArgs g,
+                          cudaStream_t st) {
+    const int hout = hin / stride;
+    const int cw = cin >= 32 ? 32 : 16;
+    ConvTcMaps maps;
+    const int nmaps = stride == 2 ? 4 : 1;
+    for (int i = 0; i < nmaps; ++i) {
+        if (int rc = make_act_map(&maps.a_hi[i], a_hi, sc, nc, hin, cin, cw, hout, stride, i)) return rc;
+        if (int rc = make_act_map(&maps.a_lo[i], a_lo, sc, nc, hin, cin, cw, hout, stride, i)) return rc;
+    }
+    for (int i = nmaps; i < 4; ++i) { maps.a_hi[i] = maps.a_hi[0]; maps.a_lo[i] = maps.a_lo[0]; }
+    {
+        const uint64_t dims[3] = {(uint64_t)9 * cin, (uint64_t)cout, (uint64_t)sc};
+        const uint64_t sb[2] = {(uint64_t)9 * cin * 4, (uint64_t)ld_packed * 4};
+        const uint32_t box[3] = {(uint32_t)cw, (uint32_t)cout, 1};
+        if (int rc = make_tensor_map(&maps.b_hi, packed + w_hi_off, 3, dims, sb, box, cw * 4)) return rc;
+        if (int rc = make_tensor_map(&maps.b_lo, packed + w_lo_off, 3, dims, sb, box, cw * 4)) return rc;
+    }
+    g.cin = cin; g.cout = cout; g.hout = hout; g.stride = stride; g.n_images = nc;
+    g.kchunks = cin / cw;
+    g.packed = packed; g.ld_packed = ld_packed;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)cout) cols <<= 1;
+    g.tmem_cols = cols;
+    const size_t stage_bytes = 2 * (size_t)128 * cw * 4 + 2 * (size_t)cout * cw * 4;
+    int stages = (int)((size_t)(200 << 10) / stage_bytes);
+    if (stages > CTC_MAX_STAGES) stages = CTC_MAX_STAGES;
+    if (stages > 9 * g.kchunks) stages = 9 * g.kchunks;
+    g.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    const int WT = hout, HT = hout >= 16 ? 128 / hout : hout, NT = 128 / (WT * HT);
+    const int tiles = NT == 1 ? nc * ((hout * hout) / 128) : (nc + NT - 1) / NT;
+    dim3 grid(tiles, sc);
+    if (cw == 16) {
+        URSA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv3x3_tc_kernel<16><<<grid, CTC_THREADS, smem, st>>>(maps, g);
+    } else {
+        URSA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv3x3_tc_kernel<32><<<grid, CTC_THREADS, smem, st>>>(maps, g);
+    }
+    URSA_LAUNCH_CHECK("conv3x3_tc_kernel");
+    return URSA_OK;
+}
+
+size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C) {
+    NetPlan pl;
+    if (!build_plan(depth, C, pl, true)) return 0;
+    return tc_chunking(S, N, pl).total;
+}
+
+int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
+                              int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
+                              double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    static thread_local NetPlan pl;
+    if (!build_plan(depth, C, pl, true)) {
+        set_error("ursa_bma_preresnet_forward: unsupported depth %d (BasicBlock PreResNet: depth = 6n+2, 8..38)", depth);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    URSA_REQUIRE(ld_bank >= pl.D, "ursa_bma_preresnet_forward: ld_bank (%lld) < D (%lld)", (long long)ld_bank, (long long)pl.D);
+    URSA_REQUIRE(ld_buf >= pl.NB, "ursa_bma_preresnet_forward: ld_buf (%lld) < %lld", (long long)ld_buf, (long long)pl.NB);
+    const TcChunking ck = tc_chunking(S, N, pl);
+    URSA_REQUIRE(workspace_bytes >= ck.total, "ursa_bma_preresnet_forward: workspace too small");
+    char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    float *Ra = reinterpret_cast<float *>(wsb);
+    float *Rb = reinterpret_cast<float *>(wsb + ck.raw_bytes);
+    float *Rs = reinterpret_cast<float *>(wsb + 2 * ck.raw_bytes);
+    float *A1h = reinterpret_cast<float *>(wsb + 3 * ck.raw_bytes), *A1l = reinterpret_cast<float *>(wsb + 4 * ck.raw_bytes);
+    float *A2h = reinterpret_cast<float *>(wsb + 5 * ck.raw_bytes), *A2l = reinterpret_cast<float *>(wsb + 6 * ck.raw_bytes);
+    float *packed = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes);
+    float *logits = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes + ck.packed_bytes);
+    const int n = pl.n_blocks;
+
+    for (int s0 = 0; s0 < S; s0 += ck.sc) {
+        const int sc = (S - s0 < ck.sc) ? (S - s0) : ck.sc;
+        preresnet_prep_kernel<<<dim3(pl.table.n, sc), 256, 0, st>>>(pl.table, bank + (int64_t)s0 * ld_bank, ld_bank,
+                                                                    bufbank + (int64_t)s0 * ld_buf, ld_buf, packed,
+                                                                    pl.packed_floats);
+        URSA_LAUNCH_CHECK("preresnet_prep_kernel");
+        for (int64_t i0 = 0; i0 < N; i0 += ck.nc) {
+            const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
+            // stem: R = conv(x), A1 = split(relu(bn1(R)))
+            stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
+                                                           pl.blocks[0][0].bn1, nc, Ra, A1h, A1l);
+            URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+            float *cur = Ra, *nxt = Rb;
+            int ch = 16, hw = 32;
+            for (int stg = 0; stg < 3; ++stg) {
+                for (int b = 0; b < n; ++b) {
+                    const NetPlan::Block &B = pl.blocks[stg][b];
+                    const bool down = B.ds >= 0;
+                    const int cout = down ? ch * 2 : ch, stride = down ? 2 : 1, hout = hw / stride;
+                    const float *res = cur;
+                    if (down) {
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B.ds, ch, cout, hout, nc, Rs);
+                        URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
+                        res = Rs;
+                    }
+                    ConvTcArgs g;
+                    // conv1: A1 -> A2 = split(relu(bn2(acc)))
+                    g.mode = 0; g.bn_off = B.bn2; g.res = nullptr; g.out_raw = nullptr; g.out_hi = A2h; g.out_lo = A2l;
+                    if (int rc = launch_conv_tc(A1h, A1l, hw, ch, cout, stride, sc, nc, packed, pl.packed_floats, B.w1, B.w1_lo, g, st))
+                        return rc;
+                    // conv2: A2 -> R' = acc + shortcut ; A1 = split(relu(bn_next(R')))
+                    int64_t bn_next = -1;
+                    if (b + 1 < n) bn_next = pl.blocks[stg][b + 1].bn1;
+                    else if (stg + 1 < 3) bn_next = pl.blocks[stg + 1][0].bn1;
+                    g.mode = 1; g.bn_off = bn_next; g.res = res; g.out_raw = nxt;
+                    g.out_hi = bn_next >= 0 ? A1h : nullptr; g.out_lo = bn_next >= 0 ? A1l : nullptr;
+                    if (int rc = launch_conv_tc(A2h, A2l, hout, cout, cout, 1, sc, nc, packed, pl.packed_floats, B.w2, B.w2_lo, g, st))
+                        return rc;
+                    float *t = cur; cur = nxt; nxt = t;
+                    ch = cout; hw = hout;
+                }
+            }
+            const int pairs = sc * nc;
+            head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);
+            URSA_LAUNCH_CHECK("head_nhwc_kernel");
+            if (int rc = ursa_bma_accumulate(logits, sc, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
+                return rc;
+            if (logits_out)
+                URSA_CUDA(cudaMemcpy2DAsync(logits_out + ((int64_t)s0 * N + i0) * C, (size_t)N * C * sizeof(float), logits,
+                                            (size_t)nc * C * sizeof(float), (size_t)nc * C * sizeof(float), sc,
+                                            cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return URSA_OK;
+}
+
+}  // namespace ursa
