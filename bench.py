@@ -402,21 +402,23 @@ def run_extras(dev, rank, world, peak):
     P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
     ws = [None]
 
-    def bma():
-        P.zero_()
-        E.zero_()
-        ws[0] = _C.bma_mlp_forward(bankm, hi - lo, x, 784, 400, 10, P, E, workspace=ws[0])
-        Pr, Er, n = udist.allreduce_bma(P, E, hi - lo)
-        return _C.bma_metrics(Pr, n, y)
-    bma()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    ms, _ = _event_time_ms(bma, 5)
-    ms = udist.allreduce_max_scalar(ms, dev)
-    out["bma_mlp400_S100_N10k"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
-                                   "img_samples_per_s": N * S_all / ms * 1e3,
-                                   "TFLOPs": 955_200 * N * S_all / ms / 1e9, "n_gpus": world}
+    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05)):
+        def bma():
+            P.zero_()
+            E.zero_()
+            ws[0] = _C.bma_mlp_forward(bankm, hi - lo, x, 784, 400, 10, P, E, workspace=ws[0], algo=algo)
+            Pr, Er, n = udist.allreduce_bma(P, E, hi - lo)
+            return _C.bma_metrics(Pr, n, y)
+        ws[0] = None
+        bma()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms, _ = _event_time_ms(bma, 5)
+        ms = udist.allreduce_max_scalar(ms, dev)
+        out["bma_mlp400_S100_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                                    "img_samples_per_s": N * S_all / ms * 1e3,
+                                                    "TFLOPs": 955_200 * N * S_all / ms / 1e9, "n_gpus": world}
     del bankm, x, P, E
     ws[0] = None
     torch.cuda.empty_cache()
@@ -439,22 +441,58 @@ def run_extras(dev, rank, world, peak):
     xi = torch.randn(N, 3, 32, 32, device=dev)
     P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
 
-    def bma_conv():
-        P.zero_()
-        E.zero_()
-        ws[0] = _C.bma_preresnet_forward(bankp, bufp, ns, xi, 20, 10, P, E, workspace=ws[0])
-        Pr, Er, n = udist.allreduce_bma(P, E, ns)
-        return _C.bma_metrics(Pr, n, y)
-    ws[0] = _C.bma_preresnet_forward(bankp[:1], bufp[:1], 1, xi[:512], 20, 10, P[:512], E[:512], workspace=None)
+    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05)):
+        def bma_conv():
+            P.zero_()
+            E.zero_()
+            ws[0] = _C.bma_preresnet_forward(bankp, bufp, ns, xi, 20, 10, P, E, workspace=ws[0], algo=algo)
+            Pr, Er, n = udist.allreduce_bma(P, E, ns)
+            return _C.bma_metrics(Pr, n, y)
+        ws[0] = None
+        ws[0] = _C.bma_preresnet_forward(bankp[:1], bufp[:1], 1, xi[:512], 20, 10, P[:512], E[:512], workspace=None,
+                                         algo=algo)
+        ws[0] = None
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms, _ = _event_time_ms(bma_conv, 2)
+        ms = udist.allreduce_max_scalar(ms, dev)
+        out["bma_preresnet20_S100_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                                         "img_samples_per_s": N * S_all / ms * 1e3,
+                                                         "TFLOPs": 81.63e6 * N * S_all / ms / 1e9, "n_gpus": world}
+    del bankp, bufp, xi, P, E
     ws[0] = None
-    if world > 1:
-        torch.distributed.barrier()
+    torch.cuda.empty_cache()
+    # HMC (BASELINE.json configs[3]): MLP 784-200-10, full batch of 1000 points, 128 chains per GPU, L = 10
+    from ursabench_b200 import inference
+    Ch, Lh = 128, 10
+    Dh = 199_210
+    ldh = (Dh + 3) // 4 * 4
+    th, rh, gh = (torch.randn(Ch, ldh, device=dev) * 0.05 for _ in range(3))
+    fn = lambda: _C.hmc_leapfrog(th, rh, gh, kick=1e-4, drift=5e-4, tau=100.0)  # noqa: E731
+    for _ in range(3):
+        fn()
+    ms, _ = _event_time_ms(fn, 20)
+    out["k5_leapfrog_128x199210"] = {"ms": ms, "GBps": 20 * Ch * ldh / ms / 1e6, "frac": 20 * Ch * ldh / ms / 1e6 / peak}
+    del th, rh, gh
+    g = torch.Generator().manual_seed(5)
+    xs, ys = torch.randn(1000, 1, 28, 28, generator=g), torch.randint(0, 10, (1000,), generator=g)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xs, ys), batch_size=1000)
+    hyp = {"step_size": 2.09e-4, "num_samples": 2, "L": Lh, "tau": 100.0, "burn": 0, "mass": 0.192, "num_chains": Ch}
+    hm = inference.HMC(hyp, models.MLP(200, 784, 10), loader, device=dev)
+    hm.sample()                                            # warm-up (cuBLAS heuristics, vmap tracing)
     torch.cuda.synchronize()
-    ms, _ = _event_time_ms(bma_conv, 2)
-    ms = udist.allreduce_max_scalar(ms, dev)
-    out["bma_preresnet20_S100_N10k"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
-                                        "img_samples_per_s": N * S_all / ms * 1e3,
-                                        "TFLOPs": 81.63e6 * N * S_all / ms / 1e9, "n_gpus": world, "algo": "ffma"}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hm.sample()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = udist.allreduce_max_scalar(e0.elapsed_time(e1), dev)
+    steps = hyp["num_samples"] * (Lh + 1)                  # gradient evaluations per chain
+    out["hmc_mlp200_N1000"] = {"chains_per_gpu": Ch, "n_gpus": world, "L": Lh, "ms_per_iteration": ms / hyp["num_samples"],
+                               "chain_leapfrog_steps_per_s": world * Ch * hyp["num_samples"] * Lh / ms * 1e3,
+                               "grad_TFLOPs": 6 * (784 * 200 + 200 * 200 + 200 * 10) * 1000 * Ch * steps / ms / 1e9,
+                               "accept_rate": float(hm.acceptance_rate.mean())}
     return out
 
 

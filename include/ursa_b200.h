@@ -177,6 +177,38 @@ int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *
                                float *proba_sum, float *entropy_sum, float *logits_out, double gamma,
                                void *workspace, size_t workspace_bytes, int algo, void *stream);
 
+/* ------------------------------------------------------------------------
+ * K5  chain-batched HMC  (replaces the call into hamiltorch.sample_model made by HMC.sample,
+ *     inference/hmc.py:62-85.  hamiltorch is a third-party dependency that is NOT vendored in the reference
+ *     (unpinned git HEAD, util.py:11) -- these entry points follow its published leapfrog / Metropolis algorithm as
+ *     restated in oracle/restate.py::hmc_*; parity is unpinned.)
+ *   State: theta, r, saved are [C, ld] fp32 (C independent chains, ld % 4 == 0); elementwise entry points take the
+ *   batch as n = C*ld flat elements because step size, mass and prior precision are shared (hmc.py:64-75).
+ *
+ *   ursa_hmc_momentum   r = sqrt_mass * z          z ~ N(0,1): `noise` (parity mode) or Philox as in K1
+ *   ursa_hmc_leapfrog   grad_logp = -(tau_out * g_nll + tau * theta)      g_nll = d/dtheta sum_i CE_i (autograd)
+ *                       r += kick * grad_logp ; if drift != 0: theta += drift * r ; snapshot = theta (nullable)
+ *                       (kick = eps/2 for the first and last half steps, eps between; drift = eps * inv_mass, 0 for
+ *                        the closing half kick)                             20 B/param
+ *   ursa_hmc_energy     sum_theta2[c] = sum_d theta[c,d]^2, sum_r2[c] = sum_d r[c,d]^2 in fp64, fixed order; the
+ *                       caller forms H = tau_out*CE_sum + tau/2*sum_theta2 + D/2*log(2*pi/tau) + inv_mass/2*sum_r2
+ *   ursa_hmc_accept     accept[c] = isfinite(H) && log u[c] <= min(0, h_old[c] - h_new[c]);  u from `logu` (parity)
+ *                       or Philox (one block per chain: chain_offset + c, `step`).  Accepted chains commit
+ *                       theta -> saved (and keep_src -> keep_dst when given), rejected chains restore
+ *                       saved -> theta; `out` (nullable, [C, ld_out]) receives the resulting state
+ *                       (keep_dst's when given, else theta's).
+ * ---------------------------------------------------------------------- */
+int ursa_hmc_momentum(float *r, const float *noise, int64_t n, float sqrt_mass, uint64_t seed, uint64_t step,
+                      uint64_t elem_offset, void *stream);
+int ursa_hmc_leapfrog(float *theta, float *r, const float *g_nll, float *snapshot, int64_t n, float kick,
+                      float drift, float tau, float tau_out, void *stream);
+size_t ursa_hmc_energy_workspace(int64_t C, int64_t D);
+int ursa_hmc_energy(const float *theta, const float *r, int64_t C, int64_t D, int64_t ld, double *sum_theta2,
+                    double *sum_r2, void *workspace, size_t workspace_bytes, void *stream);
+int ursa_hmc_accept(float *theta, float *saved, float *keep_dst, const float *keep_src, float *out, int64_t ld_out,
+                    int64_t C, int64_t ld, const double *h_old, const double *h_new, const float *logu,
+                    int32_t *accept, uint64_t seed, uint64_t step, uint64_t chain_offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

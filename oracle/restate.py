@@ -312,3 +312,88 @@ def box_muller(r):
     ta = 2.0 * np.pi * u2a
     tb = 2.0 * np.pi * u2b
     return np.stack([ra * np.cos(ta), ra * np.sin(ta), rb * np.cos(tb), rb * np.sin(tb)], axis=-1)
+
+
+# --------------------------------------------------------------------------
+# a15  HMC                        inference/hmc.py:62-85  ->  hamiltorch.sample_model
+#
+# PARITY UNPINNED.  The arithmetic lives in the third-party package `hamiltorch`
+# (git+https://github.com/AdamCobb/hamiltorch, unpinned HEAD; the demo notebook's install log shows
+# hamiltorch-0.4.0.dev1) which is neither vendored under /root/reference nor installed here.  What follows restates
+# its published algorithm (hamiltorch/samplers.py: gibbs, leapfrog, hamiltonian, sample with Sampler.HMC and a
+# diagonal `inv_mass` vector; hamiltorch/samplers.py::define_model_log_prob with Normal(0, tau^-1/2) priors and
+# `multi_class_linear_output`), anchored on the reference's own call site: hmc.py:64-75 passes one `tau` for every
+# tensor, `inv_mass = ones/mass`, `burn=-1`, `tau_out=1`, and hmc.py:78-81 thins the returned list by L.
+# --------------------------------------------------------------------------
+def hmc_momentum(z, mass):
+    """gibbs(): Normal(0, mass**0.5).sample() = sqrt(mass) * z."""
+    return _f32(z) * F32(math.sqrt(mass))
+
+
+def hmc_leapfrog_update(theta, r, g_nll, kick, drift, tau, tau_out=1.0):
+    """One kick (+ drift) of the leapfrog integrator on flat fp32 vectors.
+
+    grad log p(theta) = -(tau_out * g_nll + tau * theta)   (ll = -tau_out * sum CE ; prior Normal(0, tau^-1/2))
+    momentum += kick * grad ; params += drift * momentum    (hamiltorch leapfrog: kick = eps/2 before the loop and
+    as the closing correction, eps inside; drift = eps * inv_mass, 0 for the closing half kick)
+    """
+    theta, r, g = _f32(theta), _f32(r), _f32(g_nll)
+    glp = -fma32(F32(tau), theta, F32(tau_out) * g)
+    r = r + F32(kick) * glp
+    if drift != 0:
+        theta = theta + F32(drift) * r
+    return theta, r
+
+
+def hmc_energy_sums(theta, r):
+    """(sum theta^2, sum r^2) in float64 (fp32 products are exact in fp64)."""
+    t, q = np.asarray(theta, np.float64), np.asarray(r, np.float64)
+    return float((t * t).sum()), float((q * q).sum())
+
+
+def hmc_hamiltonian(ce_sum, sum_theta2, sum_r2, D, tau, inv_mass, tau_out=1.0):
+    """hamiltonian(): H = -log p + 0.5 * r . (inv_mass * r);  log p = -tau_out*CE_sum + sum_d log N(theta_d; 0, tau^-1/2)."""
+    log_prior = -0.5 * tau * sum_theta2 - 0.5 * D * math.log(2.0 * math.pi / tau)
+    return tau_out * ce_sum - log_prior + 0.5 * inv_mass * sum_r2
+
+
+def hmc_accept(h_old, h_new, log_u):
+    """sample(): rho = min(0, h_old - h_new); accept iff rho >= log u.  Non-finite energies reject (LogProbError)."""
+    if not (math.isfinite(h_old) and math.isfinite(h_new)):
+        return False
+    return min(0.0, h_old - h_new) >= log_u
+
+
+def hmc_chain(theta0, nll_and_grad, z_list, logu_list, step_size, L, tau, mass, tau_out=1.0):
+    """Single-chain hamiltorch.sample(...) loop with injected momentum noise z_list[n] and log-uniforms.
+
+    nll_and_grad(theta) -> (sum CE as float, d/dtheta sum CE as fp32 vector).  Returns (ret, accepts): ``ret`` is
+    hamiltorch's returned list -- the initial point followed by the L leapfrog positions of every iteration
+    (burn = -1 => every iteration is recorded; a rejected iteration re-appends the previous L entries) -- and
+    the per-iteration accept flags.  The reference wrapper then takes ret[burn*L::L] (hmc.py:80).
+    """
+    inv_mass = 1.0 / mass
+    theta = _f32(theta0).copy()
+    D = theta.size
+    ret = [theta.copy()]
+    accepts = []
+    for n in range(len(z_list)):
+        r = hmc_momentum(z_list[n], mass)
+        ce, g = nll_and_grad(theta)
+        h_old = hmc_hamiltonian(ce, *hmc_energy_sums(theta, r), D, tau, inv_mass, tau_out)
+        cur, traj = theta, []
+        for step in range(L):
+            kick = 0.5 * step_size if step == 0 else step_size
+            cur, r = hmc_leapfrog_update(cur, r, g, kick, step_size * inv_mass, tau, tau_out)
+            ce, g = nll_and_grad(cur)
+            traj.append(cur.copy())
+        _, r = hmc_leapfrog_update(cur, r, g, 0.5 * step_size, 0.0, tau, tau_out)
+        h_new = hmc_hamiltonian(ce, *hmc_energy_sums(cur, r), D, tau, inv_mass, tau_out)
+        ok = hmc_accept(h_old, h_new, logu_list[n])
+        accepts.append(ok)
+        if ok:
+            theta = cur
+            ret.extend(traj)
+        else:
+            ret.extend(ret[-L:])
+    return ret, accepts

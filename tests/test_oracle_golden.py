@@ -277,3 +277,34 @@ def test_model_forward_matches_reference_golden():
         with torch.no_grad():
             out = m(x).numpy()
         np.testing.assert_allclose(out, g["preresnet8/logits"][s], rtol=1e-5, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- HMC host logic (a15)
+def test_hmc_kept_iterations_equals_reference_slice():
+    """`kept_iterations` must select exactly what the reference wrapper's samples[burn*L::L] (inference/hmc.py:80)
+    selects from hamiltorch's list [init] + L positions per iteration."""
+    from ursabench_b200.inference.hmc import kept_iterations
+    for n in (1, 3, 10):
+        for L in (1, 4, 7):
+            lst = [("init", 0, 0)] + [("pos", it, k) for it in range(1, n + 1) for k in range(L)]
+            for burn in (-12, -3, -1, 0, 1, 2, n, n + 1):
+                want = lst[burn * L::L]
+                first, use_first = kept_iterations(n, L, burn)
+                got = []
+                if first == 0 and not use_first:
+                    got.append(("init", 0, 0))
+                got += [("pos", it, 0 if use_first else L - 1) for it in range(max(first, 1), n + 1)]
+                assert got == want, (n, L, burn)
+
+
+def test_hmc_restatement_samples_gaussian_prior():
+    """With no data term the target is the prior N(0, 1/tau): the restated chain must reproduce its variance."""
+    import math
+    rng = np.random.RandomState(0)
+    D, tau, n_it = 40, 4.0, 300
+    zs = [rng.randn(D).astype(np.float32) for _ in range(n_it)]
+    lu = [math.log(rng.rand()) for _ in range(n_it)]
+    ret, acc = R.hmc_chain(np.zeros(D, np.float32), lambda t: (0.0, np.zeros_like(t)), zs, lu, 0.15, 10, tau, 1.0)
+    assert len(ret) == n_it * 10 + 1 and np.mean(acc) > 0.9
+    s = np.stack(ret[50 * 10::10])
+    assert abs(s.var() - 1 / tau) < 0.03

@@ -41,6 +41,11 @@ SIGNATURES = {
     "ursa_bma_preresnet_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_bma_preresnet_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                           _sz, _i32, _vp]),
+    "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
+    "ursa_hmc_leapfrog": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
+    "ursa_hmc_energy_workspace": (_sz, [_i64, _i64]),
+    "ursa_hmc_energy": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "ursa_hmc_accept": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp]),
 }
 
 _lib = None
@@ -224,6 +229,61 @@ def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum,
                                           _stream(x))
     _check(rc, "ursa_bma_preresnet_forward")
     return workspace
+
+
+def hmc_momentum(r, sqrt_mass, noise=None, seed=0, step=0, elem_offset=0):
+    """r[C, ld] = sqrt_mass * z (z from ``noise`` or Philox)."""
+    _dev_f32(r, "r"), _dev_f32(noise, "noise", True)
+    if noise is not None and noise.numel() < r.numel():
+        raise ValueError("noise has fewer elements than r")
+    _check(lib().ursa_hmc_momentum(_ptr(r), _ptr(noise), r.numel(), float(sqrt_mass), int(seed), int(step),
+                                   int(elem_offset), _stream(r)), "ursa_hmc_momentum")
+    return r
+
+
+def hmc_leapfrog(theta, r, g_nll, *, kick, drift, tau, tau_out=1.0, snapshot=None):
+    """r += kick * grad_logp ; theta += drift * r  with grad_logp = -(tau_out * g_nll + tau * theta)."""
+    for t, nm, opt in ((theta, "theta", False), (r, "r", False), (g_nll, "g_nll", False), (snapshot, "snapshot", True)):
+        _dev_f32(t, nm, opt)
+    n = theta.numel()
+    for t, nm in ((r, "r"), (g_nll, "g_nll"), (snapshot, "snapshot")):
+        if t is not None and t.numel() < n:
+            raise ValueError("%s has fewer elements than theta" % nm)
+    _check(lib().ursa_hmc_leapfrog(_ptr(theta), _ptr(r), _ptr(g_nll), _ptr(snapshot), n, float(kick), float(drift),
+                                   float(tau), float(tau_out), _stream(theta)), "ursa_hmc_leapfrog")
+
+
+def hmc_energy(theta, r, D, out=None, workspace=None):
+    """theta, r: [C, ld].  Returns (sums[2, C] float64 = [sum theta^2, sum r^2], workspace)."""
+    _dev_f32(theta, "theta"), _dev_f32(r, "r")
+    C, ld = theta.shape
+    if out is None:
+        out = torch.empty(2, C, dtype=torch.float64, device=theta.device)
+    need = lib().ursa_hmc_energy_workspace(C, D)
+    if workspace is None or workspace.numel() * 8 < need:
+        workspace = torch.empty(max(1, (need + 7) // 8), dtype=torch.float64, device=theta.device)
+    _check(lib().ursa_hmc_energy(_ptr(theta), _ptr(r), C, D, ld, out[0].data_ptr(), out[1].data_ptr(), _ptr(workspace),
+                                 workspace.numel() * 8, _stream(theta)), "ursa_hmc_energy")
+    return out, workspace
+
+
+def hmc_accept(theta, saved, h_old, h_new, accept, *, logu=None, keep_dst=None, keep_src=None, out=None, seed=0, step=0,
+               chain_offset=0):
+    """Metropolis accept / restore per chain (see ursa_hmc_accept).  h_old, h_new: float64 [C]; accept: int32 [C]."""
+    for t, nm, opt in ((theta, "theta", False), (saved, "saved", False), (logu, "logu", True), (keep_dst, "keep_dst", True),
+                       (keep_src, "keep_src", True), (out, "out", True)):
+        _dev_f32(t, nm, opt)
+    C, ld = theta.shape
+    for t, nm in ((h_old, "h_old"), (h_new, "h_new")):
+        if t.dtype != torch.float64 or not t.is_cuda or t.numel() < C or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous CUDA float64 tensor of C elements" % nm)
+    if accept.dtype != torch.int32 or not accept.is_cuda or accept.numel() < C:
+        raise ValueError("accept must be a CUDA int32 tensor of C elements")
+    _check(lib().ursa_hmc_accept(_ptr(theta), _ptr(saved), _ptr(keep_dst), _ptr(keep_src), _ptr(out),
+                                 0 if out is None else out.stride(0), C, ld, h_old.data_ptr(), h_new.data_ptr(),
+                                 _ptr(logu), accept.data_ptr(), int(seed), int(step), int(chain_offset), _stream(theta)),
+           "ursa_hmc_accept")
+    return accept
 
 
 def device_info():

@@ -14,6 +14,8 @@
 //   epilogue mode 0 (conv1 of a block): A' = split(relu(bn2(acc)))
 //   epilogue mode 1 (conv2 of a block): R' = acc + shortcut ; A'' = split(relu(bn_next(R')))
 // The 3->16 stem, the 1x1 stride-2 shortcuts and the head (1.6 % of the FLOPs) stay on CUDA cores.
+#include <stdlib.h>
+
 #include "preresnet_plan.cuh"
 #include "tc_common.cuh"
 
@@ -365,7 +367,12 @@ static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin
     while (cols < (uint32_t)cout) cols <<= 1;
     g.tmem_cols = cols;
     const size_t stage_bytes = 2 * (size_t)128 * cw * 4 + 2 * (size_t)cout * cw * 4;
-    int stages = (int)((size_t)(200 << 10) / stage_bytes);
+    // one tile per CTA has only 9 * kchunks k-blocks, so the fixed per-tile latency (barrier init, TMEM alloc, first
+    // TMA round trip, epilogue) is hidden by co-resident CTAs rather than by a deep pipeline: 3 stages of 18 KB
+    // (Cin = 16) -> 4 CTAs/SM, 2-3 stages of 40-48 KB (Cin >= 32) -> 2 CTAs/SM
+    int stages = cw == 16 ? 3 : (stage_bytes * 3 + 1024 <= (size_t)(113 << 10) ? 3 : 2);
+    if (const char *e = getenv("URSA_CONV_TC_STAGES")) { const int v = atoi(e); if (v >= 1) stages = v; }
+    if ((size_t)stages * stage_bytes + 1024 > (size_t)(226 << 10)) stages = (int)(((size_t)(226 << 10) - 1024) / stage_bytes);
     if (stages > CTC_MAX_STAGES) stages = CTC_MAX_STAGES;
     if (stages > 9 * g.kchunks) stages = 9 * g.kchunks;
     g.stages = stages;
