@@ -34,7 +34,7 @@ def test_k5_momentum_external_and_philox(C, n):
     if 0 < n <= 199_212:
         C.hmc_momentum(r, math.sqrt(0.1919), seed=5, step=3, elem_offset=8)
         zz, _ = R.philox_normals(n, 5, 3, 8)
-        np.testing.assert_allclose(r.cpu().numpy(), zz * np.float32(math.sqrt(0.1919)), rtol=0, atol=3e-6)
+        np.testing.assert_allclose(r.cpu().numpy(), zz * np.float32(math.sqrt(0.1919)), rtol=0, atol=2e-5)   # MUFU log2 / sin / cos vs. libm
         # same stream as K1's generator
         ref = torch.empty(n, device=DEV)
         C.philox_normal(ref, 5, 3, 8)
@@ -209,7 +209,8 @@ def test_hmc_conjugate_gaussian_target_many_chains():
     model = torch.nn.Linear(d, 1, bias=False)
     chains = 2048
     torch.manual_seed(123)
-    hyp = {"step_size": 0.05, "num_samples": 30, "L": 8, "tau": tau, "burn": 30, "mass": 1.0, "num_chains": chains}
+    # L * eps * omega stays within ~[0.9, 2.0] rad for every posterior mode (omega^2 in [~17, ~80]): no HMC resonance
+    hyp = {"step_size": 0.0275, "num_samples": 40, "L": 8, "tau": tau, "burn": 40, "mass": 1.0, "num_chains": chains}
     inf = inference.HMC(hyperparameters=hyp, model=model, train_loader=loader, model_loss="regression", device=DEV)
     out = inf.sample()
     assert len(out) == chains

@@ -271,9 +271,12 @@ def hmc_accept(theta, saved, h_old, h_new, accept, *, logu=None, keep_dst=None, 
                chain_offset=0):
     """Metropolis accept / restore per chain (see ursa_hmc_accept).  h_old, h_new: float64 [C]; accept: int32 [C]."""
     for t, nm, opt in ((theta, "theta", False), (saved, "saved", False), (logu, "logu", True), (keep_dst, "keep_dst", True),
-                       (keep_src, "keep_src", True), (out, "out", True)):
+                       (keep_src, "keep_src", True)):
         _dev_f32(t, nm, opt)
     C, ld = theta.shape
+    if out is not None and not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1
+                                and out.shape[0] >= C and out.shape[1] >= ld):
+        raise ValueError("out must be a CUDA float32 [C, >= ld] tensor with unit column stride")
     for t, nm in ((h_old, "h_old"), (h_new, "h_new")):
         if t.dtype != torch.float64 or not t.is_cuda or t.numel() < C or not t.is_contiguous():
             raise ValueError("%s must be a contiguous CUDA float64 tensor of C elements" % nm)
