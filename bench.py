@@ -441,7 +441,7 @@ def run_extras(dev, rank, world, peak):
     xi = torch.randn(N, 3, 32, 32, device=dev)
     P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
 
-    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05)):
+    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05), ("fused", _C.ALGO_TCGEN05_FUSED)):
         def bma_conv():
             P.zero_()
             E.zero_()

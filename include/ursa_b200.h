@@ -158,6 +158,7 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
  * ---------------------------------------------------------------------- */
 #define URSA_ALGO_FFMA    0
 #define URSA_ALGO_TCGEN05 1
+#define URSA_ALGO_TCGEN05_FUSED 2   /* PreResNet only: stage-fused 3xTF32 kernel, activations in shared memory, residual in TMEM */
 
 size_t ursa_bma_mlp_workspace(int S, int64_t N, int in_dim, int hidden, int C, int algo);
 int ursa_bma_mlp_forward(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N,

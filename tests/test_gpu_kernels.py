@@ -315,10 +315,14 @@ def test_k3_mlp_forward_config1_shape_vs_torch(C):
 
 
 # ----------------------------------------------------------------------------- K3 forward, PreResNet
-@pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
+def _algo(C, name):
+    return {"ffma": C.ALGO_FFMA, "tcgen05": C.ALGO_TCGEN05, "fused": C.ALGO_TCGEN05_FUSED}[name]
+
+
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused"])
 def test_k3_preresnet8_forward_matches_reference_golden(C, algo):
     g = _npz("prediction.npz")
-    algo = C.ALGO_FFMA if algo == "ffma" else C.ALGO_TCGEN05
+    algo = _algo(C, algo)
     bank, bufs = dev(g["preresnet8/bank"]), dev(g["preresnet8/buffers"])
     x = dev(g["preresnet8/x"].astype(np.float32))
     S, N, Cc = 2, x.shape[0], 10
@@ -333,8 +337,8 @@ def test_k3_preresnet8_forward_matches_reference_golden(C, algo):
     np.testing.assert_allclose(E.cpu().numpy(), g["preresnet8/entropy"], atol=2e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
-@pytest.mark.parametrize("depth,S,N,Cc", [(20, 3, 70, 10), (14, 9, 5, 100), (20, 1, 513, 10)])
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused"])
+@pytest.mark.parametrize("depth,S,N,Cc", [(20, 3, 70, 10), (14, 9, 5, 100), (20, 1, 513, 10), (8, 2, 7, 10)])
 def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc, algo):
     """PreResNet-20 (config 2/5) with random BN statistics against a plain PyTorch fp32 forward (TF32 off);
     N not a multiple of the per-CTA image group, S crossing the sample-chunk size, image chunking (N > 512)."""
@@ -357,7 +361,7 @@ def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc, algo):
     P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
     logits = torch.empty(S, N, Cc, device="cuda")
     C.bma_preresnet_forward(bank, bufs, S, x, depth, Cc, P, E, logits_out=logits,
-                            algo=C.ALGO_FFMA if algo == "ffma" else C.ALGO_TCGEN05)
+                            algo=_algo(C, algo))
     torch.cuda.synchronize()
     with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
         ref = torch.stack([m(x) for m in ms])

@@ -18,6 +18,7 @@
 
 #include "preresnet_plan.cuh"
 #include "tc_common.cuh"
+#include "bma_conv_fused.cuh"
 
 namespace ursa {
 
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             *reinterpret_cast<float4 *>(out_raw + off + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            if (out_hi == nullptr) continue;
             float y[4], hv[4], lv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -393,7 +395,7 @@ static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin
 
 size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C) {
     NetPlan pl;
-    if (!build_plan(depth, C, pl, true)) return 0;
+    if (!build_plan(depth, C, pl, 1)) return 0;
     return tc_chunking(S, N, pl).total;
 }
 
@@ -401,7 +403,7 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
                               int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
                               double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     static thread_local NetPlan pl;
-    if (!build_plan(depth, C, pl, true)) {
+    if (!build_plan(depth, C, pl, 1)) {
         set_error("ursa_bma_preresnet_forward: unsupported depth %d (BasicBlock PreResNet: depth = 6n+2, 8..38)", depth);
         return URSA_ERR_UNSUPPORTED;
     }
@@ -460,6 +462,100 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
                     float *t = cur; cur = nxt; nxt = t;
                     ch = cout; hw = hout;
                 }
+            }
+            const int pairs = sc * nc;
+            head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);
+            URSA_LAUNCH_CHECK("head_nhwc_kernel");
+            if (int rc = ursa_bma_accumulate(logits, sc, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
+                return rc;
+            if (logits_out)
+                URSA_CUDA(cudaMemcpy2DAsync(logits_out + ((int64_t)s0 * N + i0) * C, (size_t)N * C * sizeof(float), logits,
+                                            (size_t)nc * C * sizeof(float), (size_t)nc * C * sizeof(float), sc,
+                                            cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return URSA_OK;
+}
+
+// ---- fused-stage path (URSA_ALGO_TCGEN05_FUSED): stem -> [stage kernel] -> (shortcut + stride-2 conv) -> [stage kernel] ...
+size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C) {
+    NetPlan pl;
+    if (!build_plan(depth, C, pl, 2)) return 0;
+    return tc_chunking(S, N, pl).total;
+}
+
+int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
+                            int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
+                            double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    static thread_local NetPlan pl;
+    if (!build_plan(depth, C, pl, 2)) {
+        set_error("ursa_bma_preresnet_forward: unsupported depth %d (BasicBlock PreResNet: depth = 6n+2, 8..38)", depth);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    URSA_REQUIRE(ld_bank >= pl.D, "ursa_bma_preresnet_forward: ld_bank (%lld) < D (%lld)", (long long)ld_bank, (long long)pl.D);
+    URSA_REQUIRE(ld_buf >= pl.NB, "ursa_bma_preresnet_forward: ld_buf (%lld) < %lld", (long long)ld_buf, (long long)pl.NB);
+    const TcChunking ck = tc_chunking(S, N, pl);
+    URSA_REQUIRE(workspace_bytes >= ck.total, "ursa_bma_preresnet_forward: workspace too small");
+    char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    float *Ra = reinterpret_cast<float *>(wsb);
+    float *Rb = reinterpret_cast<float *>(wsb + ck.raw_bytes);
+    float *Rs = reinterpret_cast<float *>(wsb + 2 * ck.raw_bytes);
+    float *A1h = reinterpret_cast<float *>(wsb + 3 * ck.raw_bytes), *A1l = reinterpret_cast<float *>(wsb + 4 * ck.raw_bytes);
+    float *A2h = reinterpret_cast<float *>(wsb + 5 * ck.raw_bytes), *A2l = reinterpret_cast<float *>(wsb + 6 * ck.raw_bytes);
+    float *packed = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes);
+    float *logits = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes + ck.packed_bytes);
+    const int n = pl.n_blocks;
+    URSA_REQUIRE(2 * n <= kFusedMaxConvs, "ursa_bma_preresnet_forward: depth %d exceeds the fused-stage chain length", depth);
+
+    for (int s0 = 0; s0 < S; s0 += ck.sc) {
+        const int sc = (S - s0 < ck.sc) ? (S - s0) : ck.sc;
+        preresnet_prep_kernel<<<dim3(pl.table.n, sc), 256, 0, st>>>(pl.table, bank + (int64_t)s0 * ld_bank, ld_bank,
+                                                                    bufbank + (int64_t)s0 * ld_buf, ld_buf, packed,
+                                                                    pl.packed_floats);
+        URSA_LAUNCH_CHECK("preresnet_prep_kernel");
+        for (int64_t i0 = 0; i0 < N; i0 += ck.nc) {
+            const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
+            stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
+                                                           pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr);
+            URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+            float *cur = Ra, *nxt = Rb;          // residual stream in / out of the current stage
+            int ch = 16, hw = 32;
+            for (int stg = 0; stg < 3; ++stg) {
+                FusedStageArgs g;
+                g.packed = packed; g.ld_packed = pl.packed_floats; g.n_images = nc; g.n_samples = sc;
+                g.n_convs = 0;
+                if (stg == 0) {
+                    g.bn_in_off = pl.blocks[0][0].bn1;
+                    g.r_in = cur; g.a_in_hi = g.a_in_lo = nullptr;
+                } else {
+                    // transition block: 1x1 stride-2 shortcut on the raw stream, stride-2 conv1 on the layer-wise kernel
+                    const NetPlan::Block &B0 = pl.blocks[stg][0];
+                    shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs);
+                    URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
+                    ConvTcArgs c1;
+                    c1.mode = 0; c1.bn_off = B0.bn2; c1.res = nullptr; c1.out_raw = nullptr; c1.out_hi = A2h; c1.out_lo = A2l;
+                    if (int rc = launch_conv_tc(A1h, A1l, hw, ch, 2 * ch, 2, sc, nc, packed, pl.packed_floats, B0.w1, B0.w1_lo, c1, st))
+                        return rc;
+                    ch *= 2; hw /= 2;
+                    g.bn_in_off = -1;
+                    g.r_in = Rs; g.a_in_hi = A2h; g.a_in_lo = A2l;
+                }
+                for (int b = 0; b < n; ++b) {
+                    const NetPlan::Block &B = pl.blocks[stg][b];
+                    if (!(stg > 0 && b == 0)) {                 // conv1 of the transition block ran above
+                        g.w_off[g.n_convs] = B.w1; g.mode[g.n_convs] = 0; g.bn_off[g.n_convs] = B.bn2; ++g.n_convs;
+                    }
+                    int64_t bn_next = -1;
+                    if (b + 1 < n) bn_next = pl.blocks[stg][b + 1].bn1;
+                    else if (stg + 1 < 3) bn_next = pl.blocks[stg + 1][0].bn1;
+                    g.w_off[g.n_convs] = B.w2; g.mode[g.n_convs] = 1; g.bn_off[g.n_convs] = bn_next; ++g.n_convs;
+                }
+                g.r_out = nxt;
+                g.a_out_hi = stg < 2 ? A1h : nullptr;
+                g.a_out_lo = stg < 2 ? A1l : nullptr;
+                int rc = stg == 0 ? launch_stage<16>(g, st) : (stg == 1 ? launch_stage<32>(g, st) : launch_stage<64>(g, st));
+                if (rc) return rc;
+                float *t = cur; cur = nxt; nxt = t;
             }
             const int pairs = sc * nc;
             head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);

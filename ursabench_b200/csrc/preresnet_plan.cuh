@@ -11,6 +11,8 @@ constexpr int kMaxLayers = 96;
 struct PrepEntry {
     int type;          // 0 conv3x3 -> [ci][tap][co], 1 conv1x1 -> [ci][co], 2 bn fold, 3 copy,
                        // 4 conv3x3 -> K-major [co][tap*cin + ci] split into tf32 hi (dst) / lo (dst2) planes
+                       // 5 conv3x3 (cin == cout == C) -> fused-stage layout [tap][ci/4][2C rows][4]: rows are
+                       //   [hi(co); lo(co)] when buf == 0 and [lo(co); hi(co)] when buf == 1 (see bma_conv_fused.cuh)
     int cin, cout;     // conv: channels; bn: cout = channels; copy: cout = count
     int64_t src;       // offset in the bank row (conv weight / bn weight / copy source)
     int64_t src2;      // bn: offset of bias in the bank row
@@ -58,6 +60,24 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             dst[i] = h;
             dlo[i] = __uint_as_float(lb);
         }
+    } else if (e.type == 5) {
+        const int C = e.cout;
+        const int total = 9 * (C / 4) * 2 * C * 4;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {       // i over dst [tap][j][n][e4]
+            const int e4 = i & 3;
+            const int n = (i >> 2) % (2 * C);
+            const int j = (i / (8 * C)) % (C / 4);
+            const int tap = i / (2 * C * C);
+            const int co = n % C, ci = 4 * j + e4;
+            const bool lo_part = ((n / C) != 0) != (e.buf != 0);
+            const float w = row[e.src + ((int64_t)co * C + ci) * 9 + tap];
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+            const float h = __uint_as_float(hb);
+            uint32_t lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(w - h));
+            dst[i] = lo_part ? __uint_as_float(lb) : h;
+        }
     } else if (e.type == 2) {
         for (int c = threadIdx.x; c < e.cout; c += blockDim.x) {
             const float mean = brow[e.buf + c], var = brow[e.buf + e.cout + c];
@@ -81,8 +101,10 @@ struct NetPlan {
     int64_t D, NB;              // expected bank / buffer row lengths
 };
 
-// tc == false: 3x3 filters packed [ci][tap][co] for the CUDA-core kernels; tc == true: K-major tf32 hi / lo planes
-static bool build_plan(int depth, int C, NetPlan &pl, bool tc = false) {
+// tc == 0: 3x3 filters packed [ci][tap][co] for the CUDA-core kernels; tc == 1: K-major tf32 hi / lo planes (layer-by-
+// layer tcgen05 kernels); tc == 2: fused-stage layout (type 5) for every 3x3 conv with cin == cout, type 4 for the two
+// stride-2 transition convs
+static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
     if (depth >= 44 || depth < 8 || (depth - 2) % 6 != 0 || C < 1) return false;
     const int n = (depth - 2) / 6;
     if (n > 8) return false;
@@ -92,13 +114,13 @@ static bool build_plan(int depth, int C, NetPlan &pl, bool tc = false) {
     t.n = 0;
     int64_t src = 0, buf = 0, dst = 0;
     int64_t last_lo = -1;
-    auto add_conv = [&](int type, int cin, int cout) {
+    auto add_conv = [&](int type, int cin, int cout, int fused_mode = 0) {
         PrepEntry &e = t.e[t.n++];
-        e.type = type; e.cin = cin; e.cout = cout; e.src = src; e.src2 = 0; e.buf = 0; e.dst = dst; e.dst2 = 0;
+        e.type = type; e.cin = cin; e.cout = cout; e.src = src; e.src2 = 0; e.buf = fused_mode; e.dst = dst; e.dst2 = 0;
         const int64_t cnt = (int64_t)cin * cout * (type == 1 ? 1 : 9);
         src += cnt;
         const int64_t d = dst;
-        dst += cnt;
+        dst += type == 5 ? 2 * cnt : cnt;
         if (type == 4) {                 // hi plane at d, lo plane right after; both 16-byte aligned (cnt % 4 == 0)
             e.dst2 = dst;
             last_lo = dst;
@@ -106,7 +128,7 @@ static bool build_plan(int depth, int C, NetPlan &pl, bool tc = false) {
         }
         return d;
     };
-    const int t3 = tc ? 4 : 0;
+    const int t3 = tc == 0 ? 0 : 4;
     auto add_bn = [&](int c) {
         PrepEntry &e = t.e[t.n++];
         e.type = 2; e.cin = 0; e.cout = c; e.src = src; e.src2 = src + c; e.buf = buf; e.dst = dst; e.dst2 = 0;
@@ -126,10 +148,10 @@ static bool build_plan(int depth, int C, NetPlan &pl, bool tc = false) {
             const int w = widths[st];
             NetPlan::Block &B = pl.blocks[st][b];
             B.bn1 = add_bn(inpl);
-            B.w1 = add_conv(t3, inpl, w);
+            B.w1 = (tc == 2 && inpl == w) ? add_conv(5, inpl, w, 0) : add_conv(t3, inpl, w);
             B.w1_lo = last_lo;
             B.bn2 = add_bn(w);
-            B.w2 = add_conv(t3, w, w);
+            B.w2 = tc == 2 ? add_conv(5, w, w, 1) : add_conv(t3, w, w);
             B.w2_lo = last_lo;
             B.ds = (b == 0 && st > 0) ? add_conv(1, inpl, w) : -1;
             inpl = w;
