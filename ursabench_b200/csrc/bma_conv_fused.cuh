@@ -128,14 +128,27 @@ __device__ __forceinline__ void tmem_st<32>(uint32_t taddr, const uint32_t *r) {
     tmem_st<16>(taddr, r);
     tmem_st<16>(taddr + 16, r + 16);
 }
+template <int N>
+__device__ __forceinline__ void tmem_st_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+#pragma unroll
+    for (int c = 0; c < N; c += 8)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + c), "r"(z)
+                     : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// y[0..3] -> tf32 hi / lo quads
+// y[0..3] -> tf32 hi / lo quads.  hi = y with the low 13 mantissa bits cleared (exactly representable in tf32; one LOP3
+// instead of the 4-instruction emulation of cvt.rna), lo = y - hi exactly; kind::tf32 reads only the upper 19 bits of an
+// operand, so lo needs no explicit rounding.  |y - (hi + tf32(lo))| <= 2^-21 |y|.
 __device__ __forceinline__ void split4(const float *y, float4 &hv, float4 &lv) {
-    hv.x = rn_tf32(y[0]); hv.y = rn_tf32(y[1]); hv.z = rn_tf32(y[2]); hv.w = rn_tf32(y[3]);
-    lv.x = rn_tf32(y[0] - hv.x); lv.y = rn_tf32(y[1] - hv.y); lv.z = rn_tf32(y[2] - hv.z); lv.w = rn_tf32(y[3] - hv.w);
+    hv.x = __uint_as_float(__float_as_uint(y[0]) & 0xFFFFE000u);
+    hv.y = __uint_as_float(__float_as_uint(y[1]) & 0xFFFFE000u);
+    hv.z = __uint_as_float(__float_as_uint(y[2]) & 0xFFFFE000u);
+    hv.w = __uint_as_float(__float_as_uint(y[3]) & 0xFFFFE000u);
+    lv.x = y[0] - hv.x; lv.y = y[1] - hv.y; lv.z = y[2] - hv.z; lv.w = y[3] - hv.w;
 }
 
 template <int C>
@@ -210,6 +223,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
         // ================= MMA issuer =================
         if (elect_one()) {
             const uint32_t idesc_cat = make_tf32_idesc(128, 2 * C), idesc_main = make_tf32_idesc(128, C);
+            // Descriptors are built from 32-bit words in 16-byte units so that one integer add per MMA is all the issue
+            // work: tcgen05.mma holds its operand registers until the tensor pipe accepts it, so any arithmetic between two
+            // MMAs that is longer than the MMA itself (~40 clk at N <= 32) leaves the pipe idle.
+            constexpr uint32_t DESC_HI = (uint32_t)(128 >> 4) | (1u << 14);          // SBO = 128 B, version 1
+            constexpr uint32_t PL16 = (uint32_t)(PLANE >> 4);
+            const uint32_t a_hi_w = ((planes_hi >> 4) + (uint32_t)F0) | (PL16 << 16);  // LBO = plane stride
+            const uint32_t a_lo_w = ((planes_lo >> 4) + (uint32_t)F0) | (PL16 << 16);
+            const uint32_t b_w0 = (ring >> 4) | ((uint32_t)(2 * C) << 16);             // LBO = 2C rows x 16 B
+            auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
             uint32_t it = 0, epi_phase = 0;
             for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
                 for (int k = 0; k < a.n_convs; ++k) {
@@ -217,30 +239,27 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                     epi_phase ^= 1u;
                     tc_fence_after();
                     const int mode = a.mode[k];
-                    const uint32_t col_cat = mode == 0 ? 0u : (uint32_t)C;
-                    const uint32_t col_main = mode == 0 ? 0u : (uint32_t)(2 * C);
-                    const uint32_t bhi_row_bytes = mode == 0 ? 0u : (uint32_t)(C * 16);
+                    const uint32_t d_cat = tmem + (mode == 0 ? 0u : (uint32_t)C);
+                    const uint32_t d_main = tmem + (mode == 0 ? 0u : (uint32_t)(2 * C));
+                    const uint32_t bhi_rows = mode == 0 ? 0u : (uint32_t)C;
                     for (int tap = 0; tap < 9; ++tap, ++it) {
                         const int slot = it % Cfg::NSLOT;
                         const uint32_t ph = (it / Cfg::NSLOT) & 1u;
                         mbar_wait_a(smem_u32(&full_bar[slot]), ph);
                         tc_fence_after();
-                        const int shift = (tap / 3 - 1) * PITCH + (tap % 3 - 1);
-                        const uint32_t bslot = ring + slot * Cfg::SLOT_BYTES;
+                        const uint32_t shift = (uint32_t)((tap / 3 - 1) * PITCH + (tap % 3 - 1));
+                        const uint32_t bw = b_w0 + (uint32_t)slot * (Cfg::SLOT_BYTES >> 4);
+                        uint32_t ahw = a_hi_w + shift, alw = a_lo_w + shift;
+                        uint32_t dc = d_cat, dm = d_main;
 #pragma unroll 1
                         for (int t = 0; t < T; ++t) {
-                            const uint32_t aoff = (uint32_t)((F0 + 128 * t + shift) * 16);
-                            const uint32_t dcol = tmem + (uint32_t)(t * Cfg::TILE_COLS);
 #pragma unroll
                             for (int ks = 0; ks < C / 8; ++ks) {
-                                const uint64_t d_ahi = make_plane_desc(planes_hi + 2 * ks * PLANE + aoff, PLANE);
-                                const uint64_t d_alo = make_plane_desc(planes_lo + 2 * ks * PLANE + aoff, PLANE);
-                                const uint32_t bk = bslot + 2 * ks * (2 * C * 16);
-                                const uint64_t d_bcat = make_plane_desc(bk, 2 * C * 16);
-                                const uint64_t d_bhi = make_plane_desc(bk + bhi_row_bytes, 2 * C * 16);
-                                umma_tf32(dcol + col_cat, d_ahi, d_bcat, idesc_cat, 1);
-                                umma_tf32(dcol + col_main, d_alo, d_bhi, idesc_main, 1);
+                                umma_tf32(dc, mk(ahw + ks * 2 * PL16), mk(bw + ks * 4 * C), idesc_cat, 1);
+                                umma_tf32(dm, mk(alw + ks * 2 * PL16), mk(bw + ks * 4 * C + bhi_rows), idesc_main, 1);
                             }
+                            ahw += 128; alw += 128;
+                            dc += Cfg::TILE_COLS; dm += Cfg::TILE_COLS;
                         }
                         umma_commit(smem_u32(&empty_bar[slot]));
                     }
@@ -257,10 +276,50 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
         const int etid = threadIdx.x - 64;            // 0..255
         uint32_t mma_phase = 0;
-        const uint32_t zeros[32] = {0};
+        // plane byte offset of (this thread's row of tile t, channel quad i)
+        auto plane_off = [&](int t, int i) { return (uint32_t)(((ch0 + i) >> 2) * PLANE + (F0 + 128 * t + m) * 16); };
 
-        for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        // position bookkeeping of this thread's T rows for a pass: element offset into the [S_c][N_c][H][W][C] tensors
+        // (< 2^31: a chunk holds at most 8 x 512 pairs of 16 K elements) or -1 for padding / missing images
+        auto locate = [&](int pass, int32_t *goff) {
             const int s = pass / n_groups, ig = pass - s * n_groups;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int f = F0 + 128 * t + m;
+                const int prow = f / PITCH, pcol = f - prow * PITCH;
+                const int r = prow - 1;
+                const int g = r / (H + 1), h = r - g * (H + 1);
+                const int n = ig * G + g;
+                const bool ok = pcol >= 1 && r >= 0 && g < G && h < H && n < a.n_images;
+                goff[t] = ok ? (int32_t)(((((s * a.n_images + n) * H + h) * H + (pcol - 1)) * C) + ch0) : -1;
+            }
+        };
+        // all T rows of the incoming residual stream in one batch of independent loads
+        auto load_rows = [&](const float *src, const int32_t *goff, float (*v)[NCH]) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                if (goff[t] >= 0) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(src + goff[t]);
+#pragma unroll
+                    for (int i = 0; i < NCH / 4; ++i) {
+                        const float4 x4 = __ldg(rp + i);
+                        v[t][4 * i] = x4.x; v[t][4 * i + 1] = x4.y; v[t][4 * i + 2] = x4.z; v[t][4 * i + 3] = x4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) v[t][i] = 0.f;
+                }
+            }
+        };
+
+        int32_t goff[T];
+        float rin[T][NCH];
+        if ((int)blockIdx.x < n_pass) {
+            locate(blockIdx.x, goff);
+            load_rows(a.r_in, goff, rin);
+        }
+        for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+            const int s = pass / n_groups;
             const float *pk = a.packed + (int64_t)s * a.ld_packed;
             // ---- BatchNorm (a, b) of the whole run -> shared memory
             epi_bar_sync();                            // everybody is done with the previous pass's parameters
@@ -271,64 +330,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                     for (int i = etid; i < 2 * C; i += 256) bn_s[(k + 1) * 2 * C + i] = __ldg(pk + a.bn_off[k] + i);
             epi_bar_sync();
 
-            // position bookkeeping of this thread's T rows
-            int64_t goff[T];
-            bool valid[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const int f = F0 + 128 * t + m;
-                const int prow = f / PITCH, pcol = f - prow * PITCH;
-                const int r = prow - 1;
-                const int g = r / (H + 1), h = r - g * (H + 1);
-                const int n = ig * G + g;
-                valid[t] = pcol >= 1 && r >= 0 && g < G && h < H && n < a.n_images;
-                goff[t] = ((((int64_t)s * a.n_images + n) * H + h) * H + (pcol - 1)) * C + ch0;
-            }
-
             // ---- prologue: residual -> TMEM R, activation -> planes
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const int f = F0 + 128 * t + m;
-                float v[NCH];
-                if (valid[t]) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(a.r_in + goff[t]);
-#pragma unroll
-                    for (int i = 0; i < NCH / 4; ++i) {
-                        const float4 x4 = __ldg(rp + i);
-                        v[4 * i] = x4.x; v[4 * i + 1] = x4.y; v[4 * i + 2] = x4.z; v[4 * i + 3] = x4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NCH; ++i) v[i] = 0.f;
-                }
                 const uint32_t tcol = t_lane + (uint32_t)(t * Cfg::TILE_COLS);
-                tmem_st<NCH>(tcol + 2 * C, reinterpret_cast<const uint32_t *>(v));
-                tmem_st<NCH>(tcol, zeros);
-                tmem_st<NCH>(tcol + C, zeros);
-                if (valid[t]) {
-                    if (a.bn_in_off >= 0) {
+                tmem_st<NCH>(tcol + 2 * C, reinterpret_cast<const uint32_t *>(rin[t]));
+                tmem_st_zero<NCH>(tcol);
+                tmem_st_zero<NCH>(tcol + C);
+                if (a.bn_in_off >= 0 && goff[t] >= 0) {
 #pragma unroll
-                        for (int i = 0; i < NCH; i += 4) {
-                            float y[4];
+                    for (int i = 0; i < NCH; i += 4) {
+                        float y[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                y[j] = fmaxf(fmaf(bn_s[ch0 + i + j], v[i + j], bn_s[C + ch0 + i + j]), 0.f);
-                            float4 hv, lv;
-                            split4(y, hv, lv);
-                            const uint32_t off = (uint32_t)(((ch0 + i) >> 2) * PLANE + f * 16);
-                            *reinterpret_cast<float4 *>(gen_base + off) = hv;
-                            *reinterpret_cast<float4 *>(gen_base + NPL * PLANE + off) = lv;
-                        }
-                    } else {
-                        const float4 *hp = reinterpret_cast<const float4 *>(a.a_in_hi + goff[t]);
-                        const float4 *lp = reinterpret_cast<const float4 *>(a.a_in_lo + goff[t]);
-#pragma unroll
-                        for (int i = 0; i < NCH; i += 4) {
-                            const uint32_t off = (uint32_t)(((ch0 + i) >> 2) * PLANE + f * 16);
-                            *reinterpret_cast<float4 *>(gen_base + off) = __ldg(hp + (i >> 2));
-                            *reinterpret_cast<float4 *>(gen_base + NPL * PLANE + off) = __ldg(lp + (i >> 2));
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            y[j] = fmaxf(fmaf(bn_s[ch0 + i + j], rin[t][i + j], bn_s[C + ch0 + i + j]), 0.f);
+                        float4 hv, lv;
+                        split4(y, hv, lv);
+                        *reinterpret_cast<float4 *>(gen_base + plane_off(t, i)) = hv;
+                        *reinterpret_cast<float4 *>(gen_base + NPL * PLANE + plane_off(t, i)) = lv;
                     }
+                }
+            }
+            if (a.bn_in_off < 0) {
+                // pre-activated planes from the stride-2 conv: one batch of loads per plane set (rin is free again)
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    load_rows(part == 0 ? a.a_in_hi : a.a_in_lo, goff, rin);
+#pragma unroll
+                    for (int t = 0; t < T; ++t)
+                        if (goff[t] >= 0) {
+#pragma unroll
+                            for (int i = 0; i < NCH; i += 4)
+                                *reinterpret_cast<float4 *>(gen_base + part * NPL * PLANE + plane_off(t, i)) =
+                                    make_float4(rin[t][i], rin[t][i + 1], rin[t][i + 2], rin[t][i + 3]);
+                        }
                 }
             }
             tmem_st_wait();
@@ -342,30 +377,54 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                 const int mode = a.mode[k];
                 const float *bn = bn_s + (k + 1) * 2 * C;
                 const bool has_bn = a.bn_off[k] >= 0;
+                const bool to_global = last && has_bn && a.a_out_hi != nullptr;
+                int32_t gnext[T];
+                if (last) {
+                    // the MMAs of the last conv are running: fetch the next pass's residual rows under them
+                    const int np = pass + gridDim.x;
+                    if (np < n_pass) {
+                        locate(np, gnext);
+                        load_rows(a.r_in, gnext, rin);
+                    }
+                }
                 mbar_wait_a(smem_u32(&mma_bar), mma_phase);
                 mma_phase ^= 1u;
                 tc_fence_after();
+                // double-buffered accumulator reads (the next tile's tcgen05.ld is in flight while this tile is processed)
+                // where the register budget allows it
+                constexpr bool PIPE = NCH <= 16;
+                constexpr int NBUF = PIPE ? 2 : 1;
+                uint32_t ra[NBUF][NCH], rl[NBUF][NCH];
+                if (PIPE) {
+                    tmem_ld<NCH>(t_lane + (mode == 0 ? 0 : 2 * C), ra[0]);
+                    tmem_ld<NCH>(t_lane + C, rl[0]);
+                }
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    const int f = F0 + 128 * t + m;
                     const uint32_t tcol = t_lane + (uint32_t)(t * Cfg::TILE_COLS);
-                    uint32_t ra[NCH], rl[NCH];
-                    tmem_ld<NCH>(tcol + (mode == 0 ? 0 : 2 * C), ra);
-                    tmem_ld<NCH>(tcol + C, rl);
+                    const int cur = PIPE ? (t & 1) : 0;
+                    if (!PIPE) {
+                        tmem_ld<NCH>(tcol + (mode == 0 ? 0 : 2 * C), ra[0]);
+                        tmem_ld<NCH>(tcol + C, rl[0]);
+                    }
                     tmem_ld_wait();
+                    if (PIPE && t + 1 < T) {
+                        tmem_ld<NCH>(tcol + Cfg::TILE_COLS + (mode == 0 ? 0 : 2 * C), ra[(t + 1) & (NBUF - 1)]);
+                        tmem_ld<NCH>(tcol + Cfg::TILE_COLS + C, rl[(t + 1) & (NBUF - 1)]);
+                    }
                     float v[NCH];
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) v[i] = __uint_as_float(ra[i]) + __uint_as_float(rl[i]);
-                    tmem_st<NCH>(tcol + C, zeros);
-                    if (mode == 0) tmem_st<NCH>(tcol, zeros);
+                    for (int i = 0; i < NCH; ++i) v[i] = __uint_as_float(ra[cur][i]) + __uint_as_float(rl[cur][i]);
+                    tmem_st_zero<NCH>(tcol + C);
+                    if (mode == 0) tmem_st_zero<NCH>(tcol);
                     else if (!last) tmem_st<NCH>(tcol + 2 * C, reinterpret_cast<const uint32_t *>(v));
-                    if (!valid[t]) continue;
+                    if (goff[t] < 0) continue;
                     if (last) {
                         float4 *op = reinterpret_cast<float4 *>(a.r_out + goff[t]);
 #pragma unroll
                         for (int i = 0; i < NCH; i += 4) op[i >> 2] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (!to_global) continue;
                     }
-                    if (last && (!has_bn || a.a_out_hi == nullptr)) continue;
 #pragma unroll
                     for (int i = 0; i < NCH; i += 4) {
                         float y[4];
@@ -381,9 +440,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                             reinterpret_cast<float4 *>(a.a_out_hi + goff[t])[i >> 2] = hv;
                             reinterpret_cast<float4 *>(a.a_out_lo + goff[t])[i >> 2] = lv;
                         } else {
-                            const uint32_t off = (uint32_t)(((ch0 + i) >> 2) * PLANE + f * 16);
-                            *reinterpret_cast<float4 *>(gen_base + off) = hv;
-                            *reinterpret_cast<float4 *>(gen_base + NPL * PLANE + off) = lv;
+                            *reinterpret_cast<float4 *>(gen_base + plane_off(t, i)) = hv;
+                            *reinterpret_cast<float4 *>(gen_base + NPL * PLANE + plane_off(t, i)) = lv;
                         }
                     }
                 }
@@ -392,6 +450,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                     fence_proxy_async();
                     tc_fence_before();
                     mbar_arrive(&epi_bar);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) goff[t] = gnext[t];
                 }
             }
         }
