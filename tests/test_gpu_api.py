@@ -299,7 +299,7 @@ def _mlp_models_from_golden(U, name):
     return g, ms, x, y, C
 
 
-@pytest.mark.parametrize("engine", ["auto", "generic"])
+@pytest.mark.parametrize("engine", ["auto", "ffma", "generic"])
 def test_prediction_matches_reference_golden_mlp(U, engine):
     g, ms, x, y, C = _mlp_models_from_golden(U, "mlp")
     ref = _json("prediction_metrics.json")["mlp"]
@@ -309,7 +309,9 @@ def test_prediction_matches_reference_golden_mlp(U, engine):
     task.update_statistics(ms[:3], output_performance=False)            # accumulates across calls (:38-48)
     task.update_statistics(ms[3:], output_performance=False)
     assert task.num_samples_collected == 5
-    assert task.last_engine == ("fused_mlp" if engine == "auto" else "generic")
+    assert task.last_engine == ("generic" if engine == "generic" else "fused_mlp")
+    if engine != "generic":                                             # the product path is the tcgen05 kernel
+        assert task.last_algo == (U._C.ALGO_TCGEN05 if engine == "auto" else U._C.ALGO_FFMA)
     np.testing.assert_allclose(task.ensemble_proba.numpy(), g["mlp/ensemble_proba"], atol=1e-5, rtol=0)
     np.testing.assert_allclose(task.expected_data_uncertainty.numpy(), g["mlp/entropy"], atol=1e-5, rtol=1e-5)
     m = task.get_performance_metrics()

@@ -56,7 +56,9 @@ class Prediction(_Task):
         if self.device.type != "cuda":
             raise RuntimeError("Prediction: device must be a CUDA device -- ursabench_b200 has no CPU path")
         self.distributed = distributed
-        self.engine = engine                          # 'auto' | 'generic' (force the per-sample PyTorch forward)
+        self.engine = engine      # 'auto' | 'ffma' (pin the fp32 CUDA-core kernels) | 'generic' (per-sample PyTorch forward)
+        self._ws = None           # K3 workspace, kept across calls
+        self.last_algo = None
         self.num_samples_collected = 0
         self.required_metric_list = self.supported_metric_list if metric_list == "ALL" else metric_list
         assert all(metric in self.supported_metric_list for metric in self.required_metric_list)
@@ -135,7 +137,7 @@ class Prediction(_Task):
             return
         plain = [m.materialize() if isinstance(m, BankedSample) else m for m in model_list]
         arch = _arch_of(plain[0])
-        if self.engine == "auto" and arch is not None and self._fused_available(arch) \
+        if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch) \
                 and all(_arch_of(m) == arch for m in plain):
             bank = SampleBank.from_modules(plain, self.device)       # one H2D per sample instead of 2 per batch
             self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None)
@@ -143,26 +145,43 @@ class Prediction(_Task):
         self._accumulate_generic_modules(plain)
 
     def _fused_available(self, arch):
+        return self._pick_algo(arch) is not None
+
+    def _pick_algo(self, arch):
+        """Fastest engine whose workspace query accepts the shape: the tcgen05 paths (3xTF32, fp32-level accuracy,
+        parity-tested at the same 1e-5 bar) first, the fp32 CUDA-core kernels for shapes they do not cover
+        (e.g. an MLP width that is not a multiple of 4).  ``engine='ffma'`` pins the CUDA-core kernels."""
+        lib = _C.lib()
         if arch[0] == "mlp":
-            return True
-        if arch[0] == "preresnet":
-            return _C.lib().ursa_bma_preresnet_workspace(1, 1, arch[1], arch[2], _C.ALGO_FFMA) > 0
-        return False
+            order = (_C.ALGO_FFMA,) if self.engine == "ffma" else (_C.ALGO_TCGEN05, _C.ALGO_FFMA)
+            for algo in order:
+                if lib.ursa_bma_mlp_workspace(1, 1, arch[1], arch[2], arch[3], algo) > 0:
+                    return algo
+        elif arch[0] == "preresnet":
+            order = (_C.ALGO_FFMA,) if self.engine == "ffma" else (_C.ALGO_TCGEN05_FUSED, _C.ALGO_TCGEN05, _C.ALGO_FFMA)
+            for algo in order:
+                if lib.ursa_bma_preresnet_workspace(1, 1, arch[1], arch[2], algo) > 0:
+                    return algo
+        return None
 
     def _accumulate_rows(self, w, b, arch, skeleton):
         S = w.shape[0]
-        if self.engine == "auto" and arch is not None and self._fused_available(arch):
+        if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch):
+            algo = self._pick_algo(arch)
             if arch[0] == "mlp":
                 _, in_dim, hidden, C = arch
                 x2 = self._x.view(self._n, -1)
                 if x2.shape[1] != in_dim or C != self.num_classes:
                     raise ValueError("MLP input / class dimensions do not match the task")
-                _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, self._proba, self._entropy, algo=_C.ALGO_FFMA)
+                self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, self._proba, self._entropy, algo=algo,
+                                              workspace=self._ws)
                 self.last_engine = "fused_mlp"
             else:
                 _, depth, C = arch
-                _C.bma_preresnet_forward(w, b, S, self._x, depth, C, self._proba, self._entropy, algo=_C.ALGO_FFMA)
+                self._ws = _C.bma_preresnet_forward(w, b, S, self._x, depth, C, self._proba, self._entropy, algo=algo,
+                                                    workspace=self._ws)
                 self.last_engine = "fused_preresnet"
+            self.last_algo = algo
             self.kernel_launches += 1
             return
         if skeleton is None:
