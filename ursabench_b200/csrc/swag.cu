@@ -4,9 +4,9 @@
 //  draw      reference inference/swag.py:85-97 (formula; see header)            (K + 2 + S) * 4 B/param
 //
 // The draw stages [K x 1024-column] tiles of the deviation ring in shared memory with the TMA engine
-// (cp.async.bulk + mbarrier, double buffered), keeps z2 [K, S] in shared memory (broadcast LDS.128) and all
-// S accumulators of a thread's 4 columns in registers, so the ring is read from HBM exactly once for
-// all S draws.  z1 comes from Philox in-register (or from memory in parity mode).
+// (cp.async.bulk + mbarrier, double buffered) and contracts them with z2 [S, K] on the warp-level tensor-core MMA
+// (3xTF32), so the ring is read from HBM exactly once for all S draws.  z1 comes from Philox in-register (or from
+// memory in parity mode).
 #include "async.cuh"
 #include "common.cuh"
 
@@ -61,9 +61,24 @@ __global__ void __launch_bounds__(kEwThreads) swag_variance_kernel(const float *
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kDrawThreads = 256;
-constexpr int kTileCols = kDrawThreads * 4;     // 1024 columns = 4 KB per ring row per stage
+// K2b.  CTA = 16 warps, tile = 1024 columns of the ring, double buffered in shared memory by the TMA engine.
+// A warp owns 16-column blocks of the tile.  The K x S contraction  acc[s, d] = sum_k z2[s, k] ring[k, d]  runs on
+// the warp-level tensor-core MMA (m16n8k8, 3xTF32: operands split hi + lo, lo*lo dropped, fp32 accumulate) because
+// its accumulator fragments stay in the registers of the thread that also draws the Gaussians for the same (s, d):
+//   A = z2 / rank_div  [16 draws x 8 ring rows]   constant per launch -> loaded once into registers (hi / lo)
+//   B = ring tile      [8 ring rows x 8 columns]  LDS.64 from the staged tile (row pitch = 1032 floats: conflict free)
+//   C                  [16 draws x 8 columns]     MMA column c of n-tile j <-> column 4*(c/2) + 2*(c%2) + j of the block,
+//                                                 so a thread ends up with 4 CONSECUTIVE columns of 4 draws
+// = one Philox4x32-10 block (4 normals along d) and one 16-byte store per (draw, thread).  Before this, the contraction
+// was K*S FFMAs per column and the kernel was issue bound at 44 % of HBM peak.
+constexpr int kDrawThreads = 512;
+constexpr int kDrawWarps = kDrawThreads / 32;
+constexpr int kTileCols = 1024;
+constexpr int kPitch = kTileCols + 8;           // floats; pitch % 32 == 8
+constexpr int kKP = 24;                         // ring rows padded to 3 k-steps of 8 (URSA_DRAW_MAX_K)
+constexpr int kRows = kKP + 2;                  // + the mean and var rows of the tile (staged by the same bulk copies)
 constexpr int kStages = 2;
+static_assert(URSA_DRAW_MAX_K <= kKP && URSA_DRAW_MAX_S <= 32, "fragment shapes");
 
 struct DrawArgs {
     float *out;
@@ -75,24 +90,52 @@ struct DrawArgs {
     uint64_t step;
 };
 
-// SP = padded number of draws, NG = sample groups: thread (tid % 256) owns 4 columns, group (tid / 256) owns the
-// draws [g*SP/NG, (g+1)*SP/NG): more resident warps and fewer accumulator registers per thread for large S.
-template <int SP, int NG>
-__global__ void __launch_bounds__(kDrawThreads * NG, 1) swag_draw_kernel(const DrawArgs a) {
-    constexpr int SPG = SP / NG;
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// MT = 16-draw row tiles (1: S <= 16, 2: S <= 32); RING = low-rank term present (K > 0)
+template <int MT, bool RING>
+__global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawArgs a) {
+    constexpr int NI = 2 * MT;                                                  // draws per thread: rows nrow + 8 i
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *ring_s = reinterpret_cast<float *>(smem_raw);                       // [kStages][K][kTileCols]
-    __shared__ __align__(16) float z2s[URSA_DRAW_MAX_K * SP];                  // [K][SP], zero padded
+    constexpr int TR = RING ? kRows : 2;                                        // staged rows per tile
+    constexpr int MROW = RING ? kKP : 0;                                        // row index of the mean (var = MROW + 1)
+    float *ring_s = reinterpret_cast<float *>(smem_raw);                       // [kStages][TR][kPitch]
+    __shared__ __align__(16) uint4 afrag[2][3][MT][32];                         // [hi / lo][k-step][row tile][lane]
     __shared__ __align__(8) uint64_t full_bar[kStages];
 
-    const int tid = threadIdx.x % kDrawThreads;          // column owner
-    const int grp = threadIdx.x / kDrawThreads;          // sample group (warp-uniform)
-    const int s_lo = grp * SPG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane & 3, nrow = lane >> 2;
     const int K = a.K, S = a.S;
-    const float inv_div = (K > 0) ? 1.0f / a.rank_div : 0.f;
-    for (int i = threadIdx.x; i < K * SP; i += kDrawThreads * NG) {
-        const int k = i / SP, s = i - k * SP;
-        z2s[i] = (s < S) ? a.z2[(int64_t)s * K + k] * inv_div : 0.f;      // 1/sqrt(max_rank-1) folded in (swag.py:95)
+    const int KT = (K + 7) >> 3;
+
+    if (RING) {
+        // A fragments (z2 / rank_div, split hi + lo): a0 = (row nrow, col q), a1 = (row nrow + 8, col q),
+        // a2 = (row nrow, col q + 4), a3 = (row nrow + 8, col q + 4); one uint4 per lane, conflict-free LDS.128
+        const float inv_div = 1.0f / a.rank_div;                               // 1/sqrt(max_rank-1) folded in (swag.py:95)
+        for (int e = threadIdx.x; e < 3 * MT * 32; e += kDrawThreads) {
+            const int ln = e & 31, mt = (e >> 5) % MT, kt = (e >> 5) / MT;
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = mt * 16 + (ln >> 2) + (i & 1) * 8, k = kt * 8 + (ln & 3) + (i >> 1) * 4;
+                const float z = (s < S && k < K) ? __ldg(a.z2 + (int64_t)s * K + k) * inv_div : 0.f;
+                h[i] = __float_as_uint(z) & 0xFFFFE000u;
+                l[i] = __float_as_uint(z - __uint_as_float(h[i]));
+            }
+            afrag[0][kt][mt][ln] = make_uint4(h[0], h[1], h[2], h[3]);
+            afrag[1][kt][mt][ln] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        // rows K .. 8*KT-1 of both stages are never written by the bulk copies: zero them once
+        const int zr = 8 * KT - K;
+        for (int i = threadIdx.x; i < kStages * zr * kPitch; i += kDrawThreads) {
+            const int st = i / (zr * kPitch), r = i - st * zr * kPitch;
+            ring_s[(st * TR + K) * kPitch + r] = 0.f;
+        }
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
@@ -102,58 +145,59 @@ __global__ void __launch_bounds__(kDrawThreads * NG, 1) swag_draw_kernel(const D
 
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
     const int64_t Dp4 = (a.D + 3) >> 2;                                        // Philox blocks per draw row
+    // per-thread draw rows: Philox block base and output row of draw i
+    uint64_t ctr_base[NI];
+    float *out_row[NI];
+    bool act[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int s = (i >> 1) * 16 + (i & 1) * 8 + nrow;
+        act[i] = s < S;
+        ctr_base[i] = (uint64_t)s * (uint64_t)Dp4;
+        out_row[i] = a.out + (int64_t)s * a.ld_out;
+    }
+    const bool dense = S > 16 * MT - 8 && a.z1 == nullptr;                      // (nearly) all fragment rows are real draws
+
     auto issue = [&](int64_t tile, int stage) {                                 // one thread: K bulk copies
         const int64_t c0 = tile * kTileCols;
-        int64_t rem = a.D - c0;
+        const int64_t rem = a.D - c0;
         const uint32_t cols = (uint32_t)(rem >= kTileCols ? kTileCols : ((rem + 3) & ~(int64_t)3));
         const uint32_t bytes = cols * 4u;
-        mbar_arrive_expect_tx(&full_bar[stage], bytes * (uint32_t)K);
-        float *dst = ring_s + (size_t)stage * K * kTileCols;
+        // mean / var are only guaranteed D elements: copy whole quads, the ragged last quad is read directly
+        const uint32_t mv_bytes = (uint32_t)(rem >= kTileCols ? kTileCols : (rem & ~(int64_t)3)) * 4u;
+        mbar_arrive_expect_tx(&full_bar[stage], bytes * (uint32_t)K + 2u * mv_bytes);
+        float *dst = ring_s + stage * TR * kPitch;
         for (int k = 0; k < K; ++k)
-            bulk_g2s(dst + (size_t)k * kTileCols, a.ring + (int64_t)k * a.ld_ring + c0, bytes, &full_bar[stage]);
+            bulk_g2s(dst + k * kPitch, a.ring + (int64_t)k * a.ld_ring + c0, bytes, &full_bar[stage]);
+        if (mv_bytes) {
+            bulk_g2s(dst + MROW * kPitch, a.mean + c0, mv_bytes, &full_bar[stage]);
+            bulk_g2s(dst + (MROW + 1) * kPitch, a.var + c0, mv_bytes, &full_bar[stage]);
+        }
     };
-
-    if (K > 0 && threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int stage = it & 1;
-        const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-        const int64_t next = tile + gridDim.x;
-        if (K > 0 && threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);
-
-        float acc[SPG][4];
-#pragma unroll
-        for (int s = 0; s < SPG; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
-
-        if (K > 0) {
-            mbar_wait(&full_bar[stage], parity);
-            const float4 *rs = reinterpret_cast<const float4 *>(ring_s + (size_t)stage * K * kTileCols) + tid;
-            for (int k = 0; k < K; ++k) {
-                const float4 r = rs[(size_t)k * (kTileCols / 4)];
-                const float4 *zk = reinterpret_cast<const float4 *>(z2s + k * SP + s_lo);
-#pragma unroll
-                for (int q = 0; q < SPG / 4; ++q) {
-                    const float4 z = zk[q];
-                    const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[4 * q + j][0] = fmaf(zz[j], r.x, acc[4 * q + j][0]);
-                        acc[4 * q + j][1] = fmaf(zz[j], r.y, acc[4 * q + j][1]);
-                        acc[4 * q + j][2] = fmaf(zz[j], r.z, acc[4 * q + j][2]);
-                        acc[4 * q + j][3] = fmaf(zz[j], r.w, acc[4 * q + j][3]);
-                    }
-                }
-            }
+        const float *rs = ring_s + stage * TR * kPitch;
+        const float *bfrag = rs + q * kPitch + 2 * nrow;                        // B fragment base of this lane
+        {
+            const int64_t next = tile + gridDim.x;
+            if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);
+            mbar_wait(&full_bar[stage], (uint32_t)(it >> 1) & 1u);
         }
-
-        const int64_t c0 = tile * kTileCols + (int64_t)tid * 4;
-        if (c0 < a.D) {
-            const bool full4 = c0 + 4 <= a.D;
+#pragma unroll 1
+        for (int blk = warp; blk < kTileCols / 16; blk += kDrawWarps) {
+            const int cb = blk * 16;
+            const int64_t cblk = tile * kTileCols + cb;
+            if (cblk >= a.D) break;                                             // warp-uniform
+            const int64_t c0 = cblk + 4 * q;                                    // this thread's 4 columns
+            const bool whole = cblk + 16 <= a.D;                                // warp-uniform: no ragged edge in this block
+            const bool live = c0 < a.D, full4 = c0 + 4 <= a.D;
             float m[4], sd[4];
             if (full4) {
-                const float4 mv = __ldg(reinterpret_cast<const float4 *>(a.mean + c0));
-                const float4 vv = __ldg(reinterpret_cast<const float4 *>(a.var + c0));
+                const float4 mv = *reinterpret_cast<const float4 *>(rs + MROW * kPitch + cb + 4 * q);
+                const float4 vv = *reinterpret_cast<const float4 *>(rs + (MROW + 1) * kPitch + cb + 4 * q);
                 m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
                 sd[0] = sqrtf(vv.x); sd[1] = sqrtf(vv.y); sd[2] = sqrtf(vv.z); sd[3] = sqrtf(vv.w);
             } else {
@@ -164,39 +208,99 @@ __global__ void __launch_bounds__(kDrawThreads * NG, 1) swag_draw_kernel(const D
                     sd[j] = ok ? sqrtf(a.var[c0 + j]) : 0.f;
                 }
             }
+            float acc[MT][2][4];                                                // [row tile][n-tile j][c0..c3]
 #pragma unroll
-            for (int sl = 0; sl < SPG; ++sl) {
-                const int s = s_lo + sl;
-                if (s < S) {
-                    float z[4];
-                    if (a.z1) {
-                        const float *zr = a.z1 + (int64_t)s * a.ld_z1 + c0;
-                        if (full4) {
-                            const float4 zv = __ldg(reinterpret_cast<const float4 *>(zr));
-                            z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
-                        } else {
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) z[j] = (c0 + j < a.D) ? zr[j] : 0.f;
+                for (int j = 0; j < 2; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
+            if (RING) {
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) {
+                    if (kt < KT) {
+                        // B fragments of both n-tiles: b0 = (k = q, n = nrow), b1 = (k = q + 4, n = nrow); columns cb + 2n + j
+                        const float2 r0 = *reinterpret_cast<const float2 *>(bfrag + kt * 8 * kPitch + cb);
+                        const float2 r1 = *reinterpret_cast<const float2 *>(bfrag + (kt * 8 + 4) * kPitch + cb);
+                        const float bv[2][2] = {{r0.x, r1.x}, {r0.y, r1.y}};    // [j][b0 / b1]
+                        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                bh[j][e] = __float_as_uint(bv[j][e]) & 0xFFFFE000u;
+                                bl[j][e] = __float_as_uint(bv[j][e] - __uint_as_float(bh[j][e]));
+                            }
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint4 ah4 = afrag[0][kt][mt][lane], al4 = afrag[1][kt][mt][lane];
+                            const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                mma_tf32_16x8x8(acc[mt][j], al, bh[j][0], bh[j][1]);
+                                mma_tf32_16x8x8(acc[mt][j], ah, bl[j][0], bl[j][1]);
+                                mma_tf32_16x8x8(acc[mt][j], ah, bh[j][0], bh[j][1]);
+                            }
                         }
-                    } else {
-                        const float4 zv = philox_normal4((uint64_t)s * (uint64_t)Dp4 + (uint64_t)(c0 >> 2), a.step, a.key);
-                        z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
                     }
+                }
+            }
+            // draw i covers row s = 16 (i / 2) + 8 (i % 2) + nrow; column 4q + e of the block is C element
+            // (n-tile e & 1, c = 2 (i % 2) + (e >> 1))
+            if (dense && whole) {
+                // straight-line path: the NI Philox / Box-Muller chains are independent and interleave
+                const uint64_t blk4 = (uint64_t)(c0 >> 2);
+                float4 zv[NI];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) zv[i] = philox_normal4(ctr_base[i] + blk4, a.step, a.key);
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int mt = i >> 1, h = i & 1;
+                    const float z[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+                    const float lr[4] = {acc[mt][0][2 * h], acc[mt][1][2 * h], acc[mt][0][2 * h + 1], acc[mt][1][2 * h + 1]};
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float r = __fmul_rn(sd[j], z[j]);                                  // swag.py:88-89
-                        if (K > 0) r = __fadd_rn(r, acc[sl][j]);                           // swag.py:95-96 (scale folded)
+                        if (RING) r = __fadd_rn(r, lr[j]);                                 // swag.py:95-96 (scale folded)
                         o[j] = __fadd_rn(m[j], r);                                         // swag.py:97
                     }
-                    float *orow = a.out + (int64_t)s * a.ld_out + c0;
+                    if (act[i]) *reinterpret_cast<float4 *>(out_row[i] + c0) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                continue;
+            }
+            if (!live) continue;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if (!act[i]) continue;
+                const int mt = i >> 1, h = i & 1;
+                float z[4];
+                if (a.z1) {
+                    const float *zr = a.z1 + (int64_t)((i >> 1) * 16 + (i & 1) * 8 + nrow) * a.ld_z1 + c0;
                     if (full4) {
-                        *reinterpret_cast<float4 *>(orow) = make_float4(o[0], o[1], o[2], o[3]);
+                        const float4 zv = __ldg(reinterpret_cast<const float4 *>(zr));
+                        z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (c0 + j < a.D) orow[j] = o[j];
+                        for (int j = 0; j < 4; ++j) z[j] = (c0 + j < a.D) ? zr[j] : 0.f;
                     }
+                } else {
+                    const float4 zv = philox_normal4(ctr_base[i] + (uint64_t)(c0 >> 2), a.step, a.key);
+                    z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
+                }
+                const float lr[4] = {acc[mt][0][2 * h], acc[mt][1][2 * h], acc[mt][0][2 * h + 1], acc[mt][1][2 * h + 1]};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float r = __fmul_rn(sd[j], z[j]);                                      // swag.py:88-89
+                    if (RING) r = __fadd_rn(r, lr[j]);                                     // swag.py:95-96 (scale folded)
+                    o[j] = __fadd_rn(m[j], r);                                             // swag.py:97
+                }
+                float *orow = out_row[i] + c0;
+                if (full4) {
+                    *reinterpret_cast<float4 *>(orow) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + j < a.D) orow[j] = o[j];
                 }
             }
         }
@@ -210,13 +314,13 @@ static int ew_grid(int64_t work_items) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-template <int SP, int NG>
+template <int MT, bool RING>
 static int launch_draw(const DrawArgs &a, cudaStream_t st) {
-    const size_t smem = (size_t)kStages * (a.K > 0 ? a.K : 0) * kTileCols * sizeof(float);
-    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<SP, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)kStages * (RING ? kRows : 2) * kPitch * sizeof(float);
+    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<MT, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    swag_draw_kernel<SP, NG><<<grid, kDrawThreads * NG, smem, st>>>(a);
+    swag_draw_kernel<MT, RING><<<grid, kDrawThreads, smem, st>>>(a);
     URSA_LAUNCH_CHECK("swag_draw_kernel");
     return URSA_OK;
 }
@@ -267,7 +371,6 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
     a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     a.step = step;
     cudaStream_t st = (cudaStream_t)stream;
-    if (S <= 8) return launch_draw<8, 1>(a, st);
-    if (S <= 16) return launch_draw<16, 2>(a, st);
-    return launch_draw<32, 4>(a, st);
+    if (K == 0) return S <= 16 ? launch_draw<1, false>(a, st) : launch_draw<2, false>(a, st);
+    return S <= 16 ? launch_draw<1, true>(a, st) : launch_draw<2, true>(a, st);
 }
