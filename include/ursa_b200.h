@@ -159,6 +159,9 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
 #define URSA_ALGO_FFMA    0
 #define URSA_ALGO_TCGEN05 1
 #define URSA_ALGO_TCGEN05_FUSED 2   /* PreResNet only: stage-fused 3xTF32 kernel, activations in shared memory, residual in TMEM */
+#define URSA_ALGO_TCGEN05_FUSED_F16 3 /* PreResNet only: stage-fused kernel on 2xFP16-split operands (22 significant bits, fp32
+                                       * accumulate), MMA / epilogue wavefront per 128-position tile.  Activations above ~1e6
+                                       * overflow FP16 and surface as NaN logits (never as finite wrong values). */
 
 size_t ursa_bma_mlp_workspace(int S, int64_t N, int in_dim, int hidden, int C, int algo);
 int ursa_bma_mlp_forward(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N,

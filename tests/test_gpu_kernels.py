@@ -316,10 +316,11 @@ def test_k3_mlp_forward_config1_shape_vs_torch(C):
 
 # ----------------------------------------------------------------------------- K3 forward, PreResNet
 def _algo(C, name):
-    return {"ffma": C.ALGO_FFMA, "tcgen05": C.ALGO_TCGEN05, "fused": C.ALGO_TCGEN05_FUSED}[name]
+    return {"ffma": C.ALGO_FFMA, "tcgen05": C.ALGO_TCGEN05, "fused": C.ALGO_TCGEN05_FUSED,
+            "fused16": C.ALGO_TCGEN05_FUSED_F16}[name]
 
 
-@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused"])
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused", "fused16"])
 def test_k3_preresnet8_forward_matches_reference_golden(C, algo):
     g = _npz("prediction.npz")
     algo = _algo(C, algo)
@@ -337,7 +338,7 @@ def test_k3_preresnet8_forward_matches_reference_golden(C, algo):
     np.testing.assert_allclose(E.cpu().numpy(), g["preresnet8/entropy"], atol=2e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused"])
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05", "fused", "fused16"])
 @pytest.mark.parametrize("depth,S,N,Cc", [(20, 3, 70, 10), (14, 9, 5, 100), (20, 1, 513, 10), (8, 2, 7, 10)])
 def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc, algo):
     """PreResNet-20 (config 2/5) with random BN statistics against a plain PyTorch fp32 forward (TF32 off);

@@ -10,8 +10,9 @@ from ursabench_b200 import _C, models  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
-algos = sys.argv[3:] or ["tcgen05", "fused"]
-ALGO = {"ffma": _C.ALGO_FFMA, "tcgen05": _C.ALGO_TCGEN05, "fused": _C.ALGO_TCGEN05_FUSED}
+algos = sys.argv[3:] or ["tcgen05", "fused", "fused16"]
+ALGO = {"ffma": _C.ALGO_FFMA, "tcgen05": _C.ALGO_TCGEN05, "fused": _C.ALGO_TCGEN05_FUSED,
+        "fused16": _C.ALGO_TCGEN05_FUSED_F16}
 dev = torch.device("cuda")
 torch.manual_seed(0)
 m = models.PreResNet(num_classes=10, depth=20)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libursa_b200.so")
 
 STEP_FIRST, STEP_NOISE, STEP_ZERO_GRAD = 1, 2, 4
-ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED = 0, 1, 2
+ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED, ALGO_TCGEN05_FUSED_F16 = 0, 1, 2, 3
 DRAW_MAX_S, DRAW_MAX_K = 32, 24
 
 _c = ctypes

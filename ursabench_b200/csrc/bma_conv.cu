@@ -19,10 +19,10 @@
 namespace ursa {
 
 size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C);
-size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C);
+size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C, int f16);
 int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                             int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
-                            double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st);
+                            double gamma, void *workspace, size_t workspace_bytes, int f16, cudaStream_t st);
 int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                               int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
                               double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st);
@@ -237,7 +237,8 @@ extern "C" size_t ursa_bma_preresnet_workspace(int S, int64_t N, int depth, int 
     NetPlan pl;
     if (S < 1 || N < 1) return 0;
     if (algo == URSA_ALGO_TCGEN05) return preresnet_workspace_tcgen05(S, N, depth, C);
-    if (algo == URSA_ALGO_TCGEN05_FUSED) return preresnet_workspace_fused(S, N, depth, C);
+    if (algo == URSA_ALGO_TCGEN05_FUSED || algo == URSA_ALGO_TCGEN05_FUSED_F16)
+        return preresnet_workspace_fused(S, N, depth, C, algo == URSA_ALGO_TCGEN05_FUSED_F16);
     if (algo != URSA_ALGO_FFMA || !build_plan(depth, C, pl)) return 0;
     return chunking(S, N, pl).total;
 }
@@ -251,9 +252,10 @@ extern "C" int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, co
     if (algo == URSA_ALGO_TCGEN05)
         return preresnet_forward_tcgen05(bank, ld_bank, bufbank, ld_buf, S, x, N, depth, C, proba_sum, entropy_sum,
                                          logits_out, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
-    if (algo == URSA_ALGO_TCGEN05_FUSED)
+    if (algo == URSA_ALGO_TCGEN05_FUSED || algo == URSA_ALGO_TCGEN05_FUSED_F16)
         return preresnet_forward_fused(bank, ld_bank, bufbank, ld_buf, S, x, N, depth, C, proba_sum, entropy_sum,
-                                       logits_out, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
+                                       logits_out, gamma, workspace, workspace_bytes, algo == URSA_ALGO_TCGEN05_FUSED_F16,
+                                       (cudaStream_t)stream);
     if (algo != URSA_ALGO_FFMA) {
         set_error("ursa_bma_preresnet_forward: unknown algo %d", algo);
         return URSA_ERR_UNSUPPORTED;

@@ -19,6 +19,7 @@
 #include "preresnet_plan.cuh"
 #include "tc_common.cuh"
 #include "bma_conv_fused.cuh"
+#include "bma_conv_fused16.cuh"
 
 namespace ursa {
 
@@ -174,6 +175,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
                         float t = v[i + j];
                         if (has_bn) t = fmaxf(fmaf(bn_s[c0 + i + j], t, bn_s[a.cout + c0 + i + j]), 0.f);
                         y[j] = t;
+                    }
+                    if (a.out_lo == nullptr) {          // plain fp32 activations (consumer splits them itself)
+                        hp[i >> 2] = make_float4(y[0], y[1], y[2], y[3]);
+                        continue;
                     }
                     float4 hv, lv;
                     hv.x = rn_tf32(y[0]); hv.y = rn_tf32(y[1]); hv.z = rn_tf32(y[2]); hv.w = rn_tf32(y[3]);
@@ -478,17 +483,19 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
 }
 
 // ---- fused-stage path (URSA_ALGO_TCGEN05_FUSED): stem -> [stage kernel] -> (shortcut + stride-2 conv) -> [stage kernel] ...
-size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C) {
+// f16 != 0 (URSA_ALGO_TCGEN05_FUSED_F16): FP16-split stage kernels (bma_conv_fused16.cuh), type-6 filters, and the stride-2
+// convs hand their activations over as one plain fp32 plane
+size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C, int f16) {
     NetPlan pl;
-    if (!build_plan(depth, C, pl, 2)) return 0;
+    if (!build_plan(depth, C, pl, f16 ? 3 : 2)) return 0;
     return tc_chunking(S, N, pl).total;
 }
 
 int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                             int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
-                            double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                            double gamma, void *workspace, size_t workspace_bytes, int f16, cudaStream_t st) {
     static thread_local NetPlan pl;
-    if (!build_plan(depth, C, pl, 2)) {
+    if (!build_plan(depth, C, pl, f16 ? 3 : 2)) {
         set_error("ursa_bma_preresnet_forward: unsupported depth %d (BasicBlock PreResNet: depth = 6n+2, 8..38)", depth);
         return URSA_ERR_UNSUPPORTED;
     }
@@ -533,7 +540,8 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                     shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs);
                     URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
                     ConvTcArgs c1;
-                    c1.mode = 0; c1.bn_off = B0.bn2; c1.res = nullptr; c1.out_raw = nullptr; c1.out_hi = A2h; c1.out_lo = A2l;
+                    c1.mode = 0; c1.bn_off = B0.bn2; c1.res = nullptr; c1.out_raw = nullptr; c1.out_hi = A2h;
+                    c1.out_lo = f16 ? nullptr : A2l;
                     if (int rc = launch_conv_tc(A1h, A1l, hw, ch, 2 * ch, 2, sc, nc, packed, pl.packed_floats, B0.w1, B0.w1_lo, c1, st))
                         return rc;
                     ch *= 2; hw /= 2;
@@ -553,7 +561,9 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 g.r_out = nxt;
                 g.a_out_hi = stg < 2 ? A1h : nullptr;
                 g.a_out_lo = stg < 2 ? A1l : nullptr;
-                int rc = stg == 0 ? launch_stage<16>(g, st) : (stg == 1 ? launch_stage<32>(g, st) : launch_stage<64>(g, st));
+                int rc;
+                if (f16) rc = stg == 0 ? launch_stage16<16>(g, st) : (stg == 1 ? launch_stage16<32>(g, st) : launch_stage16<64>(g, st));
+                else rc = stg == 0 ? launch_stage<16>(g, st) : (stg == 1 ? launch_stage<32>(g, st) : launch_stage<64>(g, st));
                 if (rc) return rc;
                 float *t = cur; cur = nxt; nxt = t;
             }

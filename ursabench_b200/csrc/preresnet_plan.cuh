@@ -2,6 +2,8 @@
 // where every tensor of one bank row lives (model.parameters() order, tests/golden/layouts.json) and where its
 // packed inference form goes.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ursa {
@@ -13,6 +15,8 @@ struct PrepEntry {
                        // 4 conv3x3 -> K-major [co][tap*cin + ci] split into tf32 hi (dst) / lo (dst2) planes
                        // 5 conv3x3 (cin == cout == C) -> fused-stage layout [tap][ci/4][2C rows][4]: rows are
                        //   [hi(co); lo(co)] when buf == 0 and [lo(co); hi(co)] when buf == 1 (see bma_conv_fused.cuh)
+                       // 6 conv3x3 (cin == cout == C) -> FP16-split fused-stage layout [tap][ci/8][2C rows][8 halves]:
+                       //   rows [hi(co); lo'(co)], w = hi + lo' * 2^-11 (see bma_conv_fused16.cuh); occupies cin*cout*9 floats
     int cin, cout;     // conv: channels; bn: cout = channels; copy: cout = count
     int64_t src;       // offset in the bank row (conv weight / bn weight / copy source)
     int64_t src2;      // bn: offset of bias in the bank row
@@ -78,6 +82,20 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(w - h));
             dst[i] = lo_part ? __uint_as_float(lb) : h;
         }
+    } else if (e.type == 6) {
+        const int C = e.cout;
+        __half *dh = reinterpret_cast<__half *>(dst);
+        const int total = 9 * (C / 8) * 2 * C * 8;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {       // i over dst [tap][j][n][e8]
+            const int e8 = i & 7;
+            const int n = (i >> 3) % (2 * C);
+            const int j = (i / (16 * C)) % (C / 8);
+            const int tap = i / (2 * C * C);
+            const int co = n % C, ci = 8 * j + e8;
+            const float w = row[e.src + ((int64_t)co * C + ci) * 9 + tap];
+            const __half h = __float2half_rn(w);
+            dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
+        }
     } else if (e.type == 2) {
         for (int c = threadIdx.x; c < e.cout; c += blockDim.x) {
             const float mean = brow[e.buf + c], var = brow[e.buf + e.cout + c];
@@ -103,7 +121,7 @@ struct NetPlan {
 
 // tc == 0: 3x3 filters packed [ci][tap][co] for the CUDA-core kernels; tc == 1: K-major tf32 hi / lo planes (layer-by-
 // layer tcgen05 kernels); tc == 2: fused-stage layout (type 5) for every 3x3 conv with cin == cout, type 4 for the two
-// stride-2 transition convs
+// stride-2 transition convs; tc == 3: as 2 with the FP16-split layout (type 6)
 static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
     if (depth >= 44 || depth < 8 || (depth - 2) % 6 != 0 || C < 1) return false;
     const int n = (depth - 2) / 6;
@@ -148,10 +166,10 @@ static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
             const int w = widths[st];
             NetPlan::Block &B = pl.blocks[st][b];
             B.bn1 = add_bn(inpl);
-            B.w1 = (tc == 2 && inpl == w) ? add_conv(5, inpl, w, 0) : add_conv(t3, inpl, w);
+            B.w1 = (tc >= 2 && inpl == w) ? add_conv(tc == 2 ? 5 : 6, inpl, w, 0) : add_conv(t3, inpl, w);
             B.w1_lo = last_lo;
             B.bn2 = add_bn(w);
-            B.w2 = tc == 2 ? add_conv(5, w, w, 1) : add_conv(t3, w, w);
+            B.w2 = tc == 2 ? add_conv(5, w, w, 1) : (tc == 3 ? add_conv(6, w, w, 0) : add_conv(t3, w, w));
             B.w2_lo = last_lo;
             B.ds = (b == 0 && st > 0) ? add_conv(1, inpl, w) : -1;
             inpl = w;
