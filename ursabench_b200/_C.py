@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libursa_b200.so")
+LIB_PATH = os.environ.get("URSA_B200_LIB") or os.path.join(_HERE, "libursa_b200.so")   # env override: debug builds
 
 STEP_FIRST, STEP_NOISE, STEP_ZERO_GRAD = 1, 2, 4
 ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED, ALGO_TCGEN05_FUSED_F16 = 0, 1, 2, 3

@@ -23,6 +23,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "bma_conv_fused.cuh"
 
 namespace ursa {
@@ -45,7 +47,12 @@ struct F16Cfg {
     static constexpr int SLOT_BYTES = 4 * C * C;               // one tap: [C/8][2C rows][8 halves]
     static constexpr bool TILE_OUTER = C <= 32;
     static constexpr int NSLOT = TILE_OUTER ? 18 : 6;
-    static constexpr int NCH = C / 2;                          // channels per epilogue thread
+    // epilogue: 16 warps = NGT tile groups x NGC channel groups x 4 lane quarters; group (gt, gc) owns the tiles
+    // t = gt, gt + NGT, .. and the channels [gc * CPT, (gc + 1) * CPT) -- NGT tiles are in flight at once
+    static constexpr int NGT = C == 16 ? 4 : 2;
+    static constexpr int NGC = 4 / NGT;
+    static constexpr int CPT = C / NGC;                        // channels per epilogue thread: 16, 16, 32
+    static constexpr int TPG = (T + NGT - 1) / NGT;            // tiles per group: 3, 3, 1
     static constexpr int TILE_COLS = 2 * C;                    // [ACC | LO]
     static constexpr int BN_FLOATS = (kFusedMaxConvs + 1) * 2 * C;
     static constexpr size_t SMEM = (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES + 2 * BN_FLOATS * 4 + 128;
@@ -75,12 +82,42 @@ __device__ __forceinline__ void split_h2(float y0, float y1, uint32_t &hi, uint3
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+constexpr int kF16Threads = 64 + 512;           // producer warp, MMA warp, 16 epilogue warps
+
+// Warp-level mbarrier wait for the epilogue warps: one lane polls with the NON-blocking test_wait plus a back-off, then the
+// warp reconverges.  mbarrier.try_wait may park inside the memory-instruction queue of its SM sub-partition until the phase
+// flips or a time limit expires; the MMA-issuing warp shares that queue with a quarter of the epilogue warps (TMEM lane
+// quarter = warp % 4 = sub-partition), so parked try_waits that are waiting for MMAs were sitting in front of the very
+// tcgen05.mma instructions they waited for (ncu: mio_throttle on every UTCHMMA, MMA cadence 2x the stand-alone probe).
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        for (uint32_t spin = 0; !mbar_test_wait_a(bar, parity); ++spin) {
+            __nanosleep(64);
+            if (spin > (1u << 24)) __trap();
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 // FusedStageArgs as in bma_conv_fused.cuh with two differences: w_off[] point at type-6 packed filters, and the a_in
 // path (bn_in_off < 0) reads ONE plain fp32 plane of activations (a_in_hi; a_in_lo is ignored).
 template <int C>
-__global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(const FusedStageArgs a) {
+__global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const FusedStageArgs a) {
     using Cfg = F16Cfg<C>;
-    constexpr int H = Cfg::H, G = Cfg::G, PITCH = Cfg::PITCH, F0 = Cfg::F0, T = Cfg::T, NCH = Cfg::NCH;
+    constexpr int H = Cfg::H, G = Cfg::G, PITCH = Cfg::PITCH, F0 = Cfg::F0, T = Cfg::T, CPT = Cfg::CPT, TPG = Cfg::TPG;
+    constexpr int NGT = Cfg::NGT, NGC = Cfg::NGC;
     constexpr int PLANE = Cfg::PLANE_BYTES, NPL = Cfg::NPLANES, NSLOT = Cfg::NSLOT, BNF = Cfg::BN_FLOATS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NSLOT];
@@ -107,7 +144,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
         }
         for (int i = 0; i < T; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&act_ready[i], 256);
+            mbar_init(&act_ready[i], 128 * NGC);
         }
         fence_barrier_init();
     }
@@ -115,7 +152,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
     {   // zero both plane sets once: pad positions are never written afterwards
         float4 *z = reinterpret_cast<float4 *>(gen_base);
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = threadIdx.x; i < 2 * NPL * Cfg::NPOS; i += kFusedThreads) z[i] = zero;
+        for (int i = threadIdx.x; i < 2 * NPL * Cfg::NPOS; i += kF16Threads) z[i] = zero;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -124,7 +161,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
     const uint32_t tmem = tmem_base_s;
 
     if (warp == 0) {
-        // ================= filter producer: one bulk copy per tap =================
+        // ================= filter producer =================
+        // TILE_OUTER: one bulk copy per conv (its 9 taps are contiguous) into one of two 9-slot bundles, one full / empty
+        // barrier pair per bundle; otherwise one copy and one barrier pair per tap.
         if (elect_one()) {
             uint32_t it = 0;
             for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
@@ -132,6 +171,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
                 const float *pk = a.packed + (int64_t)s * a.ld_packed;
                 for (int k = 0; k < a.n_convs; ++k) {
                     const unsigned char *w = reinterpret_cast<const unsigned char *>(pk + a.w_off[k]);
+                    if (Cfg::TILE_OUTER) {
+                        const uint32_t b = it & 1u, ph = (it >> 1) & 1u;
+                        mbar_wait_a(smem_u32(&empty_bar[b]), ph ^ 1u);
+                        mbar_expect_tx_a(smem_u32(&full_bar[b]), 9 * Cfg::SLOT_BYTES);
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                ring + b * 9 * Cfg::SLOT_BYTES),
+                            "l"(w), "r"((uint32_t)(9 * Cfg::SLOT_BYTES)), "r"(smem_u32(&full_bar[b]))
+                            : "memory");
+                        ++it;
+                    } else
                     for (int tap = 0; tap < 9; ++tap, ++it) {
                         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1u;
                         mbar_wait_a(smem_u32(&empty_bar[slot]), ph ^ 1u);
@@ -155,41 +205,87 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
             const uint32_t a_lo_w = ((planes_lo >> 4) + (uint32_t)F0) | (PL16 << 16);
             const uint32_t b_w0 = (ring >> 4) | ((uint32_t)(2 * C) << 16);             // LBO = 2C rows x 16 B
             auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
-            // one tap of one tile: C/16 K steps, [A_hi x (B_hi ; B_lo') -> ACC | LO] then [A_lo' x B_hi -> LO]
-            auto tap_mmas = [&](uint32_t slot, int tap, int t) {
-                const uint32_t shift = (uint32_t)((tap / 3 - 1) * PITCH + (tap % 3 - 1)) + (uint32_t)(128 * t);
-                const uint32_t bw = b_w0 + slot * (uint32_t)(Cfg::SLOT_BYTES >> 4);
-                const uint32_t d = tmem + (uint32_t)(t * Cfg::TILE_COLS);
+            // One tap of one tile: C/16 K steps of [A_hi x (B_hi ; B_lo') -> ACC | LO] and [A_lo' x B_hi -> LO].  TAP is a
+            // compile-time constant and the descriptors differ from per-tile / per-slot base words by constants, so the
+            // issue work per MMA is one integer add: tcgen05.mma is issued by ONE thread and any arithmetic between two MMAs
+            // that takes longer than the MMA itself (40 clk) leaves the tensor pipe idle.
+            auto tap_mmas = [&](auto tap_c, uint32_t ahw, uint32_t alw, uint32_t bw, uint32_t d) {
+                constexpr int TAP = decltype(tap_c)::value;
+                constexpr uint32_t SHIFT = (uint32_t)((TAP / 3 - 1) * PITCH + (TAP % 3 - 1));
 #pragma unroll
                 for (int ks = 0; ks < C / 16; ++ks) {
-                    umma_f16(d, mk(a_hi_w + shift + ks * 2 * PL16), mk(bw + ks * 4 * C), idesc_cat, (tap | ks) != 0);
-                    umma_f16(d + C, mk(a_lo_w + shift + ks * 2 * PL16), mk(bw + ks * 4 * C), idesc_lo, 1);
+                    umma_f16(d, mk(ahw + SHIFT + ks * 2 * PL16), mk(bw + ks * 4 * C), idesc_cat, (TAP | ks) != 0);
+                    umma_f16(d + C, mk(alw + SHIFT + ks * 2 * PL16), mk(bw + ks * 4 * C), idesc_lo, 1);
                 }
             };
+            constexpr uint32_t SLOTW = (uint32_t)(Cfg::SLOT_BYTES >> 4);
+            // Barrier waits of this thread queue up behind its own tcgen05.mma instructions, so a wait that is issued when
+            // its result is needed costs a drain of the MMA queue.  Every barrier is therefore TESTED (non-blocking) one step
+            // early -- the answer arrives while the MMAs of the current step are being issued -- and only waited for if that
+            // early test failed.
             uint32_t it = 0, item = 0;
+            bool ok_a = false, ok_b = false;        // early-test results carried into the next step
             for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
                 for (int k = 0; k < a.n_convs; ++k, ++item) {
                     const uint32_t iph = item & 1u;
                     if (Cfg::TILE_OUTER) {
-                        for (int tap = 0; tap < 9; ++tap)
-                            mbar_wait_a(smem_u32(&full_bar[(it + tap) % NSLOT]), ((it + tap) / NSLOT) & 1u);
+                        const uint32_t b = iph, fph = (item >> 1) & 1u;     // bundle b holds this conv's 9 taps
+                        mbar_wait_a(smem_u32(&full_bar[b]), fph);
+                        const uint32_t bw0 = b_w0 + b * 9u * SLOTW;
+                        // ok_a / ok_b: act_ready[0] / act_ready[1] of this conv were seen complete by the previous conv's tail
+                        if (!ok_a) mbar_wait_a(smem_u32(&act_ready[0]), iph);
+                        bool ok_next = ok_b;
+#pragma unroll 1
                         for (int t = 0; t < T; ++t) {
-                            mbar_wait_a(smem_u32(&act_ready[t + 1 < T ? t + 1 : T - 1]), iph);
+                            // tile t reads the planes of tiles t-1 .. t+1 (halo); tile groups publish independently
+                            if (t + 1 < T && !ok_next) mbar_wait_a(smem_u32(&act_ready[t + 1]), iph);
                             tc_fence_after();
-                            for (int tap = 0; tap < 9; ++tap) tap_mmas((it + tap) % NSLOT, tap, t);
+                            if (t + 2 < T) {
+                                ok_next = mbar_test_wait_a(smem_u32(&act_ready[t + 2]), iph);
+                            } else if (t + 2 == T) {                        // early tests for the next conv's first two tiles
+                                ok_a = mbar_test_wait_a(smem_u32(&act_ready[0]), iph ^ 1u);
+                                ok_next = true;
+                            } else {
+                                ok_b = T > 1 && mbar_test_wait_a(smem_u32(&act_ready[T > 1 ? 1 : 0]), iph ^ 1u);
+                            }
+                            const uint32_t ahw = a_hi_w + 128u * t, alw = a_lo_w + 128u * t, d = tmem + (uint32_t)(t * Cfg::TILE_COLS);
+                            tap_mmas(std::integral_constant<int, 0>{}, ahw, alw, bw0 + 0 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 1>{}, ahw, alw, bw0 + 1 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 2>{}, ahw, alw, bw0 + 2 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 3>{}, ahw, alw, bw0 + 3 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 4>{}, ahw, alw, bw0 + 4 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 5>{}, ahw, alw, bw0 + 5 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 6>{}, ahw, alw, bw0 + 6 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 7>{}, ahw, alw, bw0 + 7 * SLOTW, d);
+                            tap_mmas(std::integral_constant<int, 8>{}, ahw, alw, bw0 + 8 * SLOTW, d);
                             umma_commit(smem_u32(&acc_full[t]));
                         }
-                        for (int tap = 0; tap < 9; ++tap) umma_commit(smem_u32(&empty_bar[(it + tap) % NSLOT]));
-                        it += 9;
+                        umma_commit(smem_u32(&empty_bar[b]));
                     } else {
-                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                        auto one_tap = [&](auto tap_c) {
+                            constexpr int TAP = decltype(tap_c)::value;
                             const uint32_t slot = it % NSLOT;
-                            mbar_wait_a(smem_u32(&full_bar[slot]), (it / NSLOT) & 1u);
-                            if (tap == 0) mbar_wait_a(smem_u32(&act_ready[T - 1]), iph);      // in-order arrivals: all tiles
+                            if (!ok_a) mbar_wait_a(smem_u32(&full_bar[slot]), (it / NSLOT) & 1u);
+                            if (TAP == 0)
+                                for (int t = 0; t < T; ++t) mbar_wait_a(smem_u32(&act_ready[t]), iph);
                             tc_fence_after();
-                            for (int t = 0; t < T; ++t) tap_mmas(slot, tap, t);
+                            ok_a = mbar_test_wait_a(smem_u32(&full_bar[(it + 1) % NSLOT]), ((it + 1) / NSLOT) & 1u);
+                            const uint32_t bw = b_w0 + slot * SLOTW;
+#pragma unroll
+                            for (int t = 0; t < T; ++t)
+                                tap_mmas(tap_c, a_hi_w + 128u * t, a_lo_w + 128u * t, bw, tmem + (uint32_t)(t * Cfg::TILE_COLS));
                             umma_commit(smem_u32(&empty_bar[slot]));
-                        }
+                            ++it;
+                        };
+                        one_tap(std::integral_constant<int, 0>{});
+                        one_tap(std::integral_constant<int, 1>{});
+                        one_tap(std::integral_constant<int, 2>{});
+                        one_tap(std::integral_constant<int, 3>{});
+                        one_tap(std::integral_constant<int, 4>{});
+                        one_tap(std::integral_constant<int, 5>{});
+                        one_tap(std::integral_constant<int, 6>{});
+                        one_tap(std::integral_constant<int, 7>{});
+                        one_tap(std::integral_constant<int, 8>{});
                         for (int t = 0; t < T; ++t) umma_commit(smem_u32(&acc_full[t]));
                     }
                 }
@@ -198,32 +294,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
     } else {
         // ================= prologue / epilogue warps =================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;             // channel half
+        const int grp = (warp - 2) >> 2;
+        const int gt = grp % NGT, gc = grp / NGT;     // tile group, channel group
         const int m = q * 32 + lane;                  // row within a tile
-        const int ch0 = half * NCH;
+        const int ch0 = gc * CPT;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
-        const int etid = threadIdx.x - 64;            // 0..255
+        const int etid = threadIdx.x - 64;            // 0..511
         const bool from_r = a.bn_in_off >= 0;         // planes = split(relu(bn_in(r_in))) ; else planes = split(a_in)
         const bool to_global = a.a_out_hi != nullptr && a.bn_off[a.n_convs - 1] >= 0;
 
-        // this thread's T rows: element offset inside a pass's image group, image index within the group; -1 = padding
-        int32_t rel[T];
-        int gimg[T];
+        // this thread's rows (tile slot j <-> tile t = gt + j NGT): element offset inside a pass's image group and image
+        // index within the group; -1 = padding or no such tile
+        int32_t rel[TPG];
+        int gimg[TPG];
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < TPG; ++j) {
+            const int t = gt + j * NGT;
             const int f = F0 + 128 * t + m;
             const int prow = f / PITCH, pcol = f - prow * PITCH;
             const int r = prow - 1;
             const int g = r / (H + 1), h = r - g * (H + 1);
-            const bool ok = pcol >= 1 && r >= 0 && g < G && h < H;
-            rel[t] = ok ? ((g * H + h) * H + (pcol - 1)) * C + ch0 : -1;
-            gimg[t] = g;
+            const bool ok = t < T && pcol >= 1 && r >= 0 && g < G && h < H;
+            rel[j] = ok ? ((g * H + h) * H + (pcol - 1)) * C + ch0 : -1;
+            gimg[j] = g;
         }
         auto plane_off = [&](int t, int i) { return (uint32_t)(((ch0 + i) >> 3) * PLANE + (F0 + 128 * t + m) * 16); };
-        auto goff_of = [&](int pass, int t) -> int32_t {
+        auto goff_of = [&](int pass, int j) -> int32_t {
             const int s = pass / n_groups, n0 = (pass - s * n_groups) * G;
-            if (rel[t] < 0 || n0 + gimg[t] >= a.n_images) return -1;
-            return (int32_t)((s * a.n_images + n0) * (H * H * C)) + rel[t];
+            if (rel[j] < 0 || n0 + gimg[j] >= a.n_images) return -1;
+            return (int32_t)((s * a.n_images + n0) * (H * H * C)) + rel[j];
         };
         // BatchNorm (a, b) of the pass's sample -> shared memory buffer `buf`, rescaled for the /16 activation domain:
         //   entry 0 (bn_in) and entries after a mode-1 conv act on the true-domain residual R:  y/16 = relu(a/16 R + b/16)
@@ -232,35 +331,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
             const int s = pass / n_groups;
             const float *pk = a.packed + (int64_t)s * a.ld_packed;
             float *bs = bn_all + buf * BNF;
-            for (int i = etid; i < 2 * C; i += 256)
-                if (from_r) bs[i] = __ldg(pk + a.bn_in_off + i) * kActDown;
+            if (from_r)
+                for (int i = etid; i < 2 * C; i += 512) bs[i] = __ldg(pk + a.bn_in_off + i) * kActDown;
             for (int k = 0; k < a.n_convs; ++k)
                 if (a.bn_off[k] >= 0)
-                    for (int i = etid; i < 2 * C; i += 256)
+                    for (int i = etid; i < 2 * C; i += 512)
                         bs[(k + 1) * 2 * C + i] = __ldg(pk + a.bn_off[k] + i) * ((i >= C || a.mode[k] == 1) ? kActDown : 1.f);
         };
         auto load_rows = [&](const float *src, int32_t goff, float *v) {
             if (goff >= 0) {
                 const float4 *rp = reinterpret_cast<const float4 *>(src + goff);
 #pragma unroll
-                for (int i = 0; i < NCH / 4; ++i) {
+                for (int i = 0; i < CPT / 4; ++i) {
                     const float4 x4 = __ldg(rp + i);
                     v[4 * i] = x4.x; v[4 * i + 1] = x4.y; v[4 * i + 2] = x4.z; v[4 * i + 3] = x4.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) v[i] = 0.f;
+                for (int i = 0; i < CPT; ++i) v[i] = 0.f;
             }
         };
-        // y[0..NCH) (already / 16) -> fp16 hi / lo' planes of tile t
-        auto store_planes = [&](int t, const float *y) {
+        // y[0..16) (already / 16) -> fp16 hi / lo' planes of tile t, channels ch0 + c0 ..
+        auto store_planes16 = [&](int t, int c0, const float *y) {
 #pragma unroll
-            for (int i = 0; i < NCH; i += 8) {
+            for (int i = 0; i < 16; i += 8) {
                 uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) split_h2(y[i + 2 * j], y[i + 2 * j + 1], hw[j], lw[j]);
-                *reinterpret_cast<uint4 *>(gen_base + plane_off(t, i)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4 *>(gen_base + NPL * PLANE + plane_off(t, i)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int jj = 0; jj < 4; ++jj) split_h2(y[i + 2 * jj], y[i + 2 * jj + 1], hw[jj], lw[jj]);
+                *reinterpret_cast<uint4 *>(gen_base + plane_off(t, c0 + i)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(gen_base + NPL * PLANE + plane_off(t, c0 + i)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         };
         auto publish = [&](int t) {
@@ -269,23 +368,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
             mbar_arrive(&act_ready[t]);
         };
 
-        float R[T][NCH];                               // residual stream (true domain) -- or the staged prologue source
-        int32_t goff[T];
-        // the prologue of a pass: R holds the raw source rows (r_in, or the plain a_in plane)
-        auto prologue = [&](int pass, int buf) {
-            const float *bn = bn_all + buf * BNF;
+        float R[TPG][CPT];                             // residual stream (true domain) -- or the staged prologue source
+        int32_t goff[TPG] = {};
+        // the prologue of a pass for tile slot j: R[j] holds the raw source rows (r_in, or the plain a_in plane)
+        auto prologue_tile = [&](int j, int t, const float *bn) {
+            if (goff[j] >= 0) {
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                if (goff[t] >= 0) {
-                    float y[NCH];
+                for (int c0 = 0; c0 < CPT; c0 += 16) {
+                    float y[16];
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i)
-                        y[i] = from_r ? fmaxf(fmaf(bn[ch0 + i], R[t][i], bn[C + ch0 + i]), 0.f) : R[t][i] * kActDown;
-                    store_planes(t, y);
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 a4 = make_float4(kActDown, kActDown, kActDown, kActDown), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (from_r) {
+                            a4 = *reinterpret_cast<const float4 *>(bn + ch0 + c0 + i);
+                            b4 = *reinterpret_cast<const float4 *>(bn + C + ch0 + c0 + i);
+                        }
+                        // a_in activations are >= 0 already: relu(a x + 0) with a = 1/16 is the plain rescale
+                        y[i] = fmaxf(fmaf(a4.x, R[j][c0 + i], b4.x), 0.f);
+                        y[i + 1] = fmaxf(fmaf(a4.y, R[j][c0 + i + 1], b4.y), 0.f);
+                        y[i + 2] = fmaxf(fmaf(a4.z, R[j][c0 + i + 2], b4.z), 0.f);
+                        y[i + 3] = fmaxf(fmaf(a4.w, R[j][c0 + i + 3], b4.w), 0.f);
+                    }
+                    store_planes16(t, c0, y);
                 }
-                publish(t);
-                if (!from_r) load_rows(a.r_in, goff[t], R[t]);       // lands long before the first mode-1 epilogue
             }
+            publish(t);
+            if (!from_r) load_rows(a.r_in, goff[j], R[j]);           // lands long before the first mode-1 epilogue
+        };
+        auto prefetch_l2 = [&](const float *src, int32_t g) {
+            if (g >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + g));
         };
 
         uint32_t item = 0;
@@ -294,83 +405,113 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage16_kernel(con
             const int pass = blockIdx.x;
             load_bn(pass, 0);
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                goff[t] = goff_of(pass, t);
-                load_rows(from_r ? a.r_in : a.a_in_hi, goff[t], R[t]);
+            for (int j = 0; j < TPG; ++j) {
+                goff[j] = goff_of(pass, j);
+                load_rows(from_r ? a.r_in : a.a_in_hi, goff[j], R[j]);
             }
-            epi_bar_sync();
-            prologue(pass, 0);
+            epi16_bar_sync();
+#pragma unroll
+            for (int j = 0; j < TPG; ++j)
+                if (gt + j * NGT < T) prologue_tile(j, gt + j * NGT, bn_all);
         }
         for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
             for (int k = 0; k < a.n_convs; ++k, ++item) {
                 const bool last = k == a.n_convs - 1;
                 const int mode = a.mode[k];
                 const float *bn = bn_all + buf * BNF + (k + 1) * 2 * C;
-                const bool has_bn = a.bn_off[k] >= 0;
                 const int np = pass + gridDim.x;
                 const bool has_next = last && np < n_pass;
-                if (has_next) load_bn(np, buf ^ 1);
+                if (k == 0 && np < n_pass) {
+                    // Off the critical path (the MMA queue is full at this point): everybody has left the previous pass, so
+                    // its BatchNorm buffer can be refilled for the NEXT pass, and the next pass's source rows are pulled into
+                    // L2 so that the loads at the pass boundary are short.
+                    epi16_bar_sync();
+                    load_bn(np, buf ^ 1);
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    mbar_wait_a(smem_u32(&acc_full[t + 1 < T ? t + 1 : T - 1]), item & 1u);
+                    for (int j = 0; j < TPG; ++j) {
+                        const int32_t g = goff_of(np, j);
+                        prefetch_l2(from_r ? a.r_in : a.a_in_hi, g);
+                        if (!from_r) prefetch_l2(a.r_in, g);
+                    }
+                }
+                if (has_next) epi16_bar_sync();      // bn_all[buf ^ 1] is complete
+#pragma unroll
+                for (int j = 0; j < TPG; ++j) {
+                    const int t = gt + j * NGT;
+                    if (t >= T) continue;
+                    // tile t's planes are read as a halo by tile t+1's MMAs: wait for those before overwriting them
+                    mbar_wait_warp(smem_u32(&acc_full[t + 1 < T ? t + 1 : T - 1]), item & 1u);   // in-order commits: tile t too
                     tc_fence_after();
                     const uint32_t tcol = t_lane + (uint32_t)(t * Cfg::TILE_COLS);
-                    uint32_t ra[NCH], rl[NCH];
-                    tmem_ld<NCH>(tcol, ra);
-                    tmem_ld<NCH>(tcol + C, rl);
-                    tmem_ld_wait();
-                    float x[NCH];
 #pragma unroll
-                    for (int i = 0; i < NCH; ++i) {
-                        x[i] = fmaf(__uint_as_float(rl[i]), kLoUnscale, __uint_as_float(ra[i]));     // conv / 16
-                        if (mode == 1) {
-                            R[t][i] = fmaf(kActUp, x[i], R[t][i]);                                   // residual, true domain
-                            x[i] = R[t][i];
-                        }
-                    }
-                    if (!last) {
-                        if (goff[t] >= 0) {
-                            float y[NCH];
+                    for (int c0 = 0; c0 < CPT; c0 += 16) {
+                        uint32_t ra[16], rl[16];
+                        tmem_ld<16>(tcol + c0, ra);
+                        tmem_ld<16>(tcol + C + c0, rl);
+                        const float4 *ba4 = reinterpret_cast<const float4 *>(bn + ch0 + c0);
+                        const float4 *bb4 = reinterpret_cast<const float4 *>(bn + C + ch0 + c0);
+                        tmem_ld_wait();
+                        float x[16];
 #pragma unroll
-                            for (int i = 0; i < NCH; ++i) y[i] = fmaxf(fmaf(bn[ch0 + i], x[i], bn[C + ch0 + i]), 0.f);
-                            store_planes(t, y);
+                        for (int i = 0; i < 16; ++i) {
+                            x[i] = fmaf(__uint_as_float(rl[i]), kLoUnscale, __uint_as_float(ra[i]));   // conv / 16
+                            if (mode == 1) {
+                                R[j][c0 + i] = fmaf(kActUp, x[i], R[j][c0 + i]);                       // residual, true domain
+                                x[i] = R[j][c0 + i];
+                            }
                         }
-                        publish(t);
-                    } else {
-                        tc_fence_before();
-                        if (goff[t] >= 0) {
+                        if (!last) {
+                            if (goff[j] >= 0) {
+                                float y[16];
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
+                                    y[i] = fmaxf(fmaf(a4.x, x[i], b4.x), 0.f);
+                                    y[i + 1] = fmaxf(fmaf(a4.y, x[i + 1], b4.y), 0.f);
+                                    y[i + 2] = fmaxf(fmaf(a4.z, x[i + 2], b4.z), 0.f);
+                                    y[i + 3] = fmaxf(fmaf(a4.w, x[i + 3], b4.w), 0.f);
+                                }
+                                store_planes16(t, c0, y);
+                            }
+                        } else if (goff[j] >= 0) {
                             if (mode == 0) {
 #pragma unroll
-                                for (int i = 0; i < NCH; ++i) x[i] *= kActUp;
+                                for (int i = 0; i < 16; ++i) x[i] *= kActUp;
                             }
-                            float4 *op = reinterpret_cast<float4 *>(a.r_out + goff[t]);
+                            float4 *op = reinterpret_cast<float4 *>(a.r_out + goff[j] + c0);
 #pragma unroll
-                            for (int i = 0; i < NCH; i += 4) op[i >> 2] = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                            for (int i = 0; i < 16; i += 4) op[i >> 2] = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
                             if (to_global) {
 #pragma unroll
-                                for (int i = 0; i < NCH; i += 4) {
-                                    float y[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j)      // bn entry is in the /16 domain (mode 1): undo
-                                        y[j] = fmaxf(fmaf(bn[ch0 + i + j], x[i + j], bn[C + ch0 + i + j]), 0.f) * kActUp;
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
+                                    float y[4];                     // bn entry is in the /16 domain (mode 1): undo
+                                    y[0] = fmaxf(fmaf(a4.x, x[i], b4.x), 0.f) * kActUp;
+                                    y[1] = fmaxf(fmaf(a4.y, x[i + 1], b4.y), 0.f) * kActUp;
+                                    y[2] = fmaxf(fmaf(a4.z, x[i + 2], b4.z), 0.f) * kActUp;
+                                    y[3] = fmaxf(fmaf(a4.w, x[i + 3], b4.w), 0.f) * kActUp;
                                     float4 hv, lv;
                                     split4(y, hv, lv);
-                                    reinterpret_cast<float4 *>(a.a_out_hi + goff[t])[i >> 2] = hv;
-                                    reinterpret_cast<float4 *>(a.a_out_lo + goff[t])[i >> 2] = lv;
+                                    reinterpret_cast<float4 *>(a.a_out_hi + goff[j] + c0)[i >> 2] = hv;
+                                    reinterpret_cast<float4 *>(a.a_out_lo + goff[j] + c0)[i >> 2] = lv;
                                 }
                             }
                         }
-                        if (has_next) {                 // R[t] is dead: fetch the next pass's prologue source under the tail
-                            goff[t] = goff_of(np, t);
-                            load_rows(from_r ? a.r_in : a.a_in_hi, goff[t], R[t]);
+                    }
+                    if (!last) {
+                        publish(t);
+                    } else {
+                        tc_fence_before();
+                        if (has_next) {
+                            // R[j] is dead and tile t's planes are free (tile t+1's MMAs are complete): the next pass's prologue
+                            // for this tile joins the wavefront right here, under the MMAs of the remaining tiles
+                            goff[j] = goff_of(np, j);
+                            load_rows(from_r ? a.r_in : a.a_in_hi, goff[j], R[j]);
+                            prologue_tile(j, t, bn_all + (buf ^ 1) * BNF);
                         }
                     }
                 }
-                if (has_next) {
-                    epi_bar_sync();                     // the next pass's BatchNorm parameters are in bn_all[buf ^ 1]
-                    buf ^= 1;
-                    prologue(np, buf);
-                }
+                if (has_next) buf ^= 1;
             }
         }
         tc_fence_before();
@@ -391,7 +532,7 @@ static int launch_stage16(const FusedStageArgs &a, cudaStream_t st) {
     const int sms = sm_count();
     const int grid = n_pass < sms ? n_pass : sms;
     URSA_CUDA(cudaFuncSetAttribute(preresnet_stage16_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    preresnet_stage16_kernel<C><<<grid, kFusedThreads, Cfg::SMEM, st>>>(a);
+    preresnet_stage16_kernel<C><<<grid, kF16Threads, Cfg::SMEM, st>>>(a);
     URSA_LAUNCH_CHECK("preresnet_stage16_kernel");
     return URSA_OK;
 }
