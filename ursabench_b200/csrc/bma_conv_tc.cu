@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
                                                          int64_t ld_packed, int64_t w_off, int64_t bn_off, int n_images,
                                                          float *__restrict__ out_raw, float *__restrict__ out_hi,
                                                          float *__restrict__ out_lo) {
+    // one CTA per (image, sample); thread = 4 consecutive pixels of a row x all 16 output channels (64 accumulators), so a
+    // filter tap's 16 weights (4 broadcast LDS.128) feed 64 FMAs and an input row segment (6 LDS) feeds 3 taps
     __shared__ float xs[3][34][35];
     __shared__ __align__(16) float ws[27 * 16];
     __shared__ float bn[32];
@@ -216,39 +218,46 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
         xs[ci][hh][ww] = (hi >= 0 && hi < 32 && wi >= 0 && wi < 32) ? __ldg(x + ((int64_t)n * 3 + ci) * 1024 + hi * 32 + wi) : 0.f;
     }
     __syncthreads();
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const int p = threadIdx.x + j * 256;
-        const int h = p >> 5, w = p & 31;
-        float acc[16];
+    const int h = threadIdx.x >> 3, w0 = (threadIdx.x & 7) * 4;
+    float acc[4][16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+        for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float av = xs[ci][h + kh][w + kw];
-                    const float4 *wp = reinterpret_cast<const float4 *>(ws + (ci * 9 + kh * 3 + kw) * 16);
+        for (int kh = 0; kh < 3; ++kh) {
+            float xv[6];
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float4 w4 = wp[qd];
-                        acc[4 * qd + 0] = fmaf(av, w4.x, acc[4 * qd + 0]);
-                        acc[4 * qd + 1] = fmaf(av, w4.y, acc[4 * qd + 1]);
-                        acc[4 * qd + 2] = fmaf(av, w4.z, acc[4 * qd + 2]);
-                        acc[4 * qd + 3] = fmaf(av, w4.w, acc[4 * qd + 3]);
+            for (int d = 0; d < 6; ++d) xv[d] = xs[ci][h + kh][w0 + d];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 *wp = reinterpret_cast<const float4 *>(ws + (ci * 9 + kh * 3 + kw) * 16);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 w4 = wp[qd];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        acc[p][4 * qd + 0] = fmaf(xv[p + kw], w4.x, acc[p][4 * qd + 0]);
+                        acc[p][4 * qd + 1] = fmaf(xv[p + kw], w4.y, acc[p][4 * qd + 1]);
+                        acc[p][4 * qd + 2] = fmaf(xv[p + kw], w4.z, acc[p][4 * qd + 2]);
+                        acc[p][4 * qd + 3] = fmaf(xv[p + kw], w4.w, acc[p][4 * qd + 3]);
                     }
                 }
-        const int64_t off = (((int64_t)s * n_images + n) * 1024 + p) * 16;
+            }
+        }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int64_t off = (((int64_t)s * n_images + n) * 1024 + h * 32 + w0 + p) * 16;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-            *reinterpret_cast<float4 *>(out_raw + off + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            *reinterpret_cast<float4 *>(out_raw + off + i) = make_float4(acc[p][i], acc[p][i + 1], acc[p][i + 2], acc[p][i + 3]);
             if (out_hi == nullptr) continue;
             float y[4], hv[4], lv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                y[k] = fmaxf(fmaf(bn[i + k], acc[i + k], bn[16 + i + k]), 0.f);
+                y[k] = fmaxf(fmaf(bn[i + k], acc[p][i + k], bn[16 + i + k]), 0.f);
                 hv[k] = rn_tf32(y[k]);
                 lv[k] = rn_tf32(y[k] - hv[k]);
             }
@@ -262,21 +271,42 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
 __global__ void __launch_bounds__(256) shortcut_nhwc_kernel(const float *__restrict__ in, const float *__restrict__ packed,
                                                              int64_t ld_packed, int64_t w_off, int cin, int cout, int hout,
                                                              int n_images, float *__restrict__ out) {
-    __shared__ float ws[32 * 64];
+    // one CTA per (image, sample); work item = (output pixel, group of 16 output channels): the pixel's cin inputs are
+    // read as float4s, the weights [ci][co] come from shared memory as LDS.128
+    __shared__ __align__(16) float ws[32 * 64];
     const int n = blockIdx.x, s = blockIdx.y;
     const float *pk = packed + (int64_t)s * ld_packed + w_off;                    // [ci][co]
     for (int i = threadIdx.x; i < cin * cout; i += 256) ws[i] = __ldg(pk + i);
     __syncthreads();
-    const int hin = hout * 2;
+    const int hin = hout * 2, ngrp = cout >> 4;
     const float *ib = in + ((int64_t)s * n_images + n) * hin * hin * cin;
     float *ob = out + ((int64_t)s * n_images + n) * hout * hout * cout;
-    for (int i = threadIdx.x; i < hout * hout * cout; i += 256) {
-        const int co = i % cout, px = i / cout;
+    for (int item = threadIdx.x; item < hout * hout * ngrp; item += 256) {
+        const int g = item % ngrp, px = item / ngrp;
         const int h = px / hout, w = px - h * hout;
-        const float *ip = ib + ((int64_t)(2 * h) * hin + 2 * w) * cin;
-        float acc = 0.f;
-        for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(ip + ci), ws[ci * cout + co], acc);
-        ob[i] = acc;
+        const float4 *ip = reinterpret_cast<const float4 *>(ib + ((int64_t)(2 * h) * hin + 2 * w) * cin);
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        for (int c4 = 0; c4 < cin / 4; ++c4) {
+            const float4 xv = __ldg(ip + c4);
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 *wp = reinterpret_cast<const float4 *>(ws + (c4 * 4 + j) * cout + g * 16);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 w4 = wp[qd];
+                    acc[4 * qd + 0] = fmaf(xa[j], w4.x, acc[4 * qd + 0]);
+                    acc[4 * qd + 1] = fmaf(xa[j], w4.y, acc[4 * qd + 1]);
+                    acc[4 * qd + 2] = fmaf(xa[j], w4.z, acc[4 * qd + 2]);
+                    acc[4 * qd + 3] = fmaf(xa[j], w4.w, acc[4 * qd + 3]);
+                }
+            }
+        }
+        float4 *op = reinterpret_cast<float4 *>(ob + (int64_t)px * cout + g * 16);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) op[qd] = make_float4(acc[4 * qd], acc[4 * qd + 1], acc[4 * qd + 2], acc[4 * qd + 3]);
     }
 }
 
