@@ -441,7 +441,8 @@ def run_extras(dev, rank, world, peak):
     xi = torch.randn(N, 3, 32, 32, device=dev)
     P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
 
-    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05), ("fused", _C.ALGO_TCGEN05_FUSED)):
+    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05), ("fused", _C.ALGO_TCGEN05_FUSED),
+                            ("fused16", _C.ALGO_TCGEN05_FUSED_F16)):
         def bma_conv():
             P.zero_()
             E.zero_()

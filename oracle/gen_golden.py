@@ -414,16 +414,78 @@ def gen_layouts(R):
     print("layouts.json", {k: v["D"] for k, v in lay.items()})
 
 
+def gen_ood_decision(R):
+    """OODDetection (tasks/ood_detection.py:39-130) and Decision (tasks/decision_making.py:83-152) on fixed weights."""
+    import torchvision
+    out, js = {}, {}
+    # -- OOD: MLP 48-24-10, in-distribution N(0,1), out-of-distribution 3 N(0,1) + 1, two update calls
+    torch.manual_seed(21)
+    S, C = 4, 10
+    xin, xout = torch.randn(300, 1, 6, 8), torch.randn(170, 1, 6, 8) * 3.0 + 1.0
+    lin = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xin, torch.zeros(300, dtype=torch.long)), batch_size=128)
+    lout = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xout, torch.zeros(170, dtype=torch.long)), batch_size=64)
+    ms = []
+    for s in range(S):
+        m = R["models"].mlp.MLP(24, 48, C)
+        for p in m.parameters():
+            p.data.mul_(3.0)
+        ms.append(m)
+    task = R["tasks"].OODDetection({"in_distribution_test": lin, "out_distribution_test": lout}, C, torch.device("cpu"))
+    task.update_statistics(ms[:1], output_performance=False)
+    task.update_statistics(ms[1:], output_performance=False)
+    js["ood"] = {k: float(v) for k, v in task.get_performance_metrics().items()}
+    out["ood/bank"] = np.stack([_flat_params(m) for m in ms])
+    out["ood/arch"] = np.array([24, 48, C])
+    out["ood/x_in"], out["ood/x_out"] = xin.numpy(), xout.numpy()
+    for k in ("in_distribution_ensemble_proba", "out_distribution_ensemble_proba", "in_distribution_data_uncertainty",
+              "out_distribution_data_uncertainty", "in_distribution_total_uncertainty", "out_distribution_total_uncertainty",
+              "in_distribution_model_uncertainty", "out_distribution_model_uncertainty"):
+        out["ood/" + k] = getattr(task, k).numpy().copy()
+    js["ood_single"] = {k: float(v) for k, v in R["tasks"].OODDetection(
+        {"in_distribution_test": lin, "out_distribution_test": lout}, C, torch.device("cpu")).update_statistics(ms[0]).items()}
+    # -- Decision: the cost matrix is chosen by the dataset CLASS (decision_making.py:95-102), so build a torchvision MNIST
+    #    object around synthetic uint8 images without touching the disk
+    torch.manual_seed(22)
+    N = 90
+    ds = torchvision.datasets.MNIST.__new__(torchvision.datasets.MNIST)
+    ds.data = torch.randint(0, 256, (N, 28, 28), dtype=torch.uint8)
+    ds.targets = torch.randint(0, 10, (N,))
+    ds.transform = torchvision.transforms.ToTensor()
+    ds.target_transform = None
+    loader = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=False)
+    ms = []
+    for s in range(3):
+        m = R["models"].mlp.MLP(16, 784, 10)
+        for p in m.parameters():
+            p.data.mul_(2.0)
+        ms.append(m)
+    task = R["tasks"].Decision({"decision_data_test": loader}, 10, torch.device("cpu"))
+    task.update_statistics(ms[:2], output_performance=False)
+    res = task.update_statistics(ms[2:], output_performance=True)
+    out["decision/bank"] = np.stack([_flat_params(m) for m in ms])
+    out["decision/arch"] = np.array([16, 784, 10])
+    out["decision/data_u8"], out["decision/targets"] = ds.data.numpy(), ds.targets.numpy()
+    out["decision/cost_mat"] = task.cost_mat.numpy().copy()
+    out["decision/ensemble_proba"] = task.ensemble_proba.numpy().copy()
+    out["decision/risk"] = task.risk.numpy().copy()
+    out["decision/D"] = res["Decision"].numpy().copy()
+    js["decision"] = {"True_Cost": float(res["True_Cost"]), "num_samples_collected": int(task.num_samples_collected)}
+    for name, fn in (("MNIST", "MNIST_cost"), ("CIFAR10", "CIFAR10_cost"), ("CIFAR100", "CIFAR100_cost")):
+        import URSABench.tasks.decision_making as dm
+        out["cost/" + name] = getattr(dm, fn)(100 if name == "CIFAR100" else 10).numpy()
+    np.savez_compressed(os.path.join(OUT, "ood_decision.npz"), **out)
+    json.dump(js, open(os.path.join(OUT, "ood_decision.json"), "w"), indent=1)
+    print("ood_decision.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
-    gen_sgmcmc_step(R)
-    gen_csghmc_schedule(R)
-    gen_swa_collect(R)
-    gen_swag_compat(R)
-    gen_prediction(R)
-    gen_metrics_edge(R)
-    gen_layouts(R)
+    gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                ood_decision=gen_ood_decision)
+    for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
+        gens[name](R)
 
 
 if __name__ == "__main__":

@@ -409,11 +409,35 @@ def test_prediction_preresnet8_fused_matches_reference_golden(U):
     loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8, shuffle=False)
     task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate", "nll", "brier_score", "ece"])
     task.update_statistics(ms, output_performance=False)
-    assert task.last_engine == "fused_preresnet"
+    assert task.last_engine == "fused_preresnet" and task.last_algo == U._C.ALGO_TCGEN05_FUSED_F16
     np.testing.assert_allclose(task.ensemble_proba.numpy(), g["preresnet8/ensemble_proba"], atol=1e-5, rtol=0)
     m = task.get_performance_metrics()
     for k in m:
         assert m[k] == pytest.approx(ref[k], abs=2e-5, rel=2e-5), k
+
+
+def test_prediction_fp16_range_overflow_is_loud_and_falls_back(U):
+    """Activations beyond the FP16-split engine's range (|act| / 16 > 65504) must never produce finite wrong numbers:
+    the kernel's logits go NaN and Prediction redoes the call on the TF32 engine."""
+    torch.manual_seed(3)
+    ms = [U.models.PreResNet(num_classes=10, depth=8).eval() for _ in range(2)]
+    x = torch.randn(40, 3, 32, 32) * 2e7
+    y = torch.randint(0, 10, (40,))
+    # the raw kernel: NaN, not garbage
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms]).to(DEV)
+    bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms]).to(DEV)
+    P, E = torch.zeros(40, 10, device=DEV), torch.zeros(40, device=DEV)
+    U._C.bma_preresnet_forward(bank, bufs, 2, x.to(DEV), 8, 10, P, E, algo=U._C.ALGO_TCGEN05_FUSED_F16)
+    assert not bool(torch.isfinite(P).all())
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate"])
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_algo == U._C.ALGO_TCGEN05_FUSED
+    proba = task.ensemble_proba
+    assert bool(torch.isfinite(proba).all())
+    with torch.no_grad():
+        ref = torch.stack([torch.softmax(m.double()(x.double()), -1) for m in ms]).sum(0)
+    assert (proba.argmax(1) == ref.argmax(1)).float().mean().item() >= 0.95
 
 
 def test_cuda_graph_step_matches_eager(U, capsys):
@@ -450,3 +474,76 @@ def test_cuda_graph_step_matches_eager(U, capsys):
             inf.train_step(x, y, add_langevin_noise=True)
         outs.append(_flat(inf.model).clone())
     assert (outs[0] - outs[1]).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ OODDetection / Decision
+def _mlp_bank_models(U, g, key):
+    hidden, in_dim, C = (int(v) for v in g[key + "/arch"])
+    ms = []
+    for row in g[key + "/bank"]:
+        m = U.models.MLP(hidden, in_dim, C)
+        torch.nn.utils.vector_to_parameters(torch.from_numpy(row.copy()), m.parameters())
+        ms.append(m)
+    return ms, C
+
+
+@pytest.mark.parametrize("engine", ["auto", "generic"])
+def test_ood_detection_matches_reference_golden(U, engine):
+    """tasks/ood_detection.py:39-130 run by the live reference on the same weights (oracle/gen_golden.py::gen_ood_decision)."""
+    g, ref = _npz("ood_decision.npz"), _json("ood_decision.json")
+    ms, C = _mlp_bank_models(U, g, "ood")
+    xin, xout = torch.from_numpy(g["ood/x_in"]), torch.from_numpy(g["ood/x_out"])
+    lin = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xin, torch.zeros(len(xin), dtype=torch.long)), batch_size=128)
+    lout = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xout, torch.zeros(len(xout), dtype=torch.long)), batch_size=64)
+    task = U.tasks.OODDetection({"in_distribution_test": lin, "out_distribution_test": lout}, C, DEV, engine=engine)
+    task.update_statistics(ms[:1], output_performance=False)            # accumulates across calls
+    m = task.update_statistics(ms[1:], output_performance=True)
+    assert task.num_samples_collected == 4
+    assert task.last_engine == ("fused_mlp" if engine == "auto" else "generic")
+    for k in ("in_distribution_ensemble_proba", "out_distribution_ensemble_proba"):
+        np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=1e-5, rtol=0)
+    for k in ("in_distribution_data_uncertainty", "out_distribution_data_uncertainty", "in_distribution_total_uncertainty",
+              "out_distribution_total_uncertainty"):
+        np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=2e-5, rtol=1e-5)
+    for k in ("in_distribution_model_uncertainty", "out_distribution_model_uncertainty"):
+        np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=2e-5, rtol=0)
+    assert set(m) == set(ref["ood"])
+    for k, v in ref["ood"].items():
+        assert m[k] == pytest.approx(v, abs=2e-3), k                    # rank statistic of N = 470 scores
+    task.reset()
+    assert task.num_samples_collected == 0 and not task.in_distribution_data_uncertainty.any()
+    m1 = task.update_statistics(ms[0])                                  # single module, default output_performance=True
+    for k, v in ref["ood_single"].items():
+        assert m1[k] == pytest.approx(v, abs=2e-3), k
+    with pytest.raises(NotImplementedError):
+        task.update_statistics([1, 2])
+
+
+def test_decision_matches_reference_golden(U):
+    """tasks/decision_making.py:83-152 run by the live reference on a torchvision MNIST object around synthetic images."""
+    import torchvision
+    g, ref = _npz("ood_decision.npz"), _json("ood_decision.json")
+    ms, C = _mlp_bank_models(U, g, "decision")
+    ds = torchvision.datasets.MNIST.__new__(torchvision.datasets.MNIST)
+    ds.data, ds.targets = torch.from_numpy(g["decision/data_u8"]), torch.from_numpy(g["decision/targets"])
+    ds.transform, ds.target_transform = torchvision.transforms.ToTensor(), None
+    loader = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=False)
+    task = U.tasks.Decision({"decision_data_test": loader}, C, DEV)
+    assert np.array_equal(task.cost_mat.numpy(), g["decision/cost_mat"])
+    assert torch.equal(task.targets, ds.targets)
+    task.update_statistics(ms[:2], output_performance=False)
+    res = task.update_statistics(ms[2:], output_performance=True)
+    assert task.num_samples_collected == ref["decision"]["num_samples_collected"] and task.last_engine == "fused_mlp"
+    np.testing.assert_allclose(task.ensemble_proba.numpy(), g["decision/ensemble_proba"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(res["Pred_cost"].numpy(), g["decision/risk"], atol=2e-4, rtol=2e-5)
+    assert np.array_equal(res["Decision"].numpy(), g["decision/D"])
+    assert float(res["True_Cost"]) == pytest.approx(ref["decision"]["True_Cost"], rel=1e-6)
+    task.reset()
+    assert task.num_samples_collected == 0 and not task.ensemble_proba.any()
+    # datasets the reference has no cost matrix for raise like the reference; cost_mat= is the documented extension
+    tl = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.randn(8, 784), torch.zeros(8, dtype=torch.long)), batch_size=4)
+    with pytest.raises(NotImplementedError):
+        U.tasks.Decision({"decision_data_test": tl}, C, DEV)
+    t2 = U.tasks.Decision({"decision_data_test": tl}, C, DEV, cost_mat=U.tasks.decision_making.CIFAR10_cost(C))
+    out = t2.update_statistics(ms[0])
+    assert out["Decision"].shape == (8,) and out["Pred_cost"].shape == (8, C)

@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import restate as R
 
@@ -308,3 +309,22 @@ def test_hmc_restatement_samples_gaussian_prior():
     assert len(ret) == n_it * 10 + 1 and np.mean(acc) > 0.9
     s = np.stack(ret[50 * 10::10])
     assert abs(s.var() - 1 / tau) < 0.03
+
+
+def test_decision_cost_matrices_match_reference():
+    """tasks/decision_making.py:12-51: the three cost matrices, dumped from the live reference."""
+    from ursabench_b200.tasks import decision_making as dm
+    g = np.load(os.path.join(GOLD, "ood_decision.npz"))
+    for name, fn, C in (("MNIST", dm.MNIST_cost, 10), ("CIFAR10", dm.CIFAR10_cost, 10), ("CIFAR100", dm.CIFAR100_cost, 100)):
+        assert np.array_equal(fn(C).numpy(), g["cost/" + name]), name
+    y, D = torch.tensor([3, 0, 7]), torch.tensor([3, 1, 0])
+    assert float(dm.decision_cost(D, y, dm.MNIST_cost(10))) == pytest.approx(100.1)
+
+
+def test_ood_golden_is_self_consistent():
+    """The smoothed-probability sum the reference accumulates is the affine image of the unsmoothed one -- the identity
+    OODDetection / Decision rely on (sum_s p~_s = (1-g) sum_s p_s + S g / C): rows sum to S."""
+    g = np.load(os.path.join(GOLD, "ood_decision.npz"))
+    np.testing.assert_allclose(g["ood/in_distribution_ensemble_proba"].sum(1), 4.0, rtol=2e-6)
+    np.testing.assert_allclose(g["decision/ensemble_proba"].sum(1), 3.0, rtol=2e-6)
+    np.testing.assert_allclose(g["decision/risk"], g["decision/ensemble_proba"] @ g["decision/cost_mat"], rtol=2e-5, atol=1e-4)

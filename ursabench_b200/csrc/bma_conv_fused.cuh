@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
                         float y[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            y[j] = fmaxf(fmaf(bn_s[ch0 + i + j], rin[t][i + j], bn_s[C + ch0 + i + j]), 0.f);
+                            y[j] = relu_nan(fmaf(bn_s[ch0 + i + j], rin[t][i + j], bn_s[C + ch0 + i + j]));
                         float4 hv, lv;
                         split4(y, hv, lv);
                         *reinterpret_cast<float4 *>(gen_base + plane_off(t, i)) = hv;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) preresnet_stage_kernel(const
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float x = v[i + j];
-                            if (has_bn) x = fmaxf(fmaf(bn[ch0 + i + j], x, bn[C + ch0 + i + j]), 0.f);
+                            if (has_bn) x = relu_nan(fmaf(bn[ch0 + i + j], x, bn[C + ch0 + i + j]));
                             y[j] = x;
                         }
                         float4 hv, lv;

@@ -384,10 +384,10 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                             b4 = *reinterpret_cast<const float4 *>(bn + C + ch0 + c0 + i);
                         }
                         // a_in activations are >= 0 already: relu(a x + 0) with a = 1/16 is the plain rescale
-                        y[i] = fmaxf(fmaf(a4.x, R[j][c0 + i], b4.x), 0.f);
-                        y[i + 1] = fmaxf(fmaf(a4.y, R[j][c0 + i + 1], b4.y), 0.f);
-                        y[i + 2] = fmaxf(fmaf(a4.z, R[j][c0 + i + 2], b4.z), 0.f);
-                        y[i + 3] = fmaxf(fmaf(a4.w, R[j][c0 + i + 3], b4.w), 0.f);
+                        y[i] = relu_nan(fmaf(a4.x, R[j][c0 + i], b4.x));
+                        y[i + 1] = relu_nan(fmaf(a4.y, R[j][c0 + i + 1], b4.y));
+                        y[i + 2] = relu_nan(fmaf(a4.z, R[j][c0 + i + 2], b4.z));
+                        y[i + 3] = relu_nan(fmaf(a4.w, R[j][c0 + i + 3], b4.w));
                     }
                     store_planes16(t, c0, y);
                 }
@@ -466,10 +466,10 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
 #pragma unroll
                                 for (int i = 0; i < 16; i += 4) {
                                     const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
-                                    y[i] = fmaxf(fmaf(a4.x, x[i], b4.x), 0.f);
-                                    y[i + 1] = fmaxf(fmaf(a4.y, x[i + 1], b4.y), 0.f);
-                                    y[i + 2] = fmaxf(fmaf(a4.z, x[i + 2], b4.z), 0.f);
-                                    y[i + 3] = fmaxf(fmaf(a4.w, x[i + 3], b4.w), 0.f);
+                                    y[i] = relu_nan(fmaf(a4.x, x[i], b4.x));
+                                    y[i + 1] = relu_nan(fmaf(a4.y, x[i + 1], b4.y));
+                                    y[i + 2] = relu_nan(fmaf(a4.z, x[i + 2], b4.z));
+                                    y[i + 3] = relu_nan(fmaf(a4.w, x[i + 3], b4.w));
                                 }
                                 store_planes16(t, c0, y);
                             }
@@ -486,10 +486,10 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                 for (int i = 0; i < 16; i += 4) {
                                     const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
                                     float y[4];                     // bn entry is in the /16 domain (mode 1): undo
-                                    y[0] = fmaxf(fmaf(a4.x, x[i], b4.x), 0.f) * kActUp;
-                                    y[1] = fmaxf(fmaf(a4.y, x[i + 1], b4.y), 0.f) * kActUp;
-                                    y[2] = fmaxf(fmaf(a4.z, x[i + 2], b4.z), 0.f) * kActUp;
-                                    y[3] = fmaxf(fmaf(a4.w, x[i + 3], b4.w), 0.f) * kActUp;
+                                    y[0] = relu_nan(fmaf(a4.x, x[i], b4.x)) * kActUp;
+                                    y[1] = relu_nan(fmaf(a4.y, x[i + 1], b4.y)) * kActUp;
+                                    y[2] = relu_nan(fmaf(a4.z, x[i + 2], b4.z)) * kActUp;
+                                    y[3] = relu_nan(fmaf(a4.w, x[i + 3], b4.w)) * kActUp;
                                     float4 hv, lv;
                                     split4(y, hv, lv);
                                     reinterpret_cast<float4 *>(a.a_out_hi + goff[j] + c0)[i >> 2] = hv;

@@ -173,7 +173,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float t = v[i + j];
-                        if (has_bn) t = fmaxf(fmaf(bn_s[c0 + i + j], t, bn_s[a.cout + c0 + i + j]), 0.f);
+                        if (has_bn) t = relu_nan(fmaf(bn_s[c0 + i + j], t, bn_s[a.cout + c0 + i + j]));
                         y[j] = t;
                     }
                     if (a.out_lo == nullptr) {          // plain fp32 activations (consumer splits them itself)
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
             float y[4], hv[4], lv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                y[k] = fmaxf(fmaf(bn[i + k], acc[p][i + k], bn[16 + i + k]), 0.f);
+                y[k] = relu_nan(fmaf(bn[i + k], acc[p][i + k], bn[16 + i + k]));
                 hv[k] = rn_tf32(y[k]);
                 lv[k] = rn_tf32(y[k] - hv[k]);
             }
@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(256) head_nhwc_kernel(const float *__restrict_
     const float a1 = __ldg(pk + bn_off + 32 + lane), b1 = __ldg(pk + bn_off + 96 + lane);
     float f0 = 0.f, f1 = 0.f;
     for (int px = 0; px < 64; ++px) {
-        f0 += fmaxf(fmaf(a0, __ldg(x + px * 64 + lane), b0), 0.f);
-        f1 += fmaxf(fmaf(a1, __ldg(x + px * 64 + 32 + lane), b1), 0.f);
+        f0 += relu_nan(fmaf(a0, __ldg(x + px * 64 + lane), b0));
+        f1 += relu_nan(fmaf(a1, __ldg(x + px * 64 + 32 + lane), b1));
     }
     feat_s[warp][lane] = f0 * (1.f / 64.f);
     feat_s[warp][32 + lane] = f1 * (1.f / 64.f);

@@ -51,6 +51,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ReLU that PROPAGATES NaN: fmaxf(NaN, 0) = 0 would turn an FP16 range overflow (inf - inf = NaN in the accumulators of the
+// FP16-split stage kernels) into silently wrong, finite activations.  max.NaN returns NaN if either operand is NaN.
+__device__ __forceinline__ float relu_nan(float x) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rn_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
