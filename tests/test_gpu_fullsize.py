@@ -1,0 +1,142 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle only runs at small sizes):
+WideResNet-28-10 flat vectors (D = 36 546 980, configs[2]) for K1 / K2 and S = 100 PreResNet-20 samples on N = 10 000
+images (configs[4]) for K3 / K4.  Everything goes through the C ABI."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+D_WRN = 36_546_980
+
+
+@pytest.fixture(scope="module")
+def C():
+    from ursabench_b200 import _C
+    _C.lib()
+    return _C
+
+
+def test_k1_full_size_identity_linearity_and_noise_moments(C):
+    ld = (D_WRN + 3) // 4 * 4
+    torch.manual_seed(0)
+    p0 = torch.randn(ld, device="cuda")
+    g = torch.randn(ld, device="cuda")
+    # (1) zero gradient, no weight decay, no noise: parameters come back bit-identical, momentum stays zero
+    p, v = p0.clone(), torch.zeros(ld, device="cuda")
+    C.sgmcmc_step(p, torch.zeros_like(g), v, lr=0.1, momentum=0.5, wd_over_n=0.0, add_noise=False)
+    assert torch.equal(p, p0) and not v.any()
+    # (2) SGLD drift against the formula evaluated by torch in fp64 (optim_sghmc.py:47-65): p - lr (g + wd p)
+    p = p0.clone()
+    C.sgmcmc_step(p, g.clone(), None, lr=0.01, momentum=0.0, wd_over_n=1e-3, add_noise=False)
+    ref = p0.double() - 0.01 * (g.double() + 1e-3 * p0.double())
+    assert (p.double() - ref).abs().max().item() < 2e-6
+    del ref
+    # (3) linearity in the noise scale: (p(2s) - p(0)) == 2 (p(s) - p(0)) for the same Philox stream, and the injected
+    #     noise has unit variance / zero mean / zero skew over 36.5 M draws
+    outs = []
+    for mul in (0.0, 1.0, 2.0):
+        q = p0.clone()
+        C.sgmcmc_step(q, torch.zeros_like(g), None, lr=1.0, momentum=0.0, wd_over_n=0.0, noise_mul=mul, noise_div=1.0,
+                      add_noise=mul > 0, seed=7, step=3)
+        outs.append(q)
+    z1, z2 = outs[1] - outs[0], outs[2] - outs[0]
+    assert (z2 - 2 * z1).abs().max().item() < 1e-5
+    z = z1[:D_WRN].double()
+    n = z.numel()
+    assert abs(z.mean().item()) < 5 / math.sqrt(n)
+    assert abs(z.var().item() - 1) < 2e-3
+    assert abs((z ** 3).mean().item()) < 5e-3 and abs((z ** 4).mean().item() - 3) < 2e-2
+
+
+def test_k2_full_size_collect_fixed_point_and_draw_contraction(C):
+    D, K, S = D_WRN, 20, 30
+    ld = (D + 3) // 4 * 4
+    torch.manual_seed(1)
+    w = torch.randn(ld, device="cuda") * 0.05
+    mean, sq = torch.zeros(ld, device="cuda"), torch.zeros(ld, device="cuda")
+    ring = torch.empty(K, ld, device="cuda")
+    # collecting the same iterate n times is a fixed point: mean == w, sq_mean == w^2, every deviation row == 0
+    # (n = 0: mean = w / 1 exactly; later mean * n/(n+1) + w/(n+1) rounds back to within 1 ulp)
+    for n in range(3):
+        C.swag_collect(w, mean, sq, ring[n], n)
+    assert (mean - w).abs().max().item() <= 1e-8 + 2e-7 * w.abs().max().item()
+    assert (sq - w * w).abs().max().item() <= 1e-9 + 5e-7 * (w * w).max().item()
+    assert ring[0].abs().max().item() == 0.0 and ring[2].abs().max().item() < 1e-7
+    var = torch.empty(ld, device="cuda")
+    C.swag_variance(mean, sq, var, clamp=1e-30)
+    assert var.min().item() >= 1e-30 and var.max().item() < 1e-7          # clamp(sq - mean^2): rounding noise only
+    # draw with var = 0: out[s] = mean + ring^T z2[s] / sqrt(K-1) exactly; unit vectors z2 pick single ring rows, so the
+    # tensor-core contraction (3xTF32) is checked against the ring itself at full size, ragged last tile included
+    ring.normal_(0, 0.02)
+    var.zero_()
+    z2 = torch.zeros(S, K, device="cuda")
+    for s in range(S):
+        z2[s, s % K] = 1.0 + s                                            # scaled unit vectors
+    out = torch.empty(S, ld, device="cuda")
+    rd = math.sqrt(K - 1.0)
+    C.swag_draw(out, mean, var, D, ring=ring, z2=z2, rank_div=rd, seed=3, step=1)
+    worst = 0.0
+    for s in (0, 7, 19, 20, 29):
+        ref = mean[:D].double() + ring[s % K, :D].double() * ((1.0 + s) / rd)
+        worst = max(worst, (out[s, :D].double() - ref).abs().max().item())
+    assert worst < 1e-6, worst                                            # fp32-level: |term| <= 4 sigma * 0.02 * 30 / 4.4
+    # Philox z1 with K = 0 and unit variance: out - mean is the documented N(0,1) stream, row s starts at block s*ld/4
+    var.fill_(1.0)
+    out2 = torch.empty(2, ld, device="cuda")
+    C.swag_draw(out2, mean, var, D, seed=9, step=4)
+    zs = torch.empty(2 * ld, device="cuda")
+    C.philox_normal(zs, 9, 4)
+    assert (out2[:, :D] - mean[None, :D] - zs.view(2, ld)[:, :D]).abs().max().item() < 1e-6
+
+
+def test_k3_k4_full_size_bma_sharding_and_counters(C):
+    """S = 100 PreResNet-20 samples on N = 10 000 images: evaluating two halves of the samples separately and adding the
+    accumulators (what ranks do before the all-reduce) equals evaluating all of them; rows of the probability sum add up
+    to S; the K4 counters agree with torch on the same probabilities."""
+    from ursabench_b200 import models
+    S, N = 100, 10_000
+    torch.manual_seed(2)
+    m = models.PreResNet(num_classes=10, depth=20)
+    flat = torch.cat([q.detach().reshape(-1) for q in m.parameters()]).cuda()
+    bank = (flat[None, :] + 0.02 * torch.randn(S, flat.numel(), device="cuda")).contiguous()
+    nbuf = sum(b.numel() for b in m.buffers() if b.dtype == torch.float32)
+    bufs = torch.zeros(S, (nbuf + 3) // 4 * 4, device="cuda")
+    off = 0
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            c = mod.num_features
+            bufs[:, off + c:off + 2 * c] = 1.0
+            off += 2 * c
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (N,), device="cuda")
+    algo = C.ALGO_TCGEN05_FUSED_F16
+    P, E = torch.zeros(N, 10, device="cuda"), torch.zeros(N, device="cuda")
+    ws = C.bma_preresnet_forward(bank, bufs, S, x, 20, 10, P, E, algo=algo)
+    Pa, Ea = torch.zeros_like(P), torch.zeros_like(E)
+    ws = C.bma_preresnet_forward(bank[:37], bufs[:37], 37, x, 20, 10, Pa, Ea, algo=algo, workspace=ws)
+    C.bma_preresnet_forward(bank[37:], bufs[37:], 63, x, 20, 10, Pa, Ea, algo=algo, workspace=ws)
+    assert bool(torch.isfinite(P).all())
+    assert (P - Pa).abs().max().item() / S < 1e-6 and (E - Ea).abs().max().item() / S < 1e-5
+    assert (P.sum(1) - S).abs().max().item() < 2e-4
+    # spot check against the plain PyTorch fp32 forward of 3 samples on 256 images
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        ref = torch.zeros(256, 10, device="cuda", dtype=torch.float64)
+        for s in (0, 50, 99):
+            mm = models.PreResNet(num_classes=10, depth=20).cuda().eval()
+            torch.nn.utils.vector_to_parameters(bank[s], mm.parameters())
+            ref += torch.softmax(mm(x[:256]).double(), -1)
+    P3, E3 = torch.zeros(256, 10, device="cuda"), torch.zeros(256, device="cuda")
+    idx = torch.tensor([0, 50, 99], device="cuda")
+    C.bma_preresnet_forward(bank[idx].contiguous(), bufs[idx].contiguous(), 3, x[:256].contiguous(), 20, 10, P3, E3, algo=algo)
+    assert (P3.double() - ref).abs().max().item() / 3 < 1e-5                         # north star
+    # K4 on the full [N, C]: integer counters are exact
+    oi, of, pred, conf = C.bma_metrics(P, S, y, want_rows=True)
+    pbar = P / np.float32(S)
+    assert torch.equal(pred.long(), pbar.argmax(1))
+    assert int(oi[0]) == int((pbar.argmax(1) == y).sum())
+    cnt = oi[1:16]
+    assert int(cnt.sum()) == N                                                       # every confidence falls in one bin
+    nll = -torch.log((1 - 1e-4) * pbar.double().gather(1, y[:, None]) + 1e-4 / 10).sum().item()
+    assert float(of[0]) == pytest.approx(nll, rel=1e-6)
