@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                     mbar_wait_warp(smem_u32(&acc_full[t + 1 < T ? t + 1 : T - 1]), item & 1u);   // in-order commits: tile t too
                     tc_fence_after();
                     const uint32_t tcol = t_lane + (uint32_t)(t * Cfg::TILE_COLS);
+                    const int32_t gnext = has_next ? goff_of(np, j) : -1;
 #pragma unroll
                     for (int c0 = 0; c0 < CPT; c0 += 16) {
                         uint32_t ra[16], rl[16];
@@ -473,7 +474,19 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                 }
                                 store_planes16(t, c0, y);
                             }
-                        } else if (goff[j] >= 0) {
+                        } else {
+                          if (has_next) {
+                            // R[j][c0 ..] is dead (x holds it): start fetching the next pass's prologue source for this chunk
+                            // BEFORE this tile's output stores enter the memory pipeline
+                            const float *src = from_r ? a.r_in : a.a_in_hi;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (gnext >= 0) v4 = __ldg(reinterpret_cast<const float4 *>(src + gnext + c0 + i));
+                                R[j][c0 + i] = v4.x; R[j][c0 + i + 1] = v4.y; R[j][c0 + i + 2] = v4.z; R[j][c0 + i + 3] = v4.w;
+                            }
+                          }
+                          if (goff[j] >= 0) {
                             if (mode == 0) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) x[i] *= kActUp;
@@ -496,6 +509,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                     reinterpret_cast<float4 *>(a.a_out_lo + goff[j] + c0)[i >> 2] = lv;
                                 }
                             }
+                          }
                         }
                     }
                     if (!last) {
@@ -505,8 +519,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                         if (has_next) {
                             // R[j] is dead and tile t's planes are free (tile t+1's MMAs are complete): the next pass's prologue
                             // for this tile joins the wavefront right here, under the MMAs of the remaining tiles
-                            goff[j] = goff_of(np, j);
-                            load_rows(from_r ? a.r_in : a.a_in_hi, goff[j], R[j]);
+                            goff[j] = gnext;
                             prologue_tile(j, t, bn_all + (buf ^ 1) * BNF);
                         }
                     }
