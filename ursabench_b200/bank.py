@@ -63,6 +63,10 @@ class SampleBank:
     def handle(self, i):
         return BankedSample(self, i)
 
+    def handles(self):
+        """``BankedSample`` handles of rows [0, count): the list ``sample()`` returns / ``update_statistics`` takes."""
+        return [BankedSample(self, i) for i in range(self.count)]
+
     def rows(self, idx):
         """(w [n, ld], b [n, ldb]) for a list of row indices; a view when the indices are one contiguous run."""
         if len(idx) and idx == list(range(idx[0], idx[0] + len(idx))):
@@ -97,6 +101,99 @@ class SampleBank:
         bank.w[:len(models)].copy_(stage_w, non_blocking=True)
         bank.b[:len(models)].copy_(stage_b)
         bank.count = len(models)
+        return bank
+
+    # ---- on-disk wire format ---------------------------------------------------------------------
+    # The reference's interchange format is one ``state_dict`` pickle per sample (``sghmc_sample_%d.pt``,
+    # experiment.py:77-80; read back one file at a time by trtprof/run_prediction.py:50-57,218-221).  Here an ensemble
+    # is ONE file: the unpadded ``[S, D]`` weight matrix, the ``[S, nb]`` float-buffer matrix and a layout descriptor
+    # (names / shapes / offsets in ``parameters()`` / ``buffers()`` order) that lets a reader rebuild per-sample
+    # ``state_dict``s without this package.
+    FORMAT = "ursa_b200.sample_bank"
+    VERSION = 1
+
+    def layout(self):
+        """Layout descriptor of one row (None without a skeleton): parameter and float-buffer names, shapes, offsets."""
+        if self.skeleton is None:
+            return None
+        params, off = [], 0
+        for name, p in self.skeleton.named_parameters():
+            params.append({"name": name, "shape": list(p.shape), "offset": off})
+            off += p.numel()
+        bufs, off = [], 0
+        for name, b in self.skeleton.named_buffers():
+            if b.dtype == torch.float32:
+                bufs.append({"name": name, "shape": list(b.shape), "offset": off})
+                off += b.numel()
+        return {"params": params, "buffers": bufs}
+
+    def save(self, path):
+        """Write rows [0, count) as one file (one D2H copy of the two matrices)."""
+        n = self.count
+        torch.save({"format": self.FORMAT, "version": self.VERSION, "D": self.D, "nb": self.nb, "count": n,
+                    "w": self.w[:n, :self.D].detach().cpu().contiguous(),
+                    "b": self.b[:n, :self.nb].detach().cpu().contiguous(),
+                    "layout": self.layout()}, path)
+
+    @classmethod
+    def load(cls, path, device, skeleton=None):
+        """Read a bank file back onto ``device``.  ``skeleton`` (a CPU module of the same architecture) is checked
+        against the stored layout and enables lazy materialisation of ``BankedSample`` handles."""
+        blob = torch.load(path, map_location="cpu", weights_only=True)
+        if not isinstance(blob, dict) or blob.get("format") != cls.FORMAT:
+            raise ValueError("%s is not a %s file" % (path, cls.FORMAT))
+        if blob["version"] > cls.VERSION:
+            raise ValueError("%s: bank format version %d is newer than this reader (%d)" % (path, blob["version"], cls.VERSION))
+        D, nb, n = int(blob["D"]), int(blob["nb"]), int(blob["count"])
+        w, b = blob["w"], blob["b"]
+        if tuple(w.shape) != (n, D) or tuple(b.shape) != (n, nb) or w.dtype != torch.float32:
+            raise ValueError("%s: matrix shapes do not match the header" % path)
+        bank = cls(D, nb, device, capacity=n, skeleton=skeleton)
+        if skeleton is not None and blob["layout"] is not None and bank.layout() != blob["layout"]:
+            raise ValueError("%s: stored layout does not match the skeleton module" % path)
+        bank.w[:n, :D].copy_(w)
+        if nb:
+            bank.b[:n, :nb].copy_(b)
+        bank.count = n
+        return bank
+
+    def state_dict_of(self, i):
+        """Per-sample ``state_dict`` on the CPU in the reference's format (what ``torch.save(model.state_dict())`` writes)."""
+        if self.skeleton is None:
+            raise RuntimeError("this bank has no module skeleton to name its tensors")
+        if not 0 <= i < self.count:
+            raise IndexError(i)
+        sd = copy.deepcopy(self.skeleton.state_dict())
+        lay = self.layout()
+        w, b = self.w[i].cpu(), self.b[i].cpu()
+        for group, row in ((lay["params"], w), (lay["buffers"], b)):
+            for e in group:
+                if e["name"] in sd:          # non-persistent buffers are not part of a state_dict
+                    n = 1
+                    for d in e["shape"]:
+                        n *= d
+                    sd[e["name"]] = row[e["offset"]:e["offset"] + n].view(e["shape"]).clone()
+        return sd
+
+    def export_state_dicts(self, pattern):
+        """Write one reference-style ``.pt`` per sample; ``pattern`` holds one ``%d`` (e.g. ``'run/sghmc_sample_%d.pt'``)."""
+        paths = []
+        for i in range(self.count):
+            path = pattern % i
+            torch.save(self.state_dict_of(i), path)
+            paths.append(path)
+        return paths
+
+    @classmethod
+    def from_state_dict_files(cls, paths, skeleton, device):
+        """Pack reference-style per-sample ``state_dict`` files into a bank (the reverse of ``export_state_dicts``)."""
+        models = []
+        for path in paths:
+            m = copy.deepcopy(skeleton)
+            m.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
+            models.append(m)
+        bank = cls.from_modules(models, device)
+        bank.skeleton = copy.deepcopy(skeleton).cpu()
         return bank
 
 
