@@ -182,6 +182,20 @@ int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *
                                void *workspace, size_t workspace_bytes, int algo, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K3  BMA forward, WideResNet (WRN-depth-widen, WideBasic blocks, biased convs, stride on conv2;
+ *     models/wideresnet.py:78-120 -- BASELINE.json configs[2] is WRN-28-10 with C = 100).
+ *     depth = 6n+4 (n <= 8), widen even in [2, 16].  bank / bufbank / x as for the PreResNet entry point.
+ *     One posterior sample at a time over chunks of images; every 3x3 conv (and the 1x1 shortcut convs,
+ *     folded into conv2's K loop) runs as a persistent 3xTF32 tcgen05 implicit GEMM.  algo must be
+ *     URSA_ALGO_TCGEN05; the workspace query returns 0 for an unsupported shape.
+ * ---------------------------------------------------------------------- */
+size_t ursa_bma_wrn_workspace(int S, int64_t N, int depth, int widen, int C, int algo);
+int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf,
+                         int S, const float *x, int64_t N, int depth, int widen, int C,
+                         float *proba_sum, float *entropy_sum, float *logits_out, double gamma,
+                         void *workspace, size_t workspace_bytes, int algo, void *stream);
+
+/* ------------------------------------------------------------------------
  * K5  chain-batched HMC  (replaces the call into hamiltorch.sample_model made by HMC.sample,
  *     inference/hmc.py:62-85.  hamiltorch is a third-party dependency that is NOT vendored in the reference
  *     (unpinned git HEAD, util.py:11) -- these entry points follow its published leapfrog / Metropolis algorithm as

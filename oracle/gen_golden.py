@@ -332,6 +332,42 @@ def gen_prediction(R):
     print("prediction.npz")
 
 
+def gen_prediction_wrn(R):
+    """Prediction.update_statistics on the reference WideResNet (WRN-10-2: every block is a transition block with a folded
+    1x1 shortcut; WRN-16-2: identity blocks too).  Weights come from oracle/wrn_fill.py (seeded), so only x and the
+    reference's outputs are stored."""
+    import warnings
+    from oracle.wrn_fill import wrn_fill
+    Prediction = R["tasks"].Prediction
+    out, metric_json = {}, {}
+    for tag, depth, widen, C, S, N, seed, gain in (("wrn10x2", 10, 2, 10, 2, 11, 100, 1.0), ("wrn16x2", 16, 2, 100, 2, 5, 200, 0.25)):
+        rng = np.random.RandomState(seed + 50)
+        x16 = rng.randn(N, 3, 32, 32).astype(np.float16)
+        x = torch.from_numpy(x16.astype(np.float32))
+        y = torch.from_numpy(rng.randint(0, C, N))
+        ms = []
+        for s in range(S):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m = R["models"].wideresnet.WideResNet(num_classes=C, depth=depth, widen_factor=widen)
+            ms.append(wrn_fill(m, seed + s, logit_gain=gain))
+        loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=4, shuffle=False)
+        task = Prediction({"in_distribution_test": loader}, C, torch.device("cpu"), "ALL")
+        task.update_statistics(ms, output_performance=False)
+        metric_json[tag] = {k: float(v) for k, v in task.get_performance_metrics().items()}
+        out[tag + "/x"], out[tag + "/y"] = x16, y.numpy()
+        out[tag + "/arch"] = np.array([depth, widen, C, S, seed])
+        out[tag + "/gain"] = np.array([gain])
+        out[tag + "/ensemble_proba"] = task.ensemble_proba.numpy().copy()
+        out[tag + "/entropy"] = task.expected_data_uncertainty.numpy().copy()
+        with torch.no_grad():
+            out[tag + "/logits"] = torch.stack([m.eval()(x) for m in ms]).numpy()
+        out[tag + "/D"] = np.array([sum(p.numel() for p in ms[0].parameters())])
+    np.savez_compressed(os.path.join(OUT, "prediction_wrn.npz"), **out)
+    json.dump(metric_json, open(os.path.join(OUT, "prediction_wrn_metrics.json"), "w"), indent=1)
+    print("prediction_wrn.npz", {k: v for k, v in metric_json.items()})
+
+
 def gen_metrics_edge(R):
     """get_performance_metrics / _get_ece / _get_brier on crafted probabilities: confidences exactly on bin
     edges, argmax ties, one-hot rows, C = 2..100."""
@@ -482,7 +518,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

@@ -1,0 +1,120 @@
+"""WideResNet BMA forward (BASELINE.json configs[2]: SWAG on WRN-28-10, 30 draws + BMA eval).
+
+CPU: the seeded fill on ``ursabench_b200.models.WideResNet`` reproduces the live reference's logits stored in
+tests/golden/prediction_wrn.npz -- this pins parameter / buffer order (the flat bank layout) and the forward definition.
+GPU: ``ursa_bma_wrn_forward`` (persistent 3xTF32 tcgen05 implicit GEMM, 1x1 shortcuts folded into conv2's K loop) against
+that golden and against a plain PyTorch fp32 forward at widths with several output-channel tiles; ``Prediction`` routes
+WideResNet banks through it."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.wrn_fill import wrn_fill
+from ursabench_b200.models import WideResNet
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "prediction_wrn.npz")
+
+
+def _models(g, tag):
+    depth, widen, C, S, seed = (int(v) for v in g[tag + "/arch"])
+    gain = float(g[tag + "/gain"][0])
+    ms = [wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), seed + s, logit_gain=gain).eval() for s in range(S)]
+    return ms, depth, widen, C, S
+
+
+def _bank(ms, device):
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms]).to(device)
+    bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms]).to(device)
+    pad = (-bank.shape[1]) % 4
+    if pad:
+        bank = torch.nn.functional.pad(bank, (0, pad))
+    return bank.contiguous(), bufs.contiguous()
+
+
+@pytest.mark.parametrize("tag", ["wrn10x2", "wrn16x2"])
+def test_seeded_fill_reproduces_reference_logits_cpu(tag):
+    g = np.load(GOLD)
+    ms, depth, widen, C, S = _models(g, tag)
+    assert sum(p.numel() for p in ms[0].parameters()) == int(g[tag + "/D"][0])
+    x = torch.from_numpy(g[tag + "/x"].astype(np.float32))
+    with torch.no_grad():
+        logits = torch.stack([m(x) for m in ms]).numpy()
+    np.testing.assert_allclose(logits, g[tag + "/logits"], atol=2e-5, rtol=1e-5)
+    p = torch.softmax(torch.from_numpy(logits), -1).sum(0).numpy()
+    np.testing.assert_allclose(p, g[tag + "/ensemble_proba"], atol=1e-6)
+
+
+def test_wrn_workspace_query_rejects_unsupported_shapes():
+    from ursabench_b200 import _C
+    lib = _C.lib()
+    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_TCGEN05) > 0
+    assert lib.ursa_bma_wrn_workspace(1, 16, 10, 2, 10, _C.ALGO_TCGEN05) > 0
+    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_FFMA) == 0        # tcgen05 engine only
+    assert lib.ursa_bma_wrn_workspace(1, 16, 27, 10, 100, _C.ALGO_TCGEN05) == 0     # depth != 6n+4
+    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 3, 100, _C.ALGO_TCGEN05) == 0      # odd widen factor: widths % 32 != 0
+    assert lib.ursa_bma_wrn_workspace(0, 16, 28, 10, 100, _C.ALGO_TCGEN05) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["wrn10x2", "wrn16x2"])
+def test_k3_wrn_forward_matches_reference_golden(tag):
+    from ursabench_b200 import _C
+    g = np.load(GOLD)
+    ms, depth, widen, C, S = _models(g, tag)
+    bank, bufs = _bank(ms, "cuda")
+    x = torch.from_numpy(g[tag + "/x"].astype(np.float32)).cuda()
+    N = x.shape[0]
+    P, E = torch.zeros(N, C, device="cuda"), torch.zeros(N, device="cuda")
+    logits = torch.empty(S, N, C, device="cuda")
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, logits_out=logits)
+    torch.cuda.synchronize()
+    ref = g[tag + "/logits"]
+    err = np.abs(logits.cpu().numpy() - ref).max()
+    assert err < 1e-4 * max(1.0, np.abs(ref).max()), err
+    np.testing.assert_allclose(P.cpu().numpy(), g[tag + "/ensemble_proba"], atol=1e-5, rtol=0)      # north star: 1e-5
+    np.testing.assert_allclose(E.cpu().numpy(), g[tag + "/entropy"], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth,widen,S,N,Cc", [(10, 10, 2, 9, 100), (16, 4, 2, 6, 10), (10, 6, 1, 515, 10), (10, 2, 3, 1, 10)])
+def test_k3_wrn_forward_vs_torch_fp32(depth, widen, S, N, Cc):
+    """Widths with 1 / 2 / 4 output-channel tiles (widen 10: 160 / 320 / 640), identity and transition blocks, an odd image
+    count (the 8x8 tiles pair two images), N = 1, and N > 512 (image chunking) against PyTorch fp32 (TF32 off)."""
+    from ursabench_b200 import _C
+    ms = [wrn_fill(WideResNet(num_classes=Cc, depth=depth, widen_factor=widen), 7 * depth + widen + s, logit_gain=0.5).cuda().eval()
+          for s in range(S)]
+    bank, bufs = _bank(ms, "cuda")
+    torch.manual_seed(N)
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
+    logits = torch.empty(S, N, Cc, device="cuda")
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, Cc, P, E, logits_out=logits)
+    torch.cuda.synchronize()
+    mm = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            ref = torch.cat([torch.stack([m(x[i:i + 128]) for m in ms]) for i in range(0, N, 128)], 1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = mm
+    scale = max(1.0, ref.abs().max().item())
+    assert (logits - ref).abs().max().item() < 1e-4 * scale
+    pbar = torch.softmax(ref.double(), -1).mean(0)
+    assert (P.double() / S - pbar).abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_prediction_routes_wideresnet_through_the_tcgen05_engine():
+    from ursabench_b200.tasks import Prediction
+    g = np.load(GOLD)
+    ms, depth, widen, C, S = _models(g, "wrn10x2")
+    x = torch.from_numpy(g["wrn10x2/x"].astype(np.float32))
+    y = torch.from_numpy(g["wrn10x2/y"])
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=4, shuffle=False)
+    task = Prediction({"in_distribution_test": loader}, C, torch.device("cuda"), "ALL")
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_engine == "fused_wrn"
+    np.testing.assert_allclose(task.ensemble_proba.cpu().numpy(), g["wrn10x2/ensemble_proba"], atol=1e-5, rtol=0)

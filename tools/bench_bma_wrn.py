@@ -1,0 +1,80 @@
+"""WRN BMA forward timing on one GPU: python tools/bench_bma_wrn.py [depth widen C S N] [--ref]
+Prints one JSON line: ms, img*samples/s, fp32-equivalent TFLOP/s (2*MAC of convs + linear), and with --ref the
+per-sample PyTorch fp32 forward (cuDNN, TF32 off = the generic engine this kernel replaces) beside it."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.wrn_fill import wrn_fill  # noqa: E402
+from ursabench_b200 import _C  # noqa: E402
+from ursabench_b200.models import WideResNet  # noqa: E402
+
+
+def wrn_flops(depth, widen):
+    n = (depth - 4) // 6
+    w = [16, 16 * widen, 32 * widen, 64 * widen]
+    fl = 2 * 1024 * 27 * 16
+    inp, hw = 16, 32
+    for g, stride in enumerate((1, 2, 2)):
+        for b in range(n):
+            s = stride if b == 0 else 1
+            cout = w[g + 1]
+            fl += 2 * hw * hw * 9 * inp * cout
+            ho = hw // s
+            fl += 2 * ho * ho * 9 * cout * cout
+            if s != 1 or inp != cout:
+                fl += 2 * ho * ho * inp * cout
+            inp, hw = cout, ho
+    return fl
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    depth, widen, C, S, N = (int(v) for v in (args + [28, 10, 100, 2, 1024][len(args):]))
+    ms = [wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), s, logit_gain=0.25).cuda().eval() for s in range(S)]
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
+    bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms])
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    P, E = torch.zeros(N, C, device="cuda"), torch.zeros(N, device="cuda")
+    ws = _C.bma_wrn_forward(bank, bufs, 1, x[:min(N, 64)], depth, widen, C, P[:min(N, 64)], E[:min(N, 64)])   # warm-up
+    ws = _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E)
+    P.zero_(), E.zero_()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1)
+    fl = wrn_flops(depth, widen) + 2 * 64 * widen * C
+    out = {"depth": depth, "widen": widen, "C": C, "S": S, "N": N, "ms": t, "img_samples_per_s": S * N / t * 1e3,
+           "TFLOPs_fp32_equiv": fl * S * N / t / 1e9, "MFLOP_per_img": fl / 1e6}
+    if "--ref" in sys.argv:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            refs = [torch.cat([m(x[i:i + 128]) for i in range(0, N, 128)]) for m in ms]           # warm-up + reference
+            torch.cuda.synchronize()
+            e0.record()
+            refs = [torch.cat([m(x[i:i + 128]) for i in range(0, N, 128)]) for m in ms]
+            e1.record()
+            torch.cuda.synchronize()
+        tr = e0.elapsed_time(e1)
+        pref = torch.softmax(torch.stack(refs).double(), -1).sum(0)
+        import copy
+        nb = min(N, 32)                                      # fp64 forward on a few images: who is closer to the exact network?
+        with torch.no_grad():
+            l64 = torch.stack([copy.deepcopy(m).double()(x[:nb].double()) for m in ms])
+        p64 = torch.softmax(l64, -1).sum(0) / S
+        out.update({"proba_err_vs_fp64_ours": (P[:nb].double() / S - p64).abs().max().item(),
+                    "proba_err_vs_fp64_torch_fp32": (pref[:nb] / S - p64).abs().max().item(),
+                    "logit_absmax": l64.abs().max().item()})
+        out.update({"torch_fp32_ms": tr, "torch_fp32_TFLOPs": fl * S * N / tr / 1e9, "speedup": tr / t,
+                    "max_abs_proba_err": (P.double() - pref).abs().max().item() / S})
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

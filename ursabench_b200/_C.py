@@ -41,6 +41,9 @@ SIGNATURES = {
     "ursa_bma_preresnet_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_bma_preresnet_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                           _sz, _i32, _vp]),
+    "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
+    "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
+                                    _sz, _i32, _vp]),
     "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ursa_hmc_leapfrog": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "ursa_hmc_energy_workspace": (_sz, [_i64, _i64]),
@@ -228,6 +231,24 @@ def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum,
                                           _ptr(workspace), workspace.numel() * workspace.element_size(), algo,
                                           _stream(x))
     _check(rc, "ursa_bma_preresnet_forward")
+    return workspace
+
+
+def bma_wrn_forward(bank, bufbank, S, x, depth, widen, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
+                    algo=ALGO_TCGEN05, workspace=None):
+    """WideResNet (WRN-depth-widen) BMA forward: every conv is a persistent 3xTF32 tcgen05 implicit GEMM."""
+    _dev_f32(bank, "bank"), _dev_f32(bufbank, "bufbank"), _dev_f32(x, "x")
+    _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum"), _dev_f32(logits_out, "logits_out", True)
+    N = x.shape[0]
+    need = lib().ursa_bma_wrn_workspace(S, N, depth, widen, C, algo)
+    if need == 0:
+        raise UrsaError("ursa_bma_wrn_workspace: unsupported WRN-%d-%d / algo %d" % (depth, widen, algo))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_bma_wrn_forward(_ptr(bank), bank.stride(0), _ptr(bufbank), bufbank.stride(0), S, _ptr(x), N,
+                                    depth, widen, C, _ptr(proba_sum), _ptr(entropy_sum), _ptr(logits_out), gamma,
+                                    _ptr(workspace), workspace.numel() * workspace.element_size(), algo, _stream(x))
+    _check(rc, "ursa_bma_wrn_forward")
     return workspace
 
 

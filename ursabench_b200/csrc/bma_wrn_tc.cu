@@ -1,0 +1,674 @@
+// K3 (WideResNet) on 5th-generation tensor cores: BMA forward of models/wideresnet.py:78-120 (WRN-d-k, WideBasic blocks:
+// bn1-relu-conv1(+bias)-[dropout: identity in eval]-bn2-relu-conv2(stride, +bias) + shortcut(x)) straight from the
+// [S, D] weight bank and the [S, nb] BatchNorm running-statistics bank (BASELINE.json configs[2]: WRN-28-10, C = 100).
+//
+// One posterior sample at a time over a chunk of images (a WRN-28-10 sample is 146 MB of filters; its 3x3 convs are
+// 0.47 GFLOP per image each -- there is nothing to gain from batching samples inside a launch):
+//   pack     bank row -> K-major filters [Cout][tap*Cin_p + ci | shortcut ci], split into TF32 hi / lo planes
+//            (3xTF32: hi*hi + hi*lo + lo*hi, fp32 accumulate -> fp32-level accuracy, see bma_mlp_tc.cu); eval-mode BN
+//            folded to (a, b); conv bias (+ the 1x1 shortcut's bias) as an epilogue vector
+//   stem     3 -> 16 on CUDA cores, writes A = split(relu(bn(R0))) and X = split(R0) padded to 32 channels
+//   conv     persistent implicit-GEMM kernel, one CTA per SM: M = 128 output pixels (4 rows x 32 | 8 x 16 | 2 images x 8 x 8),
+//            N = a tile of <= 160 output channels, K = 9 taps x Cin (+ Cin_block for a folded 1x1 shortcut).  Every
+//            [128 pixels x 32 channels] A slice is ONE 4-D tiled TMA box at shifted coordinates (zero padding = TMA
+//            out-of-bounds fill, applied AFTER the activation like PyTorch pads relu(bn(x))); stride-2 convs read four
+//            parity-split tensor maps.  The 1x1 (strided) shortcut conv of a transition block is folded into conv2's
+//            accumulation as extra K blocks over the split RAW block input X -- no separate kernel, no extra pass.
+//            warp 0: TMA producer | warp 1: tcgen05.mma issuer (3 MMAs per K = 8 step) | warps 2-9: epilogue.
+//            TWO-LEVEL ACCUMULATION: the tensor core adds into TMEM with truncated alignment, a bias that grows with the
+//            length of the MMA chain (measured: 2e-5 on WRN-16-2 probabilities with K = 1152 chains, 20x the fp32 noise
+//            floor).  So a chain covers only WRN_SEG K blocks (K = 128, 48 MMAs); the epilogue warps drain each segment
+//            from TMEM and add it to fp32 register accumulators (round-to-nearest).  min(4, 512 / N) TMEM accumulators
+//            rotate per segment, so draining segment j overlaps the MMAs of the following segments and a tile's epilogue
+//            (bias, residual, BN, split, stores) overlaps the next tile's first segments.
+//   epilogue v = acc + bias (+ residual);  raw fp32 v | split(v) (next block's shortcut input) | split(relu(bn_next(v)))
+//   head     BN + ReLU + 8x8 average pool + linear -> logits;  accumulate (bma_metrics.cu) in sample order
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace ursa {
+
+constexpr int WRN_THREADS = 320, WRN_MAX_STAGES = 4, WRN_MAX_BLOCKS = 8;
+constexpr int WRN_SEG = 4;                         // K blocks (of 32) per TMEM accumulation segment, see the kernel comment
+constexpr int WRN_MAX_TBUF = 4;                    // TMEM accumulators: min(4, 512 / bn_tile) at a column pitch of bn_tile
+constexpr int WRN_EPI_CHUNKS = 5;                  // 16-column chunks per epilogue thread: bn_tile / 2 <= 80
+constexpr uint32_t WRN_A_BYTES = 128 * 128;        // 128 pixels x 32 channels x fp32, 128-byte swizzle rows
+constexpr int WRN_CHUNK_IMAGES = 512;
+
+struct WrnMaps {
+    CUtensorMap a_hi[4], a_lo[4];      // index = h-parity * 2 + w-parity for stride 2; [0] only for stride 1
+    CUtensorMap x_hi, x_lo;            // shortcut input (raw block input, split), parity (0, 0) lattice for stride 2
+    CUtensorMap b_hi, b_lo;            // filters [Cout][Ktot]
+};
+
+struct WrnConvArgs {
+    int cout, bn_tile, hout, stride, n_images;
+    int kchunks, xchunks, m_tiles, n_tiles, stages, seg;
+    const float *bias;                 // [cout]
+    const float *bn;                   // [2 * cout] (a, b) of the BN that follows, or null
+    const float *res;                  // identity shortcut: raw block input [P][hout][hout][cout], or null
+    float *out_raw;                    // v
+    float *out_hi, *out_lo;            // split(relu(bn(v)))
+    float *outx_hi, *outx_lo;          // split(v)
+};
+
+__global__ void __launch_bounds__(WRN_THREADS, 1)
+wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[WRN_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[WRN_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[WRN_MAX_TBUF];
+    __shared__ __align__(8) uint64_t tempty_bar[WRN_MAX_TBUF];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int WT = a.hout, HT = a.hout >= 16 ? 128 / a.hout : a.hout;
+    const int tpi = (a.hout * a.hout) / 128;                 // tiles per image (0 when one tile spans 2 images)
+    const uint32_t b_bytes = (uint32_t)a.bn_tile * 128u;
+    const uint32_t stage_bytes = 2 * WRN_A_BYTES + 2 * b_bytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int kb3 = 9 * a.kchunks, k_blocks = kb3 + a.xchunks;
+    const int total_tiles = a.m_tiles * a.n_tiles;
+    const uint32_t ntbuf = 512u / (uint32_t)a.bn_tile < (uint32_t)WRN_MAX_TBUF ? 512u / (uint32_t)a.bn_tile : (uint32_t)WRN_MAX_TBUF;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < WRN_MAX_TBUF; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], WRN_THREADS - 64);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer =====
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+                int n0, h0;
+                if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
+                for (int kb = 0; kb < k_blocks; ++kb, ++g) {
+                    const uint32_t st = g % (uint32_t)a.stages, ph = (g / (uint32_t)a.stages) & 1u;
+                    mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[st]);
+                    mbar_expect_tx_a(fb, stage_bytes);
+                    const uint32_t base = smem_base + st * stage_bytes;
+                    if (kb < kb3) {
+                        const int tap = kb / a.kchunks, cc = kb - tap * a.kchunks;
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        int mi = 0, cw = kw - 1, ch = h0 + kh - 1;
+                        if (a.stride == 2) {
+                            mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);        // parity of (kh-1, kw-1)
+                            cw = (kw - 1) >> 1;                                // floor((kw-1)/2)
+                            ch = h0 + ((kh - 1) >> 1);
+                        }
+                        tma_load_4d_a(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
+                        tma_load_4d_a(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                    } else {
+                        const int cc = kb - kb3;
+                        tma_load_4d_a(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
+                        tma_load_4d_a(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                    }
+                    tma_load_2d_a(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, nt * a.bn_tile, fb);
+                    tma_load_2d_a(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, nt * a.bn_tile, fb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_tf32_idesc(128, a.bn_tile);
+            uint32_t g = 0, sc = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < k_blocks; kb0 += a.seg, ++sc) {
+                    const uint32_t buf = sc % ntbuf;
+                    mbar_wait_a(smem_u32(&tempty_bar[buf]), ((sc / ntbuf) & 1u) ^ 1u);   // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.bn_tile;
+                    const int kb1 = kb0 + a.seg < k_blocks ? kb0 + a.seg : k_blocks;
+                    uint32_t acc = 0;
+                    for (int kb = kb0; kb < kb1; ++kb, ++g) {
+                        const uint32_t st = g % (uint32_t)a.stages, ph = (g / (uint32_t)a.stages) & 1u;
+                        mbar_wait_a(smem_u32(&full_bar[st]), ph);
+                        tc_fence_after();
+                        const uint32_t base = smem_base + st * stage_bytes;
+                        const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + WRN_A_BYTES);
+                        const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * WRN_A_BYTES);
+                        const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * WRN_A_BYTES + b_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                            umma_tf32(d_tmem, d_alo + koff, d_bhi + koff, idesc, acc);
+                            acc = 1;
+                            umma_tf32(d_tmem, d_ahi + koff, d_blo + koff, idesc, 1);
+                            umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
+                        }
+                        umma_commit(smem_u32(&empty_bar[st]));
+                    }
+                    umma_commit(smem_u32(&tfull_bar[buf]));
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread = output pixel (TMEM lane) x one half of the tile's channels =====
+        const int q = warp & 3, half_id = (warp - 2) >> 2;
+        const int half = a.bn_tile >> 1;                      // channels per thread, a multiple of 16 (<= 80)
+        const int r = q * 32 + lane;
+        const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
+        uint32_t sc = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+            int n0, h0;
+            if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
+            const int n = n0 + nl;
+            const bool valid = n < a.n_images;
+            const int cbase = nt * a.bn_tile + half_id * half;
+            const int64_t off = (((int64_t)n * a.hout + (h0 + h)) * a.hout + w) * a.cout + cbase;
+            float accr[WRN_EPI_CHUNKS][16];
+#pragma unroll
+            for (int j = 0; j < WRN_EPI_CHUNKS; ++j)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) accr[j][e] = 0.f;
+            for (int kb0 = 0; kb0 < k_blocks; kb0 += a.seg, ++sc) {
+                const uint32_t buf = sc % ntbuf;
+                mbar_wait_a(smem_u32(&tfull_bar[buf]), (sc / ntbuf) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)a.bn_tile + (uint32_t)(half_id * half);
+#pragma unroll
+                for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
+                    if (j * 16 < half) {
+                        uint32_t rr[16];
+                        tmem_ld16(taddr + (uint32_t)(j * 16), rr);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[buf]);
+            }
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
+                if (j * 16 >= half) continue;
+                const int c0 = j * 16;
+                float v[16];
+                const float4 *bp = reinterpret_cast<const float4 *>(a.bias + cbase + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = __ldg(bp + i);
+                    v[4 * i + 0] = accr[j][4 * i + 0] + b4.x;
+                    v[4 * i + 1] = accr[j][4 * i + 1] + b4.y;
+                    v[4 * i + 2] = accr[j][4 * i + 2] + b4.z;
+                    v[4 * i + 3] = accr[j][4 * i + 3] + b4.w;
+                }
+                if (a.res) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(a.res + off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 t4 = __ldg(rp + i);
+                        v[4 * i + 0] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+                    }
+                }
+                if (a.out_raw) {
+                    float4 *op = reinterpret_cast<float4 *>(a.out_raw + off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                if (a.outx_hi) {
+                    float4 *hp = reinterpret_cast<float4 *>(a.outx_hi + off + c0);
+                    float4 *lp = reinterpret_cast<float4 *>(a.outx_lo + off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 hv, lv;
+                        hv.x = rn_tf32(v[4 * i]); hv.y = rn_tf32(v[4 * i + 1]); hv.z = rn_tf32(v[4 * i + 2]); hv.w = rn_tf32(v[4 * i + 3]);
+                        lv.x = rn_tf32(v[4 * i] - hv.x); lv.y = rn_tf32(v[4 * i + 1] - hv.y);
+                        lv.z = rn_tf32(v[4 * i + 2] - hv.z); lv.w = rn_tf32(v[4 * i + 3] - hv.w);
+                        hp[i] = hv;
+                        lp[i] = lv;
+                    }
+                }
+                if (a.out_hi) {
+                    const float4 *ap = reinterpret_cast<const float4 *>(a.bn + cbase + c0);
+                    const float4 *sp = reinterpret_cast<const float4 *>(a.bn + a.cout + cbase + c0);
+                    float4 *hp = reinterpret_cast<float4 *>(a.out_hi + off + c0);
+                    float4 *lp = reinterpret_cast<float4 *>(a.out_lo + off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a4 = __ldg(ap + i), s4 = __ldg(sp + i);
+                        const float y0 = relu_nan(fmaf(a4.x, v[4 * i], s4.x)), y1 = relu_nan(fmaf(a4.y, v[4 * i + 1], s4.y));
+                        const float y2 = relu_nan(fmaf(a4.z, v[4 * i + 2], s4.z)), y3 = relu_nan(fmaf(a4.w, v[4 * i + 3], s4.w));
+                        float4 hv, lv;
+                        hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
+                        lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
+                        hp[i] = hv;
+                        lp[i] = lv;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- pack / fold (per sample) --------------------------------------------------------------------------------------
+// filters [co][ci][taps] (PyTorch) -> K-major rows dst[co][koff + tap * cin_p + ci], ci >= cin zero-filled, TF32 hi / lo
+__global__ void __launch_bounds__(256) wrn_pack_filter_kernel(const float *__restrict__ src, float *__restrict__ dhi,
+                                                              float *__restrict__ dlo, int cin, int cin_p, int cout, int taps,
+                                                              int ktot, int koff) {
+    const int64_t per_row = (int64_t)taps * cin_p, total = per_row * cout;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int co = (int)(i / per_row);
+        const int rem = (int)(i - (int64_t)co * per_row);
+        const int tap = rem / cin_p, ci = rem - tap * cin_p;
+        const float wv = ci < cin ? __ldg(src + ((int64_t)co * cin + ci) * taps + tap) : 0.f;
+        const float hv = rn_tf32(wv);
+        const int64_t d = (int64_t)co * ktot + koff + rem;
+        dhi[d] = hv;
+        dlo[d] = rn_tf32(wv - hv);
+    }
+}
+
+// eval-mode BN -> (a, b): y = a x + b, a = gamma / sqrt(var + eps), b = beta - mean a
+__global__ void wrn_bn_fold_kernel(const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   const float *__restrict__ mean, const float *__restrict__ var, int c, float *__restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
+        const float av = gamma[i] / sqrtf(var[i] + 1e-5f);
+        dst[i] = av;
+        dst[c + i] = beta[i] - mean[i] * av;
+    }
+}
+
+__global__ void wrn_bias_kernel(const float *__restrict__ b0, const float *__restrict__ b1, int c, float *__restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x)
+        dst[i] = b1 ? b0[i] + b1[i] : b0[i];
+}
+
+// ---- stem: R0 = conv3x3(x) + bias (3 -> 16); A = split(relu(bn(R0))), X = split(R0), both padded to 32 channels ------
+__global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__ x, const float *__restrict__ wsrc,
+                                                       const float *__restrict__ bsrc, const float *__restrict__ bn,
+                                                       float *__restrict__ a_hi, float *__restrict__ a_lo,
+                                                       float *__restrict__ x_hi, float *__restrict__ x_lo) {
+    // one CTA per image; thread = 4 consecutive pixels of a row x all 16 output channels
+    __shared__ float xs[3][34][35];
+    __shared__ __align__(16) float ws[27 * 16];
+    __shared__ float bs[16], bns[32];
+    const int n = blockIdx.x;
+    for (int i = threadIdx.x; i < 27 * 16; i += 256) {                 // ws[(ci * 9 + tap) * 16 + co] <- w[co][ci][tap]
+        const int co = i & 15, ct = i >> 4;
+        ws[i] = __ldg(wsrc + co * 27 + ct);
+    }
+    if (threadIdx.x < 16) bs[threadIdx.x] = __ldg(bsrc + threadIdx.x);
+    if (threadIdx.x < 32) bns[threadIdx.x] = __ldg(bn + threadIdx.x);
+    for (int i = threadIdx.x; i < 3 * 34 * 34; i += 256) {
+        const int ww = i % 34, hh = (i / 34) % 34, ci = i / (34 * 34);
+        const int hi = hh - 1, wi = ww - 1;
+        xs[ci][hh][ww] = (hi >= 0 && hi < 32 && wi >= 0 && wi < 32) ? __ldg(x + ((int64_t)n * 3 + ci) * 1024 + hi * 32 + wi) : 0.f;
+    }
+    __syncthreads();
+    const int h = threadIdx.x >> 3, w0 = (threadIdx.x & 7) * 4;
+    float acc[4][16];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            float xv[6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) xv[d] = xs[ci][h + kh][w0 + d];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 *wp = reinterpret_cast<const float4 *>(ws + (ci * 9 + kh * 3 + kw) * 16);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float4 w4 = wp[qd];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        acc[p][4 * qd + 0] = fmaf(xv[p + kw], w4.x, acc[p][4 * qd + 0]);
+                        acc[p][4 * qd + 1] = fmaf(xv[p + kw], w4.y, acc[p][4 * qd + 1]);
+                        acc[p][4 * qd + 2] = fmaf(xv[p + kw], w4.z, acc[p][4 * qd + 2]);
+                        acc[p][4 * qd + 3] = fmaf(xv[p + kw], w4.w, acc[p][4 * qd + 3]);
+                    }
+                }
+            }
+        }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int64_t off = ((int64_t)n * 1024 + h * 32 + w0 + p) * 32;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float r[4], y[4], rh[4], rl[4], yh[4], yl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                r[k] = acc[p][i + k] + bs[i + k];
+                y[k] = relu_nan(fmaf(bns[i + k], r[k], bns[16 + i + k]));
+                rh[k] = rn_tf32(r[k]); rl[k] = rn_tf32(r[k] - rh[k]);
+                yh[k] = rn_tf32(y[k]); yl[k] = rn_tf32(y[k] - yh[k]);
+            }
+            *reinterpret_cast<float4 *>(a_hi + off + i) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+            *reinterpret_cast<float4 *>(a_lo + off + i) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+            *reinterpret_cast<float4 *>(x_hi + off + i) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+            *reinterpret_cast<float4 *>(x_lo + off + i) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+            *reinterpret_cast<float4 *>(a_hi + off + 16 + i) = z4;
+            *reinterpret_cast<float4 *>(a_lo + off + 16 + i) = z4;
+            *reinterpret_cast<float4 *>(x_hi + off + 16 + i) = z4;
+            *reinterpret_cast<float4 *>(x_lo + off + 16 + i) = z4;
+        }
+    }
+}
+
+// ---- head: relu(bn(R)) -> 8x8 average pool -> linear; one CTA per image -------------------------------------------------
+__global__ void __launch_bounds__(256) wrn_head_kernel(const float *__restrict__ act, const float *__restrict__ bn, int cf,
+                                                       const float *__restrict__ lw, const float *__restrict__ lb, int C,
+                                                       float *__restrict__ logits) {
+    extern __shared__ float feat[];                                    // [cf]
+    const int n = blockIdx.x;
+    const float *xp = act + (int64_t)n * 64 * cf;
+    for (int c = threadIdx.x; c < cf; c += 256) {
+        const float av = __ldg(bn + c), bv = __ldg(bn + cf + c);
+        float f = 0.f;
+        for (int px = 0; px < 64; ++px) f += relu_nan(fmaf(av, __ldg(xp + (int64_t)px * cf + c), bv));
+        feat[c] = f * (1.f / 64.f);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < C; c += 8) {
+        float acc = 0.f;
+        for (int k = lane; k < cf; k += 32) acc = fmaf(feat[k], __ldg(lw + (int64_t)c * cf + k), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) logits[(int64_t)n * C + c] = acc + __ldg(lb + c);
+    }
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------------------
+struct WrnBlock {
+    int cin, cin_p, cout, stride;
+    bool transition;
+    // bank-row offsets (model.parameters() order: bn1.w, bn1.b, conv1.w, conv1.b, bn2.w, bn2.b, conv2.w, conv2.b, [sc.w, sc.b])
+    int64_t bn1_w, bn1_b, c1_w, c1_b, bn2_w, bn2_b, c2_w, c2_b, sc_w, sc_b;
+    int64_t bn1_buf, bn2_buf;          // buffer-row offsets of running_mean (running_var follows at + channels)
+    // packed offsets (floats)
+    int64_t p_w1_hi, p_w1_lo, p_w2_hi, p_w2_lo, p_bias1, p_bias2, p_bn1, p_bn2;
+    int k1, k2;                        // K extents of the packed filter rows
+};
+
+struct WrnPlan {
+    int n, k, C, widths[4];
+    WrnBlock blocks[3][WRN_MAX_BLOCKS];
+    int64_t conv1_w, conv1_b, bnf_w, bnf_b, bnf_buf, lin_w, lin_b;
+    int64_t p_bnf;
+    int64_t packed_floats, D, NB;
+};
+
+static bool wrn_build_plan(int depth, int widen, int C, WrnPlan &pl) {
+    if (depth < 10 || (depth - 4) % 6 != 0 || widen < 2 || widen % 2 != 0 || widen > 16 || C < 1) return false;
+    const int n = (depth - 4) / 6;
+    if (n > WRN_MAX_BLOCKS) return false;
+    pl.n = n; pl.k = widen; pl.C = C;
+    pl.widths[0] = 16; pl.widths[1] = 16 * widen; pl.widths[2] = 32 * widen; pl.widths[3] = 64 * widen;
+    int64_t src = 0, buf = 0, dst = 0;
+    auto take = [&](int64_t &cursor, int64_t cnt) { const int64_t o = cursor; cursor += cnt; return o; };
+    auto take_dst = [&](int64_t cnt) { const int64_t o = dst; dst += (cnt + 255) & ~(int64_t)255; return o; };   // 1 KB aligned
+    pl.conv1_w = take(src, 16 * 27);
+    pl.conv1_b = take(src, 16);
+    int inpl = 16;
+    const int strides[3] = {1, 2, 2};
+    for (int g = 0; g < 3; ++g)
+        for (int b = 0; b < n; ++b) {
+            WrnBlock &B = pl.blocks[g][b];
+            B.cin = inpl; B.cin_p = (inpl + 31) & ~31; B.cout = pl.widths[g + 1];
+            B.stride = b == 0 ? strides[g] : 1;
+            B.transition = B.stride != 1 || B.cin != B.cout;
+            B.bn1_w = take(src, B.cin); B.bn1_b = take(src, B.cin);
+            B.c1_w = take(src, (int64_t)B.cout * B.cin * 9); B.c1_b = take(src, B.cout);
+            B.bn2_w = take(src, B.cout); B.bn2_b = take(src, B.cout);
+            B.c2_w = take(src, (int64_t)B.cout * B.cout * 9); B.c2_b = take(src, B.cout);
+            B.sc_w = B.sc_b = -1;
+            if (B.transition) { B.sc_w = take(src, (int64_t)B.cout * B.cin); B.sc_b = take(src, B.cout); }
+            B.bn1_buf = take(buf, 2 * B.cin);
+            B.bn2_buf = take(buf, 2 * B.cout);
+            B.k1 = 9 * B.cin_p;
+            B.k2 = 9 * B.cout + (B.transition ? B.cin_p : 0);
+            B.p_w1_hi = take_dst((int64_t)B.cout * B.k1); B.p_w1_lo = take_dst((int64_t)B.cout * B.k1);
+            B.p_w2_hi = take_dst((int64_t)B.cout * B.k2); B.p_w2_lo = take_dst((int64_t)B.cout * B.k2);
+            B.p_bias1 = take_dst(B.cout); B.p_bias2 = take_dst(B.cout);
+            B.p_bn1 = take_dst(2 * B.cin); B.p_bn2 = take_dst(2 * B.cout);
+            inpl = B.cout;
+        }
+    pl.bnf_w = take(src, inpl); pl.bnf_b = take(src, inpl);
+    pl.bnf_buf = take(buf, 2 * inpl);
+    pl.lin_w = take(src, (int64_t)C * inpl); pl.lin_b = take(src, C);
+    pl.p_bnf = take_dst(2 * inpl);
+    pl.packed_floats = dst;
+    pl.D = src; pl.NB = buf;
+    return true;
+}
+
+struct WrnChunking {
+    int nc;
+    size_t unit_bytes, packed_bytes, logit_bytes, total;
+};
+
+static WrnChunking wrn_chunking(int64_t N, const WrnPlan &pl) {
+    WrnChunking c;
+    c.nc = (int)(N < WRN_CHUNK_IMAGES ? N : WRN_CHUNK_IMAGES);
+    // unit = the largest activation plane: conv1 output of block (2, 0) at 32 x 32 x 32k channels
+    c.unit_bytes = (((size_t)c.nc * 1024 * pl.widths[2] * sizeof(float)) + 1023) & ~(size_t)1023;
+    c.packed_bytes = (((size_t)pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
+    c.logit_bytes = ((((size_t)c.nc * pl.C * sizeof(float)) + 1023) & ~(size_t)1023);
+    // A1 hi/lo, A2 hi/lo (4 units), Xa hi/lo, Xb hi/lo, Ra, Rb (6 half units: <= 32 x 32 x 16k channels)
+    c.total = 7 * c.unit_bytes + c.packed_bytes + c.logit_bytes + 2048;
+    return c;
+}
+
+// plane [N][H][H][C]: stride-1 map, or the (hp, wp) parity sub-lattice for a stride-2 consumer; box = one 128-pixel tile
+static int wrn_act_map(CUtensorMap *tm, const float *plane, int nc, int H, int C, int hout, int stride, int parity) {
+    const int WT = hout, HT = hout >= 16 ? 128 / hout : hout, NT = 128 / (WT * HT);
+    const uint32_t box[4] = {32u, (uint32_t)WT, (uint32_t)HT, (uint32_t)NT};
+    if (stride == 1) {
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)nc};
+        const uint64_t st[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
+        return make_tensor_map(tm, plane, 4, dims, st, box, 128);
+    }
+    const int hp = parity >> 1, wp = parity & 1;
+    const float *base = plane + ((int64_t)hp * H + wp) * C;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)(H / 2), (uint64_t)(H / 2), (uint64_t)nc};
+    const uint64_t st[3] = {(uint64_t)2 * C * 4, (uint64_t)2 * H * C * 4, (uint64_t)H * H * C * 4};
+    return make_tensor_map(tm, base, 4, dims, st, box, 128);
+}
+
+static int wrn_pick_bn_tile(int cout) {
+    for (int nt = 1; nt <= 16; ++nt)
+        if (cout % nt == 0 && cout / nt <= 160 && (cout / nt) % 32 == 0) return cout / nt;    // two 16-column-granular halves
+    return 0;
+}
+
+// one conv launch: A planes [nc][hin][hin][cin_p] -> cout channels at hout = hin / stride; xin_p > 0 folds a 1x1 stride-`stride`
+// conv over the X planes [nc][hin][hin][xin_p] into the accumulation
+static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int cin_p, const float *x_hi, const float *x_lo,
+                           int xin_p, int cout, int stride, int nc, const float *b_hi, const float *b_lo, int ktot,
+                           WrnConvArgs g, cudaStream_t st) {
+    const int hout = hin / stride;
+    WrnMaps maps;
+    const int nmaps = stride == 2 ? 4 : 1;
+    for (int i = 0; i < nmaps; ++i) {
+        if (int rc = wrn_act_map(&maps.a_hi[i], a_hi, nc, hin, cin_p, hout, stride, i)) return rc;
+        if (int rc = wrn_act_map(&maps.a_lo[i], a_lo, nc, hin, cin_p, hout, stride, i)) return rc;
+    }
+    for (int i = nmaps; i < 4; ++i) { maps.a_hi[i] = maps.a_hi[0]; maps.a_lo[i] = maps.a_lo[0]; }
+    if (xin_p > 0) {
+        if (int rc = wrn_act_map(&maps.x_hi, x_hi, nc, hin, xin_p, hout, stride, 0)) return rc;
+        if (int rc = wrn_act_map(&maps.x_lo, x_lo, nc, hin, xin_p, hout, stride, 0)) return rc;
+    } else {
+        maps.x_hi = maps.a_hi[0];
+        maps.x_lo = maps.a_lo[0];
+    }
+    const int bn_tile = wrn_pick_bn_tile(cout);
+    URSA_REQUIRE(bn_tile > 0, "ursa_bma_wrn_forward: no output-channel tile for cout = %d", cout);
+    {
+        const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
+        const uint64_t sb[1] = {(uint64_t)ktot * 4};
+        const uint32_t box[2] = {32u, (uint32_t)bn_tile};
+        if (int rc = make_tensor_map(&maps.b_hi, b_hi, 2, dims, sb, box, 128)) return rc;
+        if (int rc = make_tensor_map(&maps.b_lo, b_lo, 2, dims, sb, box, 128)) return rc;
+    }
+    g.cout = cout; g.bn_tile = bn_tile; g.hout = hout; g.stride = stride; g.n_images = nc;
+    g.kchunks = cin_p / 32; g.xchunks = xin_p / 32;
+    const int tpi = (hout * hout) / 128;
+    g.m_tiles = tpi > 0 ? nc * tpi : (nc + 1) / 2;
+    g.n_tiles = cout / bn_tile;
+    const size_t stage_bytes = 2 * (size_t)WRN_A_BYTES + 2 * (size_t)bn_tile * 128;
+    int stages = (int)(((size_t)(226 << 10) - 1024) / stage_bytes);
+    if (stages > WRN_MAX_STAGES) stages = WRN_MAX_STAGES;
+    if (const char *e = getenv("URSA_WRN_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
+    g.stages = stages;
+    g.seg = WRN_SEG;
+    if (const char *e = getenv("URSA_WRN_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }      // accuracy / speed experiments
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    const int tiles = g.m_tiles * g.n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wrn_conv_tc_kernel<<<grid, WRN_THREADS, smem, st>>>(maps, g);
+    URSA_LAUNCH_CHECK("wrn_conv_tc_kernel");
+    return URSA_OK;
+}
+
+static int wrn_pack_sample(const WrnPlan &pl, const float *row, const float *brow, float *packed, cudaStream_t st) {
+    auto pack = [&](const float *src, float *dhi, float *dlo, int cin, int cin_p, int cout, int taps, int ktot, int koff) {
+        const int64_t total = (int64_t)cout * taps * cin_p;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        wrn_pack_filter_kernel<<<(int)blocks, 256, 0, st>>>(src, dhi, dlo, cin, cin_p, cout, taps, ktot, koff);
+    };
+    for (int g = 0; g < 3; ++g)
+        for (int b = 0; b < pl.n; ++b) {
+            const WrnBlock &B = pl.blocks[g][b];
+            pack(row + B.c1_w, packed + B.p_w1_hi, packed + B.p_w1_lo, B.cin, B.cin_p, B.cout, 9, B.k1, 0);
+            pack(row + B.c2_w, packed + B.p_w2_hi, packed + B.p_w2_lo, B.cout, B.cout, B.cout, 9, B.k2, 0);
+            if (B.transition)
+                pack(row + B.sc_w, packed + B.p_w2_hi, packed + B.p_w2_lo, B.cin, B.cin_p, B.cout, 1, B.k2, 9 * B.cout);
+            wrn_bias_kernel<<<1, 256, 0, st>>>(row + B.c1_b, nullptr, B.cout, packed + B.p_bias1);
+            wrn_bias_kernel<<<1, 256, 0, st>>>(row + B.c2_b, B.transition ? row + B.sc_b : nullptr, B.cout, packed + B.p_bias2);
+            wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + B.bn1_w, row + B.bn1_b, brow + B.bn1_buf, brow + B.bn1_buf + B.cin, B.cin,
+                                                  packed + B.p_bn1);
+            wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + B.bn2_w, row + B.bn2_b, brow + B.bn2_buf, brow + B.bn2_buf + B.cout,
+                                                  B.cout, packed + B.p_bn2);
+        }
+    const int cf = pl.widths[3];
+    wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + pl.bnf_w, row + pl.bnf_b, brow + pl.bnf_buf, brow + pl.bnf_buf + cf, cf,
+                                          packed + pl.p_bnf);
+    URSA_LAUNCH_CHECK("wrn pack kernels");
+    return URSA_OK;
+}
+
+}  // namespace ursa
+
+using namespace ursa;
+
+extern "C" size_t ursa_bma_wrn_workspace(int S, int64_t N, int depth, int widen, int C, int algo) {
+    WrnPlan pl;
+    if (S < 1 || N < 1 || algo != URSA_ALGO_TCGEN05 || !wrn_build_plan(depth, widen, C, pl)) return 0;
+    return wrn_chunking(N, pl).total;
+}
+
+extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S,
+                                    const float *x, int64_t N, int depth, int widen, int C, float *proba_sum,
+                                    float *entropy_sum, float *logits_out, double gamma, void *workspace,
+                                    size_t workspace_bytes, int algo, void *stream) {
+    URSA_REQUIRE(bank && bufbank && x && proba_sum && entropy_sum && workspace, "ursa_bma_wrn_forward: null pointer");
+    URSA_REQUIRE(S >= 1 && N >= 1, "ursa_bma_wrn_forward: bad shape");
+    if (algo != URSA_ALGO_TCGEN05) {
+        set_error("ursa_bma_wrn_forward: unknown algo %d (the WideResNet forward exists on the tcgen05 engine only)", algo);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    static thread_local WrnPlan pl;
+    if (!wrn_build_plan(depth, widen, C, pl)) {
+        set_error("ursa_bma_wrn_forward: unsupported WRN-%d-%d (depth = 6n+4 with n <= %d, even widen factor 2..16)", depth, widen,
+                  WRN_MAX_BLOCKS);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    URSA_REQUIRE(ld_bank >= pl.D, "ursa_bma_wrn_forward: ld_bank (%lld) < D (%lld)", (long long)ld_bank, (long long)pl.D);
+    URSA_REQUIRE(ld_buf >= pl.NB, "ursa_bma_wrn_forward: ld_buf (%lld) < %lld", (long long)ld_buf, (long long)pl.NB);
+    const WrnChunking ck = wrn_chunking(N, pl);
+    URSA_REQUIRE(workspace_bytes >= ck.total, "ursa_bma_wrn_forward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    const size_t U = ck.unit_bytes, Hf = ((U / 2) + 1023) & ~(size_t)1023;
+    float *A1h = reinterpret_cast<float *>(wsb), *A1l = reinterpret_cast<float *>(wsb + U);
+    float *A2h = reinterpret_cast<float *>(wsb + 2 * U), *A2l = reinterpret_cast<float *>(wsb + 3 * U);
+    char *hb = wsb + 4 * U;
+    float *Xh[2] = {reinterpret_cast<float *>(hb), reinterpret_cast<float *>(hb + 2 * Hf)};
+    float *Xl[2] = {reinterpret_cast<float *>(hb + Hf), reinterpret_cast<float *>(hb + 3 * Hf)};
+    float *Ra = reinterpret_cast<float *>(hb + 4 * Hf), *Rb = reinterpret_cast<float *>(hb + 5 * Hf);
+    float *packed = reinterpret_cast<float *>(wsb + 7 * U);
+    float *logits = reinterpret_cast<float *>(wsb + 7 * U + ck.packed_bytes);
+    const int n = pl.n, cf = pl.widths[3];
+
+    for (int s = 0; s < S; ++s) {
+        const float *row = bank + (int64_t)s * ld_bank, *brow = bufbank + (int64_t)s * ld_buf;
+        if (int rc = wrn_pack_sample(pl, row, brow, packed, st)) return rc;
+        for (int64_t i0 = 0; i0 < N; i0 += ck.nc) {
+            const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
+            int xi = 0;                                   // X plane pair holding the current block's raw input
+            wrn_stem_kernel<<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, row + pl.conv1_w, row + pl.conv1_b,
+                                                packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi]);
+            URSA_LAUNCH_CHECK("wrn_stem_kernel");
+            float *cur = Ra, *nxt = Rb;
+            int hw = 32;
+            for (int g = 0; g < 3; ++g)
+                for (int b = 0; b < n; ++b) {
+                    const WrnBlock &B = pl.blocks[g][b];
+                    const bool last = g == 2 && b == n - 1;
+                    const WrnBlock *NB = last ? nullptr : (b + 1 < n ? &pl.blocks[g][b + 1] : &pl.blocks[g + 1][0]);
+                    WrnConvArgs c1 = {};
+                    c1.bias = packed + B.p_bias1; c1.bn = packed + B.p_bn2; c1.out_hi = A2h; c1.out_lo = A2l;
+                    if (int rc = wrn_launch_conv(A1h, A1l, hw, B.cin_p, nullptr, nullptr, 0, B.cout, 1, nc, packed + B.p_w1_hi,
+                                                 packed + B.p_w1_lo, B.k1, c1, st))
+                        return rc;
+                    WrnConvArgs c2 = {};
+                    c2.bias = packed + B.p_bias2;
+                    c2.res = B.transition ? nullptr : cur;
+                    if (NB) {
+                        c2.bn = packed + NB->p_bn1; c2.out_hi = A1h; c2.out_lo = A1l;
+                        if (NB->transition) { c2.outx_hi = Xh[xi ^ 1]; c2.outx_lo = Xl[xi ^ 1]; }
+                        else c2.out_raw = nxt;
+                    } else {
+                        c2.out_raw = nxt;
+                    }
+                    if (int rc = wrn_launch_conv(A2h, A2l, hw, B.cout, Xh[xi], Xl[xi], B.transition ? B.cin_p : 0, B.cout, B.stride,
+                                                 nc, packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st))
+                        return rc;
+                    if (c2.outx_hi) xi ^= 1;
+                    if (c2.out_raw) { float *t = cur; cur = nxt; nxt = t; }
+                    hw /= B.stride;
+                }
+            wrn_head_kernel<<<nc, 256, cf * sizeof(float), st>>>(cur, packed + pl.p_bnf, cf, row + pl.lin_w, row + pl.lin_b, C, logits);
+            URSA_LAUNCH_CHECK("wrn_head_kernel");
+            if (int rc = ursa_bma_accumulate(logits, 1, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
+                return rc;
+            if (logits_out)
+                URSA_CUDA(cudaMemcpyAsync(logits_out + ((int64_t)s * N + i0) * C, logits, (size_t)nc * C * sizeof(float),
+                                          cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return URSA_OK;
+}

@@ -90,6 +90,19 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *t
         ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap *tmap, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_a(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, int c4,
                                               uint32_t bar) {
     asm volatile(

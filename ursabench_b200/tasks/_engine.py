@@ -19,7 +19,7 @@ _LOGIT_CHUNK_BYTES = 256 << 20
 
 
 def _arch_of(module):
-    """('mlp', in_dim, hidden, C) / ('preresnet', depth, C) / None -- structural match against models.py."""
+    """('mlp', in_dim, hidden, C) / ('preresnet', depth, C) / ('wrn', depth, widen, C) / None -- structural match against models.py."""
     name = type(module).__name__
     if name == "MLP" and all(hasattr(module, a) for a in ("fc1", "fc2", "fc3")):
         f1, f2, f3 = module.fc1, module.fc2, module.fc3
@@ -31,6 +31,11 @@ def _arch_of(module):
         blocks = list(module.layer1)
         if blocks and type(blocks[0]).__name__ == "BasicBlock" and module.fc.in_features == 64:
             return ("preresnet", 6 * len(blocks) + 2, module.fc.out_features)
+    if name == "WideResNet" and hasattr(module, "layer1") and hasattr(module, "linear"):
+        blocks = list(module.layer1)
+        if blocks and type(blocks[0]).__name__ == "WideBasic" and module.linear.in_features % 64 == 0 \
+                and blocks[0].conv1.bias is not None:            # dropout is the identity in eval mode (prediction.py:58)
+            return ("wrn", 6 * len(blocks) + 4, module.linear.in_features // 64, module.linear.out_features)
     return None
 
 
@@ -119,6 +124,9 @@ class BMAAccumulator:
             for algo in order:
                 if lib.ursa_bma_preresnet_workspace(1, 1, arch[1], arch[2], algo) > 0:
                     return algo
+        elif arch[0] == "wrn" and self.engine != "ffma":
+            if lib.ursa_bma_wrn_workspace(1, 1, arch[1], arch[2], arch[3], _C.ALGO_TCGEN05) > 0:
+                return _C.ALGO_TCGEN05
         return None
 
     def _accumulate_rows(self, w, b, arch, skeleton):
@@ -133,6 +141,13 @@ class BMAAccumulator:
                 self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, self._proba, self._entropy, algo=algo,
                                               workspace=self._ws)
                 self.last_engine = "fused_mlp"
+            elif arch[0] == "wrn":
+                _, depth, widen, C = arch
+                if C != self.num_classes:
+                    raise ValueError("WideResNet class dimension does not match the task")
+                self._ws = _C.bma_wrn_forward(w, b, S, self._x, depth, widen, C, self._proba, self._entropy, algo=algo,
+                                              workspace=self._ws)
+                self.last_engine = "fused_wrn"
             else:
                 _, depth, C = arch
                 guard = algo == _C.ALGO_TCGEN05_FUSED_F16
