@@ -464,6 +464,64 @@ def run_extras(dev, rank, world, peak):
     del bankp, bufp, xi, P, E
     ws[0] = None
     torch.cuda.empty_cache()
+    # BMA: WideResNet-28-10, C = 100 (BASELINE.json configs[2]): S = 30 SWAG draws sharded over ranks, N = 10 000 test images.
+    # Every conv runs on the persistent 3xTF32 tcgen05 implicit-GEMM kernel (csrc/bma_wrn_tc.cu); beside it the engine it
+    # replaces -- the per-sample PyTorch forward with cuDNN fp32 (TF32 off, as parity demands) -- on a bounded sample.
+    S_w, C_w = 30, 100
+    lo_w, hi_w = udist.shard_range(S_w, rank, world)
+    ns = hi_w - lo_w
+    m = models.WideResNet(num_classes=C_w, depth=28, widen_factor=10)
+    Dw = sum(q.numel() for q in m.parameters())
+    nbuf = sum(b.numel() for b in m.buffers() if b.dtype == torch.float32)
+    flat = torch.cat([q.detach().reshape(-1) for q in m.parameters()]).to(dev)
+    bankw = torch.empty(max(ns, 1), Dw, device=dev)
+    for i in range(max(ns, 1)):                               # row by row: no [S, D] temporary next to the 4.4 GB bank
+        bankw[i] = flat + 0.002 * torch.randn(Dw, device=dev)
+    bufw = torch.zeros(max(ns, 1), (nbuf + 3) // 4 * 4, device=dev)
+    off = 0
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            c = mod.num_features
+            bufw[:, off + c:off + 2 * c] = 1.0
+            off += 2 * c
+    xi = torch.randn(N, 3, 32, 32, device=dev)
+    yw = torch.randint(0, C_w, (N,), device=dev)
+    P, E = torch.zeros(N, C_w, device=dev), torch.zeros(N, device=dev)
+    wrn_flop = 11_902_350_336                                 # 2*MAC per image and sample (convs + shortcuts + linear)
+
+    def bma_wrn():
+        P.zero_()
+        E.zero_()
+        if ns > 0:
+            ws[0] = _C.bma_wrn_forward(bankw, bufw, ns, xi, 28, 10, C_w, P, E, workspace=ws[0])
+        Pr, Er, n = udist.allreduce_bma(P, E, ns)
+        return _C.bma_metrics(Pr, n, yw)
+    ws[0] = _C.bma_wrn_forward(bankw[:1], bufw[:1], 1, xi[:512], 28, 10, C_w, P[:512], E[:512], workspace=None)   # warm-up
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms, _ = _event_time_ms(bma_wrn, 1)
+    ms = udist.allreduce_max_scalar(ms, dev)
+    out["bma_wrn28x10_S30_N10k_tcgen05"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                            "img_samples_per_s": N * S_w / ms * 1e3,
+                                            "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world}
+    if rank == 0:
+        worker = m.to(dev).eval()
+        mm_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+                fwd = lambda: [worker(xi[i:i + 128]) for i in range(0, 512, 128)]  # noqa: E731
+                fwd()
+                tms, _ = _event_time_ms(fwd, 2)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = mm_tf32
+        out["bma_wrn28x10_torch_cudnn_fp32"] = {"sample": "S=1, N=512, batch 128", "ms": tms, "img_samples_per_s": 512 / tms * 1e3,
+                                                "TFLOPs": wrn_flop * 512 / tms / 1e9}
+        del worker
+    del bankw, bufw, xi, P, E
+    ws[0] = None
+    torch.cuda.empty_cache()
     # HMC (BASELINE.json configs[3]): MLP 784-200-10, full batch of 1000 points, 128 chains per GPU, L = 10
     from ursabench_b200 import inference
     Ch, Lh = 128, 10

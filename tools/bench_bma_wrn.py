@@ -37,6 +37,7 @@ def main():
     ms = [wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), s, logit_gain=0.25).cuda().eval() for s in range(S)]
     bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
     bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms])
+    torch.manual_seed(0)
     x = torch.randn(N, 3, 32, 32, device="cuda")
     P, E = torch.zeros(N, C, device="cuda"), torch.zeros(N, device="cuda")
     ws = _C.bma_wrn_forward(bank, bufs, 1, x[:min(N, 64)], depth, widen, C, P[:min(N, 64)], E[:min(N, 64)])   # warm-up

@@ -18,7 +18,10 @@
 //            TWO-LEVEL ACCUMULATION: the tensor core adds into TMEM with truncated alignment, a bias that grows with the
 //            length of the MMA chain (measured: 2e-5 on WRN-16-2 probabilities with K = 1152 chains, 20x the fp32 noise
 //            floor).  So a chain covers only WRN_SEG K blocks (K = 128, 48 MMAs); the epilogue warps drain each segment
-//            from TMEM and add it to fp32 register accumulators (round-to-nearest).  min(4, 512 / N) TMEM accumulators
+//            from TMEM and add it to fp32 register accumulators (round-to-nearest).  Measured on WRN-28-10 (max |p - p_fp64|,
+//            cuDNN fp32 = 1.9e-5 on the same inputs): SEG 2 / 4 / 9 / 18 / 45 / one chain = 0.8 / 1.1 / 2.5 / 4.7 / 10.6 / 48 e-5
+//            at 192 / 212 / 238-250 / 234 / 235 / 250 TFLOP/s -- every accumulator switch costs ~1 k cycles of tensor-pipe
+//            idle (independent of the drain itself: skipping the tcgen05.ld of the drains recovers only 4 %).  min(4, 512 / N) TMEM accumulators
 //            rotate per segment, so draining segment j overlaps the MMAs of the following segments and a tile's epilogue
 //            (bias, residual, BN, split, stores) overlaps the next tile's first segments.
 //   epilogue v = acc + bias (+ residual);  raw fp32 v | split(v) (next block's shortcut input) | split(relu(bn_next(v)))
@@ -79,7 +82,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         }
         for (int i = 0; i < WRN_MAX_TBUF; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], WRN_THREADS - 64);
+            mbar_init(&tempty_bar[i], (WRN_THREADS - 64) / 32);      // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -163,7 +166,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         // ===== epilogue: thread = output pixel (TMEM lane) x one half of the tile's channels =====
         const int q = warp & 3, half_id = (warp - 2) >> 2;
         const int half = a.bn_tile >> 1;                      // channels per thread, a multiple of 16 (<= 80)
-        const int r = q * 32 + lane;
+        const int qi = lane & 3, qb = lane & ~3;
+        const int r = q * 32 + qb;                            // first pixel of this lane's quad (4 consecutive pixels of a row)
         const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
         uint32_t sc = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -194,64 +198,61 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tempty_bar[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             }
-            if (!valid) continue;
+            // The TMEM layout gives a thread one pixel (row) x 16 columns: stored as is, every warp-level access touches 32
+            // different 128-byte lines (32 L1 tag cycles each -- measured: the epilogue then takes ~3/4 of a tile's MMA time and
+            // the MMA issuer stalls on it).  A 4 x 4 transpose inside each lane quad makes lane (qb + qi) own columns
+            // [4 qi, 4 qi + 4) of the quad's 4 rows, so a quad reads / writes 64 contiguous bytes of one pixel per access.
 #pragma unroll
             for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
                 if (j * 16 >= half) continue;
-                const int c0 = j * 16;
-                float v[16];
-                const float4 *bp = reinterpret_cast<const float4 *>(a.bias + cbase + c0);
+                float tr[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b4 = __ldg(bp + i);
-                    v[4 * i + 0] = accr[j][4 * i + 0] + b4.x;
-                    v[4 * i + 1] = accr[j][4 * i + 1] + b4.y;
-                    v[4 * i + 2] = accr[j][4 * i + 2] + b4.z;
-                    v[4 * i + 3] = accr[j][4 * i + 3] + b4.w;
-                }
-                if (a.res) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(a.res + off + c0);
+                for (int rd = 0; rd < 4; ++rd) {
+                    const int sb = (qi + rd) & 3, jr = (qi - rd) & 3;       // block sent / quad row received in this round
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 t4 = __ldg(rp + i);
-                        v[4 * i + 0] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+                    for (int e = 0; e < 4; ++e) {
+                        const float sv = sb == 0 ? accr[j][e] : (sb == 1 ? accr[j][4 + e] : (sb == 2 ? accr[j][8 + e] : accr[j][12 + e]));
+                        const float rv = rd == 0 ? sv : __shfl_sync(0xffffffffu, sv, qb + jr);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (jr == jj) tr[jj][e] = rv;
                     }
                 }
-                if (a.out_raw) {
-                    float4 *op = reinterpret_cast<float4 *>(a.out_raw + off + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-                if (a.outx_hi) {
-                    float4 *hp = reinterpret_cast<float4 *>(a.outx_hi + off + c0);
-                    float4 *lp = reinterpret_cast<float4 *>(a.outx_lo + off + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 hv, lv;
-                        hv.x = rn_tf32(v[4 * i]); hv.y = rn_tf32(v[4 * i + 1]); hv.z = rn_tf32(v[4 * i + 2]); hv.w = rn_tf32(v[4 * i + 3]);
-                        lv.x = rn_tf32(v[4 * i] - hv.x); lv.y = rn_tf32(v[4 * i + 1] - hv.y);
-                        lv.z = rn_tf32(v[4 * i + 2] - hv.z); lv.w = rn_tf32(v[4 * i + 3] - hv.w);
-                        hp[i] = hv;
-                        lp[i] = lv;
-                    }
-                }
+                if (!valid) continue;
+                const int c0 = j * 16 + 4 * qi;
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + cbase + c0));
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = a4;
                 if (a.out_hi) {
-                    const float4 *ap = reinterpret_cast<const float4 *>(a.bn + cbase + c0);
-                    const float4 *sp = reinterpret_cast<const float4 *>(a.bn + a.cout + cbase + c0);
-                    float4 *hp = reinterpret_cast<float4 *>(a.out_hi + off + c0);
-                    float4 *lp = reinterpret_cast<float4 *>(a.out_lo + off + c0);
+                    a4 = __ldg(reinterpret_cast<const float4 *>(a.bn + cbase + c0));
+                    s4 = __ldg(reinterpret_cast<const float4 *>(a.bn + a.cout + cbase + c0));
+                }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 a4 = __ldg(ap + i), s4 = __ldg(sp + i);
-                        const float y0 = relu_nan(fmaf(a4.x, v[4 * i], s4.x)), y1 = relu_nan(fmaf(a4.y, v[4 * i + 1], s4.y));
-                        const float y2 = relu_nan(fmaf(a4.z, v[4 * i + 2], s4.z)), y3 = relu_nan(fmaf(a4.w, v[4 * i + 3], s4.w));
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int64_t o = off + (int64_t)jj * a.cout + c0;
+                    float4 v = make_float4(tr[jj][0] + b4.x, tr[jj][1] + b4.y, tr[jj][2] + b4.z, tr[jj][3] + b4.w);
+                    if (a.res) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(a.res + o));
+                        v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                    }
+                    if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + o) = v;
+                    if (a.outx_hi) {
+                        float4 hv, lv;
+                        hv.x = rn_tf32(v.x); hv.y = rn_tf32(v.y); hv.z = rn_tf32(v.z); hv.w = rn_tf32(v.w);
+                        lv.x = rn_tf32(v.x - hv.x); lv.y = rn_tf32(v.y - hv.y); lv.z = rn_tf32(v.z - hv.z); lv.w = rn_tf32(v.w - hv.w);
+                        *reinterpret_cast<float4 *>(a.outx_hi + o) = hv;
+                        *reinterpret_cast<float4 *>(a.outx_lo + o) = lv;
+                    }
+                    if (a.out_hi) {
+                        const float y0 = relu_nan(fmaf(a4.x, v.x, s4.x)), y1 = relu_nan(fmaf(a4.y, v.y, s4.y));
+                        const float y2 = relu_nan(fmaf(a4.z, v.z, s4.z)), y3 = relu_nan(fmaf(a4.w, v.w, s4.w));
                         float4 hv, lv;
                         hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
                         lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
-                        hp[i] = hv;
-                        lp[i] = lv;
+                        *reinterpret_cast<float4 *>(a.out_hi + o) = hv;
+                        *reinterpret_cast<float4 *>(a.out_lo + o) = lv;
                     }
                 }
             }
