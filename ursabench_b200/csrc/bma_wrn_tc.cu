@@ -54,6 +54,8 @@ struct WrnConvArgs {
     float *out_raw;                    // v
     float *out_hi, *out_lo;            // split(relu(bn(v)))
     float *outx_hi, *outx_lo;          // split(v)
+    double *stats;                     // train mode (BatchNorm re-estimation): [batches][2][cout] sums of v and v^2, or null
+    int batch;                         // images per batch (train mode)
 };
 
 __global__ void __launch_bounds__(WRN_THREADS, 1)
@@ -221,38 +223,65 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             if (jr == jj) tr[jj][e] = rv;
                     }
                 }
-                if (!valid) continue;
                 const int c0 = j * 16 + 4 * qi;
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + cbase + c0));
-                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = a4;
-                if (a.out_hi) {
-                    a4 = __ldg(reinterpret_cast<const float4 *>(a.bn + cbase + c0));
-                    s4 = __ldg(reinterpret_cast<const float4 *>(a.bn + a.cout + cbase + c0));
-                }
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int64_t o = off + (int64_t)jj * a.cout + c0;
-                    float4 v = make_float4(tr[jj][0] + b4.x, tr[jj][1] + b4.y, tr[jj][2] + b4.z, tr[jj][3] + b4.w);
-                    if (a.res) {
-                        const float4 t4 = __ldg(reinterpret_cast<const float4 *>(a.res + o));
-                        v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
-                    }
-                    if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + o) = v;
-                    if (a.outx_hi) {
-                        float4 hv, lv;
-                        hv.x = rn_tf32(v.x); hv.y = rn_tf32(v.y); hv.z = rn_tf32(v.z); hv.w = rn_tf32(v.w);
-                        lv.x = rn_tf32(v.x - hv.x); lv.y = rn_tf32(v.y - hv.y); lv.z = rn_tf32(v.z - hv.z); lv.w = rn_tf32(v.w - hv.w);
-                        *reinterpret_cast<float4 *>(a.outx_hi + o) = hv;
-                        *reinterpret_cast<float4 *>(a.outx_lo + o) = lv;
-                    }
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + cbase + c0));
+                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = a4;
                     if (a.out_hi) {
-                        const float y0 = relu_nan(fmaf(a4.x, v.x, s4.x)), y1 = relu_nan(fmaf(a4.y, v.y, s4.y));
-                        const float y2 = relu_nan(fmaf(a4.z, v.z, s4.z)), y3 = relu_nan(fmaf(a4.w, v.w, s4.w));
-                        float4 hv, lv;
-                        hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
-                        lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
-                        *reinterpret_cast<float4 *>(a.out_hi + o) = hv;
-                        *reinterpret_cast<float4 *>(a.out_lo + o) = lv;
+                        a4 = __ldg(reinterpret_cast<const float4 *>(a.bn + cbase + c0));
+                        s4 = __ldg(reinterpret_cast<const float4 *>(a.bn + a.cout + cbase + c0));
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int64_t o = off + (int64_t)jj * a.cout + c0;
+                        float4 v = make_float4(tr[jj][0] + b4.x, tr[jj][1] + b4.y, tr[jj][2] + b4.z, tr[jj][3] + b4.w);
+                        if (a.res) {
+                            const float4 t4 = __ldg(reinterpret_cast<const float4 *>(a.res + o));
+                            v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                        }
+                        if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + o) = v;
+                        if (a.stats) {
+                            s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                            s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+                            s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+                        }
+                        if (a.outx_hi) {
+                            float4 hv, lv;
+                            hv.x = rn_tf32(v.x); hv.y = rn_tf32(v.y); hv.z = rn_tf32(v.z); hv.w = rn_tf32(v.w);
+                            lv.x = rn_tf32(v.x - hv.x); lv.y = rn_tf32(v.y - hv.y); lv.z = rn_tf32(v.z - hv.z); lv.w = rn_tf32(v.w - hv.w);
+                            *reinterpret_cast<float4 *>(a.outx_hi + o) = hv;
+                            *reinterpret_cast<float4 *>(a.outx_lo + o) = lv;
+                        }
+                        if (a.out_hi) {
+                            const float y0 = relu_nan(fmaf(a4.x, v.x, s4.x)), y1 = relu_nan(fmaf(a4.y, v.y, s4.y));
+                            const float y2 = relu_nan(fmaf(a4.z, v.z, s4.z)), y3 = relu_nan(fmaf(a4.w, v.w, s4.w));
+                            float4 hv, lv;
+                            hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
+                            lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
+                            *reinterpret_cast<float4 *>(a.out_hi + o) = hv;
+                            *reinterpret_cast<float4 *>(a.out_lo + o) = lv;
+                        }
+                    }
+                }
+                if (a.stats) {
+                    // a warp's 32 pixels belong to one image, hence to one batch: reduce over the 8 quads, then one fp64 atomic
+                    // per (channel, moment) from the lanes of quad 0
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+                        }
+                    }
+                    if (qb == 0 && valid) {
+                        double *sp = a.stats + (int64_t)(n / a.batch) * 2 * a.cout + cbase + c0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            atomicAdd(sp + e, (double)s1[e]);
+                            atomicAdd(sp + a.cout + e, (double)s2[e]);
+                        }
                     }
                 }
             }
