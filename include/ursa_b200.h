@@ -196,6 +196,18 @@ int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const float *bufban
                          void *workspace, size_t workspace_bytes, int algo, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K3b BatchNorm re-estimation for one posterior sample (replaces util.bn_update, util.py:212-247, called once per SWAG
+ *     sample at inference/swag.py:123-124): ONE train-mode pass of the WideResNet over x [N, 3, 32, 32] in batches of
+ *     `batch` images (the last may be ragged): every BatchNorm normalises with its batch statistics, the running
+ *     statistics are reset and re-estimated with the cumulative momentum b / (n + b) (unbiased running variance, as
+ *     PyTorch).  bank_row: [D] parameters; buf_row: [nb] running statistics, overwritten.  Same tcgen05 conv kernel as
+ *     ursa_bma_wrn_forward with a statistics epilogue (fp64 sums); batch must be even, 2..512.
+ * ---------------------------------------------------------------------- */
+size_t ursa_wrn_bn_update_workspace(int64_t N, int batch, int depth, int widen, int C);
+int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch,
+                       int depth, int widen, int C, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * K5  chain-batched HMC  (replaces the call into hamiltorch.sample_model made by HMC.sample,
  *     inference/hmc.py:62-85.  hamiltorch is a third-party dependency that is NOT vendored in the reference
  *     (unpinned git HEAD, util.py:11) -- these entry points follow its published leapfrog / Metropolis algorithm as

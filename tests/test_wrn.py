@@ -118,3 +118,67 @@ def test_prediction_routes_wideresnet_through_the_tcgen05_engine():
     task.update_statistics(ms, output_performance=False)
     assert task.last_engine == "fused_wrn"
     np.testing.assert_allclose(task.ensemble_proba.cpu().numpy(), g["wrn10x2/ensemble_proba"], atol=1e-5, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm re-estimation
+def _flat_buffers(m):
+    return torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth,widen,N,batch", [(10, 2, 300, 128), (16, 4, 70, 32), (10, 10, 40, 16), (10, 2, 1030, 256)])
+def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
+    """ursa_wrn_bn_update (train-mode pass on the tcgen05 conv kernel, fp64 batch sums) against util.bn_update's PyTorch pass
+    (reference util.py:212-247): ragged last batch, several chunks (N > 512), identity and transition blocks."""
+    from ursabench_b200 import _C
+    from ursabench_b200.util import bn_update
+    m = wrn_fill(WideResNet(num_classes=10, depth=depth, widen_factor=widen), 31 * depth + widen).cuda()
+    torch.manual_seed(N)
+    x = torch.randn(N, 3, 32, 32)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.zeros(N, dtype=torch.long)), batch_size=batch,
+                                         shuffle=False)
+    row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).contiguous()
+    mm = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            bn_update(loader, m, device=torch.device("cuda"))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = mm
+    ref = _flat_buffers(m)
+    buf = torch.full_like(ref, float("nan"))                       # the kernel must overwrite every statistic
+    ws = _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, 10)
+    torch.cuda.synchronize()
+    assert ws is not None
+    err = (buf - ref).abs() / (ref.abs() + 1e-2)
+    assert torch.isfinite(buf).all()
+    assert err.max().item() < 2e-4, err.max().item()
+
+
+@pytest.mark.gpu
+def test_swag_sample_uses_the_engine_bn_update_for_wideresnets():
+    """SWAG.sample on a WideResNet: every returned sample carries BatchNorm statistics re-estimated by ursa_wrn_bn_update
+    (no PyTorch pass), equal to what util.bn_update computes for the same weights."""
+    from ursabench_b200 import inference
+    from ursabench_b200.util import bn_update
+    torch.manual_seed(0)
+    N = 96
+    x, y = torch.randn(N, 3, 32, 32), torch.randint(0, 10, (N,))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=32, shuffle=False)
+    hyp = {"lr_init": 0.01, "swag_lr": 0.005, "swag_wd": 1e-4, "momentum": 0.9, "burn_in_epochs": 1, "num_iterates": 2,
+           "num_samples": 2}
+    model = WideResNet(num_classes=10, depth=10, widen_factor=2)
+    sw = inference.SWAG(hyp, model=model, train_loader=loader, device=torch.device("cuda"))
+    samples = sw.sample()
+    assert len(samples) == 2 and getattr(sw, "_bn_x", None) is not None          # the engine path ran
+    for i in range(2):
+        ref_m = WideResNet(num_classes=10, depth=10, widen_factor=2).cuda()
+        off = 0
+        for p in ref_m.parameters():
+            p.data.copy_(sw.bank.w[i, off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            bn_update(loader, ref_m, device=torch.device("cuda"))
+        ref = _flat_buffers(ref_m)
+        got = sw.bank.b[i, :ref.numel()]
+        assert ((got - ref).abs() / (ref.abs() + 1e-2)).max().item() < 5e-4

@@ -44,6 +44,8 @@ SIGNATURES = {
     "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
     "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                     _sz, _i32, _vp]),
+    "ursa_wrn_bn_update_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
+    "ursa_wrn_bn_update": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ursa_hmc_leapfrog": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "ursa_hmc_energy_workspace": (_sz, [_i64, _i64]),
@@ -249,6 +251,22 @@ def bma_wrn_forward(bank, bufbank, S, x, depth, widen, C, proba_sum, entropy_sum
                                     depth, widen, C, _ptr(proba_sum), _ptr(entropy_sum), _ptr(logits_out), gamma,
                                     _ptr(workspace), workspace.numel() * workspace.element_size(), algo, _stream(x))
     _check(rc, "ursa_bma_wrn_forward")
+    return workspace
+
+
+def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
+    """Re-estimate the BatchNorm running statistics of ONE WideResNet sample with a train-mode pass over ``x`` (batches of
+    ``batch`` images); ``buf_row`` [nb] is overwritten.  Returns the workspace (None if the shape is not covered)."""
+    _dev_f32(bank_row, "bank_row"), _dev_f32(buf_row, "buf_row"), _dev_f32(x, "x")
+    N = x.shape[0]
+    need = lib().ursa_wrn_bn_update_workspace(N, batch, depth, widen, C)
+    if need == 0:
+        return None
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_wrn_bn_update(_ptr(bank_row), _ptr(buf_row), _ptr(x), N, batch, depth, widen, C, _ptr(workspace),
+                                  workspace.numel() * workspace.element_size(), _stream(x))
+    _check(rc, "ursa_wrn_bn_update")
     return workspace
 
 

@@ -329,10 +329,12 @@ __global__ void wrn_bias_kernel(const float *__restrict__ b0, const float *__res
 }
 
 // ---- stem: R0 = conv3x3(x) + bias (3 -> 16); A = split(relu(bn(R0))), X = split(R0), both padded to 32 channels ------
+// Train mode (bn == null): no A planes; the raw 16-channel output goes to raw16 and its per-batch sums to stats.
 __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__ x, const float *__restrict__ wsrc,
                                                        const float *__restrict__ bsrc, const float *__restrict__ bn,
                                                        float *__restrict__ a_hi, float *__restrict__ a_lo,
-                                                       float *__restrict__ x_hi, float *__restrict__ x_lo) {
+                                                       float *__restrict__ x_hi, float *__restrict__ x_lo,
+                                                       float *__restrict__ raw16, double *__restrict__ stats, int batch) {
     // one CTA per image; thread = 4 consecutive pixels of a row x all 16 output channels
     __shared__ float xs[3][34][35];
     __shared__ __align__(16) float ws[27 * 16];
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
         ws[i] = __ldg(wsrc + co * 27 + ct);
     }
     if (threadIdx.x < 16) bs[threadIdx.x] = __ldg(bsrc + threadIdx.x);
-    if (threadIdx.x < 32) bns[threadIdx.x] = __ldg(bn + threadIdx.x);
+    if (threadIdx.x < 32) bns[threadIdx.x] = bn ? __ldg(bn + threadIdx.x) : 0.f;
     for (int i = threadIdx.x; i < 3 * 34 * 34; i += 256) {
         const int ww = i % 34, hh = (i / 34) % 34, ci = i / (34 * 34);
         const int hi = hh - 1, wi = ww - 1;
@@ -380,6 +382,9 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
             }
         }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float st1[16], st2[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) st1[c] = st2[c] = 0.f;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int64_t off = ((int64_t)n * 1024 + h * 32 + w0 + p) * 32;
@@ -392,15 +397,41 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
                 y[k] = relu_nan(fmaf(bns[i + k], r[k], bns[16 + i + k]));
                 rh[k] = rn_tf32(r[k]); rl[k] = rn_tf32(r[k] - rh[k]);
                 yh[k] = rn_tf32(y[k]); yl[k] = rn_tf32(y[k] - yh[k]);
+                st1[i + k] += r[k];
+                st2[i + k] = fmaf(r[k], r[k], st2[i + k]);
             }
-            *reinterpret_cast<float4 *>(a_hi + off + i) = make_float4(yh[0], yh[1], yh[2], yh[3]);
-            *reinterpret_cast<float4 *>(a_lo + off + i) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+            if (bn) {
+                *reinterpret_cast<float4 *>(a_hi + off + i) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+                *reinterpret_cast<float4 *>(a_lo + off + i) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+                *reinterpret_cast<float4 *>(a_hi + off + 16 + i) = z4;
+                *reinterpret_cast<float4 *>(a_lo + off + 16 + i) = z4;
+            } else {
+                *reinterpret_cast<float4 *>(raw16 + (off >> 1) + i) = make_float4(r[0], r[1], r[2], r[3]);
+            }
             *reinterpret_cast<float4 *>(x_hi + off + i) = make_float4(rh[0], rh[1], rh[2], rh[3]);
             *reinterpret_cast<float4 *>(x_lo + off + i) = make_float4(rl[0], rl[1], rl[2], rl[3]);
-            *reinterpret_cast<float4 *>(a_hi + off + 16 + i) = z4;
-            *reinterpret_cast<float4 *>(a_lo + off + 16 + i) = z4;
             *reinterpret_cast<float4 *>(x_hi + off + 16 + i) = z4;
             *reinterpret_cast<float4 *>(x_lo + off + 16 + i) = z4;
+        }
+    }
+    if (stats) {                                           // per-image sums -> one fp64 atomic per (channel, moment)
+        __shared__ float red[8][32];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                st1[c] += __shfl_xor_sync(0xffffffffu, st1[c], o);
+                st2[c] += __shfl_xor_sync(0xffffffffu, st2[c], o);
+            }
+            if (lane == 0) { red[warp][c] = st1[c]; red[warp][16 + c] = st2[c]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+            atomicAdd(stats + (int64_t)(n / batch) * 32 + threadIdx.x, (double)t);      // [batch][2][16]
         }
     }
 }
@@ -426,6 +457,72 @@ __global__ void __launch_bounds__(256) wrn_head_kernel(const float *__restrict__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) logits[(int64_t)n * C + c] = acc + __ldg(lb + c);
+    }
+}
+
+// ---- train-mode BatchNorm (re-estimation of the running statistics, reference util.py:212-247) ---------------------------
+// stats: [nb][2][C] fp64 sums over the batch's pixels.  One thread per channel walks the chunk's batches in order: batch
+// statistics -> (a, b) for the normalisation of THIS batch, running statistics with the cumulative momentum b / (n + b)
+// (util.py:239-241) and PyTorch's unbiased running variance.  The sums are cleared for the next layer.
+__global__ void wrn_bn_finalize_kernel(double *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                       int C, int hw, int nc, int batch, int64_t n_before, float *__restrict__ run_mean,
+                                       float *__restrict__ run_var, float *__restrict__ ab) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float rm = run_mean[c], rv = run_var[c];
+    int64_t n = n_before;
+    if (n == 0) { rm = 0.f; rv = 1.f; }                    // reset_bn (util.py:196-199)
+    const int nb = (nc + batch - 1) / batch;
+    for (int j = 0; j < nb; ++j) {
+        const int bj = nc - j * batch < batch ? nc - j * batch : batch;
+        const double cnt = (double)bj * hw;
+        double *sp = stats + (int64_t)j * 2 * C;
+        const double mean = sp[c] / cnt;
+        double var = sp[C + c] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        sp[c] = 0.0;
+        sp[C + c] = 0.0;
+        const float av = gamma[c] / sqrtf((float)var + 1e-5f);
+        ab[(int64_t)j * 2 * C + c] = av;
+        ab[(int64_t)j * 2 * C + C + c] = beta[c] - (float)mean * av;
+        const float mom = (float)((double)bj / (double)(n + bj));
+        const float unbiased = (float)(cnt > 1.0 ? var * cnt / (cnt - 1.0) : var);
+        rm = (1.f - mom) * rm + mom * (float)mean;
+        rv = (1.f - mom) * rv + mom * unbiased;
+        n += bj;
+    }
+    run_mean[c] = rm;
+    run_var[c] = rv;
+}
+
+// raw [P][hw][C] -> A planes split(relu(a_j v + b_j)) [P][hw][c_pad] (channels >= C zero) and, optionally, X planes split(v)
+__global__ void __launch_bounds__(256) wrn_bn_apply_kernel(const float *__restrict__ raw, const float *__restrict__ ab, int C,
+                                                           int c_pad, int hw, int batch, int64_t total4, float *__restrict__ a_hi,
+                                                           float *__restrict__ a_lo, float *__restrict__ x_hi,
+                                                           float *__restrict__ x_lo) {
+    const int cp4 = c_pad >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % cp4) * 4;
+        const int64_t px = i / cp4;
+        const int j = (int)(px / hw) / batch;
+        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), lv = hv, xh = hv, xl = hv;
+        if (c < C) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(raw + px * C + c));
+            const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ab + (int64_t)j * 2 * C + c));
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(ab + (int64_t)j * 2 * C + C + c));
+            const float y0 = relu_nan(fmaf(a4.x, v.x, b4.x)), y1 = relu_nan(fmaf(a4.y, v.y, b4.y));
+            const float y2 = relu_nan(fmaf(a4.z, v.z, b4.z)), y3 = relu_nan(fmaf(a4.w, v.w, b4.w));
+            hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
+            lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
+            xh.x = rn_tf32(v.x); xh.y = rn_tf32(v.y); xh.z = rn_tf32(v.z); xh.w = rn_tf32(v.w);
+            xl.x = rn_tf32(v.x - xh.x); xl.y = rn_tf32(v.y - xh.y); xl.z = rn_tf32(v.z - xh.z); xl.w = rn_tf32(v.w - xh.w);
+        }
+        *reinterpret_cast<float4 *>(a_hi + px * c_pad + c) = hv;
+        *reinterpret_cast<float4 *>(a_lo + px * c_pad + c) = lv;
+        if (x_hi) {
+            *reinterpret_cast<float4 *>(x_hi + px * c_pad + c) = xh;
+            *reinterpret_cast<float4 *>(x_lo + px * c_pad + c) = xl;
+        }
     }
 }
 
@@ -582,7 +679,8 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     return URSA_OK;
 }
 
-static int wrn_pack_sample(const WrnPlan &pl, const float *row, const float *brow, float *packed, cudaStream_t st) {
+static int wrn_pack_sample(const WrnPlan &pl, const float *row, const float *brow, float *packed, cudaStream_t st,
+                           bool fold_bn = true) {
     auto pack = [&](const float *src, float *dhi, float *dlo, int cin, int cin_p, int cout, int taps, int ktot, int koff) {
         const int64_t total = (int64_t)cout * taps * cin_p;
         int64_t blocks = (total + 255) / 256;
@@ -598,14 +696,16 @@ static int wrn_pack_sample(const WrnPlan &pl, const float *row, const float *bro
                 pack(row + B.sc_w, packed + B.p_w2_hi, packed + B.p_w2_lo, B.cin, B.cin_p, B.cout, 1, B.k2, 9 * B.cout);
             wrn_bias_kernel<<<1, 256, 0, st>>>(row + B.c1_b, nullptr, B.cout, packed + B.p_bias1);
             wrn_bias_kernel<<<1, 256, 0, st>>>(row + B.c2_b, B.transition ? row + B.sc_b : nullptr, B.cout, packed + B.p_bias2);
+            if (!fold_bn) continue;
             wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + B.bn1_w, row + B.bn1_b, brow + B.bn1_buf, brow + B.bn1_buf + B.cin, B.cin,
                                                   packed + B.p_bn1);
             wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + B.bn2_w, row + B.bn2_b, brow + B.bn2_buf, brow + B.bn2_buf + B.cout,
                                                   B.cout, packed + B.p_bn2);
         }
     const int cf = pl.widths[3];
-    wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + pl.bnf_w, row + pl.bnf_b, brow + pl.bnf_buf, brow + pl.bnf_buf + cf, cf,
-                                          packed + pl.p_bnf);
+    if (fold_bn)
+        wrn_bn_fold_kernel<<<1, 256, 0, st>>>(row + pl.bnf_w, row + pl.bnf_b, brow + pl.bnf_buf, brow + pl.bnf_buf + cf, cf,
+                                              packed + pl.p_bnf);
     URSA_LAUNCH_CHECK("wrn pack kernels");
     return URSA_OK;
 }
@@ -660,7 +760,7 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
             const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
             int xi = 0;                                   // X plane pair holding the current block's raw input
             wrn_stem_kernel<<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, row + pl.conv1_w, row + pl.conv1_b,
-                                                packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi]);
+                                                packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi], nullptr, nullptr, 1);
             URSA_LAUNCH_CHECK("wrn_stem_kernel");
             float *cur = Ra, *nxt = Rb;
             int hw = 32;
@@ -699,6 +799,117 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
                 URSA_CUDA(cudaMemcpyAsync(logits_out + ((int64_t)s * N + i0) * C, logits, (size_t)nc * C * sizeof(float),
                                           cudaMemcpyDeviceToDevice, st));
         }
+    }
+    return URSA_OK;
+}
+
+// ---- BatchNorm re-estimation: one train-mode pass of ONE sample over the training images -----------------
+namespace ursa {
+struct WrnTrainLayout {
+    int nc, nbmax;
+    size_t unit_bytes, packed_bytes, stats_bytes, ab_bytes, total;
+};
+static bool wrn_train_layout(int64_t N, int batch, const WrnPlan &pl, WrnTrainLayout &L) {
+    if (batch < 2 || (batch & 1) || batch > WRN_CHUNK_IMAGES || N < 1) return false;    // 8 x 8 tiles pair two images of a batch
+    int64_t nc = (int64_t)batch * (WRN_CHUNK_IMAGES / batch);
+    if (N < nc) nc = N;
+    L.nc = (int)nc;
+    L.nbmax = (int)((nc + batch - 1) / batch);
+    L.unit_bytes = (((size_t)nc * 1024 * pl.widths[2] * sizeof(float)) + 1023) & ~(size_t)1023;
+    L.packed_bytes = (((size_t)pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
+    L.stats_bytes = (((size_t)L.nbmax * 2 * pl.widths[3] * sizeof(double)) + 1023) & ~(size_t)1023;
+    L.ab_bytes = (((size_t)L.nbmax * 2 * pl.widths[3] * sizeof(float)) + 1023) & ~(size_t)1023;
+    L.total = 8 * L.unit_bytes + L.packed_bytes + L.stats_bytes + L.ab_bytes + 2048;
+    return true;
+}
+}  // namespace ursa
+
+extern "C" size_t ursa_wrn_bn_update_workspace(int64_t N, int batch, int depth, int widen, int C) {
+    WrnPlan pl;
+    WrnTrainLayout L;
+    if (!wrn_build_plan(depth, widen, C, pl) || !wrn_train_layout(N, batch, pl, L)) return 0;
+    return L.total;
+}
+
+extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch, int depth,
+                                  int widen, int C, void *workspace, size_t workspace_bytes, void *stream) {
+    URSA_REQUIRE(bank_row && buf_row && x && workspace, "ursa_wrn_bn_update: null pointer");
+    static thread_local WrnPlan pl;
+    WrnTrainLayout L;
+    if (!wrn_build_plan(depth, widen, C, pl) || !wrn_train_layout(N, batch, pl, L)) {
+        set_error("ursa_wrn_bn_update: unsupported WRN-%d-%d / batch %d (depth = 6n+4, even widen 2..16, even batch 2..%d)", depth,
+                  widen, batch, WRN_CHUNK_IMAGES);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    URSA_REQUIRE(workspace_bytes >= L.total, "ursa_wrn_bn_update: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    const size_t U = L.unit_bytes, Hf = ((U / 2) + 1023) & ~(size_t)1023;
+    float *A1h = reinterpret_cast<float *>(wsb), *A1l = reinterpret_cast<float *>(wsb + U);
+    float *A2h = reinterpret_cast<float *>(wsb + 2 * U), *A2l = reinterpret_cast<float *>(wsb + 3 * U);
+    float *T = reinterpret_cast<float *>(wsb + 4 * U);
+    char *hb = wsb + 5 * U;
+    float *Xh[2] = {reinterpret_cast<float *>(hb), reinterpret_cast<float *>(hb + 2 * Hf)};
+    float *Xl[2] = {reinterpret_cast<float *>(hb + Hf), reinterpret_cast<float *>(hb + 3 * Hf)};
+    float *Ra = reinterpret_cast<float *>(hb + 4 * Hf), *Rb = reinterpret_cast<float *>(hb + 5 * Hf);
+    char *tail = wsb + 8 * U;
+    float *packed = reinterpret_cast<float *>(tail);
+    double *stats = reinterpret_cast<double *>(tail + L.packed_bytes);
+    float *ab = reinterpret_cast<float *>(tail + L.packed_bytes + L.stats_bytes);
+    const int n = pl.n;
+
+    if (int rc = wrn_pack_sample(pl, bank_row, buf_row, packed, st, false)) return rc;
+    URSA_CUDA(cudaMemsetAsync(stats, 0, L.stats_bytes, st));
+    auto finalize = [&](int64_t gw, int64_t gb, int64_t bufo, int Cc, int hw, int nc, int64_t n_before) {
+        wrn_bn_finalize_kernel<<<(Cc + 127) / 128, 128, 0, st>>>(stats, bank_row + gw, bank_row + gb, Cc, hw, nc, batch, n_before,
+                                                               buf_row + bufo, buf_row + bufo + Cc, ab);
+    };
+    auto apply = [&](const float *raw, int Cc, int c_pad, int hw, int nc, float *ah, float *al, float *xh, float *xl) {
+        const int64_t total4 = (int64_t)nc * hw * (c_pad / 4);
+        int64_t blocks = (total4 + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        wrn_bn_apply_kernel<<<(int)blocks, 256, 0, st>>>(raw, ab, Cc, c_pad, hw, batch, total4, ah, al, xh, xl);
+    };
+    for (int64_t i0 = 0; i0 < N; i0 += L.nc) {
+        const int nc = (int)((N - i0 < L.nc) ? (N - i0) : L.nc);
+        int xi = 0;
+        float *cur = Ra, *nxt = Rb;
+        const WrnBlock &B0 = pl.blocks[0][0];
+        wrn_stem_kernel<<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
+                                            nullptr, Xh[xi], Xl[xi], cur, stats, batch);
+        URSA_LAUNCH_CHECK("wrn_stem_kernel");
+        finalize(B0.bn1_w, B0.bn1_b, B0.bn1_buf, 16, 1024, nc, i0);
+        apply(cur, 16, 32, 1024, nc, A1h, A1l, nullptr, nullptr);
+        int hw = 32;
+        for (int g = 0; g < 3; ++g)
+            for (int b = 0; b < n; ++b) {
+                const WrnBlock &B = pl.blocks[g][b];
+                const bool last = g == 2 && b == n - 1;
+                const WrnBlock *NB = last ? nullptr : (b + 1 < n ? &pl.blocks[g][b + 1] : &pl.blocks[g + 1][0]);
+                WrnConvArgs c1 = {};
+                c1.bias = packed + B.p_bias1; c1.out_raw = T; c1.stats = stats; c1.batch = batch;
+                if (int rc = wrn_launch_conv(A1h, A1l, hw, B.cin_p, nullptr, nullptr, 0, B.cout, 1, nc, packed + B.p_w1_hi,
+                                             packed + B.p_w1_lo, B.k1, c1, st))
+                    return rc;
+                finalize(B.bn2_w, B.bn2_b, B.bn2_buf, B.cout, hw * hw, nc, i0);
+                apply(T, B.cout, B.cout, hw * hw, nc, A2h, A2l, nullptr, nullptr);
+                WrnConvArgs c2 = {};
+                c2.bias = packed + B.p_bias2; c2.res = B.transition ? nullptr : cur; c2.out_raw = nxt; c2.stats = stats; c2.batch = batch;
+                if (int rc = wrn_launch_conv(A2h, A2l, hw, B.cout, Xh[xi], Xl[xi], B.transition ? B.cin_p : 0, B.cout, B.stride, nc,
+                                             packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st))
+                    return rc;
+                hw /= B.stride;
+                if (NB) {
+                    finalize(NB->bn1_w, NB->bn1_b, NB->bn1_buf, B.cout, hw * hw, nc, i0);
+                    const bool nx = NB->transition;
+                    apply(nxt, B.cout, B.cout, hw * hw, nc, A1h, A1l, nx ? Xh[xi ^ 1] : nullptr, nx ? Xl[xi ^ 1] : nullptr);
+                    if (nx) xi ^= 1;
+                } else {
+                    finalize(pl.bnf_w, pl.bnf_b, pl.bnf_buf, B.cout, hw * hw, nc, i0);
+                }
+                float *t = cur; cur = nxt; nxt = t;
+            }
+        URSA_LAUNCH_CHECK("wrn train-mode kernels");
     }
     return URSA_OK;
 }

@@ -76,10 +76,36 @@ class SWAG(SWA):
         self.bank.count = first + num
         return list(range(first, first + num))
 
+    def _engine_bn_update(self, row):
+        """BatchNorm re-estimation on the tcgen05 conv engine (``ursa_wrn_bn_update``, WideResNets): the train-mode pass runs
+        straight from the bank row and writes the row's running statistics in place.  The training images are uploaded
+        once (one pass over ``train_loader``, its batch size kept) and reused for every sample -- the reference re-iterates
+        the loader per sample (util.py:233), i.e. sees a fresh shuffle / augmentation draw each time; the estimator is the
+        same.  Returns False when the model / loader shape is not covered (the caller then runs the PyTorch pass)."""
+        from ..tasks._engine import _arch_of
+        arch = _arch_of(self.swag_model)
+        batch = getattr(self.train_loader, "batch_size", None)
+        if arch is None or arch[0] != "wrn" or not batch or getattr(self.train_loader, "drop_last", False):
+            return False
+        _, depth, widen, C = arch
+        if _C.lib().ursa_wrn_bn_update_workspace(max(len(self.train_loader.dataset), 1), batch, depth, widen, C) == 0:
+            return False
+        if getattr(self, "_bn_x", None) is None:
+            xs = [xb for xb, _ in self.train_loader]
+            if any(len(xb) != batch for xb in xs[:-1]) or xs[0].dim() != 4 or tuple(xs[0].shape[1:]) != (3, 32, 32):
+                return False
+            self._bn_x = torch.cat(xs).to(self.device, non_blocking=True).float().contiguous()
+            self._bn_ws = None
+        self._bn_ws = _C.wrn_bn_update(self.bank.w[row], self.bank.b[row], self._bn_x, batch, depth, widen, C,
+                                       workspace=self._bn_ws)
+        return self._bn_ws is not None
+
     def _finish_sample(self, row, update_bn):
         """Load the draw into ``swag_model``, re-estimate BatchNorm statistics (reference :99-102,:123-124 -- one full
         pass over the train set per sample) and store them with the row."""
         if update_bn and check_bn(self.swag_model):
+            if self._engine_bn_update(row):
+                return self.bank.handle(row)
             self.swag_flat.load_vector(self.bank.w[row])
             bn_update(self.train_loader, self.swag_model, device=self.device)
         self.bank.set_buffers(row, self.swag_flat.b)
