@@ -461,6 +461,30 @@ def run_extras(dev, rank, world, peak):
         out["bma_preresnet20_S100_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
                                                          "img_samples_per_s": N * S_all / ms * 1e3,
                                                          "TFLOPs": 81.63e6 * N * S_all / ms / 1e9, "n_gpus": world}
+    # BASELINE.json configs[4]: the S = 10 / 100 / 1000 sweep on the product engine (S = 100 is the line above)
+    for S_sw in (10, 1000):
+        lo_s, hi_s = udist.shard_range(S_sw, rank, world)
+        ns_s = hi_s - lo_s
+        bank_s = (flat[None, :] + 0.01 * torch.randn(max(ns_s, 1), Dp, device=dev)).contiguous()
+        buf_s = bufp[:1].expand(max(ns_s, 1), -1).contiguous()
+
+        def bma_sweep():
+            P.zero_()
+            E.zero_()
+            if ns_s > 0:
+                ws[0] = _C.bma_preresnet_forward(bank_s, buf_s, ns_s, xi, 20, 10, P, E, workspace=ws[0],
+                                                 algo=_C.ALGO_TCGEN05_FUSED_F16)
+            Pr, Er, n = udist.allreduce_bma(P, E, ns_s)
+            return _C.bma_metrics(Pr, n, y)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms, _ = _event_time_ms(bma_sweep, 1)
+        ms = udist.allreduce_max_scalar(ms, dev)
+        out["bma_preresnet20_S%d_N10k_fused16" % S_sw] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                                          "img_samples_per_s": N * S_sw / ms * 1e3,
+                                                          "TFLOPs": 81.63e6 * N * S_sw / ms / 1e9, "n_gpus": world}
+        del bank_s, buf_s
     del bankp, bufp, xi, P, E
     ws[0] = None
     torch.cuda.empty_cache()

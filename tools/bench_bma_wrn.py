@@ -31,9 +31,46 @@ def wrn_flops(depth, widen):
     return fl
 
 
+def bench_bn(depth, widen, C, N, batch=128):
+    """ursa_wrn_bn_update vs. util.bn_update's PyTorch pass (cuDNN fp32) for one sample over N training images."""
+    from ursabench_b200.util import bn_update
+    m = wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), 0, logit_gain=0.25).cuda()
+    row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).contiguous()
+    nbuf = sum(b.numel() for b in m.buffers() if b.dtype == torch.float32)
+    buf = torch.zeros(nbuf, device="cuda")
+    torch.manual_seed(0)
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    ws = _C.wrn_bn_update(row, buf, x[:batch * 2], batch, depth, widen, C)
+    ws = _C.wrn_bn_update(row, buf, x, batch, depth, widen, C)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _C.wrn_bn_update(row, buf, x, batch, depth, widen, C, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1)
+    loader = [(x[i:i + batch], None) for i in range(0, N, batch)]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        bn_update(loader, m, device=torch.device("cuda"))
+        torch.cuda.synchronize()
+        e0.record()
+        bn_update(loader, m, device=torch.device("cuda"))
+        e1.record()
+        torch.cuda.synchronize()
+    tr = e0.elapsed_time(e1)
+    ref = torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32])
+    fl = wrn_flops(depth, widen)
+    print(json.dumps({"bn_update": True, "depth": depth, "widen": widen, "N": N, "batch": batch, "ms": t, "img_per_s": N / t * 1e3,
+                      "TFLOPs_fp32_equiv": fl * N / t / 1e9, "torch_fp32_ms": tr, "speedup": tr / t,
+                      "max_rel_err_vs_torch": ((buf - ref).abs() / (ref.abs() + 1e-2)).max().item()}))
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     depth, widen, C, S, N = (int(v) for v in (args + [28, 10, 100, 2, 1024][len(args):]))
+    if "--bn" in sys.argv:
+        return bench_bn(depth, widen, C, N)
     ms = [wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), s, logit_gain=0.25).cuda().eval() for s in range(S)]
     bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
     bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms])
