@@ -121,6 +121,15 @@ int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, const float *v
                    uint64_t seed, uint64_t step, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K2c Gram matrix of the deviation ring, gram[K, K] (fp64, device) = R R^T over ring[K, D] in one streaming pass.
+ *     First half of the PCA subspace (inference/subspaces.py:116-156 runs a randomized SVD of the K x D matrix on
+ *     the host): with K <= URSA_DRAW_MAX_K rows, s and U come from eigh(gram) and the components s V^T = U^T R from
+ *     ursa_swag_draw with z2 = U^T, var = 0 (the same call evaluates SubspaceModel.forward, mean + P^T t,
+ *     inference/projection_model.py:13-14).
+ * ---------------------------------------------------------------------- */
+int ursa_swag_gram(const float *ring, int64_t ld_ring, int K, int64_t D, double *gram, void *stream);
+
+/* ------------------------------------------------------------------------
  * K3  BMA accumulation  (replaces the inner loop of Prediction.update_statistics,
  *     tasks/prediction.py:52-75: per sample softmax twice + 2 D2H + CPU accumulate)
  *   for s in order: p = softmax(logits[s, i, :]) ; proba_sum[i, :] += p ;

@@ -368,6 +368,34 @@ def gen_prediction_wrn(R):
     print("prediction_wrn.npz", {k: v for k, v in metric_json.items()})
 
 
+def gen_pca_space(R):
+    """PCASpace.collect_vector / get_space (inference/subspaces.py:103-156, integer pca_rank) and SubspaceModel.forward
+    (inference/projection_model.py:6-14) on the live reference: ring wrap (11 collects into max_rank 8), pca_rank 5; a
+    second case with fewer collects than max_rank (rank 3 < pca_rank)."""
+    from URSABench.inference.projection_model import SubspaceModel
+    out = {}
+    for tag, D, max_rank, pca_rank, ncollect, seed in (("wrap", 503, 8, 5, 11, 0), ("short", 130, 20, 6, 3, 1)):
+        rng = np.random.RandomState(seed)
+        sp = R["subspaces"].PCASpace(num_parameters=D, pca_rank=pca_rank, max_rank=max_rank)
+        scales = np.linspace(2.0, 0.2, ncollect)
+        vecs = (rng.randn(ncollect, D) * scales[:, None]).astype(np.float32)
+        for v in vecs:
+            sp.collect_vector(torch.from_numpy(v))
+        np.random.seed(seed)                              # randomized_svd draws its test matrix from the global numpy RNG
+        space = sp.get_space()
+        out[tag + "/vecs"] = vecs
+        out[tag + "/cfg"] = np.array([D, max_rank, pca_rank, ncollect])
+        out[tag + "/ring"] = sp.cov_mat_sqrt.numpy().copy()
+        out[tag + "/rank"] = sp.rank.numpy().copy()
+        out[tag + "/space"] = space.numpy().copy()
+        mean = torch.from_numpy(rng.randn(D).astype(np.float32))
+        t = torch.from_numpy(rng.randn(space.shape[0]).astype(np.float32))
+        out[tag + "/mean"], out[tag + "/t"] = mean.numpy(), t.numpy()
+        out[tag + "/projected"] = SubspaceModel(mean, space)(t).numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "pca_space.npz"), **out)
+    print("pca_space.npz", {k: out[k].shape for k in out if k.endswith("space")})
+
+
 def gen_metrics_edge(R):
     """get_performance_metrics / _get_ece / _get_brier on crafted probabilities: confidences exactly on bin
     edges, argmax ties, one-hot rows, C = 2..100."""
@@ -518,7 +546,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, pca_space=gen_pca_space, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

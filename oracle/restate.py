@@ -397,3 +397,26 @@ def hmc_chain(theta0, nll_and_grad, z_list, logu_list, step_size, L, tau, mass, 
         else:
             ret.extend(ret[-L:])
     return ret, accepts
+
+
+# --------------------------------------------------------------------------
+# SURVEY 8(f).3  PCASpace.get_space (integer pca_rank)      inference/subspaces.py:116-131,154-156
+#                SubspaceModel.forward                      inference/projection_model.py:13-14
+# The reference runs sklearn's randomized_svd (n_iter = 5, flip_sign -> svd_flip, u-based) on A = ring / sqrt(max(1, rank-1));
+# for rank <= max_rank <= 24 rows that converges to the exact SVD, restated here with numpy's.
+# --------------------------------------------------------------------------
+def pca_space(ring_rows, rank, pca_rank):
+    """ring_rows: [r, D] (any row order); returns s[:k, None] * Vt[:k] as float32, k = max(1, min(pca_rank, rank))."""
+    A = _f32(ring_rows).astype(np.float64) / (max(1, int(rank) - 1)) ** 0.5          # :121
+    U, sv, Vt = np.linalg.svd(A, full_matrices=False)
+    idx = np.argmax(np.abs(U), axis=0)                                                # svd_flip(u_based_decision=True)
+    signs = np.sign(U[idx, np.arange(U.shape[1])])
+    signs[signs == 0] = 1.0
+    Vt = Vt * signs[:, None]
+    k = max(1, min(int(pca_rank), int(rank)))                                         # :128
+    return (sv[:k, None] * Vt[:k]).astype(np.float32)                                 # :156
+
+
+def subspace_project(mean, cov_factor, t):
+    """mean + cov_factor^T t (projection_model.py:14)."""
+    return (_f32(mean).astype(np.float64) + _f32(cov_factor).astype(np.float64).T @ _f32(t).astype(np.float64)).astype(np.float32)

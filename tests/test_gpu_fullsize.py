@@ -140,3 +140,44 @@ def test_k3_k4_full_size_bma_sharding_and_counters(C):
     assert int(cnt.sum()) == N                                                       # every confidence falls in one bin
     nll = -torch.log((1 - 1e-4) * pbar.double().gather(1, y[:, None]) + 1e-4 / 10).sum().item()
     assert float(of[0]) == pytest.approx(nll, rel=1e-6)
+
+
+def test_k3_wrn28x10_full_size_accuracy_bracket_and_invariances(C):
+    """WideResNet-28-10, C = 100 (configs[2]) at its real widths (160 / 320 / 640: 1 / 2 / 4 output-channel tiles, K up to
+    5 760 + 320): (1) against an fp64 forward of the same network the BMA probabilities are no further off than twice what
+    PyTorch's own fp32 forward (cuDNN, TF32 off -- the arithmetic the reference runs) is, i.e. the kernel sits inside the fp32
+    noise of this ill-conditioned random network; (2) reversing the image order reverses the outputs bit for bit (a pixel's
+    result does not depend on its tile neighbours, the 8 x 8 tiles pair different images); (3) the same sample twice doubles
+    the accumulators exactly."""
+    import copy
+    from oracle.wrn_fill import wrn_fill
+    from ursabench_b200.models import WideResNet
+    Cc, N = 100, 33
+    m = wrn_fill(WideResNet(num_classes=Cc, depth=28, widen_factor=10), 5, logit_gain=0.25).cuda().eval()
+    row = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    bufs = torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32])
+    assert row.numel() == D_WRN
+    torch.manual_seed(1)
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    bank, bufbank = row[None].contiguous(), bufs[None].contiguous()
+    P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
+    ws = C.bma_wrn_forward(bank, bufbank, 1, x, 28, 10, Cc, P, E)
+    mm = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+            p32 = torch.softmax(m(x), -1).double()
+            p64 = torch.softmax(copy.deepcopy(m).double()(x.double()), -1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = mm
+    err_ours = (P.double() - p64).abs().max().item()
+    err_t32 = (p32 - p64).abs().max().item()
+    assert err_ours <= max(2.0 * err_t32, 2e-5), (err_ours, err_t32)
+    # (2) image permutation
+    P2, E2 = torch.zeros_like(P), torch.zeros_like(E)
+    C.bma_wrn_forward(bank, bufbank, 1, x.flip(0).contiguous(), 28, 10, Cc, P2, E2, workspace=ws)
+    assert torch.equal(P2.flip(0), P) and torch.equal(E2.flip(0), E)
+    # (3) the same sample twice
+    P3, E3 = torch.zeros_like(P), torch.zeros_like(E)
+    C.bma_wrn_forward(torch.cat([bank, bank]), torch.cat([bufbank, bufbank]), 2, x, 28, 10, Cc, P3, E3)
+    assert torch.equal(P3, P + P) and torch.equal(E3, E + E)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
     "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                     _sz, _i32, _vp]),
+    "ursa_swag_gram": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "ursa_wrn_bn_update_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "ursa_wrn_bn_update": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
@@ -175,6 +176,15 @@ def swag_draw(out, mean, var, D, ring=None, z2=None, z1=None, rank_div=1.0, seed
                               0 if z1 is None else z1.stride(0), S, D, rank_div, seed, step, _stream(out))
     _check(rc, "ursa_swag_draw")
     return out
+
+
+def swag_gram(ring, D):
+    """ring: [K, ld] device fp32 -> [K, K] float64 device tensor R R^T over the first D columns."""
+    _dev_f32(ring, "ring")
+    K = ring.shape[0]
+    gram = torch.empty(K, K, dtype=torch.float64, device=ring.device)
+    _check(lib().ursa_swag_gram(_ptr(ring), ring.stride(0), K, D, _ptr(gram), _stream(ring)), "ursa_swag_gram")
+    return gram
 
 
 def bma_accumulate(logits, proba_sum, entropy_sum, gamma=1e-4):

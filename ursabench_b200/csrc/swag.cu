@@ -308,6 +308,100 @@ __global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gram matrix of the deviation ring, G = R R^T (K x K, fp64), one streaming pass over [K, D]: the first half of the PCA
+// subspace (reference inference/subspaces.py:116-131 runs sklearn's randomized SVD on the K x D matrix on the host; with
+// K <= 24 rows the SVD is the eigen-decomposition of G, and s V^T = U^T R is one more K2b-shaped pass).
+// CTA = 8 warps, slab = 128 columns staged [24][128] in shared memory (coalesced float4 loads, double buffered through
+// registers); warp w owns up to three 4 x 4 blocks (ib <= jb) of G, its lanes own columns -- conflict-free LDS along a row,
+// 16 FMAs per 8 LDS.  fp32 partial sums per lane, shuffle reduce, fp64 atomicAdd per entry.
+constexpr int kGramCols = 128, kGramRows = URSA_DRAW_MAX_K, kGramThreads = 256;
+static_assert(kGramRows == 24, "6 x 6 blocks of 4 rows");
+
+__global__ void __launch_bounds__(kGramThreads) ring_gram_kernel(const float *__restrict__ ring, int64_t ld, int K, int64_t D,
+                                                                 int vec_ok, double *__restrict__ gram) {
+    __shared__ __align__(16) float sm[kGramRows][kGramCols];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the 21 upper-triangular 4 x 4 blocks, dealt round-robin to the 8 warps
+    int ib[3], jb[3], nblk = 0;
+    {
+        int t = 0;
+        for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j, ++t)
+                if ((t & 7) == warp && nblk < 3) { ib[nblk] = i; jb[nblk] = j; ++nblk; }
+    }
+    float acc[3][16];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[b][e] = 0.f;
+    const int64_t nslab = (D + kGramCols - 1) / kGramCols;
+    auto load = [&](int64_t slab, float4 (&r)[3]) {                       // 24 rows x 32 float4 = 768 = 3 per thread
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int idx = threadIdx.x + u * kGramThreads;
+            const int row = idx >> 5, c4 = (idx & 31) * 4;
+            const int64_t c = slab * kGramCols + c4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < K && c < D) {
+                const float *src = ring + (int64_t)row * ld + c;
+                if (vec_ok && c + 4 <= D) v = __ldg(reinterpret_cast<const float4 *>(src));
+                else {
+                    v.x = __ldg(src);
+                    if (c + 1 < D) v.y = __ldg(src + 1);
+                    if (c + 2 < D) v.z = __ldg(src + 2);
+                    if (c + 3 < D) v.w = __ldg(src + 3);
+                }
+            }
+            r[u] = v;
+        }
+    };
+    float4 regs[3];
+    int64_t slab = blockIdx.x;
+    if (slab < nslab) load(slab, regs);
+    for (; slab < nslab; slab += gridDim.x) {
+        __syncthreads();                                                   // previous slab consumed
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int idx = threadIdx.x + u * kGramThreads;
+            *reinterpret_cast<float4 *>(&sm[idx >> 5][(idx & 31) * 4]) = regs[u];
+        }
+        __syncthreads();
+        if (slab + gridDim.x < nslab) load(slab + gridDim.x, regs);        // next slab's loads fly during the FMAs
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (b < nblk) {
+#pragma unroll
+                for (int q = 0; q < kGramCols / 32; ++q) {
+                    const int c = q * 32 + lane;
+                    float vi[4], vj[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { vi[e] = sm[ib[b] * 4 + e][c]; vj[e] = sm[jb[b] * 4 + e][c]; }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) acc[b][e * 4 + f] = fmaf(vi[e], vj[f], acc[b][e * 4 + f]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        if (b >= nblk) continue;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            float v = acc[b][e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int i = ib[b] * 4 + (e >> 2), j = jb[b] * 4 + (e & 3);
+            if (lane == 0 && i < K && j < K) {
+                atomicAdd(gram + (int64_t)i * K + j, (double)v);
+                if (ib[b] != jb[b]) atomicAdd(gram + (int64_t)j * K + i, (double)v);
+            }
+        }
+    }
+}
+
 static int ew_grid(int64_t work_items) {
     const int64_t want = (work_items + kEwThreads - 1) / kEwThreads;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -373,4 +467,19 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 0) return S <= 16 ? launch_draw<1, false>(a, st) : launch_draw<2, false>(a, st);
     return S <= 16 ? launch_draw<1, true>(a, st) : launch_draw<2, true>(a, st);
+}
+
+extern "C" int ursa_swag_gram(const float *ring, int64_t ld_ring, int K, int64_t D, double *gram, void *stream) {
+    URSA_REQUIRE(ring && gram && D >= 0, "ursa_swag_gram: bad arguments");
+    URSA_REQUIRE(K >= 1 && K <= URSA_DRAW_MAX_K, "ursa_swag_gram: K must be in [1, %d]", URSA_DRAW_MAX_K);
+    URSA_REQUIRE(ld_ring >= D, "ursa_swag_gram: ld_ring < D");
+    cudaStream_t st = (cudaStream_t)stream;
+    URSA_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * K * K, st));
+    if (D == 0) return URSA_OK;
+    const int64_t nslab = (D + kGramCols - 1) / kGramCols;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    const int vec_ok = aligned16(ring) && (ld_ring & 3) == 0;
+    ring_gram_kernel<<<(int)(nslab < cap ? nslab : cap), kGramThreads, 0, st>>>(ring, ld_ring, K, D, vec_ok, gram);
+    URSA_LAUNCH_CHECK("ring_gram_kernel");
+    return URSA_OK;
 }

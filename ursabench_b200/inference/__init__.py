@@ -6,9 +6,10 @@ from .inference_base import _Inference
 from .optim_sghmc import optimSGHMC
 from .sghmc import SGHMC
 from .sgld import SGLD
+from .projection_model import SubspaceModel
 from .subspaces import CovarianceSpace, PCASpace, Subspace
 from .swa import SWA
 from .swag import SWAG
 
 __all__ = ["_Inference", "optimSGHMC", "SGHMC", "SGLD", "cSGHMC", "cSGLD", "SWA", "SWAG", "HMC", "Subspace",
-           "CovarianceSpace", "PCASpace"]
+           "CovarianceSpace", "PCASpace", "SubspaceModel"]
