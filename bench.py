@@ -389,6 +389,11 @@ def run_extras(dev, rank, world, peak):
     ms, _ = _event_time_ms(fn, 10)
     out["k2_draw_S30_K20_wrn28x10"] = {"ms": ms, "GBps": (K + 2 + S) * 4 * D / ms / 1e6,
                                        "frac": (K + 2 + S) * 4 * D / ms / 1e6 / peak, "us_per_draw": ms * 1e3 / S}
+    fn = lambda: _C.swag_gram(ring, D)  # noqa: E731
+    for _ in range(3):
+        fn()
+    ms, _ = _event_time_ms(fn, 10)
+    out["k2c_gram_K20_wrn28x10"] = {"ms": ms, "GBps": K * 4 * D / ms / 1e6, "frac": K * 4 * D / ms / 1e6 / peak}
     del p, g, v, mean, sq, ring, var, bank
     torch.cuda.empty_cache()
     # BMA: MLP 784-400-400-10, S = 100 posterior samples sharded over ranks, N = 10 000
