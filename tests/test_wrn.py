@@ -125,6 +125,10 @@ def _flat_buffers(m):
     return torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32])
 
 
+def _flat_buffers_any(m):
+    return torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype.is_floating_point])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("depth,widen,N,batch", [(10, 2, 300, 128), (16, 4, 70, 32), (10, 10, 40, 16), (10, 2, 1030, 256)])
 def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
@@ -138,6 +142,11 @@ def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
     loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.zeros(N, dtype=torch.long)), batch_size=batch,
                                          shuffle=False)
     row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).contiguous()
+    import copy
+    m64 = copy.deepcopy(m).double()
+    loader64 = [(xb.double(), yb) for xb, yb in loader]
+    bn_update(loader64, m64, device=torch.device("cuda"))                 # the exact statistics of this network
+    exact = _flat_buffers_any(m64)
     mm = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
@@ -150,9 +159,25 @@ def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
     ws = _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, 10)
     torch.cuda.synchronize()
     assert ws is not None
-    err = (buf - ref).abs() / (ref.abs() + 1e-2)
     assert torch.isfinite(buf).all()
-    assert err.max().item() < 2e-4, err.max().item()
+    # errors in units that mean something: a running mean against the layer's standard deviation, a running variance
+    # relatively.  The tensor core's truncated accumulation is a SYSTEMATIC ~1e-6 relative offset of every conv output (it does
+    # not average out over the pixels like fp32 round-to-nearest does), so the means sit ~10x further from the exact value than
+    # PyTorch's -- a few 1e-6 standard deviations.
+    e_mean = e_var = t_mean = t_var = 0.0
+    off = 0
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            c = mod.num_features
+            mu, var = exact[off:off + c], exact[off + c:off + 2 * c]
+            sd = var.sqrt()
+            e_mean = max(e_mean, ((buf[off:off + c].double() - mu).abs() / sd).max().item())
+            e_var = max(e_var, ((buf[off + c:off + 2 * c].double() - var).abs() / var).max().item())
+            t_mean = max(t_mean, ((ref[off:off + c].double() - mu).abs() / sd).max().item())
+            t_var = max(t_var, ((ref[off + c:off + 2 * c].double() - var).abs() / var).max().item())
+            off += 2 * c
+    assert off == buf.numel()
+    assert e_mean < 2e-5 and e_var < 5e-5, (e_mean, e_var, t_mean, t_var)
 
 
 @pytest.mark.gpu

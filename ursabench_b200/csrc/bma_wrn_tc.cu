@@ -20,8 +20,12 @@
 //            floor).  So a chain covers only WRN_SEG K blocks (K = 128, 48 MMAs); the epilogue warps drain each segment
 //            from TMEM and add it to fp32 register accumulators (round-to-nearest).  Measured on WRN-28-10 (max |p - p_fp64|,
 //            cuDNN fp32 = 1.9e-5 on the same inputs): SEG 2 / 4 / 9 / 18 / 45 / one chain = 0.8 / 1.1 / 2.5 / 4.7 / 10.6 / 48 e-5
-//            at 192 / 212 / 238-250 / 234 / 235 / 250 TFLOP/s -- every accumulator switch costs ~1 k cycles of tensor-pipe
-//            idle (independent of the drain itself: skipping the tcgen05.ld of the drains recovers only 4 %).  min(4, 512 / N) TMEM accumulators
+//            at 192 / 212 / 238-250 / 234 / 235 / 250 TFLOP/s.  Restarting a chain / rotating the accumulator costs 3-5 % by itself
+//            (timing experiment without the hand-shakes); the rest of the gap is the epilogue BETWEEN two tiles (bias, residual,
+//            BN, split, stores: ~10 k cycles) during which nobody drains, while three rotating accumulators only cover
+//            2 segments - the issuer's lead.  So a tile's first segment is WRN_SEG0_FACTOR x longer (12 K blocks: 207 -> 224
+//            TFLOP/s at unchanged accuracy, 0.8e-5 on the same inputs); prefetching the residual one chunk ahead was tried and
+//            lost to register spills (the kernel sits at ptxas' 168-register ceiling for 320 threads).  min(4, 512 / N) TMEM accumulators
 //            rotate per segment, so draining segment j overlaps the MMAs of the following segments and a tile's epilogue
 //            (bias, residual, BN, split, stores) overlaps the next tile's first segments.
 //   epilogue v = acc + bias (+ residual);  raw fp32 v | split(v) (next block's shortcut input) | split(relu(bn_next(v)))
@@ -33,6 +37,7 @@
 namespace ursa {
 
 constexpr int WRN_THREADS = 320, WRN_MAX_STAGES = 4, WRN_MAX_BLOCKS = 8;
+constexpr int WRN_SEG0_FACTOR = 3;                 // a tile's FIRST segment is this many times longer, see the kernel comment
 constexpr int WRN_SEG = 4;                         // K blocks (of 32) per TMEM accumulation segment, see the kernel comment
 constexpr int WRN_MAX_TBUF = 4;                    // TMEM accumulators: min(4, 512 / bn_tile) at a column pitch of bn_tile
 constexpr int WRN_EPI_CHUNKS = 5;                  // 16-column chunks per epilogue thread: bn_tile / 2 <= 80
@@ -47,7 +52,7 @@ struct WrnMaps {
 
 struct WrnConvArgs {
     int cout, bn_tile, hout, stride, n_images;
-    int kchunks, xchunks, m_tiles, n_tiles, stages, seg;
+    int kchunks, xchunks, m_tiles, n_tiles, stages, seg, seg0;
     const float *bias;                 // [cout]
     const float *bn;                   // [2 * cout] (a, b) of the BN that follows, or null
     const float *res;                  // identity shortcut: raw block input [P][hout][hout][cout], or null
@@ -135,12 +140,12 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             const uint32_t idesc = make_tf32_idesc(128, a.bn_tile);
             uint32_t g = 0, sc = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                for (int kb0 = 0; kb0 < k_blocks; kb0 += a.seg, ++sc) {
+                for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg, ++sc) {
                     const uint32_t buf = sc % ntbuf;
                     mbar_wait_a(smem_u32(&tempty_bar[buf]), ((sc / ntbuf) & 1u) ^ 1u);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.bn_tile;
-                    const int kb1 = kb0 + a.seg < k_blocks ? kb0 + a.seg : k_blocks;
+                    const int kb1 = kb0 + len < k_blocks ? kb0 + len : k_blocks;
                     uint32_t acc = 0;
                     for (int kb = kb0; kb < kb1; ++kb, ++g) {
                         const uint32_t st = g % (uint32_t)a.stages, ph = (g / (uint32_t)a.stages) & 1u;
@@ -185,7 +190,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             for (int j = 0; j < WRN_EPI_CHUNKS; ++j)
 #pragma unroll
                 for (int e = 0; e < 16; ++e) accr[j][e] = 0.f;
-            for (int kb0 = 0; kb0 < k_blocks; kb0 += a.seg, ++sc) {
+            for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg, ++sc) {
                 const uint32_t buf = sc % ntbuf;
                 mbar_wait_a(smem_u32(&tfull_bar[buf]), (sc / ntbuf) & 1u);
                 tc_fence_after();
@@ -670,6 +675,10 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     g.stages = stages;
     g.seg = WRN_SEG;
     if (const char *e = getenv("URSA_WRN_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }      // accuracy / speed experiments
+    g.seg0 = WRN_SEG0_FACTOR * g.seg;                        // ... but never more than a quarter of the K extent
+    if (g.seg0 > (g.kchunks * 9 + g.xchunks) / 4) g.seg0 = (g.kchunks * 9 + g.xchunks) / 4;
+    if (g.seg0 < g.seg) g.seg0 = g.seg;
+    if (const char *e = getenv("URSA_WRN_SEG0")) { const int v = atoi(e); if (v >= 1) g.seg0 = v; }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
