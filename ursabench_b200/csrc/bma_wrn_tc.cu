@@ -102,13 +102,13 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
-            uint32_t g = 0;
+            uint32_t st = 0, ph = 0;                                   // ring position / phase, advanced at the loop bottom
+            const uint32_t nstages = (uint32_t)a.stages;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = t % a.n_tiles, mt = t / a.n_tiles;
                 int n0, h0;
                 if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
-                for (int kb = 0; kb < k_blocks; ++kb, ++g) {
-                    const uint32_t st = g % (uint32_t)a.stages, ph = (g / (uint32_t)a.stages) & 1u;
+                for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
                     const uint32_t fb = smem_u32(&full_bar[st]);
                     mbar_expect_tx_a(fb, stage_bytes);
@@ -131,6 +131,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                     }
                     tma_load_2d_a(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, nt * a.bn_tile, fb);
                     tma_load_2d_a(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, nt * a.bn_tile, fb);
+                    if (++st == nstages) { st = 0; ph ^= 1u; }
                 }
             }
         }
@@ -138,17 +139,16 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         if (elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_tf32_idesc(128, a.bn_tile);
-            uint32_t g = 0, sc = 0;
+            uint32_t st = 0, ph = 0, buf = 0, bph = 0;
+            const uint32_t nstages = (uint32_t)a.stages;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg, ++sc) {
-                    const uint32_t buf = sc % ntbuf;
-                    mbar_wait_a(smem_u32(&tempty_bar[buf]), ((sc / ntbuf) & 1u) ^ 1u);   // epilogue has drained this accumulator
+                for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
+                    mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);                   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.bn_tile;
                     const int kb1 = kb0 + len < k_blocks ? kb0 + len : k_blocks;
                     uint32_t acc = 0;
-                    for (int kb = kb0; kb < kb1; ++kb, ++g) {
-                        const uint32_t st = g % (uint32_t)a.stages, ph = (g / (uint32_t)a.stages) & 1u;
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait_a(smem_u32(&full_bar[st]), ph);
                         tc_fence_after();
                         const uint32_t base = smem_base + st * stage_bytes;
@@ -164,8 +164,10 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
                         }
                         umma_commit(smem_u32(&empty_bar[st]));
+                        if (++st == nstages) { st = 0; ph ^= 1u; }
                     }
                     umma_commit(smem_u32(&tfull_bar[buf]));
+                    if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
                 }
             }
         }
@@ -176,7 +178,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         const int qi = lane & 3, qb = lane & ~3;
         const int r = q * 32 + qb;                            // first pixel of this lane's quad (4 consecutive pixels of a row)
         const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
-        uint32_t sc = 0;
+        uint32_t buf = 0, bph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int nt = t % a.n_tiles, mt = t / a.n_tiles;
             int n0, h0;
@@ -190,9 +192,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             for (int j = 0; j < WRN_EPI_CHUNKS; ++j)
 #pragma unroll
                 for (int e = 0; e < 16; ++e) accr[j][e] = 0.f;
-            for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg, ++sc) {
-                const uint32_t buf = sc % ntbuf;
-                mbar_wait_a(smem_u32(&tfull_bar[buf]), (sc / ntbuf) & 1u);
+            for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
+                mbar_wait_a(smem_u32(&tfull_bar[buf]), bph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)a.bn_tile + (uint32_t)(half_id * half);
 #pragma unroll
@@ -207,6 +208,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
             }
             // The TMEM layout gives a thread one pixel (row) x 16 columns: stored as is, every warp-level access touches 32
             // different 128-byte lines (32 L1 tag cycles each -- measured: the epilogue then takes ~3/4 of a tile's MMA time and
