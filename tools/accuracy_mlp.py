@@ -32,6 +32,21 @@ def main():
         P, E = torch.zeros(N, 10, device="cuda"), torch.zeros(N, device="cuda")
         _C.bma_mlp_forward(bank, 1, x, 784, 400, 10, P, E, algo=algo)
         out[name] = (P.double() - p64).abs().max().item()
+    # speed: the bench's BMA configuration (S = 100, N = 10 000)
+    S, Nb = 100, 10_000
+    bk = (bank[:, :bank.shape[1]] + 0.01 * torch.randn(S, bank.shape[1], device="cuda")).contiguous()
+    xb = torch.randn(Nb, 784, device="cuda")
+    P, E = torch.zeros(Nb, 10, device="cuda"), torch.zeros(Nb, device="cuda")
+    ws = _C.bma_mlp_forward(bk, S, xb, 784, 400, 10, P, E, algo=_C.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        _C.bma_mlp_forward(bk, S, xb, 784, 400, 10, P, E, algo=_C.ALGO_TCGEN05, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out.update({"S100_N10k_ms": ms, "TFLOPs": 955_200 * S * Nb / ms / 1e9})
     print(json.dumps(out))
 
 

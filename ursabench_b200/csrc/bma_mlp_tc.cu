@@ -12,12 +12,20 @@
 //               stage; tcgen05.commit frees the stage / signals the epilogue
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 16 columns) -> + bias -> ReLU -> split hi/lo -> global (the next
 //               layer's TMA source), or plain fp32 logits for the last layer
+// TWO-LEVEL ACCUMULATION (as in bma_wrn_tc.cu): the tensor core adds into TMEM with truncated alignment, a bias that grows
+// with the length of an MMA chain -- one chain over K = 784 (300 MMAs) put the probabilities 13x further from an fp64
+// forward than PyTorch's fp32 is (7.1e-6 vs 5.4e-7 at |logit| <= 2.6).  A chain now covers TC_SEG K blocks (48 MMAs);
+// up to 4 TMEM accumulators rotate per segment and the epilogue warps drain each finished segment into fp32 registers
+// (round-to-nearest) while the next segments' MMAs run.
 // Operand layout: K-major rows of 128 bytes, SWIZZLE_128B in both the tensor maps and the UMMA descriptors.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace ursa {
 
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 4, TC_THREADS = 192;
+constexpr int TC_SEG = 4, TC_MAX_TBUF = 4, TC_EPI_CHUNKS = 8;          // BN <= 128 = 8 chunks of 16 columns
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;     // 16 KB per A tile
 
 struct TcGemmArgs {
@@ -34,6 +42,7 @@ struct TcGemmArgs {
     int relu;
     int stages;                   // smem ring depth (<= TC_STAGES)
     uint32_t tmem_cols;
+    int seg, ntbuf;               // K blocks per TMEM accumulation segment; rotating accumulators (column pitch BN)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -43,11 +52,13 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tfull_bar[TC_MAX_TBUF];
+    __shared__ __align__(8) uint64_t tempty_bar[TC_MAX_TBUF];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x, n_blk = blockIdx.y, s = blockIdx.z;
+    const uint32_t ntbuf = (uint32_t)a.ntbuf;
     const uint32_t b_bytes = (uint32_t)a.BN * TC_BK * 4;
     const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle-128B tiles need 1024-byte alignment
@@ -57,7 +68,10 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int i = 0; i < TC_MAX_TBUF; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);                                    // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -94,47 +108,81 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===== MMA issuer (one elected lane) =====
         if (elect_one()) {
             const uint32_t idesc = make_tf32_idesc(TC_BM, a.BN);
-            uint32_t acc = 0;
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-                const int st = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
-                mbar_wait_a(smem_u32(&full_bar[st]), ph);                    // TMA bytes have landed
+            uint32_t buf = 0, bph = 0;
+            for (int kb0 = 0; kb0 < a.k_blocks; kb0 += a.seg) {
+                mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);           // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
-                const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + TC_A_BYTES);
-                const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * TC_A_BYTES);
-                const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * TC_A_BYTES + b_bytes);
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.BN;
+                const int kb1 = kb0 + a.seg < a.k_blocks ? kb0 + a.seg : a.k_blocks;
+                uint32_t acc = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int st = kb % a.stages;
+                    const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+                    mbar_wait_a(smem_u32(&full_bar[st]), ph);                // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                    const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + TC_A_BYTES);
+                    const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * TC_A_BYTES);
+                    const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t koff = (uint64_t)((k * 32) >> 4);         // advance 32 bytes inside the swizzle row
-                    umma_tf32(tmem_base, d_alo + koff, d_bhi + koff, idesc, acc);
-                    acc = 1;
-                    umma_tf32(tmem_base, d_ahi + koff, d_blo + koff, idesc, 1);
-                    umma_tf32(tmem_base, d_ahi + koff, d_bhi + koff, idesc, 1);
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)((k * 32) >> 4);     // advance 32 bytes inside the swizzle row
+                        umma_tf32(d_tmem, d_alo + koff, d_bhi + koff, idesc, acc);
+                        acc = 1;
+                        umma_tf32(d_tmem, d_ahi + koff, d_blo + koff, idesc, 1);
+                        umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
+                    }
+                    umma_commit(smem_u32(&empty_bar[st]));                   // frees the smem slot when the MMAs retire
                 }
-                umma_commit(smem_u32(&empty_bar[st]));                       // frees the smem slot when the MMAs retire
+                umma_commit(smem_u32(&tfull_bar[buf]));                      // segment complete -> epilogue drains it
+                if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
             }
-            umma_commit(smem_u32(&tmem_full_bar));                           // accumulator complete -> epilogue
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait_a(smem_u32(&tmem_full_bar), 0);
-        tc_fence_after();
+        float accr[TC_EPI_CHUNKS][16];
+#pragma unroll
+        for (int j = 0; j < TC_EPI_CHUNKS; ++j)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) accr[j][e] = 0.f;
+        {
+            uint32_t buf = 0, bph = 0;
+            for (int kb0 = 0; kb0 < a.k_blocks; kb0 += a.seg) {
+                mbar_wait_a(smem_u32(&tfull_bar[buf]), bph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)a.BN;
+#pragma unroll
+                for (int j = 0; j < TC_EPI_CHUNKS; ++j) {
+                    if (j * 16 < a.BN) {
+                        uint32_t rr[16];
+                        tmem_ld16(taddr + (uint32_t)(j * 16), rr);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
+            }
+        }
         const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
         const float *bias = a.bias + (int64_t)s * a.bias_stride;
         const bool split = a.out_lo != nullptr;
         float *ohi = a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out;
         float *olo = split ? a.out_lo + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
-        for (int c0 = 0; c0 < a.BN; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < TC_EPI_CHUNKS; ++j) {
+            const int c0 = j * 16;
+            if (c0 >= a.BN) continue;
+            const float (&r)[16] = accr[j];
             const int col0 = n_blk * a.BN + c0;
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int col = col0 + i;
-                float x = __uint_as_float(r[i]) + (col < a.n_valid ? __ldg(bias + col) : 0.f);
+                float x = r[i] + (col < a.n_valid ? __ldg(bias + col) : 0.f);
                 if (a.relu) x = fmaxf(x, 0.f);
                 v[i] = x;
             }
@@ -249,8 +297,11 @@ static int launch_tc_gemm(const float *a_hi, const float *a_lo, int64_t a_rows, 
     g.BN = BN;
     g.k_blocks = Kp / TC_BK;
     g.a_batched = a_batch > 1 ? 1 : 0;
+    g.seg = TC_SEG;
+    if (const char *e = getenv("URSA_MLP_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }   // accuracy / speed experiments
+    g.ntbuf = 512 / BN < TC_MAX_TBUF ? 512 / BN : TC_MAX_TBUF;
     uint32_t cols = 32;
-    while (cols < (uint32_t)BN) cols <<= 1;
+    while (cols < (uint32_t)(g.ntbuf * BN)) cols <<= 1;
     g.tmem_cols = cols;
     const size_t stage_bytes = 2 * TC_A_BYTES + 2 * (size_t)BN * TC_BK * 4;
     int stages = (int)((size_t)(226 << 10) / stage_bytes);
