@@ -90,25 +90,25 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // ===== TMA producer (one elected lane) =====
         if (elect_one()) {
             const int a_b = a.a_batched ? s : 0;
+            uint32_t st = 0, ph = 0;                                         // ring position / phase (no division on the issue path)
             for (int kb = 0; kb < a.k_blocks; ++kb) {
-                const int st = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
                 mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);              // slot free (first pass: passes at once)
                 const uint32_t fb = smem_u32(&full_bar[st]);
                 mbar_expect_tx_a(fb, stage_bytes);
-                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const uint32_t base = smem_base + st * stage_bytes;
                 const int k0 = kb * TC_BK;
                 tma_load_3d_a(base, &tm_a_hi, k0, m_blk * TC_BM, a_b, fb);
                 tma_load_3d_a(base + TC_A_BYTES, &tm_a_lo, k0, m_blk * TC_BM, a_b, fb);
                 tma_load_3d_a(base + 2 * TC_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, s, fb);
                 tma_load_3d_a(base + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, s, fb);
+                if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (elect_one()) {
             const uint32_t idesc = make_tf32_idesc(TC_BM, a.BN);
-            uint32_t buf = 0, bph = 0;
+            uint32_t buf = 0, bph = 0, st = 0, ph = 0;
             for (int kb0 = 0; kb0 < a.k_blocks; kb0 += a.seg) {
                 mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);           // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -116,11 +116,9 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const int kb1 = kb0 + a.seg < a.k_blocks ? kb0 + a.seg : a.k_blocks;
                 uint32_t acc = 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    const int st = kb % a.stages;
-                    const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
                     mbar_wait_a(smem_u32(&full_bar[st]), ph);                // TMA bytes have landed
                     tc_fence_after();
-                    const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                    const uint32_t base = smem_base + st * stage_bytes;
                     const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + TC_A_BYTES);
                     const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * TC_A_BYTES);
                     const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * TC_A_BYTES + b_bytes);
@@ -133,6 +131,7 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
                     }
                     umma_commit(smem_u32(&empty_bar[st]));                   // frees the smem slot when the MMAs retire
+                    if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
                 }
                 umma_commit(smem_u32(&tfull_bar[buf]));                      // segment complete -> epilogue drains it
                 if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
