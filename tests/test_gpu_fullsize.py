@@ -181,3 +181,40 @@ def test_k3_wrn28x10_full_size_accuracy_bracket_and_invariances(C):
     P3, E3 = torch.zeros_like(P), torch.zeros_like(E)
     C.bma_wrn_forward(torch.cat([bank, bank]), torch.cat([bufbank, bufbank]), 2, x, 28, 10, Cc, P3, E3)
     assert torch.equal(P3, P + P) and torch.equal(E3, E + E)
+
+
+def test_config3_pipeline_swag_wrn28x10_end_to_end(C):
+    """BASELINE.json configs[2] at its real width, shortened in length: SWAG (rank-20 ring) on WideResNet-28-10 / C = 100 ->
+    low-rank draws (K2b) -> BatchNorm re-estimation per draw on the conv engine (K3b) -> Prediction over the bank (K3 WideResNet
+    forward + K4 metrics).  Checks that every stage ran on the engine and that the numbers are sane and self-consistent."""
+    from ursabench_b200 import inference, tasks
+    from ursabench_b200.models import WideResNet
+    torch.manual_seed(0)
+    Cc, n_train, n_test = 100, 256, 130
+    xtr, ytr = torch.randn(n_train, 3, 32, 32), torch.randint(0, Cc, (n_train,))
+    xte, yte = torch.randn(n_test, 3, 32, 32), torch.randint(0, Cc, (n_test,))
+    train = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xtr, ytr), batch_size=128, shuffle=False)
+    test = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xte, yte), batch_size=64, shuffle=False)
+    hyp = {"lr_init": 0.01, "swag_lr": 0.005, "swag_wd": 5e-4, "momentum": 0.9, "burn_in_epochs": 1, "num_iterates": 3,
+           "num_samples": 3, "subspace_type": "covariance"}
+    sw = inference.SWAG(hyp, model=WideResNet(num_classes=Cc, depth=28, widen_factor=10), train_loader=train,
+                        device=torch.device("cuda"))
+    assert sw.num_parameters == D_WRN
+    samples = sw.sample(full_cov=True)
+    assert len(samples) == 3 and getattr(sw, "_bn_x", None) is not None            # K3b ran (no PyTorch bn_update pass)
+    w = sw.bank.w[:3, :D_WRN]
+    assert torch.isfinite(w).all() and (w[0] - w[1]).abs().max().item() > 0         # distinct low-rank draws
+    b = sw.bank.b[:3]
+    assert torch.isfinite(b).all() and (b[0] - b[1]).abs().max().item() > 0         # per-draw BatchNorm statistics
+    task = tasks.Prediction({"in_distribution_test": test}, Cc, torch.device("cuda"), "ALL")
+    task.update_statistics(samples, output_performance=False)
+    assert task.last_engine == "fused_wrn"
+    m = task.get_performance_metrics()
+    P = task.ensemble_proba
+    assert torch.allclose(P.sum(1).cpu(), torch.full((n_test,), 3.0), atol=1e-4)      # three softmax rows per image
+    assert 0.0 <= m["error_rate"] <= 1.0 and math.isfinite(m["nll"]) and 0.0 <= m["ece"] <= 1.0 and 0.0 <= m["brier_score"] <= 2.0
+    # the same samples through the model's own PyTorch forward (generic engine): the BMA probabilities agree
+    ref = tasks.Prediction({"in_distribution_test": test}, Cc, torch.device("cuda"), "ALL", engine="generic")
+    ref.update_statistics(samples, output_performance=False)
+    assert ref.last_engine == "generic"
+    assert (ref.ensemble_proba - P).abs().max().item() < 3e-5 * 3
