@@ -89,7 +89,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
 // bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait_a(bar, parity); ++spin)
-        if (spin > (1u << 27)) __trap();
+        if (spin > (1u << 22)) __trap();   // ~seconds: no legitimate wait in these kernels exceeds milliseconds
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
