@@ -15,6 +15,11 @@
 //            parity-split tensor maps.  The 1x1 (strided) shortcut conv of a transition block is folded into conv2's
 //            accumulation as extra K blocks over the split RAW block input X -- no separate kernel, no extra pass.
 //            warp 0: TMA producer | warp 1: tcgen05.mma issuer (3 MMAs per K = 8 step) | warps 2-9: epilogue.
+//            CTA PAIRS (default): the two CTAs of a cluster take adjacent M tiles of one N tile and run ONE M = 256
+//            tcgen05.mma.cta_group::2 -- each SM streams its own A tile and HALF of B (52 KB instead of 72 KB per K block, so the
+//            ring has 4 stages); both CTAs' TMA copies are counted on the leader's barrier, the leader's commits are multicast
+//            to both CTAs, both epilogues release the leader's accumulator barrier.  One chain per tile: 259 -> 280 TFLOP/s;
+//            with the accumulation segments: 228-238 -> 242.
 //            TWO-LEVEL ACCUMULATION: the tensor core adds into TMEM with truncated alignment, a bias that grows with the
 //            length of the MMA chain (measured: 2e-5 on WRN-16-2 probabilities with K = 1152 chains, 20x the fp32 noise
 //            floor).  So a chain covers only WRN_SEG K blocks (K = 128, 48 MMAs); the epilogue warps drain each segment
@@ -63,6 +68,10 @@ struct WrnConvArgs {
     int batch;                         // images per batch (train mode)
 };
 
+// NCTA = 2: CTA pair (cta_group::2).  The two CTAs of a cluster take adjacent M tiles of the same N tile and run ONE M = 256 MMA:
+// each streams its own A tile and HALF of the B tile from its shared memory (52 KB instead of 72 KB per K block -> a 4-stage
+// ring), the leader (cluster rank 0) issues the MMAs and multicasts its commits; both epilogues release the leader's accumulator.
+template <int NCTA>
 __global__ void __launch_bounds__(WRN_THREADS, 1)
 wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -75,11 +84,15 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int WT = a.hout, HT = a.hout >= 16 ? 128 / a.hout : a.hout;
     const int tpi = (a.hout * a.hout) / 128;                 // tiles per image (0 when one tile spans 2 images)
-    const uint32_t b_bytes = (uint32_t)a.bn_tile * 128u;
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    const uint32_t b_rows = (uint32_t)a.bn_tile / NCTA;        // rows of the B tile this CTA stages
+    const uint32_t b_bytes = b_rows * 128u;
     const uint32_t stage_bytes = 2 * WRN_A_BYTES + 2 * b_bytes;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int kb3 = 9 * a.kchunks, k_blocks = kb3 + a.xchunks;
-    const int total_tiles = a.m_tiles * a.n_tiles;
+    // work units: (M tile [pair], N tile), N fastest; unit u -> this CTA's tile (mt, nt)
+    const int total_tiles = ((a.m_tiles + NCTA - 1) / NCTA) * a.n_tiles;
+    const int first_unit = (int)blockIdx.x / NCTA, unit_stride = (int)gridDim.x / NCTA;
     const uint32_t ntbuf = 512u / (uint32_t)a.bn_tile < (uint32_t)WRN_MAX_TBUF ? 512u / (uint32_t)a.bn_tile : (uint32_t)WRN_MAX_TBUF;
 
     if (threadIdx.x == 0) {
@@ -89,13 +102,17 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         }
         for (int i = 0; i < WRN_MAX_TBUF; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], (WRN_THREADS - 64) / 32);      // one arrival per epilogue warp
+            mbar_init(&tempty_bar[i], NCTA * (WRN_THREADS - 64) / 32);   // one arrival per epilogue warp (of both CTAs)
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    if (warp == 1) {
+        if (NCTA == 2) tmem_alloc_2cta(&tmem_base_s, 512);
+        else tmem_alloc(&tmem_base_s, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();                        // the peer's barriers are initialised before anybody signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
@@ -104,15 +121,23 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             // ===== TMA producer =====
             uint32_t st = 0, ph = 0;                                   // ring position / phase, advanced at the loop bottom
             const uint32_t nstages = (uint32_t)a.stages;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+            for (int t = first_unit; t < total_tiles; t += unit_stride) {
+                const int nt = t % a.n_tiles, mt = (t / a.n_tiles) * NCTA + (int)cta_rank;
                 int n0, h0;
                 if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
-                    const uint32_t fb = smem_u32(&full_bar[st]);
-                    mbar_expect_tx_a(fb, stage_bytes);
-                    const uint32_t base = smem_base + st * stage_bytes;
+                    uint32_t fb = smem_u32(&full_bar[st]);
+                    uint32_t base = smem_base + st * stage_bytes;
+                    if (NCTA == 2) {
+                        // both CTAs' copies are counted on the LEADER's barrier (cluster addresses), which expects both stages
+                        if (cta_rank == 0) mbar_expect_tx_a(fb, 2 * stage_bytes);
+                        fb = mapa_u32(fb, 0);
+                        base = mapa_u32(base, cta_rank);
+                    } else {
+                        mbar_expect_tx_a(fb, stage_bytes);
+                    }
+                    const int brow = nt * a.bn_tile + (int)(cta_rank * b_rows);
                     if (kb < kb3) {
                         const int tap = kb / a.kchunks, cc = kb - tap * a.kchunks;
                         const int kh = tap / 3, kw = tap - kh * 3;
@@ -122,26 +147,41 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             cw = (kw - 1) >> 1;                                // floor((kw-1)/2)
                             ch = h0 + ((kh - 1) >> 1);
                         }
-                        tma_load_4d_a(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
-                        tma_load_4d_a(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                        if (NCTA == 2) {
+                            tma_load_4d_2cta(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
+                            tma_load_4d_2cta(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                        } else {
+                            tma_load_4d_a(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
+                            tma_load_4d_a(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                        }
                     } else {
                         const int cc = kb - kb3;
-                        tma_load_4d_a(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
-                        tma_load_4d_a(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                        if (NCTA == 2) {
+                            tma_load_4d_2cta(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
+                            tma_load_4d_2cta(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                        } else {
+                            tma_load_4d_a(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
+                            tma_load_4d_a(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                        }
                     }
-                    tma_load_2d_a(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, nt * a.bn_tile, fb);
-                    tma_load_2d_a(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, nt * a.bn_tile, fb);
+                    if (NCTA == 2) {
+                        tma_load_2d_2cta(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, brow, fb);
+                        tma_load_2d_2cta(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
+                    } else {
+                        tma_load_2d_a(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, brow, fb);
+                        tma_load_2d_a(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
+                    }
                     if (++st == nstages) { st = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = make_tf32_idesc(128, a.bn_tile);
+        if (cta_rank == 0 && elect_one()) {
+            // ===== MMA issuer (the leader CTA of a pair) =====
+            const uint32_t idesc = make_tf32_idesc(128 * NCTA, a.bn_tile);
             uint32_t st = 0, ph = 0, buf = 0, bph = 0;
             const uint32_t nstages = (uint32_t)a.stages;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = first_unit; t < total_tiles; t += unit_stride) {
                 for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
                     mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);                   // epilogue has drained this accumulator
                     tc_fence_after();
@@ -158,15 +198,24 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
-                            umma_tf32(d_tmem, d_alo + koff, d_bhi + koff, idesc, acc);
-                            acc = 1;
-                            umma_tf32(d_tmem, d_ahi + koff, d_blo + koff, idesc, 1);
-                            umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
+                            if (NCTA == 2) {
+                                umma_tf32_2cta(d_tmem, d_alo + koff, d_bhi + koff, idesc, acc);
+                                acc = 1;
+                                umma_tf32_2cta(d_tmem, d_ahi + koff, d_blo + koff, idesc, 1);
+                                umma_tf32_2cta(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
+                            } else {
+                                umma_tf32(d_tmem, d_alo + koff, d_bhi + koff, idesc, acc);
+                                acc = 1;
+                                umma_tf32(d_tmem, d_ahi + koff, d_blo + koff, idesc, 1);
+                                umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
+                            }
                         }
-                        umma_commit(smem_u32(&empty_bar[st]));
+                        if (NCTA == 2) umma_commit_2cta(smem_u32(&empty_bar[st]), 3);     // frees the stage in BOTH CTAs
+                        else umma_commit(smem_u32(&empty_bar[st]));
                         if (++st == nstages) { st = 0; ph ^= 1u; }
                     }
-                    umma_commit(smem_u32(&tfull_bar[buf]));
+                    if (NCTA == 2) umma_commit_2cta(smem_u32(&tfull_bar[buf]), 3);         // both epilogues drain their half
+                    else umma_commit(smem_u32(&tfull_bar[buf]));
                     if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
                 }
             }
@@ -179,8 +228,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         const int r = q * 32 + qb;                            // first pixel of this lane's quad (4 consecutive pixels of a row)
         const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
         uint32_t buf = 0, bph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+        for (int t = first_unit; t < total_tiles; t += unit_stride) {
+            const int nt = t % a.n_tiles, mt = (t / a.n_tiles) * NCTA + (int)cta_rank;
             int n0, h0;
             if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
             const int n = n0 + nl;
@@ -207,7 +256,10 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                if (lane == 0) {
+                    if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+                    else mbar_arrive(&tempty_bar[buf]);
+                }
                 if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
             }
             // The TMEM layout gives a thread one pixel (row) x 16 columns: stored as is, every warp-level access touches 32
@@ -295,10 +347,12 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();                        // nobody frees TMEM / exits while the peer may still signal it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (NCTA == 2) tmem_dealloc_2cta(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -658,10 +712,12 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     }
     const int bn_tile = wrn_pick_bn_tile(cout);
     URSA_REQUIRE(bn_tile > 0, "ursa_bma_wrn_forward: no output-channel tile for cout = %d", cout);
+    int ncta = 2;                                                       // CTA pairs (cta_group::2); URSA_WRN_2CTA=0 selects single CTAs
+    if (const char *e = getenv("URSA_WRN_2CTA")) ncta = atoi(e) == 0 ? 1 : 2;
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
         const uint64_t sb[1] = {(uint64_t)ktot * 4};
-        const uint32_t box[2] = {32u, (uint32_t)bn_tile};
+        const uint32_t box[2] = {32u, (uint32_t)(bn_tile / ncta)};
         if (int rc = make_tensor_map(&maps.b_hi, b_hi, 2, dims, sb, box, 128)) return rc;
         if (int rc = make_tensor_map(&maps.b_lo, b_lo, 2, dims, sb, box, 128)) return rc;
     }
@@ -670,7 +726,7 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     const int tpi = (hout * hout) / 128;
     g.m_tiles = tpi > 0 ? nc * tpi : (nc + 1) / 2;
     g.n_tiles = cout / bn_tile;
-    const size_t stage_bytes = 2 * (size_t)WRN_A_BYTES + 2 * (size_t)bn_tile * 128;
+    const size_t stage_bytes = 2 * (size_t)WRN_A_BYTES + 2 * (size_t)(bn_tile / ncta) * 128;
     int stages = (int)(((size_t)(226 << 10) - 1024) / stage_bytes);
     if (stages > WRN_MAX_STAGES) stages = WRN_MAX_STAGES;
     if (const char *e = getenv("URSA_WRN_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
@@ -682,10 +738,27 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     if (g.seg0 < g.seg) g.seg0 = g.seg;
     if (const char *e = getenv("URSA_WRN_SEG0")) { const int v = atoi(e); if (v >= 1) g.seg0 = v; }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
+    if (ncta == 2) {
+        const int units = ((g.m_tiles + 1) / 2) * g.n_tiles, pairs = sm_count() / 2;
+        URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (units < pairs ? units : pairs));
+        cfg.blockDim = dim3(WRN_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        URSA_CUDA(cudaLaunchKernelEx(&cfg, wrn_conv_tc_kernel<2>, maps, g));
+        URSA_LAUNCH_CHECK("wrn_conv_tc_kernel<2>");
+        return URSA_OK;
+    }
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wrn_conv_tc_kernel<<<grid, WRN_THREADS, smem, st>>>(maps, g);
+    URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wrn_conv_tc_kernel<1><<<grid, WRN_THREADS, smem, st>>>(maps, g);
     URSA_LAUNCH_CHECK("wrn_conv_tc_kernel");
     return URSA_OK;
 }
