@@ -529,11 +529,14 @@ def run_extras(dev, rank, world, peak):
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
+    wsampler = _ClockSampler(dev.index if dev.index is not None else 0)
+    wsampler.start()
     ms, _ = _event_time_ms(bma_wrn, 1)
+    wclocks = wsampler.stop()                               # a 5-17 s tensor-core run: the SM clock under its own power draw
     ms = udist.allreduce_max_scalar(ms, dev)
     out["bma_wrn28x10_S30_N10k_tcgen05"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
                                             "img_samples_per_s": N * S_w / ms * 1e3,
-                                            "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world}
+                                            "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world, "clocks": wclocks}
     # K3b: BatchNorm re-estimation of one SWAG draw (util.bn_update, once per sample): bounded sample of the 50 000-image pass
     Nbn, Bbn = 2048, 128
     bn_fn = lambda: _C.wrn_bn_update(bankw[0], bufw[0], xi[:Nbn], Bbn, 28, 10, C_w, workspace=ws[0])  # noqa: E731
