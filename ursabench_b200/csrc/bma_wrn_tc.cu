@@ -690,6 +690,33 @@ static int wrn_pick_bn_tile(int cout) {
     return 0;
 }
 
+// Can a CTA pair of this kernel be co-scheduled on this device / partition at all?  (asked once per thread and device)
+static bool wrn_pairs_supported() {
+    static thread_local int cached = -1, cached_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cached < 0 || dev != cached_dev) {
+        cached_dev = dev;
+        cached = 0;
+        const size_t smem = 4 * (2 * (size_t)WRN_A_BYTES + 2 * (size_t)80 * 128) + 1024;        // 4 stages at N = 160
+        if (cudaFuncSetAttribute(wrn_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2);
+            cfg.blockDim = dim3(WRN_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, wrn_conv_tc_kernel<2>, &cfg) == cudaSuccess && n >= 1) cached = 1;
+        }
+        (void)cudaGetLastError();
+    }
+    return cached == 1;
+}
+
 // one conv launch: A planes [nc][hin][hin][cin_p] -> cout channels at hout = hin / stride; xin_p > 0 folds a 1x1 stride-`stride`
 // conv over the X planes [nc][hin][hin][xin_p] into the accumulation
 static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int cin_p, const float *x_hi, const float *x_lo,
@@ -714,6 +741,7 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     URSA_REQUIRE(bn_tile > 0, "ursa_bma_wrn_forward: no output-channel tile for cout = %d", cout);
     int ncta = 2;                                                       // CTA pairs (cta_group::2); URSA_WRN_2CTA=0 selects single CTAs
     if (const char *e = getenv("URSA_WRN_2CTA")) ncta = atoi(e) == 0 ? 1 : 2;
+    if (ncta == 2 && !wrn_pairs_supported()) ncta = 1;
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
         const uint64_t sb[1] = {(uint64_t)ktot * 4};
