@@ -207,3 +207,24 @@ def test_swag_sample_uses_the_engine_bn_update_for_wideresnets():
         ref = _flat_buffers(ref_m)
         got = sw.bank.b[i, :ref.numel()]
         assert ((got - ref).abs() / (ref.abs() + 1e-2)).max().item() < 5e-4
+
+
+def test_arch_detection_accepts_the_reference_modules():
+    """The engine recognises WideResNets structurally (class / attribute names), so the reference's OWN module objects -- what
+    `inference.sample()` of the reference returns -- route through the tcgen05 forward too.  Needs the reference checkout
+    (absent on the GPU box): skipped there."""
+    from oracle import stubs
+    if not stubs.reference_available():
+        pytest.skip("reference checkout not present")
+    stubs.install()
+    import warnings
+    from URSABench import models as ref_models
+    from ursabench_b200.tasks._engine import _arch_of
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_models.wideresnet.WideResNet(num_classes=10, depth=16, widen_factor=4)
+    assert _arch_of(ref) == ("wrn", 16, 4, 10)
+    ours = WideResNet(num_classes=10, depth=16, widen_factor=4)
+    assert _arch_of(ours) == ("wrn", 16, 4, 10)
+    assert [tuple(p.shape) for p in ref.parameters()] == [tuple(p.shape) for p in ours.parameters()]
+    assert [n for n, _ in ref.named_buffers()] == [n for n, _ in ours.named_buffers()]
