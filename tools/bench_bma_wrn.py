@@ -8,9 +8,30 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.wrn_fill import wrn_fill  # noqa: E402
 from ursabench_b200 import _C  # noqa: E402
 from ursabench_b200.models import WideResNet  # noqa: E402
+
+
+def wrn_fill(model, seed, logit_gain=4.0):
+    """Seeded weights with O(1) activations and non-trivial BatchNorm statistics (a local twin of the test suite's filler:
+    tools do not import the oracle package)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 4:
+                p.copy_(torch.randn(p.shape, generator=g) * (2.0 / (p.shape[1] * p.shape[2] * p.shape[3])) ** 0.5)
+            elif p.dim() == 2:
+                p.copy_(torch.randn(p.shape, generator=g) * (logit_gain / p.shape[1] ** 0.5))
+            elif name.endswith("weight"):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        for name, b in model.named_buffers():
+            if name.endswith("running_mean"):
+                b.copy_(torch.randn(b.shape, generator=g) * 0.3)
+            elif name.endswith("running_var"):
+                b.copy_(torch.rand(b.shape, generator=g) * 1.5 + 0.5)
+    return model
 
 
 def wrn_flops(depth, widen):
