@@ -129,6 +129,47 @@ class HMC(_Inference):
 
         return torch.func.vmap(torch.func.grad_and_value(nll_of))
 
+    def _build_grad_fn_mlp(self, arch):
+        """Chain-batched gradient of the summed cross entropy for the 3-layer MLP (models/mlp.py:8-23) written out as GEMMs:
+        the shared input makes layers 1 of ALL chains one GEMM ([C*h, in] x [in, N]) forward and one backward, layers 2 / 3
+        are batched GEMMs in a feature-major [C, h, N] layout -- no per-chain graph, no transposed copies.  Same arithmetic
+        as ``vmap(grad)`` of the module (fp32), 2-3x its throughput on 128 chains x 1000 points."""
+        _, in_dim, hid, ncls = arch
+        xT = self.x.reshape(self.x.shape[0], -1).t().contiguous()          # [in, N]
+        xN = xT.t().contiguous()                                            # [N, in]
+        y = self.y.long()
+        o_w1, o_b1 = 0, hid * in_dim
+        o_w2, o_b2 = o_b1 + hid, o_b1 + hid + hid * hid
+        o_w3, o_b3 = o_b2 + hid, o_b2 + hid + ncls * hid
+
+        def fn(rows):
+            c = rows.shape[0]
+            W1 = rows[:, o_w1:o_b1].reshape(c * hid, in_dim)
+            b1 = rows[:, o_b1:o_w2].reshape(c, hid, 1)
+            W2 = rows[:, o_w2:o_b2].reshape(c, hid, hid)
+            b2 = rows[:, o_b2:o_w3].reshape(c, hid, 1)
+            W3 = rows[:, o_w3:o_b3].reshape(c, ncls, hid)
+            b3 = rows[:, o_b3:o_b3 + ncls].reshape(c, ncls, 1)
+            a1 = torch.relu_(torch.mm(W1, xT).view(c, hid, -1).add_(b1))
+            a2 = torch.relu_(torch.baddbmm(b2, W2, a1))
+            lo = torch.baddbmm(b3, W3, a2)                                   # [c, C, N]
+            logp = torch.log_softmax(lo, dim=1)
+            val = -logp.gather(1, y.view(1, 1, -1).expand(c, 1, -1)).sum(dim=(1, 2))
+            dlo = logp.exp_()
+            dlo.scatter_add_(1, y.view(1, 1, -1).expand(c, 1, -1), torch.full((1, 1, 1), -1.0, device=rows.device).expand(c, 1, y.numel()))
+            gr = torch.empty(c, self.D, dtype=torch.float32, device=rows.device)
+            gr[:, o_w3:o_b3] = torch.bmm(dlo, a2.transpose(1, 2)).reshape(c, -1)
+            gr[:, o_b3:o_b3 + ncls] = dlo.sum(2)
+            da2 = torch.bmm(W3.transpose(1, 2), dlo).mul_(a2 > 0)
+            gr[:, o_w2:o_b2] = torch.bmm(da2, a1.transpose(1, 2)).reshape(c, -1)
+            gr[:, o_b2:o_w3] = da2.sum(2)
+            da1 = torch.bmm(W2.transpose(1, 2), da2).mul_(a1 > 0)
+            gr[:, o_w1:o_b1] = torch.mm(da1.view(c * hid, -1), xN).view(c, -1)
+            gr[:, o_b1:o_w2] = da1.sum(2)
+            return gr, val
+
+        return fn
+
     def _grad(self, theta, g, ce):
         """g[c, :D] = d/dtheta sum_i loss_i(theta_c) ; ce[c] = sum_i loss_i(theta_c)   (fp32 forward/backward)."""
         C = theta.shape[0]
@@ -191,6 +232,14 @@ class HMC(_Inference):
         self.bank.reserve(max(1, n_keep * C))
         self.model.eval()
         self._grad_fn = self._build_grad_fn()
+        from ..tasks._engine import _arch_of
+        arch = _arch_of(self.model)
+        self.grad_engine = "vmap"
+        if arch is not None and arch[0] == "mlp" and self.model_loss == "multi_class_linear_output" \
+                and getattr(self, "force_vmap_grad", False) is False and self.D == arch[2] * arch[1] + arch[2] \
+                + arch[2] * arch[2] + arch[2] + arch[3] * arch[2] + arch[3]:
+            self._grad_fn = self._build_grad_fn_mlp(arch)
+            self.grad_engine = "mlp_gemm"
         self._sums, self._energy_ws = None, None
         with torch.no_grad():
             theta = self._initial_state()
