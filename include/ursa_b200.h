@@ -179,6 +179,19 @@ int ursa_bma_mlp_forward(const float *bank, int64_t ld_bank, int S, const float 
                          int algo, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K3' batched GEMM on the MLP engine (3xTF32, two-level accumulation, fp32 in / out):
+ *       out[b, m, n] = sum_k A[b or shared, m, k] * B[b, n, k]  (+ bias[b, n])  (ReLU)
+ *     A: [batch or 1][M][lda] (a_batch_stride = 0: one A shared by the batch), B: [batch][N][ldb], out: [batch][M][ldo].
+ *     Used by the chain-batched HMC likelihood gradient of the MLPs (config 4), where hamiltorch / torch.func run
+ *     one autograd graph per chain (inference/hmc.py:71-75).  Workspace holds the TF32 hi / lo planes.
+ * ---------------------------------------------------------------------- */
+size_t ursa_gemm_nt_3xtf32_workspace(int batch, int64_t M, int N, int K, int a_batched);
+int ursa_gemm_nt_3xtf32(const float *A, int64_t lda, int64_t a_batch_stride, const float *B, int64_t ldb,
+                        int64_t b_batch_stride, const float *bias, int64_t bias_stride, int relu,
+                        float *out, int64_t ldo, int64_t out_batch_stride, int batch, int64_t M, int N, int K,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * K3  sample-batched BMA forward, PreResNet (BasicBlock, depth = 6n+2 < 44; models/preresnet.py:90-151)
  *     bank: [S, ld_bank] parameters; bufbank: [S, ld_buf] BatchNorm running stats in named_buffers()
  *     order with the int64 num_batches_tracked entries dropped (mean, var per BN layer);

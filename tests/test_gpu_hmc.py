@@ -242,8 +242,10 @@ def test_hmc_mlp_gemm_gradient_matches_vmap_grad():
     hyp = {"step_size": 1e-3, "num_samples": 1, "L": 2, "tau": 10.0, "burn": 0, "mass": 1.0, "num_chains": 5}
     inf = inference.HMC(hyperparameters=dict(hyp), model=models.MLP(40, 36, 7), train_loader=loader, device=DEV)
     inf.sample()
-    assert inf.grad_engine == "mlp_gemm"
+    assert inf.grad_engine == "mlp_gemm"                    # fp32 GEMM formulation (the faster of the two fast paths)
+    from ursabench_b200.tasks._engine import _arch_of
     theta = torch.randn(5, inf.ld, device=DEV) * 0.2
+    inf._grad_fn = inf._build_grad_fn_mlp_tc(_arch_of(inf.model))        # the same GEMMs on ursa_gemm_nt_3xtf32
     g1, ce1 = torch.zeros_like(theta), torch.zeros(5, device=DEV)
     inf._grad(theta, g1, ce1)
     inf._grad_fn = inf._build_grad_fn()                     # the generic engine
@@ -252,8 +254,31 @@ def test_hmc_mlp_gemm_gradient_matches_vmap_grad():
     scale = g2.abs().max().item()
     assert (g1 - g2).abs().max().item() < 2e-5 * scale
     assert torch.allclose(ce1, ce2, rtol=2e-6, atol=1e-4)
+    inf._grad_fn = inf._build_grad_fn_mlp(_arch_of(inf.model))          # the cuBLAS fp32 formulation of the same GEMMs
+    g3, ce3 = torch.zeros_like(theta), torch.zeros(5, device=DEV)
+    inf._grad(theta, g3, ce3)
+    assert (g3 - g2).abs().max().item() < 2e-5 * scale and torch.allclose(ce3, ce2, rtol=2e-6, atol=1e-4)
     # a module the fast path does not cover keeps the generic engine
     inf2 = inference.HMC(hyperparameters=dict(hyp), model=torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(36, 7)),
                          train_loader=loader, device=DEV)
     inf2.sample()
     assert inf2.grad_engine == "vmap"
+
+
+@pytest.mark.parametrize("batch,M,N,K,shared,relu", [(3, 70, 40, 36, True, True), (2, 257, 10, 200, False, False),
+                                                       (4, 10, 200, 1000, False, False), (1, 130, 129, 31, True, False)])
+def test_gemm_nt_3xtf32_matches_fp64(batch, M, N, K, shared, relu):
+    """ursa_gemm_nt_3xtf32 (the MLP engine as a plain batched GEMM): ragged M / N / K, shared or batched A, strided operands,
+    bias + ReLU epilogue, against an fp64 product."""
+    from ursabench_b200 import _C
+    torch.manual_seed(batch * 1000 + M)
+    A = torch.randn((M, K + 3) if shared else (batch, M, K + 3), device=DEV)[..., :K]          # lda > K
+    Bm = torch.randn(batch, N, K + 5, device=DEV)[..., :K]
+    bias = torch.randn(batch, N, device=DEV)
+    out = torch.full((batch, M, N + 2), float("nan"), device=DEV)[..., :N]                      # ldo > N
+    _C.gemm_nt(A, Bm, out, bias=bias, relu=relu)
+    ref = torch.matmul((A if not shared else A[None]).double(), Bm.double().transpose(1, 2)) + bias.double()[:, None, :]
+    if relu:
+        ref = ref.clamp_min(0)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 3e-6 * max(1.0, ref.abs().max().item()) * (K ** 0.5) / 8 + 1e-6, err

@@ -41,6 +41,9 @@ SIGNATURES = {
     "ursa_bma_preresnet_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_bma_preresnet_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                           _sz, _i32, _vp]),
+    "ursa_gemm_nt_3xtf32_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
+    "ursa_gemm_nt_3xtf32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _i64, _i32, _i32,
+                                   _vp, _sz, _vp]),
     "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
     "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                     _sz, _i32, _vp]),
@@ -243,6 +246,28 @@ def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum,
                                           _ptr(workspace), workspace.numel() * workspace.element_size(), algo,
                                           _stream(x))
     _check(rc, "ursa_bma_preresnet_forward")
+    return workspace
+
+
+def gemm_nt(A, B, out, bias=None, relu=False, workspace=None):
+    """out[b] = A[b or shared] @ B[b]^T (+ bias[b]) (ReLU) on the 3xTF32 tcgen05 GEMM.  A: [M, K] (shared) or [batch, M, K];
+    B: [batch, N, K]; out: [batch, M, N]; bias: [batch, N] or None.  Innermost dims contiguous.  Returns the workspace."""
+    for t, nm in ((A, "A"), (B, "B"), (out, "out"), (bias, "bias")):        # strided views are fine: strides are passed down
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1):
+            raise ValueError("%s must be a CUDA float32 tensor with a contiguous last dimension" % nm)
+    batch, N, K = B.shape
+    shared = A.dim() == 2
+    M = A.shape[-2]
+    if A.shape[-1] != K or tuple(out.shape) != (batch, M, N) or A.stride(-1) != 1 or B.stride(-1) != 1 or out.stride(-1) != 1:
+        raise ValueError("gemm_nt: shape / stride mismatch")
+    need = lib().ursa_gemm_nt_3xtf32_workspace(batch, M, N, K, 0 if shared else 1)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=B.device)
+    rc = lib().ursa_gemm_nt_3xtf32(_ptr(A), A.stride(-2), 0 if shared else A.stride(0), _ptr(B), B.stride(1), B.stride(0),
+                                   _ptr(bias), 0 if bias is None else bias.stride(0), 1 if relu else 0, _ptr(out), out.stride(1),
+                                   out.stride(0), batch, M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                   _stream(B))
+    _check(rc, "ursa_gemm_nt_3xtf32")
     return workspace
 
 

@@ -384,3 +384,64 @@ int mlp_forward_tcgen05(const float *bank, int64_t ld_bank, int S, const float *
 }
 
 }  // namespace ursa
+
+// ---- generic entry: batched  out[b] = A[b or shared] B[b]^T (+ bias[b]) (ReLU)  on the same 3xTF32 kernel ----------------------
+// (the chain-batched HMC likelihood gradient of the MLPs runs its nine GEMMs through this; SURVEY 8(d) cfg 4)
+using namespace ursa;
+
+static void gemm_plan(int batch, int64_t M, int N, int K, int a_batched, int &Kp, int &BN, int &Np, size_t &a_plane, size_t &b_plane,
+                      size_t &total) {
+    Kp = round_up_i(K, TC_BK);
+    BN = pick_bn(N);
+    Np = round_up_i(round_up_i(N, 16), BN);
+    a_plane = (size_t)(a_batched ? batch : 1) * (size_t)M * Kp;
+    b_plane = (size_t)batch * (size_t)Np * Kp;
+    total = (2 * a_plane + 2 * b_plane + (size_t)Np) * sizeof(float) + 2048;
+}
+
+extern "C" size_t ursa_gemm_nt_3xtf32_workspace(int batch, int64_t M, int N, int K, int a_batched) {
+    if (batch < 1 || M < 1 || N < 1 || K < 1) return 0;
+    int Kp, BN, Np;
+    size_t ap, bp, total;
+    gemm_plan(batch, M, N, K, a_batched, Kp, BN, Np, ap, bp, total);
+    return total;
+}
+
+extern "C" int ursa_gemm_nt_3xtf32(const float *A, int64_t lda, int64_t a_batch_stride, const float *B, int64_t ldb,
+                                   int64_t b_batch_stride, const float *bias, int64_t bias_stride, int relu, float *out,
+                                   int64_t ldo, int64_t out_batch_stride, int batch, int64_t M, int N, int K, void *workspace,
+                                   size_t workspace_bytes, void *stream) {
+    URSA_REQUIRE(A && B && out && workspace, "ursa_gemm_nt_3xtf32: null pointer");
+    URSA_REQUIRE(batch >= 1 && M >= 1 && N >= 1 && K >= 1 && lda >= K && ldb >= K && ldo >= N, "ursa_gemm_nt_3xtf32: bad shape");
+    URSA_REQUIRE(M < (int64_t)1 << 31, "ursa_gemm_nt_3xtf32: M too large");
+    const int a_batched = a_batch_stride != 0;
+    int Kp, BN, Np;
+    size_t ap, bp, total;
+    gemm_plan(batch, M, N, K, a_batched, Kp, BN, Np, ap, bp, total);
+    URSA_REQUIRE(workspace_bytes >= total, "ursa_gemm_nt_3xtf32: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    float *a_hi = ws, *a_lo = a_hi + ap, *b_hi = a_lo + ap, *b_lo = b_hi + bp, *zero_bias = b_lo + bp;
+    auto split = [&](const float *src, int64_t ld, int64_t bstride, int rows, int cols, float *hi, float *lo, int rows_p, int cols_p,
+                     int nb) -> int {
+        const int64_t tot = (int64_t)rows_p * cols_p;
+        int gx = (int)((tot + 255) / 256);
+        if (gx > 148 * 8) gx = 148 * 8;
+        split_tf32_kernel<<<dim3(gx, nb), 256, 0, st>>>(src, ld, bstride, rows, cols, hi, lo, rows_p, cols_p);
+        URSA_LAUNCH_CHECK("split_tf32_kernel");
+        return URSA_OK;
+    };
+    if (int rc = split(A, lda, a_batch_stride, (int)M, K, a_hi, a_lo, (int)M, Kp, a_batched ? batch : 1)) return rc;
+    if (int rc = split(B, ldb, b_batch_stride, N, K, b_hi, b_lo, Np, Kp, batch)) return rc;
+    TcGemmArgs g;
+    g.M = M;
+    if (bias) { g.bias = bias; g.bias_stride = bias_stride; }
+    else {
+        URSA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)Np * sizeof(float), st));
+        g.bias = zero_bias; g.bias_stride = 0;
+    }
+    g.out_hi = out; g.out_lo = nullptr; g.out_batch_stride = out_batch_stride; g.ld_out = (int)ldo;
+    g.n_valid = N; g.relu = relu ? 1 : 0;
+    return launch_tc_gemm(a_hi, a_lo, M, a_batched ? batch : 1, Kp, b_hi, b_lo, Np, BN, batch, g, st);
+}
+
