@@ -396,6 +396,33 @@ def gen_pca_space(R):
     print("pca_space.npz", {k: out[k].shape for k in out if k.endswith("space")})
 
 
+def gen_bn_update(R):
+    """util.bn_update (util.py:212-247) of the LIVE reference on its own WideResNet (WRN-10-2), CPU: the reference hard-codes
+    ``input.cuda(non_blocking=True)`` (util.py:236), patched out harness-side for the call.  Weights from oracle/wrn_fill.py
+    (seeded), ragged last batch (N = 44, batch 16)."""
+    import warnings
+    from oracle.wrn_fill import wrn_fill
+    depth, widen, C, N, batch, seed = 10, 2, 10, 44, 16, 300
+    rng = np.random.RandomState(seed + 1)
+    x16 = rng.randn(N, 3, 32, 32).astype(np.float16)
+    x = torch.from_numpy(x16.astype(np.float32))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.zeros(N, dtype=torch.long)), batch_size=batch,
+                                         shuffle=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = wrn_fill(R["models"].wideresnet.WideResNet(num_classes=C, depth=depth, widen_factor=widen), seed)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # harness-side: no GPU in this container
+    try:
+        R["util"].bn_update(loader, m)
+    finally:
+        torch.Tensor.cuda = orig
+    out = {"x": x16, "cfg": np.array([depth, widen, C, N, batch, seed]), "buffers": _flat_buffers(m),
+           "momentum_after": np.array([mod.momentum for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)], np.float64)}
+    np.savez_compressed(os.path.join(OUT, "bn_update.npz"), **out)
+    print("bn_update.npz", out["buffers"].shape, out["momentum_after"][:3])
+
+
 def gen_metrics_edge(R):
     """get_performance_metrics / _get_ece / _get_brier on crafted probabilities: confidences exactly on bin
     edges, argmax ties, one-hot rows, C = 2..100."""
@@ -546,7 +573,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, pca_space=gen_pca_space, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

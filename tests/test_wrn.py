@@ -228,3 +228,50 @@ def test_arch_detection_accepts_the_reference_modules():
     assert _arch_of(ours) == ("wrn", 16, 4, 10)
     assert [tuple(p.shape) for p in ref.parameters()] == [tuple(p.shape) for p in ours.parameters()]
     assert [n for n, _ in ref.named_buffers()] == [n for n, _ in ours.named_buffers()]
+
+
+# ---- bn_update pinned to the live reference (tests/golden/bn_update.npz, oracle/gen_golden.py::gen_bn_update) -----------------
+BN_GOLD = os.path.join(os.path.dirname(__file__), "golden", "bn_update.npz")
+
+
+def _bn_golden_problem():
+    g = np.load(BN_GOLD)
+    depth, widen, C, N, batch, seed = (int(v) for v in g["cfg"])
+    m = wrn_fill(WideResNet(num_classes=C, depth=depth, widen_factor=widen), seed)
+    x = torch.from_numpy(g["x"].astype(np.float32))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.zeros(N, dtype=torch.long)), batch_size=batch,
+                                         shuffle=False)
+    return g, m, x, loader, (depth, widen, C, N, batch)
+
+
+def test_bn_update_port_reproduces_the_reference_cpu():
+    """ursabench_b200.util.bn_update (the PyTorch pass, here on the CPU) against the running statistics the LIVE reference's
+    util.bn_update produced for the same weights and batches; the modules' momenta are restored like the reference does."""
+    from ursabench_b200.util import bn_update
+    g, m, x, loader, _ = _bn_golden_problem()
+    bn_update(loader, m, device=torch.device("cpu"))
+    got = _flat_buffers(m).numpy()
+    np.testing.assert_allclose(got, g["buffers"], rtol=2e-5, atol=2e-6)
+    mom = [mod.momentum for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    np.testing.assert_array_equal(np.array(mom, np.float64), g["momentum_after"])
+
+
+@pytest.mark.gpu
+def test_wrn_bn_update_matches_reference_golden():
+    """ursa_wrn_bn_update against the same golden: means within 2e-5 of the layer's standard deviation, variances within 5e-5
+    relative (the tensor core's systematic ~1e-6 offset, see the fp64-bracket test above)."""
+    from ursabench_b200 import _C
+    g, m, x, loader, (depth, widen, C, N, batch) = _bn_golden_problem()
+    row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cuda().contiguous()
+    ref = torch.from_numpy(g["buffers"]).cuda()
+    buf = torch.full_like(ref, float("nan"))
+    assert _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, C) is not None
+    off = 0
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            c = mod.num_features
+            mu, var = ref[off:off + c].double(), ref[off + c:off + 2 * c].double()
+            assert ((buf[off:off + c].double() - mu).abs() / var.sqrt()).max().item() < 2e-5
+            assert ((buf[off + c:off + 2 * c].double() - var).abs() / var).max().item() < 5e-5
+            off += 2 * c
+    assert off == buf.numel()
