@@ -506,7 +506,9 @@ def test_ood_detection_matches_reference_golden(U, engine):
               "out_distribution_total_uncertainty"):
         np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=2e-5, rtol=1e-5)
     for k in ("in_distribution_model_uncertainty", "out_distribution_model_uncertainty"):
-        np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=2e-5, rtol=0)
+        # total - data uncertainty: the difference of two O(1) fp32 entropies, each good to ~1e-5 (the fp32 forward's summation
+        # order -- cuBLAS heuristics in the generic engine -- moves single elements by 2e-5)
+        np.testing.assert_allclose(getattr(task, k).numpy(), g["ood/" + k], atol=5e-5, rtol=0)
     assert set(m) == set(ref["ood"])
     for k, v in ref["ood"].items():
         assert m[k] == pytest.approx(v, abs=2e-3), k                    # rank statistic of N = 470 scores
