@@ -73,3 +73,26 @@ def test_no_cpu_path():
         tasks.Prediction({"in_distribution_test": loader}, 3, torch.device("cpu"), "ALL")
     with pytest.raises((RuntimeError, ValueError)):
         inference.SGHMC(None, model=m, train_loader=loader, device=torch.device("cpu"))
+
+
+def test_argument_errors_are_reported_without_touching_the_gpu():
+    """Error behaviour of the C ABI (host-side checks only: no kernel is launched, so this runs without a GPU): a negative return
+    code plus a message from ursa_last_error(), never a crash or a silent success."""
+    from ursabench_b200 import _C
+    lib = _C.lib()
+
+    def err():
+        return lib.ursa_last_error().decode()
+
+    assert lib.ursa_swag_gram(None, 0, 3, 10, None, None) < 0 and "ursa_swag_gram" in err()
+    assert lib.ursa_bma_wrn_forward(None, 0, None, 0, 1, None, 1, 28, 10, 100, None, None, None, 1e-4, None, 0,
+                                    _C.ALGO_TCGEN05, None) < 0 and "null pointer" in err()
+    assert lib.ursa_wrn_bn_update(None, None, None, 10, 128, 28, 10, 100, None, 0, None) < 0 and "null pointer" in err()
+    assert lib.ursa_gemm_nt_3xtf32(None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0, 1, 1, 1, 1, None, 0, None) < 0
+    assert "ursa_gemm_nt_3xtf32" in err()
+    # workspace queries answer 0 for shapes an engine does not cover (the Python layer then picks another engine)
+    assert lib.ursa_bma_wrn_workspace(1, 8, 28, 10, 100, _C.ALGO_FFMA) == 0
+    assert lib.ursa_wrn_bn_update_workspace(100, 127, 28, 10, 100) == 0          # odd batch
+    assert lib.ursa_wrn_bn_update_workspace(100, 1024, 28, 10, 100) == 0         # batch larger than a chunk
+    assert lib.ursa_gemm_nt_3xtf32_workspace(0, 1, 1, 1, 0) == 0
+    assert lib.ursa_gemm_nt_3xtf32_workspace(2, 100, 10, 50, 1) > 0
