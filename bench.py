@@ -1,20 +1,28 @@
 """bench.py -- contract benchmark of the URSABench hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--skip-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--skip-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): cyclical SGHMC on PreResNet-20 (D = 272 282), synthetic CIFAR-10-shaped
-batches of 128, N_train = 50 000, ONE independent chain per GPU (no data-path collective; "scaling": "weak").
-A step = forward + backward (PyTorch autograd, as the north star keeps them) + ONE fused K1 launch that applies the
-cSGHMC update with in-register Philox noise and zeroes the gradients.
+Workload (BASELINE.json configs[4], the "BMA img/s over S samples at 1/2/4/8 B200" half of the metric): Bayesian model
+averaging of S = 100 PreResNet-20 posterior samples over N = 10 000 synthetic CIFAR-10-shaped test images through
+``tasks.Prediction`` -- the sample-batched tcgen05 forward (stem, three fused stage kernels, two transitions, head),
+the softmax-average / entropy accumulation, ONE NCCL all-reduce of the [N, C] + [N] sums when N_gpus > 1, and the K4
+metric counters (accuracy, NLL, Brier, ECE bins).  A step = one complete evaluation; the unit of work is one
+(image, sample) pair: value = S * N / t  [img*samples/s], whole job.  Total work is fixed ("scaling": "strong"): the
+(sample, image) grid is split into balanced contiguous shares (``dist.shard_pairs``) -- whole samples when S divides
+over the ranks, image blocks otherwise.
 
-  value     whole-job steps/s (sum over chains), batches resident in HBM (a pool larger than L2), device-timed
-  e2e       same metric through the public class API (`cSGHMC.train_step`) with pinned HOST batches: H2D of every
-            batch and a D2H read of every step's loss inside the timed region
-  roofline  the K1 kernel on the HBM-bound layout the north star names (chain-batched [128, D], 697 MB/launch,
-            20 B/param) timed live with CUDA events; `in_step` is the same kernel at the single-chain size
-  cpu_baseline / --impl reference   the reference's CPU path (oracle/port_torch.py, same op sequence as
-            optimSGHMC.step + the sampler loop) on the box's host cores
+  value     inputs resident in HBM when the timed region starts (test images + replicated sample bank, 232 MB > L2),
+            device-timed with CUDA events, max over ranks
+  e2e       the call a reference user makes, from HOST data: ``Prediction(dataloader, ...)`` (upload of the pinned
+            123 MB test set), ``update_statistics(list of CPU modules)`` (upload of every sample this rank touches),
+            ``get_performance_metrics()`` (all-reduce, K4, counters read back into the metrics dict)
+  roofline  the dominant kernel of the step, ``preresnet_stage16_kernel<16>`` (tensor bound): algorithmic FLOPs per
+            launch / its average launch duration, measured live with CUDA events on the launching stream inside the
+            timed steps (``ursa_profile_begin/end``); per-kernel times of the whole forward beside it
+  cpu_baseline / --impl reference   the reference's own ``tasks.Prediction`` (unmodified, staged by oracle/make_ref.py
+            into oracle/_ref; the torch-CPU port in oracle/port_torch.py if that is absent) on the box's host cores,
+            each step a bounded sample of the same workload (S_ref samples x N_ref images), extrapolated linearly
 """
 import argparse
 import json
@@ -23,7 +31,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import torch
@@ -31,20 +38,28 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "cSGHMC PreResNet-20 (D=272282) CIFAR-10-shaped batch 128, 1 chain/GPU (BASELINE.json configs[1])"
-HYP = {"lr_0": 0.5, "prior_std": 0.5, "num_samples_per_cycle": 3, "cycle_length": 50, "burn_in_epochs": 0,
-       "num_cycles": 17, "alpha": 0.5}           # hyperparams/WideResNet28x10CIFAR10/csghmc_hyperparams.json shape
-N_TRAIN, BATCH, NUM_CLASSES = 50_000, 128, 10
-POOL_BATCHES = 96                                 # 96 x 1.57 MB = 151 MB of distinct inputs (> 126 MB L2)
-K1_CHAINS = 128                                   # roofline layout: [128 chains, D] = 697 MB per launch at 20 B/param
+S_ALL, N_TEST, NUM_CLASSES, DEPTH, BATCH = 100, 10_000, 10, 20, 128
+METRICS = ["error_rate", "nll", "brier_score", "ece"]
+FLOP_PER_PAIR = 81.63e6                           # 2*MAC over convs + fc of PreResNet-20
+STAGE_FLOP = {"stage_c16": 6 * 4.718592e6, "stage_c32": 5 * 4.718592e6, "stage_c64": 5 * 4.718592e6}   # per (image, sample)
+REF_S, REF_N = 2, 1024                            # bounded sample of the reference arm per step
+# identical in both arms (the driver compares the dicts)
+CONFIG = {
+    "workload": "BMA evaluation (tasks.Prediction) of S=100 PreResNet-20 posterior samples on N=10000 synthetic "
+                "CIFAR-10-shaped test images (BASELINE.json configs[4])",
+    "S": S_ALL, "N": N_TEST, "num_classes": NUM_CLASSES, "batch_size": BATCH, "metrics": METRICS,
+    "unit_of_work": "one (image, sample) forward + softmax-average; step = S*N pairs + metrics",
+    "parallelism": "(sample, image-block) grid sharded over ranks, one all-reduce of N*C+N+1 floats",
+    "l2": "inputs larger than L2 (123 MB test set + 109 MB sample bank vs 126 MB)",
+}
 
 
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1600.0, "bf16_tflops_sustained": 1350.0}, "fallback (B200_PROFILING.md)"
 
 
 class _ClockSampler:
@@ -93,10 +108,308 @@ class _ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def _make_model():
-    from ursabench_b200 import models
+
+# ------------------------------------------------------------------------------------------------ synthetic workload
+def _host_data(n=N_TEST, pin=True):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 3, 32, 32, generator=g)
+    y = torch.randint(0, NUM_CLASSES, (n,), generator=g)
+    if pin and torch.cuda.is_available():
+        x, y = x.pin_memory(), y.pin_memory()
+    return x, y
+
+
+def _loader(x, y):
+    return torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BATCH, shuffle=False)
+
+
+def _fill_sample(module, base_flat, s):
+    """Sample s = the seed-0 initialisation + 0.01 * N(0, 1) (seed 1000 + s), BatchNorm statistics at their defaults."""
+    g = torch.Generator().manual_seed(1000 + s)
+    flat = base_flat + 0.01 * torch.randn(base_flat.numel(), generator=g)
+    off = 0
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    return module
+
+
+def _samples(model_ctor, n_samples):
+    """``n_samples`` CPU modules built by ``model_ctor`` (ours or the reference's class: same architecture, same values)."""
+    import copy
     torch.manual_seed(0)
-    return models.PreResNet(num_classes=NUM_CLASSES, depth=20)
+    base = model_ctor()
+    base_flat = torch.cat([p.detach().reshape(-1) for p in base.parameters()])
+    return [_fill_sample(copy.deepcopy(base), base_flat, s) for s in range(n_samples)]
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _reference_modules():
+    """(tasks.Prediction, PreResNet ctor, optimSGHMC, kind) from the UNMODIFIED reference when its staged copy (or
+    /root/reference) is importable, else from the torch-CPU port."""
+    from oracle import stubs
+    try:
+        if not os.path.isdir(os.path.join(stubs.REF_ROOT, "URSABench")):
+            raise ImportError("no reference package under %s" % stubs.REF_ROOT)
+        stubs.install()
+        from URSABench import tasks as rtasks
+        from URSABench.inference.optim_sghmc import optimSGHMC as ref_opt
+        from URSABench.models import preresnet as rpre
+        return rtasks.Prediction, (lambda: rpre.PreResNet(num_classes=NUM_CLASSES, depth=DEPTH)), ref_opt, "reference"
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("bench.py: unmodified reference not importable (%r); timing the torch-CPU port\n" % (e,))
+        return None, None, None, "port"
+
+
+class _PortPrediction:
+    """oracle/port_torch.py behind the reference's Prediction call shape (used only when oracle/_ref is absent)."""
+
+    def __init__(self, dataloader, num_classes, device, metric_list):
+        from oracle import port_torch as PT
+        self.PT, self.loader, self.C = PT, dataloader["in_distribution_test"], num_classes
+        self.targets = torch.cat([yb for _, yb in self.loader])
+        self.n = 0
+        self.proba = None
+
+    def update_statistics(self, models, output_performance=True, smoothing=True):
+        self.proba, _ = self.PT.port_prediction_update(models, list(self.loader), self.C)
+        self.n += len(models)
+
+    def get_performance_metrics(self):
+        return self.PT.port_metrics(self.proba, self.n, self.targets)
+
+
+def cpu_reference_prediction(steps, warmup, s_ref=REF_S, n_ref=REF_N):
+    """The reference's BMA evaluation on the host cores: each step = Prediction(...) + update_statistics(S_ref modules
+    over N_ref images) + get_performance_metrics(), i.e. S_ref * N_ref pairs.  Returns img*samples/s and the sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    RefPrediction, ctor, _, kind = _reference_modules()
+    if kind == "port":
+        from ursabench_b200 import models as M
+        ctor = lambda: M.PreResNet(num_classes=NUM_CLASSES, depth=DEPTH)      # noqa: E731
+        RefPrediction = _PortPrediction
+    models = _samples(ctor, s_ref)
+    x, y = _host_data(n_ref, pin=False)
+    loader = {"in_distribution_test": _loader(x, y)}
+
+    def one():
+        task = RefPrediction(loader, NUM_CLASSES, torch.device("cpu"), METRICS)
+        task.update_statistics(models, output_performance=False)
+        return task.get_performance_metrics()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = one()
+    dt = time.perf_counter() - t0
+    pairs = s_ref * n_ref
+    return {"value": steps * pairs / dt, "unit": "img*samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d steps x (S=%d samples x N=%d images, batch %d) of tasks.Prediction on the host CPU in %.1f s; "
+                      "linear in S*N, so the S=100 x N=10000 figure is this rate (extrapolated, BASELINE.md 4)"
+                      % (steps, s_ref, n_ref, BATCH, dt),
+            "ms_per_step": dt / steps * 1e3, "metrics_of_sample": {k: float(v) for k, v in out.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_prediction(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "bma_img_samples_per_s", "value": cb["value"], "unit": "img*samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": CONFIG,
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "img*samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "img_per_s_over_S_samples": cb["value"] / S_ALL,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def _event_time_ms(fn, iters, stream_sync=True):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
+    return sum(ts) / len(ts), ts
+
+
+def run_ours(args):
+    from ursabench_b200 import _C, dist as udist, models, tasks
+    from ursabench_b200.bank import SampleBank
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path (use --impl reference for the CPU arm)")
+    rank, world = udist.init_from_env("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _C.lib()
+    K, W = args.steps, max(args.warmup, 3)
+    S, N = args.samples, args.images
+
+    # ---- host side of the workload: pinned test set + S posterior samples as CPU modules (what sample() hands a user) ----
+    ctor = lambda: models.PreResNet(num_classes=NUM_CLASSES, depth=DEPTH)      # noqa: E731
+    host_models = _samples(ctor, S)
+    x_host, y_host = _host_data(N)
+    loaders = {"in_distribution_test": _loader(x_host, y_host)}
+    dist_on = world > 1
+
+    def barrier():
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: everything resident (test set uploaded by the task, samples in a device bank replicated on each rank) ----
+    task = tasks.Prediction(loaders, NUM_CLASSES, dev, METRICS, distributed=dist_on, replicated_samples=True)
+    bank = SampleBank.from_modules(host_models, dev)
+    bank.skeleton = ctor()
+    y_dev = task._y
+
+    def resident_step():
+        task.reset()
+        task._entropy.zero_()
+        task.update_from_bank(bank)
+        proba, _, n_s = task._reduced()                      # ONE all-reduce when world > 1
+        return _C.bma_metrics(proba, n_s, y_dev)             # K4 counters stay on the device
+
+    for _ in range(W):
+        resident_step()
+    sampler = _ClockSampler(local)
+    barrier()
+    l0 = _C.launch_count()
+    _C.profile_begin()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        oi, of, _, _ = resident_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    prof = _C.profile_end()
+    my_launches = _C.launch_count() - l0
+    t_ms = udist.allreduce_max_scalar(e0.elapsed_time(e1), dev)
+    value = K * S * N / (t_ms / 1e3)
+    algo = task.last_algo
+    counters_dev = (oi.clone(), of.clone())
+    proba_dev = task._reduced()[0].clone()
+
+    # ---- verification: the sharded + all-reduced result equals the single-rank evaluation ----------------------
+    verify = None
+    if dist_on:
+        solo = tasks.Prediction(loaders, NUM_CLASSES, dev, METRICS, distributed=False)
+        solo.update_from_bank(bank)
+        so_i, so_f, _, _ = _C.bma_metrics(solo._proba, S, y_dev)
+        diff = float((proba_dev / S - solo._proba / S).abs().max())
+        verify = {"max_abs_diff_mean_proba_vs_single_rank": diff, "counters_equal": bool(torch.equal(so_i, counters_dev[0])),
+                  "counters_max_abs_diff": int((so_i - counters_dev[0]).abs().max())}
+        if diff > 1e-5:
+            raise SystemExit("bench.py: sharded BMA differs from the single-rank result by %.3g (> 1e-5)" % diff)
+        del solo
+
+    # ---- e2e: from host data through the public API, metrics dict read back, every step --------------------------
+    h2d = [0]
+
+    def host_step():
+        t = tasks.Prediction(loaders, NUM_CLASSES, dev, METRICS, distributed=dist_on, replicated_samples=True)
+        t.update_statistics(host_models, output_performance=False)
+        out = t.get_performance_metrics()
+        h2d[0] = t.h2d_bytes + y_host.numel() * 8 + t.h2d_sample_bytes
+        return out
+
+    del task
+    for _ in range(min(W, 3)):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        metrics = host_step()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = udist.allreduce_max_scalar(max(e0.elapsed_time(e1), wall_ms), dev)
+    e2e_value = K * S * N / (e2e_ms / 1e3)
+    d2h = (1 + 2 * 15) * 8 + (2 + 15) * 8
+
+    # ---- roofline of the dominant kernel, from the event pairs recorded inside the timed steps ---------------------
+    peaks, peak_src = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    pairs_rank = sum(hi - lo for _, lo, hi in udist.shard_pairs(S, N, rank, world))
+    per_kernel = {}
+    for kind, (ms, cnt) in prof.items():
+        if cnt:
+            per_kernel[kind] = {"launches": cnt, "ms_total": ms, "us_per_launch": ms * 1e3 / cnt,
+                                "share_of_step": ms / t_ms}
+    dom = "stage_c16"
+    roofline = None
+    if dom in per_kernel:
+        ms, cnt = prof[dom]
+        flops_per_launch = STAGE_FLOP[dom] * pairs_rank * K / cnt
+        achieved = flops_per_launch / (ms / cnt * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "stage16_ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "preresnet_stage16_kernel<16> (6 fused 3x3 convs of stage 1, 2xFP16-split tcgen05)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
+                    "flops_per_launch": flops_per_launch, "ms_per_launch": ms / cnt, "launches": cnt,
+                    "note": "algorithmic = fp32-equivalent 2*MAC (28.31 MFLOP per pair); the tensor pipe issues 3 FP16 products "
+                            "per MAC, i.e. %.1f TFLOP/s of MMA work" % (3 * achieved)}
+        stage_ms = sum(prof[k][0] for k in STAGE_FLOP)
+        roofline["all_stage_kernels"] = {"achieved": sum(STAGE_FLOP.values()) * pairs_rank * K / (stage_ms * 1e-3) / 1e12,
+                                         "ms_per_step": stage_ms / K}
+        roofline["whole_forward"] = {"achieved": FLOP_PER_PAIR * S * N / (t_ms / K * 1e-3) / 1e12 / world,
+                                     "note": "81.63 MFLOP x pairs / step time, per GPU"}
+    line = {
+        "metric": "bma_img_samples_per_s", "value": value, "unit": "img*samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": CONFIG,
+        "img_per_s_over_S_samples": value / S,
+        "engine": {"algo": int(algo) if algo is not None else None,
+                   "name": "URSA_ALGO_TCGEN05_FUSED_F16 (2xFP16-split operands, fp32 accumulate in TMEM)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "img*samples/s", "h2d_bytes_per_step": h2d[0], "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K,
+                "api": "tasks.Prediction({'in_distribution_test': DataLoader(pinned host tensors)}, ...) + "
+                       "update_statistics(list of CPU nn.Modules) + get_performance_metrics() -> dict"},
+        "gpu_launches": my_launches,
+        "roofline": roofline,
+        "per_kernel": per_kernel,
+        "metrics": {k: float(v) for k, v in metrics.items()},
+    }
+    if verify is not None:
+        line["verify"] = verify
+
+    if not args.skip_extras:
+        try:
+            line["extras"] = run_extras(dev, rank, world, float(peaks["hbm_gbs"]))
+        except Exception as e:  # noqa: BLE001  (extras never invalidate the headline line)
+            line["extras"] = {"error": repr(e)}
+    if rank == 0 and world == 1:
+        cb = cpu_reference_prediction(steps=3, warmup=1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.skip_extras:
+            try:
+                line["extras"]["cpu"] = cpu_extras()
+            except Exception as e:  # noqa: BLE001
+                line["extras"]["cpu"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+HYP_CSGHMC = {"lr_0": 0.5, "prior_std": 0.5, "num_samples_per_cycle": 3, "cycle_length": 50, "burn_in_epochs": 0,
+              "num_cycles": 17, "alpha": 0.5}     # hyperparams/WideResNet28x10CIFAR10/csghmc_hyperparams.json shape
 
 
 class _ListLoader:
@@ -119,234 +432,181 @@ class _ListLoader:
         return len(self.batches)
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_steps_per_s(budget_s, max_steps, warm=1):
-    """Reference CPU path: PreResNet-20 fwd/bwd + optimSGHMC.step op sequence (oracle/port_torch.py)."""
-    from oracle import port_torch as PT
-    from oracle import restate as R
-    torch.set_num_threads(os.cpu_count() or 1)
-    model = _make_model()
-    g = torch.Generator().manual_seed(1)
-    batches = [(torch.randn(BATCH, 3, 32, 32, generator=g), torch.randint(0, NUM_CLASSES, (BATCH,), generator=g))
-               for _ in range(4)]
-    opt = PT.PortOptimSGHMC(model.parameters(), HYP["lr_0"], 1 - HYP["alpha"], 1 / HYP["prior_std"] ** 2, N_TRAIN)
-    nb = R.csghmc_num_batch(N_TRAIN, BATCH)
-    crit = torch.nn.CrossEntropyLoss()
-    model.train()
+def sampler_extras(dev, rank, world, peak):
+    """BASELINE.json configs[1] (last round's contract line, now an extra): one cSGHMC chain per GPU on PreResNet-20,
+    batch 128 -- forward + backward on stock PyTorch / cuDNN + ONE fused K1 launch -- and, next to it, what the K1 launch
+    replaces: the reference's own optimSGHMC.step (7-8 ATen launches per parameter tensor) run on the same GPU."""
+    from ursabench_b200 import _C, dist as udist, inference, models
+    out = {}
+    torch.manual_seed(0)
+    model = models.PreResNet(num_classes=NUM_CLASSES, depth=DEPTH).to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    pool = 96                                                        # 96 x 1.57 MB of distinct batches (> L2)
+    hx = torch.randn(pool, BATCH, 3, 32, 32, generator=g).pin_memory()
+    hy = torch.randint(0, NUM_CLASSES, (pool, BATCH), generator=g).pin_memory()
+    dx, dy = hx.to(dev), hy.to(dev)
+    loader = _ListLoader([(hx[i], hy[i]) for i in range(pool)], 50_000, BATCH)
+    torch.manual_seed(1234 + rank)
+    inf = inference.cSGHMC(dict(HYP_CSGHMC), model, loader, device=dev)
+    inf.optimizer.elem_offset = udist.chain_elem_offset(rank, inf.flat.D)
+    inf.model.train()
+    inf.enable_cuda_graph(dx[0], dy[0])
+    n = [0]
 
-    def one(i):
-        x, y = batches[i % len(batches)]
-        opt.lr = PT.port_csghmc_lr(HYP["lr_0"], 0, i, nb, HYP["cycle_length"], HYP["num_cycles"])
-        logits = model(x)
+    def step(host):
+        i = n[0] % pool
+        inf._adjust_learning_rate(inf.optimizer, 0, n[0] % 391)
+        n[0] += 1
+        if host:
+            return inf.train_step(hx[i], hy[i], True).item()
+        return inf.train_step(dx[i], dy[i], True)
+    for host, name in ((False, "resident"), (True, "e2e_host_batches_loss_item")):
+        for _ in range(5):
+            step(host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(60):
+            step(host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 if host else 0.0)
+        ms = udist.allreduce_max_scalar(ms, dev)
+        out["csghmc_preresnet20_b128_steps_per_s_" + name] = {"value": world * 60 / ms * 1e3, "ms_per_step": ms / 60,
+                                                              "chains": world, "note": "fwd/bwd = PyTorch autograd + cuDNN; K1 = 1 launch"}
+    inf.disable_cuda_graph()
+    del inf, dx, dy
+    # K1 on the HBM-bound chain-batched layout [128 chains, D = 272 284]
+    D = 272_282
+    ld = (D + 3) // 4 * 4
+    nb = 128 * ld
+    pb, gb, vb = (torch.randn(nb, device=dev) for _ in range(3))
+    kw = dict(lr=0.1, momentum=0.5, wd_over_n=4.0 / 50_000, noise_mul=math.sqrt(2 * 0.5 * 0.1), noise_div=5e4, seed=7)
+    c = [0]
+
+    def k1():
+        c[0] += 1
+        _C.sgmcmc_step(pb, gb, vb, step=c[0], **kw)
+    for _ in range(5):
+        k1()
+    ms, _ = _event_time_ms(k1, 30)
+    out["k1_sghmc_128chains_preresnet20"] = {"ms": ms, "GBps": 20 * nb / ms / 1e6, "frac": 20 * nb / ms / 1e6 / peak,
+                                             "bytes_per_launch": 20 * nb}
+    del pb, gb, vb
+    # the reference's optimSGHMC.step itself on this GPU (stock ATen), WRN-28-10-sized parameter list, momentum 0.5, noise on
+    if rank == 0:
+        _, _, ref_opt, kind = _reference_modules()
+        wrn = models.WideResNet(num_classes=100, depth=28, widen_factor=10).to(dev)
+        for q in wrn.parameters():
+            q.grad = torch.randn_like(q)
+        if ref_opt is not None:
+            opt = ref_opt(wrn.parameters(), lr=0.01, momentum=0.5, weight_decay=1e-4 * 5e4, num_training_samples=50_000)
+            fn = lambda: opt.step(add_langevin_noise=True)      # noqa: E731
+        else:
+            from oracle import port_torch as PT
+            opt = PT.PortOptimSGHMC(wrn.parameters(), 0.01, 0.5, 1e-4 * 5e4, 50_000)
+            fn = lambda: opt.step(add_langevin_noise=True)      # noqa: E731
+        for _ in range(3):
+            fn()
+        ms, _ = _event_time_ms(fn, 10)
+        Dw = sum(q.numel() for q in wrn.parameters())
+        out["reference_optimSGHMC_step_on_gpu_wrn28x10"] = {"ms": ms, "steps_per_s": 1e3 / ms, "kind": kind,
+                                                            "GBps_at_20B_per_param": 20 * Dw / ms / 1e6,
+                                                            "note": "stock ATen, 108 parameter tensors x 7-8 launches; compare k1_sghmc_wrn28x10"}
+        del wrn, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_extras():
+    """Host-CPU timings of the reference's code for the other configs, each on a bounded sample; the
+    matching GPU figures are the same-named entries of ``extras``.  Unmodified reference classes when staged
+    (kind "reference"), else the torch-CPU port."""
+    from oracle import port_torch as PT
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    RefPrediction, _, ref_opt, kind = _reference_modules()
+    out = {"cores": cores, "kind": kind}
+
+    def timeit(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    # config 3 sizes: optimSGHMC.step, SWA._collect_model and the (restated) rank-20 draw at D = 36.5 M
+    D = 36_546_980
+    p = torch.nn.Parameter(torch.randn(D) * 0.05)
+    p.grad = torch.randn(D)
+    if ref_opt is not None:
+        opt = ref_opt([p], lr=0.01, momentum=0.5, weight_decay=5.0, num_training_samples=50_000)
+    else:
+        opt = PT.PortOptimSGHMC([p], 0.01, 0.5, 5.0, 50_000)
+    t = timeit(lambda: opt.step(add_langevin_noise=True), 3)
+    out["optimSGHMC_step_D36.5M"] = {"ms": t * 1e3, "steps_per_s": 1 / t, "GBps_at_20B_per_param": 20 * D / t / 1e9,
+                                     "sample": "3 steps, one flat tensor of D = 36 546 980, momentum 0.5, noise on"}
+    w = p.detach()
+    mean, sq = torch.zeros(D), torch.zeros(D)
+    t = timeit(lambda: PT.port_swa_collect(w, mean, sq, 3), 3)
+    out["swa_collect_D36.5M"] = {"ms": t * 1e3, "GBps_at_24B_per_param": 24 * D / t / 1e9,
+                                 "sample": "3 collects (inference/swa.py:79-90 op sequence), D = 36 546 980", "kind": "port"}
+    K = 20
+    ring = torch.randn(K, D) * 0.01
+    var = torch.full((D,), 1e-4)
+    t = timeit(lambda: PT.port_swag_draw(mean, var, ring, K, 1), 2)
+    out["swag_draw_K20_D36.5M"] = {"ms_per_draw": t * 1e3, "ms_for_30_draws_extrapolated": 30 * t * 1e3,
+                                   "sample": "2 single draws (inference/swag.py:88-97 restated; the shipped branch raises), K = 20",
+                                   "kind": "port"}
+    del ring, var, mean, sq, p, w
+    # config 1: Prediction on MLP 784-400-400-10, bounded S = 5 x N = 2000
+    from ursabench_b200 import models as M
+    torch.manual_seed(0)
+    mlps = [M.MLP(400, 784, 10) for _ in range(5)]
+    g = torch.Generator().manual_seed(3)
+    xm, ym = torch.randn(2000, 1, 28, 28, generator=g), torch.randint(0, 10, (2000,), generator=g)
+    lm = {"in_distribution_test": torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xm, ym), batch_size=BATCH)}
+    Pred = RefPrediction if RefPrediction is not None else _PortPrediction
+
+    def mlp_eval():
+        tk = Pred(lm, 10, torch.device("cpu"), METRICS)
+        tk.update_statistics(mlps, output_performance=False)
+        return tk.get_performance_metrics()
+    t = timeit(mlp_eval, 3)
+    out["bma_mlp400"] = {"img_samples_per_s": 5 * 2000 / t, "sample": "3 x (S = 5 x N = 2000) through tasks.Prediction"}
+    # config 2: one cSGHMC step (PreResNet-20 fwd + bwd + optimSGHMC.step), batch 128
+    from oracle import restate as R
+    torch.manual_seed(0)
+    model = M.PreResNet(num_classes=NUM_CLASSES, depth=DEPTH)
+    if ref_opt is not None:
+        opt = ref_opt(model.parameters(), lr=0.5, momentum=0.5, weight_decay=4.0, num_training_samples=50_000)
+    else:
+        opt = PT.PortOptimSGHMC(model.parameters(), 0.5, 0.5, 4.0, 50_000)
+    xb, yb = torch.randn(BATCH, 3, 32, 32, generator=g), torch.randint(0, 10, (BATCH,), generator=g)
+    crit = torch.nn.CrossEntropyLoss()
+    nbatch = R.csghmc_num_batch(50_000, BATCH)
+    model.train()
+    i = [0]
+
+    def sgmcmc_step():
+        lr = PT.port_csghmc_lr(0.5, 0, i[0], nbatch, 50, 17)
+        i[0] += 1
+        if ref_opt is not None:
+            for gq in opt.param_groups:
+                gq["lr"] = lr
+        else:
+            opt.lr = lr
+        logits = model(xb)
         opt.zero_grad()
-        loss = crit(logits, y)
+        loss = crit(logits, yb)
         loss.backward()
         loss.item()
         opt.step(add_langevin_noise=True)
-
-    for i in range(warm):
-        one(i)
-    t0 = time.perf_counter()
-    n = 0
-    while n < max_steps and (n < 2 or time.perf_counter() - t0 < budget_s):
-        one(warm + n)
-        n += 1
-    dt = time.perf_counter() - t0
-    return n / dt, n, dt, torch.get_num_threads()
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    sps, n, dt, cores = cpu_reference_steps_per_s(budget_s=60.0, max_steps=max(args.steps, 2), warm=min(args.warmup, 2))
-    line = {
-        "impl": "reference", "metric": "sgmcmc_steps_per_s", "value": sps, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": n, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / sps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path (torch-CPU port of the reference's op sequence), "
-                   "one chain on the host cores; /root/reference does not exist on the GPU box"},
-        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d cSGHMC steps (fwd+bwd+optimSGHMC.step), batch 128, %.1f s" % (n, dt)},
-        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
-
-
-# ------------------------------------------------------------------------------------------------ our arm
-def _event_time_ms(fn, iters, stream_sync=True):
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for a, b in evs:
-        a.record()
-        fn()
-        b.record()
-    torch.cuda.synchronize()
-    ts = [a.elapsed_time(b) for a, b in evs]
-    return sum(ts) / len(ts), ts
-
-
-def run_ours(args):
-    from ursabench_b200 import _C, dist as udist, inference
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path (use --impl reference for the CPU arm)")
-    rank, world = udist.init_from_env("nccl")
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    _C.lib()
-    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
-    K, W = args.steps, max(args.warmup, 3)
-
-    # ---- the chain of this rank --------------------------------------------------------------------------------
-    model = _make_model().to(dev)
-    g = torch.Generator().manual_seed(100 + rank)
-    host_x = torch.randn(POOL_BATCHES, BATCH, 3, 32, 32, generator=g).pin_memory()
-    host_y = torch.randint(0, NUM_CLASSES, (POOL_BATCHES, BATCH), generator=g).pin_memory()
-    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
-    loader = _ListLoader([(host_x[i], host_y[i]) for i in range(POOL_BATCHES)], N_TRAIN, BATCH)
-    torch.manual_seed(1234 + rank)                         # Philox key of this chain
-    inf = inference.cSGHMC(dict(HYP), model, loader, device=dev)
-    inf._channels_last = bool(args.channels_last)          # default on: NHWC activations for cuDNN
-    inf.optimizer.elem_offset = udist.chain_elem_offset(rank, inf.flat.D)
-    inf.model.train()
-    if not args.no_graph:
-        inf.enable_cuda_graph(dev_x[0], dev_y[0])
-    step_no = [0]
-
-    def lr_and_gate():
-        i = step_no[0]
-        step_no[0] += 1
-        inf._adjust_learning_rate(inf.optimizer, 0, i % 391)
-        return True
-
-    def resident_step():
-        i = step_no[0] % POOL_BATCHES
-        noise = lr_and_gate()
-        return inf.train_step(dev_x[i], dev_y[i], noise)
-
-    def host_step():
-        i = step_no[0] % POOL_BATCHES
-        noise = lr_and_gate()
-        loss = inf.train_step(host_x[i], host_y[i], noise)
-        return loss.item()                                 # D2H of the step's result, every step (sghmc.py:82)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: resident inputs ---------------------------------------------------------------------------------
-    for _ in range(W):
-        resident_step()
-    launches0 = inf.optimizer.launches
-    replays0 = inf._graph.replays if getattr(inf, "_graph", None) is not None else 0
-    sampler = _ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        resident_step()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    t_ms = udist.allreduce_max_scalar(e0.elapsed_time(e1), dev)
-    graph_replays = (inf._graph.replays - replays0) if getattr(inf, "_graph", None) is not None else 0
-    my_launches = (inf.optimizer.launches - launches0) + graph_replays   # set_dyn + K1-in-graph, or K1 eager
-    value = world * K / (t_ms / 1e3)
-
-    # ---- e2e: host batches through the public API, loss read back every step -------------------------------------
-    for _ in range(W):
-        host_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(K):
-        host_step()
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = udist.allreduce_max_scalar(max(e0.elapsed_time(e1), wall_ms), dev)
-    e2e_value = world * K / (e2e_ms / 1e3)
-    h2d = BATCH * 3 * 32 * 32 * 4 + BATCH * 8
-
-    # ---- roofline: K1 on the HBM-bound layout, live CUDA events ---------------------------------------------------
-    peak, peak_src = _peaks()
-    D = inf.flat.D
-    ld = (D + 3) // 4 * 4
-    n_big = K1_CHAINS * ld
-    pb, gb, vb = (torch.randn(n_big, device=dev) for _ in range(3))
-    mom = 1 - HYP["alpha"]
-    kw = dict(lr=0.1, momentum=mom, wd_over_n=(1 / HYP["prior_std"] ** 2) / N_TRAIN,
-              noise_mul=math.sqrt(2 * (1 - mom) * 0.1), noise_div=float(N_TRAIN), seed=7)
-    cnt = [0]
-
-    def k1_big():
-        cnt[0] += 1
-        _C.sgmcmc_step(pb, gb, vb, step=cnt[0], **kw)
-    for _ in range(5):
-        k1_big()
-    torch.cuda.synchronize()
-    k1_ms, _ = _event_time_ms(k1_big, max(20, min(K, 100)))
-    alg_bytes = 20 * n_big
-    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    # the same kernel at the single-chain size inside the step (L2 resident, launch bound): CUDA-graph replay of
-    # 20 back-to-back launches so that host launch latency is excluded
-    p1, g1, v1 = (torch.randn(ld, device=dev) for _ in range(3))
-    gr = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        _C.sgmcmc_step(p1, g1, v1, step=1, **kw)
-    torch.cuda.current_stream().wait_stream(s)
-    with torch.cuda.graph(gr):
-        for j in range(20):
-            _C.sgmcmc_step(p1, g1, v1, step=2 + j, **kw)
-    gr.replay()
-    torch.cuda.synchronize()
-    small_ms, _ = _event_time_ms(gr.replay, 20)
-    small_us = small_ms * 1e3 / 20
-    del pb, gb, vb
-    roofline = {"bound": "hbm", "kernel": "sgmcmc_step_kernel<momentum, philox>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "layout": "[%d chains, D=%d] flat fp32, %d MB algorithmic per launch (20 B/param)" % (K1_CHAINS, D, alg_bytes >> 20),
-                "ms_per_launch": k1_ms,
-                "in_step": {"D": D, "bytes": 20 * D, "us_per_launch_graph_replay": small_us,
-                            "achieved_GBps": 20 * D / (small_us * 1e-6) / 1e9,
-                            "note": "single chain: 5.4 MB, L2 resident, launch-latency bound (SURVEY 7.3)"}}
-
-    line = {
-        "metric": "sgmcmc_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "chains": world, "parallelism": "chains x%d, no collective" % world,
-                   "cuda_graph": not args.no_graph, "channels_last": bool(args.channels_last), "cudnn_benchmark": bool(args.cudnn_benchmark), "l2": "inputs cycle through a %d-batch pool (%d MB > 126 MB L2)" % (POOL_BATCHES, POOL_BATCHES * h2d >> 20),
-                   "hyper": HYP},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / K, "api": "ursabench_b200.inference.cSGHMC.train_step(host pinned batch) + loss.item()"},
-        "gpu_launches": my_launches,
-        "roofline": roofline,
-    }
-
-    if not args.skip_extras:
-        try:
-            line["extras"] = run_extras(dev, rank, world, peak)
-        except Exception as e:  # noqa: BLE001  (extras never invalidate the headline line)
-            line["extras"] = {"error": repr(e)}
-    if rank == 0 and world == 1:
-        sps, n, dt, cores = cpu_reference_steps_per_s(budget_s=15.0, max_steps=60)
-        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d cSGHMC steps (PreResNet-20 fwd+bwd+optimSGHMC.step op sequence), batch 128, %.1f s"
-                                          % (n, dt)}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    t = timeit(sgmcmc_step, 20, warm=2)
+    out["csghmc_preresnet20_b128"] = {"steps_per_s": 1 / t, "sample": "20 steps (csghmc.py:80-93 loop body), one chain"}
+    return out
 
 
 def run_extras(dev, rank, world, peak):
@@ -354,6 +614,7 @@ def run_extras(dev, rank, world, peak):
     BMA img/s with samples sharded over ranks + the single all-reduce."""
     from ursabench_b200 import _C, dist as udist, models
     out = {}
+    out.update(sampler_extras(dev, rank, world, peak))
     D = 36_546_980
     ld = (D + 3) // 4 * 4
     p, g, v = (torch.randn(ld, device=dev) * 0.05 for _ in range(3))
@@ -461,7 +722,7 @@ def run_extras(dev, rank, world, peak):
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
-        ms, _ = _event_time_ms(bma_conv, 2)
+        ms, _ = _event_time_ms(bma_conv, 1)
         ms = udist.allreduce_max_scalar(ms, dev)
         out["bma_preresnet20_S100_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
                                                          "img_samples_per_s": N * S_all / ms * 1e3,
@@ -596,16 +857,17 @@ def run_extras(dev, rank, world, peak):
     return out
 
 
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-extras", action="store_true")
-    ap.add_argument("--channels-last", type=int, default=1, help="NHWC activations in fwd/bwd (engine default)")
-    ap.add_argument("--cudnn-benchmark", type=int, default=0, help="torch.backends.cudnn.benchmark for fwd/bwd")
+    ap.add_argument("--samples", type=int, default=S_ALL, help="posterior samples S (default: the contract's 100)")
+    ap.add_argument("--images", type=int, default=N_TEST, help="test images N (default: the contract's 10000)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,7 @@
  *  - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
  *  - return value: 0 = URSA_OK, negative = error; ursa_last_error() returns a
  *    thread-local message for the last failing call on this thread;
- *  - no global mutable state besides that message: thread-compatible;
+ *  - no global mutable state besides that message and the launch counter: thread-compatible;
  *  - all arithmetic is fp32 unless stated; "n" counts elements, "ld" strides
  *    are in elements.
  */
@@ -39,6 +39,25 @@ extern "C" {
 
 int ursa_abi_version(void);
 const char *ursa_last_error(void);
+/* Number of kernel launches this library has issued in this process so far (monotonic, all threads, all devices):
+ * a diagnostic counter for benchmarks ("gpu_launches"); nothing on the path reads it. */
+uint64_t ursa_launch_count(void);
+/* Per-kernel timing of the PreResNet BMA forward with CUDA events recorded on the launching stream (diagnostic for
+ * bench.py's `roofline`: the kernel's average launch duration measured live inside the timed step).  Between
+ * ursa_profile_begin(capacity) and ursa_profile_end() every instrumented launch records an event pair (at most
+ * `capacity` pairs); ursa_profile_end synchronises on them and returns, per kind, the summed milliseconds and the
+ * number of launches.  Process-wide; do not use from two threads at once. */
+#define URSA_PROF_STAGE_C16  0   /* preresnet_stage16_kernel<16> / preresnet_stage_kernel<16> */
+#define URSA_PROF_STAGE_C32  1
+#define URSA_PROF_STAGE_C64  2
+#define URSA_PROF_STEM       3
+#define URSA_PROF_SHORTCUT   4
+#define URSA_PROF_CONV_S2    5   /* stride-2 transition conv (conv3x3_tc_kernel) */
+#define URSA_PROF_HEAD       6   /* head + softmax-average accumulation */
+#define URSA_PROF_PREP       7
+#define URSA_PROF_KINDS      8
+int ursa_profile_begin(int capacity);
+int ursa_profile_end(double *ms_sum, int64_t *count, int n_kinds);
 /* SM count and compute capability of the current device. */
 int ursa_device_info(int *sm_count, int *cc_major, int *cc_minor);
 

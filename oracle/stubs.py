@@ -10,7 +10,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("URSA_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/make_ref.py (travels to the GPU box)
+
+
+def _default_root():
+    env = os.environ.get("URSA_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/URSABench"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _default_root()
 
 
 class _Anything:
@@ -37,8 +49,11 @@ def reference_available():
     return os.path.isdir(os.path.join(REF_ROOT, "URSABench"))
 
 
-def install():
-    """Register the stubs and put the reference root on sys.path."""
+def install(root=None):
+    """Register the stubs and put the reference root (``root`` or REF_ROOT) on sys.path."""
+    global REF_ROOT
+    if root is not None:
+        REF_ROOT = root
     os.environ.setdefault("WANDB_MODE", "disabled")
     if "hamiltorch" not in sys.modules:
         ham = _module("hamiltorch")

@@ -22,6 +22,26 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_pairs_covers_the_grid_once_and_balances():
+    """Hybrid (sample, image-block) sharding: every pair exactly once, shares within one 64-image block of each other,
+    whole samples when S divides over the ranks (so the bank rows stay where the chains ran)."""
+    for S, N, world in ((10, 10_000, 8), (100, 10_000, 8), (3, 1000, 4), (1, 10, 4), (7, 130, 2), (100, 10_000, 4), (5, 63, 3)):
+        seen = np.zeros((S, N), dtype=np.int32)
+        sizes = []
+        for r in range(world):
+            sh = udist.shard_pairs(S, N, r, world)
+            sizes.append(sum(hi - lo for _, lo, hi in sh))
+            for s, lo, hi in sh:
+                assert 0 <= lo < hi <= N
+                seen[s, lo:hi] += 1
+            if S % world == 0:
+                assert all(lo == 0 and hi == N for _, lo, hi in sh) and len(sh) == S // world
+        assert (seen == 1).all()
+        if S * ((N + 63) // 64) >= world:
+            assert max(sizes) - min(sizes) <= 2 * 64, (S, N, world, sizes)
+    assert udist.shard_pairs(0, 10, 0, 2) == [] and udist.shard_pairs(4, 0, 1, 2) == []
+
+
 def test_chain_elem_offsets_disjoint_and_aligned():
     D = 272_282
     offs = [udist.chain_elem_offset(c, D) for c in range(8)]
@@ -60,6 +80,17 @@ def _worker(rank, world, port, out_dir):
         dist.all_gather(gathered, P.contiguous())
         assert all(torch.equal(gathered[0], g) for g in gathered)
         assert udist.allreduce_max_scalar(float(rank + 1), torch.device("cpu")) == float(world)
+        # hybrid sharding, S = 3 samples over 2 ranks: each rank sums its (sample, image-range) shares into a full-size
+        # accumulator, counts the samples on rank 0 only, and the same single all-reduce completes the evaluation
+        S3 = 3
+        acc_p, acc_e = torch.zeros(N, C), torch.zeros(N)
+        for s_i, lo_i, hi_i in udist.shard_pairs(S3, N, quantum=8):
+            acc_p[lo_i:hi_i] += torch.from_numpy(p[s_i, lo_i:hi_i])
+            acc_e[lo_i:hi_i] += torch.from_numpy(e[s_i, lo_i:hi_i])
+        P3, E3, cnt3 = udist.allreduce_bma(acc_p, acc_e, S3 if rank == 0 else 0)
+        assert cnt3 == S3
+        np.testing.assert_allclose(P3.numpy(), p[:S3].sum(0), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(E3.numpy(), e[:S3].sum(0), rtol=1e-6, atol=1e-6)
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -549,3 +549,127 @@ def test_decision_matches_reference_golden(U):
     t2 = U.tasks.Decision({"decision_data_test": tl}, C, DEV, cost_mat=U.tasks.decision_making.CIFAR10_cost(C))
     out = t2.update_statistics(ms[0])
     assert out["Decision"].shape == (8,) and out["Pred_cost"].shape == (8, C)
+
+
+# ------------------------------------------------------------------------------------------ sharded evaluation
+def _preresnet8_ensemble(U, n_models=3, n=150, seed=5):
+    torch.manual_seed(seed)
+    ms = [U.models.PreResNet(num_classes=10, depth=8).eval() for _ in range(n_models)]
+    g = torch.Generator().manual_seed(seed)
+    x, y = torch.randn(n, 3, 32, 32, generator=g), torch.randint(0, 10, (n,), generator=g)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=32, shuffle=False)
+    return ms, {"in_distribution_test": loader}
+
+
+def test_prediction_pair_shards_sum_to_the_unsharded_result(U):
+    """dist.shard_pairs splits the (sample, image) grid between ranks; summing the ranks' accumulators (what the single
+    all-reduce does) must reproduce the unsharded evaluation: same kernels, same per-image sample order."""
+    ms, loaders = _preresnet8_ensemble(U)
+    full = U.tasks.Prediction(loaders, 10, DEV, ["error_rate", "nll", "brier_score", "ece"])
+    full.update_statistics(ms, output_performance=False)
+    world = 4
+    P = torch.zeros_like(full._proba)
+    E = torch.zeros_like(full._entropy)
+    for r in range(world):
+        part = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+        part.accumulate(ms, U.dist.shard_pairs(len(ms), 150, r, world, quantum=16))
+        assert part.last_engine == "fused_preresnet"
+        P += part._proba
+        E += part._entropy
+    assert float((P - full._proba).abs().max()) <= 2e-6
+    assert float((E - full._entropy).abs().max()) <= 2e-5
+    oi_a, of_a, _, _ = U._C.bma_metrics(P, 3, full._y)
+    oi_b, of_b, _, _ = U._C.bma_metrics(full._proba, 3, full._y)
+    assert torch.equal(oi_a, oi_b)
+
+
+def test_tensor_shaped_loader_fast_path_equals_iteration(U):
+    """A sequential DataLoader over a TensorDataset is ingested without re-collating; a shuffled-off custom dataset is
+    iterated -- both must give the same resident inputs and targets."""
+    ms, loaders = _preresnet8_ensemble(U, n_models=1, n=70)
+    a = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    ds = loaders["in_distribution_test"].dataset
+
+    class Wrapped(torch.utils.data.Dataset):
+        def __len__(self):
+            return len(ds)
+
+        def __getitem__(self, i):
+            return ds[i]
+    b = U.tasks.Prediction({"in_distribution_test": torch.utils.data.DataLoader(Wrapped(), batch_size=32)}, 10, DEV, ["error_rate"])
+    assert torch.equal(a._x, b._x) and torch.equal(a.targets, b.targets) and a._batch_sizes == b._batch_sizes
+
+
+def test_non_cifar_inputs_do_not_reach_the_fused_conv_forward(U):
+    """The fused conv forwards only take (pointer, N): a loader whose images are not [3, 32, 32] must go through the
+    module's own forward and raise the reference's shape error instead of reading out of bounds."""
+    torch.manual_seed(0)
+    m = U.models.PreResNet(num_classes=10, depth=8).eval()
+    x, y = torch.randn(16, 1, 32, 32), torch.randint(0, 10, (16,))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate"])
+    with pytest.raises(RuntimeError):
+        task.update_statistics([m], output_performance=False)
+    assert task.last_engine != "fused_preresnet"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_classes_run_on_a_non_current_device(U):
+    """``device=cuda:1`` while the current device stays 0 (the reference never calls set_device): the C-ABI launches
+    must follow the tensors' device."""
+    assert torch.cuda.current_device() == 0
+    dev1 = torch.device("cuda", 1)
+    ms, loaders = _preresnet8_ensemble(U, n_models=2, n=64)
+    t0 = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    t1 = U.tasks.Prediction(loaders, 10, dev1, ["error_rate"])
+    t0.update_statistics(ms, output_performance=False)
+    t1.update_statistics(ms, output_performance=False)
+    assert t1._proba.device == dev1 and torch.cuda.current_device() == 0
+    assert torch.allclose(t0.ensemble_proba, t1.ensemble_proba, atol=1e-6)
+    ds, loader = _toy()
+    torch.manual_seed(0)
+    inf = U.inference.SGHMC({"lr": 0.1, "prior_std": 1.0, "num_samples": 2, "alpha": 0.3, "burn_in_epochs": 1},
+                            U.models.MLP(16, 20, 3), loader, device=dev1)
+    out = inf.sample()
+    assert len(out) == 2 and inf.flat.p.device == dev1
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import ursabench_b200 as U
+    U.dist.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    try:
+        ms, loaders = _preresnet8_ensemble(U, n_models=3, n=150)
+        task = U.tasks.Prediction(loaders, 10, dev, ["error_rate", "nll", "brier_score", "ece"], distributed=True,
+                                  replicated_samples=True)
+        task.update_statistics(ms, output_performance=False)
+        got = task.get_performance_metrics()
+        proba, _, n_s = task._reduced()
+        solo = U.tasks.Prediction(loaders, 10, dev, ["error_rate", "nll", "brier_score", "ece"])
+        solo.update_statistics(ms, output_performance=False)
+        want = solo.get_performance_metrics()
+        assert n_s == 3
+        assert float((proba - solo._proba).abs().max()) <= 2e-6
+        assert task.get_counters()["correct"] == solo.get_counters()["correct"]
+        for k in want:
+            assert got[k] == pytest.approx(want[k], abs=1e-6), k
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_multi_gpu_equals_single_gpu_on_nccl(tmp_path):
+    """Real NCCL, two ranks, S = 3 samples (S mod world != 0 -> hybrid sample x image sharding): reduced probabilities,
+    counters and metrics equal the single-GPU evaluation."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(2))

@@ -6,6 +6,7 @@ raises.  Device pointers come from ``tensor.data_ptr()`` and the stream from
 device memory and streams.
 """
 import ctypes
+import functools
 import os
 
 import torch
@@ -25,6 +26,9 @@ _vp, _i64, _i32, _u32, _u64, _f32, _f64, _sz = (_c.c_void_p, _c.c_int64, _c.c_in
 SIGNATURES = {
     "ursa_abi_version": (_i32, []),
     "ursa_last_error": (_c.c_char_p, []),
+    "ursa_launch_count": (_u64, []),
+    "ursa_profile_begin": (_i32, [_i32]),
+    "ursa_profile_end": (_i32, [_c.POINTER(_f64), _c.POINTER(_i64), _i32]),
     "ursa_device_info": (_i32, [_c.POINTER(_i32)] * 3),
     "ursa_sgmcmc_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _u32, _u64, _u64, _u64, _vp]),
     "ursa_sgmcmc_step_dyn": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _u32, _u64, _u64, _vp]),
@@ -97,6 +101,21 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _on_device(fn):
+    """Run ``fn`` with the CUDA device of its first tensor argument current: the kernels launch on the *current*
+    device (cudaGetDevice), the reference's classes accept any ``device=`` without a prior ``set_device``."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
+
+
 def _dev_f32(t, name, allow_none=False):
     if t is None:
         if allow_none:
@@ -108,6 +127,7 @@ def _dev_f32(t, name, allow_none=False):
         raise ValueError("%s must be contiguous float32" % name)
 
 
+@_on_device
 def sgmcmc_step(p, g, v=None, snapshot=None, noise=None, *, lr, momentum, wd_over_n, noise_mul=0.0, noise_div=1.0,
                 first_step=False, add_noise=True, zero_grad=False, seed=0, step=0, elem_offset=0):
     """Fused optimSGHMC update over flat buffers (see ursa_sgmcmc_step in the header)."""
@@ -124,6 +144,7 @@ def sgmcmc_step(p, g, v=None, snapshot=None, noise=None, *, lr, momentum, wd_ove
     _check(rc, "ursa_sgmcmc_step")
 
 
+@_on_device
 def sgmcmc_step_dyn(p, g, v, snapshot, noise, dyn, *, first_step=False, add_noise=True, zero_grad=False, seed=0,
                     elem_offset=0):
     """K1 with [lr, momentum, wd_over_n, noise_scale, step_lo, step_hi] read from the device tensor ``dyn``
@@ -137,6 +158,7 @@ def sgmcmc_step_dyn(p, g, v, snapshot, noise, dyn, *, first_step=False, add_nois
     _check(rc, "ursa_sgmcmc_step_dyn")
 
 
+@_on_device
 def sgmcmc_set_dyn(dyn, lr, momentum, wd_over_n, noise_scale, step):
     _dev_f32(dyn, "dyn")
     if dyn.numel() < 6:
@@ -145,12 +167,14 @@ def sgmcmc_set_dyn(dyn, lr, momentum, wd_over_n, noise_scale, step):
                                      int(step), _stream(dyn)), "ursa_sgmcmc_set_dyn")
 
 
+@_on_device
 def philox_normal(out, seed, step, elem_offset=0):
     _dev_f32(out, "out")
     _check(lib().ursa_philox_normal(_ptr(out), out.numel(), seed, step, elem_offset, _stream(out)), "ursa_philox_normal")
     return out
 
 
+@_on_device
 def swag_collect(w, mean, sq_mean, dev_row, n_collected):
     for t, nm in ((w, "w"), (mean, "mean"), (sq_mean, "sq_mean"), (dev_row, "dev_row")):
         _dev_f32(t, nm)
@@ -160,6 +184,7 @@ def swag_collect(w, mean, sq_mean, dev_row, n_collected):
     _check(rc, "ursa_swag_collect")
 
 
+@_on_device
 def swag_variance(mean, sq_mean, var, clamp=1e-30):
     for t, nm in ((mean, "mean"), (sq_mean, "sq_mean"), (var, "var")):
         _dev_f32(t, nm)
@@ -168,6 +193,7 @@ def swag_variance(mean, sq_mean, var, clamp=1e-30):
     return var
 
 
+@_on_device
 def swag_draw(out, mean, var, D, ring=None, z2=None, z1=None, rank_div=1.0, seed=0, step=0):
     """out: [S, ld]; ring: [K, ld] or None; z2: [S, K]; z1: [S, ld] or None (Philox)."""
     _dev_f32(out, "out"), _dev_f32(mean, "mean"), _dev_f32(var, "var")
@@ -181,6 +207,7 @@ def swag_draw(out, mean, var, D, ring=None, z2=None, z1=None, rank_div=1.0, seed
     return out
 
 
+@_on_device
 def swag_gram(ring, D):
     """ring: [K, ld] device fp32 -> [K, K] float64 device tensor R R^T over the first D columns."""
     _dev_f32(ring, "ring")
@@ -190,6 +217,7 @@ def swag_gram(ring, D):
     return gram
 
 
+@_on_device
 def bma_accumulate(logits, proba_sum, entropy_sum, gamma=1e-4):
     """logits: [S, N, C] contiguous."""
     _dev_f32(logits, "logits"), _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum")
@@ -199,6 +227,7 @@ def bma_accumulate(logits, proba_sum, entropy_sum, gamma=1e-4):
     _check(rc, "ursa_bma_accumulate")
 
 
+@_on_device
 def bma_metrics(proba_sum, num_samples, targets, gamma=1e-4, n_bins=15, want_rows=False):
     """Returns (i64[1+2*nb], f64[2+nb], pred|None, conf|None) as device tensors."""
     _dev_f32(proba_sum, "proba_sum")
@@ -218,6 +247,7 @@ def bma_metrics(proba_sum, num_samples, targets, gamma=1e-4, n_bins=15, want_row
     return out_i, out_f, pred, conf
 
 
+@_on_device
 def bma_mlp_forward(bank, S, x, in_dim, hidden, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
                     algo=ALGO_FFMA, workspace=None):
     _dev_f32(bank, "bank"), _dev_f32(x, "x"), _dev_f32(proba_sum, "proba_sum"), _dev_f32(entropy_sum, "entropy_sum")
@@ -233,6 +263,7 @@ def bma_mlp_forward(bank, S, x, in_dim, hidden, C, proba_sum, entropy_sum, logit
     return workspace
 
 
+@_on_device
 def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
                           algo=ALGO_FFMA, workspace=None):
     _dev_f32(bank, "bank"), _dev_f32(bufbank, "bufbank"), _dev_f32(x, "x")
@@ -249,6 +280,7 @@ def bma_preresnet_forward(bank, bufbank, S, x, depth, C, proba_sum, entropy_sum,
     return workspace
 
 
+@_on_device
 def gemm_nt(A, B, out, bias=None, relu=False, workspace=None):
     """out[b] = A[b or shared] @ B[b]^T (+ bias[b]) (ReLU) on the 3xTF32 tcgen05 GEMM.  A: [M, K] (shared) or [batch, M, K];
     B: [batch, N, K]; out: [batch, M, N]; bias: [batch, N] or None.  Innermost dims contiguous.  Returns the workspace."""
@@ -271,6 +303,7 @@ def gemm_nt(A, B, out, bias=None, relu=False, workspace=None):
     return workspace
 
 
+@_on_device
 def bma_wrn_forward(bank, bufbank, S, x, depth, widen, C, proba_sum, entropy_sum, logits_out=None, gamma=1e-4,
                     algo=ALGO_TCGEN05, workspace=None):
     """WideResNet (WRN-depth-widen) BMA forward: every conv is a persistent 3xTF32 tcgen05 implicit GEMM."""
@@ -289,6 +322,7 @@ def bma_wrn_forward(bank, bufbank, S, x, depth, widen, C, proba_sum, entropy_sum
     return workspace
 
 
+@_on_device
 def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
     """Re-estimate the BatchNorm running statistics of ONE WideResNet sample with a train-mode pass over ``x`` (batches of
     ``batch`` images); ``buf_row`` [nb] is overwritten.  Returns the workspace (None if the shape is not covered)."""
@@ -305,6 +339,7 @@ def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
     return workspace
 
 
+@_on_device
 def hmc_momentum(r, sqrt_mass, noise=None, seed=0, step=0, elem_offset=0):
     """r[C, ld] = sqrt_mass * z (z from ``noise`` or Philox)."""
     _dev_f32(r, "r"), _dev_f32(noise, "noise", True)
@@ -315,6 +350,7 @@ def hmc_momentum(r, sqrt_mass, noise=None, seed=0, step=0, elem_offset=0):
     return r
 
 
+@_on_device
 def hmc_leapfrog(theta, r, g_nll, *, kick, drift, tau, tau_out=1.0, snapshot=None):
     """r += kick * grad_logp ; theta += drift * r  with grad_logp = -(tau_out * g_nll + tau * theta)."""
     for t, nm, opt in ((theta, "theta", False), (r, "r", False), (g_nll, "g_nll", False), (snapshot, "snapshot", True)):
@@ -327,6 +363,7 @@ def hmc_leapfrog(theta, r, g_nll, *, kick, drift, tau, tau_out=1.0, snapshot=Non
                                    float(tau), float(tau_out), _stream(theta)), "ursa_hmc_leapfrog")
 
 
+@_on_device
 def hmc_energy(theta, r, D, out=None, workspace=None):
     """theta, r: [C, ld].  Returns (sums[2, C] float64 = [sum theta^2, sum r^2], workspace)."""
     _dev_f32(theta, "theta"), _dev_f32(r, "r")
@@ -341,6 +378,7 @@ def hmc_energy(theta, r, D, out=None, workspace=None):
     return out, workspace
 
 
+@_on_device
 def hmc_accept(theta, saved, h_old, h_new, accept, *, logu=None, keep_dst=None, keep_src=None, out=None, seed=0, step=0,
                chain_offset=0):
     """Metropolis accept / restore per chain (see ursa_hmc_accept).  h_old, h_new: float64 [C]; accept: int32 [C]."""
@@ -361,6 +399,26 @@ def hmc_accept(theta, saved, h_old, h_new, accept, *, logu=None, keep_dst=None, 
                                  _ptr(logu), accept.data_ptr(), int(seed), int(step), int(chain_offset), _stream(theta)),
            "ursa_hmc_accept")
     return accept
+
+
+def launch_count():
+    """Kernel launches issued by the library in this process so far."""
+    return int(lib().ursa_launch_count())
+
+
+PROF_KINDS = ("stage_c16", "stage_c32", "stage_c64", "stem", "shortcut", "conv_s2", "head", "prep")
+
+
+def profile_begin(capacity=1 << 16):
+    _check(lib().ursa_profile_begin(int(capacity)), "ursa_profile_begin")
+
+
+def profile_end():
+    """{kind: (summed ms, launches)} of the instrumented PreResNet-forward kernels since ``profile_begin``."""
+    n = len(PROF_KINDS)
+    ms, cnt = (_f64 * n)(), (_i64 * n)()
+    _check(lib().ursa_profile_end(ms, cnt, n), "ursa_profile_end")
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
 
 
 def device_info():

@@ -546,15 +546,21 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
 
     for (int s0 = 0; s0 < S; s0 += ck.sc) {
         const int sc = (S - s0 < ck.sc) ? (S - s0) : ck.sc;
-        preresnet_prep_kernel<<<dim3(pl.table.n, sc), 256, 0, st>>>(pl.table, bank + (int64_t)s0 * ld_bank, ld_bank,
-                                                                    bufbank + (int64_t)s0 * ld_buf, ld_buf, packed,
-                                                                    pl.packed_floats);
-        URSA_LAUNCH_CHECK("preresnet_prep_kernel");
+        {
+            ProfScope ps(URSA_PROF_PREP, st);
+            preresnet_prep_kernel<<<dim3(pl.table.n, sc), 256, 0, st>>>(pl.table, bank + (int64_t)s0 * ld_bank, ld_bank,
+                                                                        bufbank + (int64_t)s0 * ld_buf, ld_buf, packed,
+                                                                        pl.packed_floats);
+            URSA_LAUNCH_CHECK("preresnet_prep_kernel");
+        }
         for (int64_t i0 = 0; i0 < N; i0 += ck.nc) {
             const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
-            stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
-                                                           pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr);
-            URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+            {
+                ProfScope ps(URSA_PROF_STEM, st);
+                stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
+                                                               pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr);
+                URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+            }
             float *cur = Ra, *nxt = Rb;          // residual stream in / out of the current stage
             int ch = 16, hw = 32;
             for (int stg = 0; stg < 3; ++stg) {
@@ -567,13 +573,19 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 } else {
                     // transition block: 1x1 stride-2 shortcut on the raw stream, stride-2 conv1 on the layer-wise kernel
                     const NetPlan::Block &B0 = pl.blocks[stg][0];
-                    shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs);
-                    URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
+                    {
+                        ProfScope ps(URSA_PROF_SHORTCUT, st);
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs);
+                        URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
+                    }
                     ConvTcArgs c1;
                     c1.mode = 0; c1.bn_off = B0.bn2; c1.res = nullptr; c1.out_raw = nullptr; c1.out_hi = A2h;
                     c1.out_lo = f16 ? nullptr : A2l;
-                    if (int rc = launch_conv_tc(A1h, A1l, hw, ch, 2 * ch, 2, sc, nc, packed, pl.packed_floats, B0.w1, B0.w1_lo, c1, st))
-                        return rc;
+                    {
+                        ProfScope ps(URSA_PROF_CONV_S2, st);
+                        if (int rc = launch_conv_tc(A1h, A1l, hw, ch, 2 * ch, 2, sc, nc, packed, pl.packed_floats, B0.w1, B0.w1_lo, c1, st))
+                            return rc;
+                    }
                     ch *= 2; hw /= 2;
                     g.bn_in_off = -1;
                     g.r_in = Rs; g.a_in_hi = A2h; g.a_in_lo = A2l;
@@ -592,16 +604,22 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 g.a_out_hi = stg < 2 ? A1h : nullptr;
                 g.a_out_lo = stg < 2 ? A1l : nullptr;
                 int rc;
-                if (f16) rc = stg == 0 ? launch_stage16<16>(g, st) : (stg == 1 ? launch_stage16<32>(g, st) : launch_stage16<64>(g, st));
-                else rc = stg == 0 ? launch_stage<16>(g, st) : (stg == 1 ? launch_stage<32>(g, st) : launch_stage<64>(g, st));
+                {
+                    ProfScope ps(URSA_PROF_STAGE_C16 + stg, st);
+                    if (f16) rc = stg == 0 ? launch_stage16<16>(g, st) : (stg == 1 ? launch_stage16<32>(g, st) : launch_stage16<64>(g, st));
+                    else rc = stg == 0 ? launch_stage<16>(g, st) : (stg == 1 ? launch_stage<32>(g, st) : launch_stage<64>(g, st));
+                }
                 if (rc) return rc;
                 float *t = cur; cur = nxt; nxt = t;
             }
             const int pairs = sc * nc;
-            head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);
-            URSA_LAUNCH_CHECK("head_nhwc_kernel");
-            if (int rc = ursa_bma_accumulate(logits, sc, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
-                return rc;
+            {
+                ProfScope ps(URSA_PROF_HEAD, st);
+                head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);
+                URSA_LAUNCH_CHECK("head_nhwc_kernel");
+                if (int rc = ursa_bma_accumulate(logits, sc, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
+                    return rc;
+            }
             if (logits_out)
                 URSA_CUDA(cudaMemcpy2DAsync(logits_out + ((int64_t)s0 * N + i0) * C, (size_t)N * C * sizeof(float), logits,
                                             (size_t)nc * C * sizeof(float), (size_t)nc * C * sizeof(float), sc,

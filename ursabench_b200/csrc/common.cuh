@@ -12,6 +12,7 @@ namespace ursa {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int sm_count();
+void count_launch();                       // process-wide count of kernel launches issued by this library (ursa_launch_count)
 
 #define URSA_REQUIRE(cond, ...)                \
     do {                                       \
@@ -29,9 +30,23 @@ int sm_count();
 
 #define URSA_LAUNCH_CHECK(name)                                  \
     do {                                                         \
+        ::ursa::count_launch();                                  \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) return ::ursa::cuda_fail(e__, name); \
     } while (0)
+
+// ---- optional per-kernel CUDA-event timing (ursa_profile_begin / ursa_profile_end): a diagnostic for benchmarks ----
+// ProfScope records an event pair on `st` around the launches in its scope when profiling is on; otherwise it is two
+// relaxed loads.  Only the PreResNet BMA forward is instrumented (the kernels bench.py's roofline names).
+bool prof_on();
+void prof_mark(int kind, cudaStream_t st, bool begin);
+struct ProfScope {
+    int kind;
+    cudaStream_t st;
+    bool on;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(prof_on()) { if (on) prof_mark(kind, st, true); }
+    ~ProfScope() { if (on) prof_mark(kind, st, false); }
+};
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -44,6 +44,30 @@ def shard_range(n, rank=None, world=None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_pairs(n_samples, n_images, rank=None, world=None, quantum=64):
+    """Balanced share of the ``n_samples x n_images`` (sample, image) grid for ``rank`` as a list of
+    ``(sample, img_lo, img_hi)``: whole samples when ``n_samples`` divides evenly over the ranks, otherwise a contiguous
+    run of ``quantum``-image blocks in sample-major order, so that S < G or S mod G != 0 no longer leaves ranks idle
+    (the partial [N, C] sums of all ranks still meet in the same single all-reduce)."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    if n_samples <= 0 or n_images <= 0:
+        return []
+    if n_samples % world == 0:
+        lo, hi = shard_range(n_samples, rank, world)
+        return [(s, 0, n_images) for s in range(lo, hi)]
+    nb = (n_images + quantum - 1) // quantum                 # image blocks per sample
+    lo, hi = shard_range(n_samples * nb, rank, world)
+    out = []
+    u = lo
+    while u < hi:
+        s, b0 = divmod(u, nb)
+        b1 = min(nb, b0 + (hi - u))
+        out.append((s, b0 * quantum, min(n_images, b1 * quantum)))
+        u += b1 - b0
+    return out
+
+
 def chain_elem_offset(chain_id, D):
     """Philox element base of chain ``chain_id`` so that chains on different ranks never share a noise stream
     (K1's counter is the global element index; multiple of 4 as the kernel requires)."""

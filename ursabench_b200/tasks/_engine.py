@@ -27,16 +27,44 @@ def _arch_of(module):
                 and f2.in_features == f1.out_features == f2.out_features == f3.in_features \
                 and len(list(module.parameters())) == 6:
             return ("mlp", f1.in_features, f1.out_features, f3.out_features)
-    if name == "PreResNet" and hasattr(module, "layer1") and hasattr(module, "fc"):
+    if name == "PreResNet" and all(hasattr(module, a) for a in ("conv1", "layer1", "layer2", "layer3", "bn", "fc")):
         blocks = list(module.layer1)
-        if blocks and type(blocks[0]).__name__ == "BasicBlock" and module.fc.in_features == 64:
-            return ("preresnet", 6 * len(blocks) + 2, module.fc.out_features)
-    if name == "WideResNet" and hasattr(module, "layer1") and hasattr(module, "linear"):
+        n = len(blocks)
+        if n and type(blocks[0]).__name__ == "BasicBlock" and module.fc.in_features == 64 \
+                and len(list(module.layer2)) == n and len(list(module.layer3)) == n \
+                and tuple(module.conv1.weight.shape) == (16, 3, 3, 3) and module.conv1.bias is None \
+                and len(list(module.parameters())) == 6 * n * 3 + 3 + 2 + 2:
+            # 61 tensors at depth 20: conv1, 3n blocks x (bn1 w/b, conv1, bn2 w/b, conv2), 2 downsamples, bn w/b, fc w/b
+            C = module.fc.out_features
+            if sum(q.numel() for q in module.parameters()) == _preresnet_numel(n, C):
+                return ("preresnet", 6 * n + 2, C)
+    if name == "WideResNet" and all(hasattr(module, a) for a in ("conv1", "layer1", "layer2", "layer3", "bn1", "linear")):
         blocks = list(module.layer1)
-        if blocks and type(blocks[0]).__name__ == "WideBasic" and module.linear.in_features % 64 == 0 \
-                and blocks[0].conv1.bias is not None:            # dropout is the identity in eval mode (prediction.py:58)
-            return ("wrn", 6 * len(blocks) + 4, module.linear.in_features // 64, module.linear.out_features)
+        n = len(blocks)
+        if n and type(blocks[0]).__name__ == "WideBasic" and module.linear.in_features % 64 == 0 \
+                and blocks[0].conv1.bias is not None and len(list(module.layer2)) == n and len(list(module.layer3)) == n \
+                and tuple(module.conv1.weight.shape[1:]) == (3, 3, 3):   # dropout is the identity in eval mode (prediction.py:58)
+            return ("wrn", 6 * n + 4, module.linear.in_features // 64, module.linear.out_features)
     return None
+
+
+def _preresnet_numel(n, C):
+    """Parameter count of the reference's BasicBlock PreResNet (models/preresnet.py:98-151) with n blocks per stage."""
+    total = 16 * 27
+    cin = 16
+    for stage, ch in enumerate((16, 32, 64)):
+        for b in range(n):
+            c_in = cin if b == 0 else ch
+            total += 2 * c_in + ch * c_in * 9 + 2 * ch + ch * ch * 9
+            if b == 0 and stage > 0:
+                total += ch * c_in
+        cin = ch
+    return total + 2 * 64 + 64 * C + C
+
+
+def wrn_dropout_is_identity(module):
+    """True when every Dropout of a (Wide)ResNet has p == 0, i.e. the train-mode engine pass equals the module's."""
+    return all(m.p == 0 for m in module.modules() if isinstance(m, torch.nn.Dropout))
 
 
 
@@ -59,19 +87,42 @@ class BMAAccumulator:
         self.last_algo = None
         # one pass over the loader (the reference tasks do the same to cache the targets); the inputs are uploaded once
         # and stay resident -- the loader must not shuffle
-        xs, ys = [], []
-        for batch_data, batch_labels in loader:
-            xs.append(batch_data)
-            ys.append(batch_labels)
-        self.targets = torch.cat(ys)
+        whole = self._whole_tensors(loader)
+        if whole is not None:
+            # a sequential DataLoader over a TensorDataset yields exactly dataset.tensors in order: upload them in one
+            # copy instead of re-collating N / batch_size batches on the host
+            x_host, self.targets = whole
+            bs = loader.batch_size
+            self._batch_sizes = [min(bs, len(x_host) - i) for i in range(0, len(x_host), bs)]
+        else:
+            xs, ys = [], []
+            for batch_data, batch_labels in loader:
+                xs.append(batch_data)
+                ys.append(batch_labels)
+            self.targets = torch.cat(ys)
+            self._batch_sizes = [len(x) for x in xs]
+            x_host = torch.cat(xs)
         self._n = len(loader.dataset)
-        self._batch_sizes = [len(x) for x in xs]
-        self._x = torch.cat(xs).to(self.device, non_blocking=True).float().contiguous()
+        self.h2d_bytes = x_host.numel() * x_host.element_size()       # test set uploaded by this constructor
+        self.h2d_sample_bytes = 0                                      # posterior samples uploaded by accumulate()
+        self._x = x_host.to(self.device, non_blocking=True).float().contiguous()
         self._proba = torch.zeros(self._n, num_classes, device=self.device)
         self._entropy = torch.zeros(self._n, device=self.device)
         self._workers = {}
         self.last_engine = None
         self.kernel_launches = 0
+
+    @staticmethod
+    def _whole_tensors(loader):
+        """(x, y) when ``loader`` is a plain sequential, non-dropping DataLoader over a 2-tensor TensorDataset, else None."""
+        data = torch.utils.data
+        ds = getattr(loader, "dataset", None)
+        if type(loader) is not data.DataLoader or type(ds) is not data.TensorDataset or len(ds.tensors) != 2:
+            return None
+        if not isinstance(loader.sampler, data.SequentialSampler) or loader.drop_last or loader.batch_size is None \
+                or loader.collate_fn is not data.default_collate:
+            return None
+        return ds.tensors[0], ds.tensors[1]
 
     @staticmethod
     def as_model_list(models):
@@ -84,26 +135,42 @@ class BMAAccumulator:
             return [models]
         raise NotImplementedError
 
-    def accumulate(self, model_list):
-        if model_list:
-            with torch.no_grad():
-                self._accumulate(model_list)
+    def accumulate(self, model_list, pairs=None):
+        """``pairs`` = None: every model over every image.  Otherwise a list of ``(index into model_list, img_lo, img_hi)``
+        -- this rank's share of the (sample, image) grid (``dist.shard_pairs``); the other ranks' shares meet in the
+        all-reduce of the accumulators."""
+        if not model_list:
+            return
+        with torch.no_grad():
+            if pairs is None:
+                self._accumulate(model_list, 0, self._n)
+                return
+            i = 0
+            while i < len(pairs):                       # runs of samples over the same image range go down in one call
+                j = i
+                while j + 1 < len(pairs) and pairs[j + 1][1:] == pairs[i][1:]:
+                    j += 1
+                _, lo, hi = pairs[i]
+                if hi > lo:
+                    self._accumulate([model_list[k] for k, _, _ in pairs[i:j + 1]], lo, hi)
+                i = j + 1
 
-    def _accumulate(self, model_list):
+    def _accumulate(self, model_list, lo, hi):
         banked = all(isinstance(m, BankedSample) and m.is_pristine() for m in model_list)
         if banked and len({id(m._ursa_bank) for m in model_list}) == 1:
             bank = model_list[0]._ursa_bank
             w, b = bank.rows([m._ursa_row for m in model_list])
-            self._accumulate_rows(w, b, _arch_of(bank.skeleton), bank.skeleton)
+            self._accumulate_rows(w, b, _arch_of(bank.skeleton), bank.skeleton, lo, hi)
             return
         plain = [m.materialize() if isinstance(m, BankedSample) else m for m in model_list]
         arch = _arch_of(plain[0])
         if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch) \
                 and all(_arch_of(m) == arch for m in plain):
             bank = SampleBank.from_modules(plain, self.device)       # one H2D per sample instead of 2 per batch
-            self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None)
+            self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
+            self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
             return
-        self._accumulate_generic_modules(plain)
+        self._accumulate_generic_modules(plain, lo, hi)
 
     def _fused_available(self, arch):
         return self._pick_algo(arch) is not None
@@ -129,39 +196,46 @@ class BMAAccumulator:
                 return _C.ALGO_TCGEN05
         return None
 
-    def _accumulate_rows(self, w, b, arch, skeleton):
+    def _accumulate_rows(self, w, b, arch, skeleton, lo=0, hi=None):
         S = w.shape[0]
-        if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch):
+        hi = self._n if hi is None else hi
+        x, proba, entropy = self._x[lo:hi], self._proba[lo:hi], self._entropy[lo:hi]     # contiguous row ranges
+        if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch) \
+                and self._inputs_match(arch):
             algo = self._pick_algo(arch)
             if arch[0] == "mlp":
                 _, in_dim, hidden, C = arch
-                x2 = self._x.view(self._n, -1)
+                x2 = self._x.view(self._n, -1)[lo:hi]
                 if x2.shape[1] != in_dim or C != self.num_classes:
                     raise ValueError("MLP input / class dimensions do not match the task")
-                self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, self._proba, self._entropy, algo=algo,
-                                              workspace=self._ws)
+                if w.shape[1] < (in_dim + 1) * hidden + (hidden + 1) * hidden + (hidden + 1) * C:
+                    raise ValueError("bank rows are shorter than the MLP's parameter vector")
+                self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_mlp"
             elif arch[0] == "wrn":
                 _, depth, widen, C = arch
                 if C != self.num_classes:
                     raise ValueError("WideResNet class dimension does not match the task")
-                self._ws = _C.bma_wrn_forward(w, b, S, self._x, depth, widen, C, self._proba, self._entropy, algo=algo,
-                                              workspace=self._ws)
+                self._ws = _C.bma_wrn_forward(w, b, S, x, depth, widen, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_wrn"
             else:
                 _, depth, C = arch
-                guard = algo == _C.ALGO_TCGEN05_FUSED_F16
-                if guard:                                   # FP16-split operands: activations beyond ~1e6 overflow to NaN
-                    keep = (self._proba.clone(), self._entropy.clone())
-                self._ws = _C.bma_preresnet_forward(w, b, S, self._x, depth, C, self._proba, self._entropy, algo=algo,
-                                                    workspace=self._ws)
-                if guard and not bool(torch.isfinite(self._proba).all()):
-                    # loud by construction (inf -> NaN logits): redo this call on the TF32 engine, which has fp32's range
-                    self._proba.copy_(keep[0])
-                    self._entropy.copy_(keep[1])
-                    algo = _C.ALGO_TCGEN05_FUSED
-                    self._ws = _C.bma_preresnet_forward(w, b, S, self._x, depth, C, self._proba, self._entropy, algo=algo,
-                                                        workspace=None)
+                if C != self.num_classes:
+                    raise ValueError("PreResNet class dimension does not match the task")
+                if algo == _C.ALGO_TCGEN05_FUSED_F16:
+                    # FP16-split operands: activations beyond ~1e6 overflow to inf -> NaN logits (loud by construction).
+                    # The call accumulates into a zeroed scratch pair, ONE flag read decides, then the scratch is added:
+                    # the accumulators never see a NaN and nothing is cloned.
+                    sp, se = self._scratch(hi - lo)
+                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp, se, algo=algo, workspace=self._ws)
+                    if bool(torch.isfinite(sp.sum())):
+                        proba.add_(sp)
+                        entropy.add_(se)
+                    else:                                       # redo on the TF32 engine, which has fp32's range
+                        algo = _C.ALGO_TCGEN05_FUSED
+                        self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=None)
+                else:
+                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_preresnet"
             self.last_algo = algo
             self.kernel_launches += 1
@@ -176,7 +250,24 @@ class BMAAccumulator:
             flat.load_buffers(b[i])
             return worker
 
-        self._accumulate_generic(S, load)
+        self._accumulate_generic(S, load, None, lo, hi)
+
+    def _scratch(self, n):
+        if getattr(self, "_scratch_p", None) is None:
+            self._scratch_p = torch.empty(self._n, self.num_classes, device=self.device)
+            self._scratch_e = torch.empty(self._n, device=self.device)
+        sp, se = self._scratch_p[:n], self._scratch_e[:n]
+        sp.zero_()
+        se.zero_()
+        return sp, se
+
+    def _inputs_match(self, arch):
+        """The fused conv forwards take only (pointer, N): the resident test tensor must be the [N, 3, 32, 32] the
+        CIFAR-shaped networks expect -- anything else goes through the module's own forward (which raises the
+        reference's shape error)."""
+        if arch[0] == "mlp":
+            return True
+        return tuple(self._x.shape[1:]) == (3, 32, 32)
 
     def _worker_for(self, skeleton):
         key = id(skeleton)
@@ -187,7 +278,7 @@ class BMAAccumulator:
             self._workers[key] = worker
         return self._workers[key]
 
-    def _accumulate_generic_modules(self, plain):
+    def _accumulate_generic_modules(self, plain, lo=0, hi=None):
         homes = [next(m.parameters()).device for m in plain]
 
         def load(i):
@@ -198,35 +289,35 @@ class BMAAccumulator:
         def unload(i):
             plain[i].to(homes[i])
 
-        self._accumulate_generic(len(plain), load, unload)
+        self._accumulate_generic(len(plain), load, unload, lo, hi)
 
-    def _accumulate_generic(self, S, load, unload=None):
+    def _accumulate_generic(self, S, load, unload=None, lo=0, hi=None):
         """Per-sample PyTorch forward on the device over the resident test set; logits are gathered per chunk of
         samples and reduced by ONE ``ursa_bma_accumulate`` launch per chunk (sample order preserved)."""
-        N, C = self._n, self.num_classes
+        hi = self._n if hi is None else hi
+        N, C = hi - lo, self.num_classes
         chunk = max(1, min(S, _LOGIT_CHUNK_BYTES // max(1, N * C * 4)))
         logits = torch.empty(chunk, N, C, device=self.device)
         tf32_matmul = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False          # fp32 parity with the reference's CPU forward
         try:
             with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
-                self._generic_chunks(S, chunk, logits, load, unload)
+                self._generic_chunks(S, chunk, logits, load, unload, lo, hi)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32_matmul
         self.last_engine = "generic"
 
-    def _generic_chunks(self, S, chunk, logits, load, unload):
+    def _generic_chunks(self, S, chunk, logits, load, unload, lo, hi):
+        bs = max(self._batch_sizes) if self._batch_sizes else 128
         for s0 in range(0, S, chunk):
             ns = min(chunk, S - s0)
             for j in range(ns):
                 model = load(s0 + j)
-                off = 0
-                for bs in self._batch_sizes:
-                    out = model(self._x[off:off + bs])
-                    logits[j, off:off + bs] = out.float()
-                    off += bs
+                for off in range(lo, hi, bs):                    # eval mode: batch boundaries do not change the result
+                    end = min(hi, off + bs)
+                    logits[j, off - lo:end - lo] = model(self._x[off:end]).float()
                 if unload is not None:
                     unload(s0 + j)
-            _C.bma_accumulate(logits[:ns], self._proba, self._entropy)
+            _C.bma_accumulate(logits[:ns], self._proba[lo:hi], self._entropy[lo:hi])
             self.kernel_launches += 1
 

@@ -25,12 +25,19 @@ class Prediction(_Task, BMAAccumulator):
                              "misclass_total_uncertainty_aucpr", "misclass_confidence_auroc",
                              "misclass_confidence_aucpr"]
 
-    def __init__(self, dataloader, num_classes, device, metric_list, distributed=False, engine="auto"):
+    def __init__(self, dataloader, num_classes, device, metric_list, distributed=False, engine="auto",
+                 replicated_samples=False):
+        """``distributed``: the accumulators of all ranks are summed with one all-reduce before the metrics.
+        ``replicated_samples=False``: every rank passes ITS OWN posterior samples (they live where the chain ran) --
+        pure sample sharding.  ``replicated_samples=True``: every rank passes the SAME list and evaluates only its
+        balanced share of the (sample, image) grid (``dist.shard_pairs``), which keeps all ranks busy when S < world or
+        S mod world != 0."""
         super().__init__(dataloader, num_classes, device)
         self.data_loader = dataloader["in_distribution_test"]
         self._setup(self.data_loader, num_classes, device, engine)   # engine='generic' forces the per-sample PyTorch forward
         self._y = self.targets.to(self.device).long().contiguous()
         self.distributed = distributed
+        self.replicated_samples = bool(replicated_samples)
         self.num_samples_collected = 0
         self.required_metric_list = self.supported_metric_list if metric_list == "ALL" else metric_list
         assert all(metric in self.supported_metric_list for metric in self.required_metric_list)
@@ -60,20 +67,41 @@ class Prediction(_Task, BMAAccumulator):
     # -- accumulation ------------------------------------------------------------------------------------------
     def update_statistics(self, models, output_performance=True, smoothing=True):
         model_list = self.as_model_list(models)
-        self.num_samples_collected += len(model_list)
-        self.accumulate(model_list)
+        if self.distributed and self.replicated_samples and udist.is_distributed():
+            rank, world = udist.rank_world()
+            # the sample count is all-reduced with the accumulators: every sample is counted once, on rank 0
+            self.num_samples_collected += len(model_list) if rank == 0 else 0
+            self.accumulate(model_list, udist.shard_pairs(len(model_list), self._n, rank, world))
+        else:
+            self.num_samples_collected += len(model_list)
+            self.accumulate(model_list)
         if output_performance:
             return self.get_performance_metrics(output_performance, smoothing)
 
     def update_from_bank(self, bank, rows=None):
-        """Fast path without module handles: evaluate bank rows directly (used by bench.py / multi-GPU drivers)."""
+        """Fast path without module handles: evaluate bank rows directly (used by bench.py / multi-GPU drivers).  With
+        ``distributed`` + ``replicated_samples`` the rows are the same on every rank and each rank evaluates its share of
+        the (row, image) grid."""
         rows = list(range(bank.count)) if rows is None else list(rows)
-        self.num_samples_collected += len(rows)
-        if rows:
-            w, b = bank.rows(rows)
-            arch = _arch_of(bank.skeleton) if bank.skeleton is not None else None
-            with torch.no_grad():
-                self._accumulate_rows(w, b, arch, bank.skeleton)
+        arch = _arch_of(bank.skeleton) if bank.skeleton is not None else None
+        if self.distributed and self.replicated_samples and udist.is_distributed():
+            rank, world = udist.rank_world()
+            self.num_samples_collected += len(rows) if rank == 0 else 0
+            pairs = udist.shard_pairs(len(rows), self._n, rank, world)
+        else:
+            self.num_samples_collected += len(rows)
+            pairs = [(i, 0, self._n) for i in range(len(rows))]
+        with torch.no_grad():
+            i = 0
+            while i < len(pairs):
+                j = i
+                while j + 1 < len(pairs) and pairs[j + 1][1:] == pairs[i][1:]:
+                    j += 1
+                _, lo, hi = pairs[i]
+                if hi > lo:
+                    w, b = bank.rows([rows[k] for k, _, _ in pairs[i:j + 1]])
+                    self._accumulate_rows(w, b, arch, bank.skeleton, lo, hi)
+                i = j + 1
 
     # -- metrics --------------------------------------------------------------------------------------------------
     def _reduced(self):
