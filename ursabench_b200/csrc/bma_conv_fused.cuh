@@ -48,6 +48,17 @@ struct FusedStageArgs {
     float *r_out;                      // [S_c][N_c][H][W][C]
     float *a_out_hi, *a_out_lo;        // nullable: split(relu(bn_off[last](r_out))) for the next stage's stride-2 conv
     int n_images, n_samples;
+    // FP16-split stage kernels: y = relu(bn_off[last](r_out)) / 16 for the next stage's stride-2 conv leaves as FP16 hi / lo'
+    // rows [pass][position][hi(C) | lo'(C)] halves through a swizzled staging tile and ONE TMA tensor store per tile
+    // (out_map: 2-D fp32 view, C floats x positions, box C x 128, swizzle = row bytes); replaces a_out_hi / a_out_lo
+    CUtensorMap out_map;
+    int has_out_map = 0;
+    int r_out_compact = 0;             // FP16-split stage kernels: r_out holds only the even-row / even-column pixels,
+                                       // [S_c][N_c][H/2][W/2][C] -- all the 1x1 stride-2 shortcut of the next stage reads
+    int stagger_ns = 0;                // CTA i starts i / gridDim * stagger_ns late (see launch_stage16)
+    int dbg_skip = 0;                  // development aid: 1 skip a_out stores, 2 skip r_out stores, 4 skip next-pass R loads, 8 skip plane fetch
+    unsigned long long *dbg = nullptr; // development aid (URSA_STAGE_DBG=1): per-CTA clock64 breakdown, see launch_stage16
+    const void *pi_in;                 // FP16-split stage kernels only: plane images of the passes (see F16Cfg), replaces a_in_* / bn_in_off
 };
 
 template <int C>

@@ -55,7 +55,18 @@ struct F16Cfg {
     static constexpr int TPG = (T + NGT - 1) / NGT;            // tiles per group: 3, 3, 1
     static constexpr int TILE_COLS = 2 * C;                    // [ACC | LO]
     static constexpr int BN_FLOATS = (kFusedMaxConvs + 1) * 2 * C;
-    static constexpr size_t SMEM = (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES + 2 * BN_FLOATS * 4 + 128;
+    // "plane image" of one pass in GLOBAL memory: the activation planes of the tile range [F0, F0 + 128 T) in exactly the
+    // shared-memory layout, [hi | lo'][plane][position][8 halves], zero at every pad position -- written by the producer
+    // kernel (stem / stride-2 transition conv), pulled in by 2 KB bulk copies per (part, plane, tile)
+    static constexpr int IMG_POS = T * 128;
+    static constexpr int PASS_BYTES = 2 * NPLANES * IMG_POS * 16;
+    static constexpr int TILE_TX = 2 * NPLANES * 2048;
+    // output staging (C <= 32, the stages that feed a stride-2 conv): one 128-row tile of [hi(C) | lo'(C)] halves per tile
+    // group, 64- / 128-byte swizzled so that row-per-lane 16-byte stores are conflict free and one TMA tensor store drains it
+    static constexpr int OUT_ROW_BYTES = 4 * C;
+    static constexpr int STG_BYTES = C <= 32 ? 128 * OUT_ROW_BYTES : 0;
+    static constexpr size_t SMEM = (size_t)NGT * STG_BYTES + (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES +
+                                   2 * BN_FLOATS * 4 + 1024;
     static_assert(T * TILE_COLS <= 512, "TMEM columns");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -109,12 +120,35 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
     }
     __syncwarp();
 }
+// add `bytes` to the barrier's pending transaction count WITHOUT arriving (the issuing thread arrives later, with the others)
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// FusedStageArgs as in bma_conv_fused.cuh with two differences: w_off[] point at type-6 packed filters, and the a_in
-// path (bn_in_off < 0) reads ONE plain fp32 plane of activations (a_in_hi; a_in_lo is ignored).
-template <int C>
-__global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const FusedStageArgs a) {
+// FusedStageArgs as in bma_conv_fused.cuh with two differences: w_off[] point at type-6 packed filters, and the input
+// activations of a pass do not pass through registers at all: they arrive as the pass's PLANE IMAGE (a.pi_in, see F16Cfg)
+// by bulk copies straight into the planes, tile by tile, as soon as the previous pass's last MMAs on the neighbouring
+// tiles have completed.  Round 1 computed them in the epilogue warps from global loads (r_in -> BN -> ReLU -> split):
+// three serial global round trips per thread at every pass boundary, during which the tensor pipe idled for ~30 k clk per
+// pass (live event timing: 66 / 75 / 74 k clk per pass against an MMA floor of 39 / 40 / 41 k at C = 16 / 32 / 64).
+// r_in only feeds the residual registers and is consumed one conv later.
+// DBG: development build with clock64 accounting per role (URSA_STAGE_DBG=1, see launch_stage16); compiled out otherwise
+template <int C, bool DBG>
+__global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const __grid_constant__ FusedStageArgs a) {
     using Cfg = F16Cfg<C>;
     constexpr int H = Cfg::H, G = Cfg::G, PITCH = Cfg::PITCH, F0 = Cfg::F0, T = Cfg::T, CPT = Cfg::CPT, TPG = Cfg::TPG;
     constexpr int NGT = Cfg::NGT, NGC = Cfg::NGC;
@@ -126,10 +160,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
     __shared__ __align__(8) uint64_t act_ready[T];             // epilogue -> MMA: the planes of tile t hold the next input
     __shared__ uint32_t tmem_base_s;
 
-    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t smem_base0 = (smem_u32(smem_raw) + 1023u) & ~1023u;       // staging tiles first (swizzle atoms: 1 KB aligned)
+    const uint32_t smem_base = smem_base0 + NGT * Cfg::STG_BYTES;
     const uint32_t planes_hi = smem_base;
     const uint32_t planes_lo = smem_base + NPL * PLANE;
     const uint32_t ring = smem_base + 2 * NPL * PLANE;
+    unsigned char *stg_base = smem_raw + (smem_base0 - smem_u32(smem_raw));
     unsigned char *gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
     float *bn_all = reinterpret_cast<float *>(gen_base + 2 * NPL * PLANE + NSLOT * Cfg::SLOT_BYTES);   // [2][BNF]
 
@@ -147,6 +183,13 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             mbar_init(&act_ready[i], 128 * NGC);
         }
         fence_barrier_init();
+    }
+    if (threadIdx.x == 0 && a.stagger_ns > 0) {
+        // All CTAs run passes of equal length, so without a phase offset every SM reaches its pass boundary -- the burst of
+        // output stores and input copies -- at the same moment and the bursts queue up in L2 / HBM while the tensor pipes
+        // wait (clock64: the first MMA of a pass waited ~14 k clk for its planes; ~0.7 k with the stores removed).
+        const long long t_end = (long long)globaltimer_ns() + (long long)a.stagger_ns * blockIdx.x / gridDim.x;
+        while ((long long)globaltimer_ns() < t_end) __nanosleep(256);
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 512);
     {   // zero both plane sets once: pad positions are never written afterwards
@@ -225,20 +268,22 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             // early test failed.
             uint32_t it = 0, item = 0;
             bool ok_a = false, ok_b = false;        // early-test results carried into the next step
+            long long d_wait_full = 0, d_wait_act = 0, d_wait_act0 = 0, d_t0 = clock64();
+#define DBG_T(var, stmt) do { if (DBG && a.dbg) { const long long c0__ = clock64(); stmt; var += clock64() - c0__; } else { stmt; } } while (0)
             for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
                 for (int k = 0; k < a.n_convs; ++k, ++item) {
                     const uint32_t iph = item & 1u;
                     if (Cfg::TILE_OUTER) {
                         const uint32_t b = iph, fph = (item >> 1) & 1u;     // bundle b holds this conv's 9 taps
-                        mbar_wait_a(smem_u32(&full_bar[b]), fph);
+                        DBG_T(d_wait_full, mbar_wait_a(smem_u32(&full_bar[b]), fph));
                         const uint32_t bw0 = b_w0 + b * 9u * SLOTW;
                         // ok_a / ok_b: act_ready[0] / act_ready[1] of this conv were seen complete by the previous conv's tail
-                        if (!ok_a) mbar_wait_a(smem_u32(&act_ready[0]), iph);
+                        if (!ok_a) DBG_T(d_wait_act0, mbar_wait_a(smem_u32(&act_ready[0]), iph));
                         bool ok_next = ok_b;
 #pragma unroll 1
                         for (int t = 0; t < T; ++t) {
                             // tile t reads the planes of tiles t-1 .. t+1 (halo); tile groups publish independently
-                            if (t + 1 < T && !ok_next) mbar_wait_a(smem_u32(&act_ready[t + 1]), iph);
+                            if (t + 1 < T && !ok_next) { if (k == 0) DBG_T(d_wait_act0, mbar_wait_a(smem_u32(&act_ready[t + 1]), iph)); else DBG_T(d_wait_act, mbar_wait_a(smem_u32(&act_ready[t + 1]), iph)); }
                             tc_fence_after();
                             if (t + 2 < T) {
                                 ok_next = mbar_test_wait_a(smem_u32(&act_ready[t + 2]), iph);
@@ -265,9 +310,9 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                         auto one_tap = [&](auto tap_c) {
                             constexpr int TAP = decltype(tap_c)::value;
                             const uint32_t slot = it % NSLOT;
-                            if (!ok_a) mbar_wait_a(smem_u32(&full_bar[slot]), (it / NSLOT) & 1u);
+                            if (!ok_a) DBG_T(d_wait_full, mbar_wait_a(smem_u32(&full_bar[slot]), (it / NSLOT) & 1u));
                             if (TAP == 0)
-                                for (int t = 0; t < T; ++t) mbar_wait_a(smem_u32(&act_ready[t]), iph);
+                                for (int t = 0; t < T; ++t) DBG_T(d_wait_act, mbar_wait_a(smem_u32(&act_ready[t]), iph));
                             tc_fence_after();
                             ok_a = mbar_test_wait_a(smem_u32(&full_bar[(it + 1) % NSLOT]), ((it + 1) / NSLOT) & 1u);
                             const uint32_t bw = b_w0 + slot * SLOTW;
@@ -290,6 +335,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                     }
                 }
             }
+            if (DBG && a.dbg) {
+                a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - d_t0);
+                a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)d_wait_full;
+                a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)d_wait_act;
+                a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)d_wait_act0;
+            }
         }
     } else {
         // ================= prologue / epilogue warps =================
@@ -300,12 +351,13 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
         const int ch0 = gc * CPT;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ch0;
         const int etid = threadIdx.x - 64;            // 0..511
-        const bool from_r = a.bn_in_off >= 0;         // planes = split(relu(bn_in(r_in))) ; else planes = split(a_in)
-        const bool to_global = a.a_out_hi != nullptr && a.bn_off[a.n_convs - 1] >= 0;
+        const bool to_global = Cfg::STG_BYTES > 0 && a.has_out_map != 0 && a.bn_off[a.n_convs - 1] >= 0;
+        const bool copier = gc == 0 && m == 0;        // ONE thread per tile group issues the plane-image copies of its tiles
+        const unsigned char *pimg = reinterpret_cast<const unsigned char *>(a.pi_in);
 
         // this thread's rows (tile slot j <-> tile t = gt + j NGT): element offset inside a pass's image group and image
         // index within the group; -1 = padding or no such tile
-        int32_t rel[TPG];
+        int32_t rel[TPG], rel00[TPG];                 // rel00: offset in the compact even-pixel output (r_out_compact)
         int gimg[TPG];
 #pragma unroll
         for (int j = 0; j < TPG; ++j) {
@@ -316,6 +368,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             const int g = r / (H + 1), h = r - g * (H + 1);
             const bool ok = t < T && pcol >= 1 && r >= 0 && g < G && h < H;
             rel[j] = ok ? ((g * H + h) * H + (pcol - 1)) * C + ch0 : -1;
+            rel00[j] = (ok && !(h & 1) && !((pcol - 1) & 1)) ? ((g * (H / 2) + h / 2) * (H / 2) + (pcol - 1) / 2) * C + ch0 : -1;
             gimg[j] = g;
         }
         auto plane_off = [&](int t, int i) { return (uint32_t)(((ch0 + i) >> 3) * PLANE + (F0 + 128 * t + m) * 16); };
@@ -325,14 +378,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             return (int32_t)((s * a.n_images + n0) * (H * H * C)) + rel[j];
         };
         // BatchNorm (a, b) of the pass's sample -> shared memory buffer `buf`, rescaled for the /16 activation domain:
-        //   entry 0 (bn_in) and entries after a mode-1 conv act on the true-domain residual R:  y/16 = relu(a/16 R + b/16)
-        //   entries after a mode-0 conv act on x = conv/16:                                      y/16 = relu(a x + b/16)
+        //   entries after a mode-1 conv act on the true-domain residual R:  y/16 = relu(a/16 R + b/16)
+        //   entries after a mode-0 conv act on x = conv/16:                  y/16 = relu(a x + b/16)
         auto load_bn = [&](int pass, int buf) {
             const int s = pass / n_groups;
             const float *pk = a.packed + (int64_t)s * a.ld_packed;
             float *bs = bn_all + buf * BNF;
-            if (from_r)
-                for (int i = etid; i < 2 * C; i += 512) bs[i] = __ldg(pk + a.bn_in_off + i) * kActDown;
             for (int k = 0; k < a.n_convs; ++k)
                 if (a.bn_off[k] >= 0)
                     for (int i = etid; i < 2 * C; i += 512)
@@ -367,38 +418,33 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             tc_fence_before();
             mbar_arrive(&act_ready[t]);
         };
-
-        float R[TPG][CPT];                             // residual stream (true domain) -- or the staged prologue source
-        int32_t goff[TPG] = {};
-        // the prologue of a pass for tile slot j: R[j] holds the raw source rows (r_in, or the plain a_in plane)
-        auto prologue_tile = [&](int j, int t, const float *bn) {
-            if (goff[j] >= 0) {
+        // the planes of tile t <- plane image of `pass`: 2 KB per (part, plane), completion counted on act_ready[t] next
+        // to the arrivals of the tile's epilogue threads (which guard the TMEM columns of the tile)
+        auto fetch_planes = [&](int pass, int t) {
+            const unsigned char *src = pimg + (int64_t)pass * Cfg::PASS_BYTES + (size_t)t * 2048;
+            const uint32_t bar = smem_u32(&act_ready[t]);
+            mbar_expect_tx_only(bar, Cfg::TILE_TX);
 #pragma unroll
-                for (int c0 = 0; c0 < CPT; c0 += 16) {
-                    float y[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float4 a4 = make_float4(kActDown, kActDown, kActDown, kActDown), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (from_r) {
-                            a4 = *reinterpret_cast<const float4 *>(bn + ch0 + c0 + i);
-                            b4 = *reinterpret_cast<const float4 *>(bn + C + ch0 + c0 + i);
-                        }
-                        // a_in activations are >= 0 already: relu(a x + 0) with a = 1/16 is the plain rescale
-                        y[i] = relu_nan(fmaf(a4.x, R[j][c0 + i], b4.x));
-                        y[i + 1] = relu_nan(fmaf(a4.y, R[j][c0 + i + 1], b4.y));
-                        y[i + 2] = relu_nan(fmaf(a4.z, R[j][c0 + i + 2], b4.z));
-                        y[i + 3] = relu_nan(fmaf(a4.w, R[j][c0 + i + 3], b4.w));
-                    }
-                    store_planes16(t, c0, y);
-                }
+            for (int pl = 0; pl < NPL; ++pl) {
+                bulk_g2s_a(planes_hi + pl * PLANE + (F0 + 128 * t) * 16, src + (size_t)pl * Cfg::IMG_POS * 16, 2048, bar);
+                bulk_g2s_a(planes_lo + pl * PLANE + (F0 + 128 * t) * 16, src + (size_t)(NPL + pl) * Cfg::IMG_POS * 16, 2048, bar);
             }
-            publish(t);
-            if (!from_r) load_rows(a.r_in, goff[j], R[j]);           // lands long before the first mode-1 epilogue
+        };
+        // where this thread's row of tile slot j goes in r_out (full NHWC, or the compact even-pixel tensor)
+        auto rout_of = [&](int pass, int j) -> int32_t {
+            if (!a.r_out_compact) return goff_of(pass, j);
+            const int s = pass / n_groups, n0 = (pass - s * n_groups) * G;
+            if (rel00[j] < 0 || n0 + gimg[j] >= a.n_images) return -1;
+            return (int32_t)((s * a.n_images + n0) * (H * H * C / 4)) + rel00[j];
         };
         auto prefetch_l2 = [&](const float *src, int32_t g) {
             if (g >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + g));
         };
 
+        float R[TPG][CPT];                             // residual stream (true domain)
+        int32_t goff[TPG] = {};
+        long long d_wait_acc = 0, d_work = 0, d_sync = 0, d_work_last = 0;
+        const bool dbg_me = DBG && a.dbg != nullptr && m == 0 && gc == 0 && (gt == 0 || gt == NGT - 1);
         uint32_t item = 0;
         int buf = 0;
         {
@@ -406,13 +452,15 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
             load_bn(pass, 0);
 #pragma unroll
             for (int j = 0; j < TPG; ++j) {
+                const int t = gt + j * NGT;
+                if (t < T && copier) fetch_planes(pass, t);
                 goff[j] = goff_of(pass, j);
-                load_rows(from_r ? a.r_in : a.a_in_hi, goff[j], R[j]);
+                load_rows(a.r_in, goff[j], R[j]);
             }
             epi16_bar_sync();
 #pragma unroll
             for (int j = 0; j < TPG; ++j)
-                if (gt + j * NGT < T) prologue_tile(j, gt + j * NGT, bn_all);
+                if (gt + j * NGT < T) publish(gt + j * NGT);
         }
         for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
             for (int k = 0; k < a.n_convs; ++k, ++item) {
@@ -423,16 +471,13 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                 const bool has_next = last && np < n_pass;
                 if (k == 0 && np < n_pass) {
                     // Off the critical path (the MMA queue is full at this point): everybody has left the previous pass, so
-                    // its BatchNorm buffer can be refilled for the NEXT pass, and the next pass's source rows are pulled into
-                    // L2 so that the loads at the pass boundary are short.
+                    // its BatchNorm buffer can be refilled for the NEXT pass, and the next pass's plane image and residual
+                    // rows are pulled into L2 so that the copies at the pass boundary are short.
                     epi16_bar_sync();
                     load_bn(np, buf ^ 1);
+                    if (etid == 0) bulk_prefetch_l2(pimg + (int64_t)np * Cfg::PASS_BYTES, Cfg::PASS_BYTES);
 #pragma unroll
-                    for (int j = 0; j < TPG; ++j) {
-                        const int32_t g = goff_of(np, j);
-                        prefetch_l2(from_r ? a.r_in : a.a_in_hi, g);
-                        if (!from_r) prefetch_l2(a.r_in, g);
-                    }
+                    for (int j = 0; j < TPG; ++j) prefetch_l2(a.r_in, goff_of(np, j));
                 }
                 if (has_next) epi16_bar_sync();      // bn_all[buf ^ 1] is complete
 #pragma unroll
@@ -440,10 +485,13 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                     const int t = gt + j * NGT;
                     if (t >= T) continue;
                     // tile t's planes are read as a halo by tile t+1's MMAs: wait for those before overwriting them
-                    mbar_wait_warp(smem_u32(&acc_full[t + 1 < T ? t + 1 : T - 1]), item & 1u);   // in-order commits: tile t too
+                    DBG_T(d_wait_acc, mbar_wait_warp(smem_u32(&acc_full[t + 1 < T ? t + 1 : T - 1]), item & 1u));   // in-order commits: tile t too
+                    const long long w0__ = (DBG && a.dbg) ? clock64() : 0;
                     tc_fence_after();
+                    // pass boundary: the planes of tile t are free from here on -- start pulling in the next pass's input
+                    // BEFORE touching the accumulators, so the copy flies under this tile's epilogue
+                    if (has_next && copier && !(DBG && (a.dbg_skip & 8))) fetch_planes(np, t);
                     const uint32_t tcol = t_lane + (uint32_t)(t * Cfg::TILE_COLS);
-                    const int32_t gnext = has_next ? goff_of(np, j) : -1;
 #pragma unroll
                     for (int c0 = 0; c0 < CPT; c0 += 16) {
                         uint32_t ra[16], rl[16];
@@ -459,72 +507,94 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                             if (mode == 1) {
                                 R[j][c0 + i] = fmaf(kActUp, x[i], R[j][c0 + i]);                       // residual, true domain
                                 x[i] = R[j][c0 + i];
+                            } else if (last) {
+                                R[j][c0 + i] = x[i] * kActUp;                                           // a run ending in a mode-0 conv
                             }
                         }
-                        if (!last) {
-                            if (goff[j] >= 0) {
-                                float y[16];
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4) {
-                                    const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
-                                    y[i] = relu_nan(fmaf(a4.x, x[i], b4.x));
-                                    y[i + 1] = relu_nan(fmaf(a4.y, x[i + 1], b4.y));
-                                    y[i + 2] = relu_nan(fmaf(a4.z, x[i + 2], b4.z));
-                                    y[i + 3] = relu_nan(fmaf(a4.w, x[i + 3], b4.w));
-                                }
-                                store_planes16(t, c0, y);
-                            }
-                        } else {
-                          if (has_next) {
-                            // R[j][c0 ..] is dead (x holds it): start fetching the next pass's prologue source for this chunk
-                            // BEFORE this tile's output stores enter the memory pipeline
-                            const float *src = from_r ? a.r_in : a.a_in_hi;
+                        if (!last && goff[j] >= 0) {
+                            float y[16];
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
-                                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (gnext >= 0) v4 = __ldg(reinterpret_cast<const float4 *>(src + gnext + c0 + i));
-                                R[j][c0 + i] = v4.x; R[j][c0 + i + 1] = v4.y; R[j][c0 + i + 2] = v4.z; R[j][c0 + i + 3] = v4.w;
+                                const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
+                                y[i] = relu_nan(fmaf(a4.x, x[i], b4.x));
+                                y[i + 1] = relu_nan(fmaf(a4.y, x[i + 1], b4.y));
+                                y[i + 2] = relu_nan(fmaf(a4.z, x[i + 2], b4.z));
+                                y[i + 3] = relu_nan(fmaf(a4.w, x[i + 3], b4.w));
                             }
-                          }
-                          if (goff[j] >= 0) {
-                            if (mode == 0) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) x[i] *= kActUp;
-                            }
-                            float4 *op = reinterpret_cast<float4 *>(a.r_out + goff[j] + c0);
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) op[i >> 2] = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-                            if (to_global) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4) {
-                                    const float4 a4 = ba4[i >> 2], b4 = bb4[i >> 2];
-                                    float y[4];                     // bn entry is in the /16 domain (mode 1): undo
-                                    y[0] = relu_nan(fmaf(a4.x, x[i], b4.x)) * kActUp;
-                                    y[1] = relu_nan(fmaf(a4.y, x[i + 1], b4.y)) * kActUp;
-                                    y[2] = relu_nan(fmaf(a4.z, x[i + 2], b4.z)) * kActUp;
-                                    y[3] = relu_nan(fmaf(a4.w, x[i + 3], b4.w)) * kActUp;
-                                    float4 hv, lv;
-                                    split4(y, hv, lv);
-                                    reinterpret_cast<float4 *>(a.a_out_hi + goff[j] + c0)[i >> 2] = hv;
-                                    reinterpret_cast<float4 *>(a.a_out_lo + goff[j] + c0)[i >> 2] = lv;
-                                }
-                            }
-                          }
+                            store_planes16(t, c0, y);
                         }
                     }
                     if (!last) {
                         publish(t);
-                    } else {
-                        tc_fence_before();
+                        if (DBG && a.dbg) d_work += clock64() - w0__;
+                        continue;
+                    }
+                    // ---- last conv of the pass: the run's output sits in R[j].  Release the tile at once (the next pass's MMAs on
+                    // it only wait for the accumulator reads above and for the plane copy); the output is written from the
+                    // registers AFTER all tiles of this thread have been released (below), under the next pass's first MMAs.
+                    tc_fence_before();
+                    if (has_next) mbar_arrive(&act_ready[t]);
+                    if (DBG && a.dbg) d_work_last += clock64() - w0__;
+                }
+                if (last) {
+                    const long long s0__ = (DBG && a.dbg) ? clock64() : 0;
+#pragma unroll
+                    for (int j = 0; j < TPG; ++j) {
+                        const int t = gt + j * NGT;
+                        if (t >= T) continue;                       // warp-uniform
+                        const int32_t my_r = rout_of(pass, j);
+                        if (my_r >= 0 && !(DBG && (a.dbg_skip & 2))) {
+                            float4 *op = reinterpret_cast<float4 *>(a.r_out + my_r);
+#pragma unroll
+                            for (int i = 0; i < CPT; i += 4) op[i >> 2] = make_float4(R[j][i], R[j][i + 1], R[j][i + 2], R[j][i + 3]);
+                        }
+                        if (Cfg::STG_BYTES > 0 && to_global && !(DBG && (a.dbg_skip & 1))) {
+                            // y / 16 = relu(bn_next(R)) / 16, split like the planes, leaves through the tile group's staging
+                            // tile and ONE asynchronous TMA tensor store: no thread waits on a global store (round 1: 8
+                            // STG.128 per row held every thread in the store queue for ~5 k clk per tile at the pass boundary)
+                            unsigned char *slot = stg_base + gt * Cfg::STG_BYTES;
+                            if (copier) bulk_wait_group_read0();                    // the previous store has read the slot
+                            asm volatile("bar.sync %0, %1;" ::"r"(2 + gt), "r"(128 * NGC) : "memory");
+                            if (goff[j] >= 0) {
+                                const int sw = C == 16 ? ((m >> 1) & 3) : (m & 7);
+#pragma unroll
+                                for (int i = 0; i < 16; i += 8) {
+                                    uint32_t hw[4], lw[4];
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) {
+                                        const int c = i + 2 * jj;
+                                        split_h2(relu_nan(fmaf(bn[ch0 + c], R[j][c], bn[C + ch0 + c])),
+                                                 relu_nan(fmaf(bn[ch0 + c + 1], R[j][c + 1], bn[C + ch0 + c + 1])), hw[jj], lw[jj]);
+                                    }
+                                    const int ck = (ch0 + i) >> 3;                 // 16-byte chunk of the hi half of the row
+                                    *reinterpret_cast<uint4 *>(slot + m * Cfg::OUT_ROW_BYTES + ((ck ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                    *reinterpret_cast<uint4 *>(slot + m * Cfg::OUT_ROW_BYTES + (((C / 8 + ck) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                                }
+                            }
+                            fence_proxy_async();
+                            asm volatile("bar.sync %0, %1;" ::"r"(2 + gt), "r"(128 * NGC) : "memory");
+                            if (copier) {
+                                tma_store_2d(&a.out_map, smem_u32(slot), 0, pass * Cfg::IMG_POS + 128 * t);
+                                bulk_commit_group();
+                            }
+                        }
                         if (has_next) {
-                            // R[j] is dead and tile t's planes are free (tile t+1's MMAs are complete): the next pass's prologue
-                            // for this tile joins the wavefront right here, under the MMAs of the remaining tiles
-                            goff[j] = gnext;
-                            prologue_tile(j, t, bn_all + (buf ^ 1) * BNF);
+                            goff[j] = goff_of(np, j);
+                            if (!(DBG && (a.dbg_skip & 4))) load_rows(a.r_in, goff[j], R[j]);
                         }
                     }
+                    if (DBG && a.dbg) d_sync += clock64() - s0__;
                 }
                 if (has_next) buf ^= 1;
+            }
+        }
+        if (copier) bulk_wait_group0();              // the CTA's last tensor stores have left shared memory
+        if (dbg_me) {
+            if (gt == 0) {
+                a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)d_wait_acc;
+                a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)d_work;
+                a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)d_work_last;
+                a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)d_sync;
             }
         }
         tc_fence_before();
@@ -537,15 +607,41 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
 }
 
 template <int C>
-static int launch_stage16(const FusedStageArgs &a, cudaStream_t st) {
+static int launch_stage16(const FusedStageArgs &a_in, cudaStream_t st) {
     using Cfg = F16Cfg<C>;
-    const int n_groups = (a.n_images + Cfg::G - 1) / Cfg::G;
-    const int n_pass = n_groups * a.n_samples;
+    const int n_groups = (a_in.n_images + Cfg::G - 1) / Cfg::G;
+    const int n_pass = n_groups * a_in.n_samples;
     if (n_pass <= 0) return URSA_OK;
     const int sms = sm_count();
     const int grid = n_pass < sms ? n_pass : sms;
-    URSA_CUDA(cudaFuncSetAttribute(preresnet_stage16_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    preresnet_stage16_kernel<C><<<grid, kF16Threads, Cfg::SMEM, st>>>(a);
+    URSA_CUDA(cudaFuncSetAttribute(preresnet_stage16_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    static const bool dbg_on = getenv("URSA_STAGE_DBG") != nullptr;
+    static const int stagger_env = getenv("URSA_STAGE_STAGGER_NS") ? atoi(getenv("URSA_STAGE_STAGGER_NS")) : -1;
+    FusedStageArgs a = a_in;
+    a.stagger_ns = stagger_env >= 0 ? stagger_env : 0;
+    if (n_pass < 2 * grid) a.stagger_ns = 0;        // short launches: nothing to spread
+    if (dbg_on) {
+        // development aid: clock64 breakdown of CTA 0 and the average over CTAs (synchronous; never on in production)
+        FusedStageArgs b = a;
+        if (const char *e = getenv("URSA_STAGE_SKIP")) b.dbg_skip = atoi(e);
+        URSA_CUDA(cudaMalloc(&b.dbg, (size_t)grid * 8 * sizeof(unsigned long long)));
+        URSA_CUDA(cudaMemsetAsync(b.dbg, 0, (size_t)grid * 8 * sizeof(unsigned long long), st));
+        URSA_CUDA(cudaFuncSetAttribute(preresnet_stage16_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        preresnet_stage16_kernel<C, true><<<grid, kF16Threads, Cfg::SMEM, st>>>(b);
+        URSA_LAUNCH_CHECK("preresnet_stage16_kernel");
+        URSA_CUDA(cudaStreamSynchronize(st));
+        unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 8 * sizeof(unsigned long long));
+        URSA_CUDA(cudaMemcpy(h, b.dbg, (size_t)grid * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double avg[8] = {};
+        for (int i = 0; i < grid; ++i) for (int k = 0; k < 8; ++k) avg[k] += (double)h[i * 8 + k] / grid;
+        const double np_cta = (double)n_pass / grid;
+        fprintf(stderr, "[stage16<%d>] passes/CTA %.1f convs %d | per pass (clk): mma total %.0f wait_full %.0f wait_act(k>0) %.0f | epi g0: wait_acc %.0f work(k<last) %.0f | mma wait_act(k=0) %.0f | epi g0 work(last, release) %.0f store phase %.0f\n",
+                C, np_cta, a.n_convs, avg[0] / np_cta, avg[1] / np_cta, avg[2] / np_cta, avg[3] / np_cta, avg[4] / np_cta, avg[5] / np_cta, avg[6] / np_cta, avg[7] / np_cta);
+        free(h);
+        cudaFree(b.dbg);
+        return URSA_OK;
+    }
+    preresnet_stage16_kernel<C, false><<<grid, kF16Threads, Cfg::SMEM, st>>>(a);
     URSA_LAUNCH_CHECK("preresnet_stage16_kernel");
     return URSA_OK;
 }

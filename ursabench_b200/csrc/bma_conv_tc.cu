@@ -39,6 +39,10 @@ struct ConvTcArgs {
     const float *res;                  // mode 1: shortcut [P][hout][hout][cout]
     float *out_raw;                    // mode 1
     float *out_hi, *out_lo;            // split outputs (may be null in mode 1 for the last block)
+    // mode 0, FP16-split consumer: relu(bn(acc)) / 16 goes out as the next stage kernel's PLANE IMAGE (bma_conv_fused16.cuh)
+    unsigned char *pi_out = nullptr;   // nullable
+    int pi_G = 1, pi_pitch = 0, pi_img_pos = 0, pi_nplanes = 0, pi_ngroups = 0;
+    int64_t pi_pass_bytes = 0;
 };
 
 constexpr int CTC_THREADS = 192, CTC_MAX_STAGES = 8;
@@ -147,6 +151,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         const bool has_bn = a.bn_off >= 0;
         mbar_wait_a(smem_u32(&tmem_full_bar), 0);
         tc_fence_after();
+        // plane-image address of this pixel: pass = (sample, image group), position = (g (H + 1) + h) pitch + w
+        unsigned char *pi_px = nullptr;
+        if (a.pi_out != nullptr && valid) {
+            const int grp = n / a.pi_G, g = n - grp * a.pi_G;
+            pi_px = a.pi_out + ((int64_t)s * a.pi_ngroups + grp) * a.pi_pass_bytes +
+                    (int64_t)((g * (a.hout + 1) + (h0 + h)) * a.pi_pitch + w) * 16;
+        }
         for (int c0 = 0; c0 < a.cout; c0 += 16) {
             uint32_t rr[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
@@ -154,6 +165,23 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+            if (pi_px != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int c = c0 + i + 2 * jj;
+                        const float y0 = relu_nan(fmaf(bn_s[c], v[i + 2 * jj], bn_s[a.cout + c])) * kActDown;
+                        const float y1 = relu_nan(fmaf(bn_s[c + 1], v[i + 2 * jj + 1], bn_s[a.cout + c + 1])) * kActDown;
+                        split_h2(y0, y1, hw[jj], lw[jj]);
+                    }
+                    const int64_t pl = (int64_t)((c0 + i) >> 3) * a.pi_img_pos * 16;
+                    *reinterpret_cast<uint4 *>(pi_px + pl) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4 *>(pi_px + (int64_t)a.pi_nplanes * a.pi_img_pos * 16 + pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                continue;
+            }
             if (a.mode == 1) {
                 const float4 *rp = reinterpret_cast<const float4 *>(a.res + off + c0);
                 float4 *op = reinterpret_cast<float4 *>(a.out_raw + off + c0);
@@ -202,7 +230,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
 __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ packed,
                                                          int64_t ld_packed, int64_t w_off, int64_t bn_off, int n_images,
                                                          float *__restrict__ out_raw, float *__restrict__ out_hi,
-                                                         float *__restrict__ out_lo) {
+                                                         float *__restrict__ out_lo, unsigned char *__restrict__ pi_out) {
     // one CTA per (image, sample); thread = 4 consecutive pixels of a row x all 16 output channels (64 accumulators), so a
     // filter tap's 16 weights (4 broadcast LDS.128) feed 64 FMAs and an input row segment (6 LDS) feeds 3 taps
     __shared__ float xs[3][34][35];
@@ -250,6 +278,23 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int64_t off = (((int64_t)s * n_images + n) * 1024 + h * 32 + w0 + p) * 16;
+        if (pi_out != nullptr) {
+            // stage-1 plane image (F16Cfg<16>: one image per pass, pitch 33, 2 planes of 8 channels, hi then lo')
+            using P16 = F16Cfg<16>;
+            unsigned char *px = pi_out + ((int64_t)s * n_images + n) * P16::PASS_BYTES + (int64_t)(h * P16::PITCH + w0 + p) * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = i + 2 * jj;
+                    split_h2(relu_nan(fmaf(bn[c], acc[p][c], bn[16 + c])) * kActDown,
+                             relu_nan(fmaf(bn[c + 1], acc[p][c + 1], bn[16 + c + 1])) * kActDown, hw[jj], lw[jj]);
+                }
+                *reinterpret_cast<uint4 *>(px + (int64_t)(i >> 3) * P16::IMG_POS * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(px + (int64_t)(2 + (i >> 3)) * P16::IMG_POS * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             *reinterpret_cast<float4 *>(out_raw + off + i) = make_float4(acc[p][i], acc[p][i + 1], acc[p][i + 2], acc[p][i + 3]);
@@ -270,7 +315,7 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
 // 1x1 stride-2 shortcut on the raw NHWC block input
 __global__ void __launch_bounds__(256) shortcut_nhwc_kernel(const float *__restrict__ in, const float *__restrict__ packed,
                                                              int64_t ld_packed, int64_t w_off, int cin, int cout, int hout,
-                                                             int n_images, float *__restrict__ out) {
+                                                             int n_images, float *__restrict__ out, int compact) {
     // one CTA per (image, sample); work item = (output pixel, group of 16 output channels): the pixel's cin inputs are
     // read as float4s, the weights [ci][co] come from shared memory as LDS.128
     __shared__ __align__(16) float ws[32 * 64];
@@ -278,13 +323,14 @@ __global__ void __launch_bounds__(256) shortcut_nhwc_kernel(const float *__restr
     const float *pk = packed + (int64_t)s * ld_packed + w_off;                    // [ci][co]
     for (int i = threadIdx.x; i < cin * cout; i += 256) ws[i] = __ldg(pk + i);
     __syncthreads();
-    const int hin = hout * 2, ngrp = cout >> 4;
+    // compact != 0: `in` holds only the even-row / even-column pixels, [P][hout][hout][cin] (FP16-split stage kernels)
+    const int hin = compact ? hout : hout * 2, ngrp = cout >> 4, step = compact ? 1 : 2;
     const float *ib = in + ((int64_t)s * n_images + n) * hin * hin * cin;
     float *ob = out + ((int64_t)s * n_images + n) * hout * hout * cout;
     for (int item = threadIdx.x; item < hout * hout * ngrp; item += 256) {
         const int g = item % ngrp, px = item / ngrp;
         const int h = px / hout, w = px - h * hout;
-        const float4 *ip = reinterpret_cast<const float4 *>(ib + ((int64_t)(2 * h) * hin + 2 * w) * cin);
+        const float4 *ip = reinterpret_cast<const float4 *>(ib + ((int64_t)(step * h) * hin + step * w) * cin);
         float acc[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[c] = 0.f;
@@ -428,6 +474,193 @@ static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin
     return URSA_OK;
 }
 
+
+// ---- stride-2 transition conv of the FP16-split path ------------------------------------------------------------------
+// conv1 of layer2.0 / layer3.0 (3x3, stride 2, Cin -> 2 Cin) as an implicit GEMM like conv3x3_tc_kernel, but on the FP16-split
+// operands the stage kernels use: the input is what the previous stage kernel's last epilogue stored by TMA -- rows
+// [pass][position][hi(Cin) | lo'(Cin)] halves of relu(bn1(R)) / 16 in the padded-pitch position space of that stage -- so a
+// tap's A tile is ONE 5-D TMA box (64- / 128-byte rows: hi and lo' of a pixel travel together; parity-split maps make the
+// stride-2 taps dense; out-of-bounds fill = zero padding) and the filters are K-major rows [co][tap][hi | lo'] (prep type 7).
+// Three kind::f16 MMAs per 16 channels: hi x hi -> ACC, hi x lo' -> LO, lo' x hi -> LO (the operands of the second and third
+// are the same tiles at a 2 Cin-byte K offset).  The epilogue applies bn2 + ReLU and writes the next stage kernel's plane image.
+struct ConvS2Maps {
+    CUtensorMap a[4];                  // index = h-parity * 2 + w-parity of (kh - 1, kw - 1)
+    CUtensorMap b;
+};
+struct ConvS2Args {
+    int cout, hout, n_images, stages;
+    int g_in, n_groups_in;             // images per pass / passes per sample of the PRODUCER stage
+    const float *packed;
+    int64_t ld_packed, bn_off;
+    unsigned char *pi_out;             // plane image of the consumer stage (bma_conv_fused16.cuh)
+    int pi_G, pi_pitch, pi_img_pos, pi_nplanes, pi_ngroups;
+    int64_t pi_pass_bytes;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(CTC_THREADS, 1)
+conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a) {
+    constexpr int ROW_BYTES = CIN * 4;                          // [hi(CIN) | lo'(CIN)] halves
+    constexpr uint32_t A_BYTES = 128 * ROW_BYTES;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[CTC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[CTC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bn_s[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.y;
+    const int WT = a.hout, HT = a.hout >= 16 ? 128 / a.hout : a.hout, NT = 128 / (WT * HT);
+    const int tpi = (a.hout * a.hout) / 128;
+    int n0, h0;
+    if (NT == 1) { n0 = blockIdx.x / tpi; h0 = (blockIdx.x % tpi) * HT; } else { n0 = blockIdx.x * NT; h0 = 0; }
+
+    const uint32_t b_bytes = (uint32_t)a.cout * ROW_BYTES;
+    const uint32_t stage_bytes = A_BYTES + b_bytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tmem_cols = 2 * a.cout;                      // [ACC | LO]: 64 or 128 columns
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (warp >= 2) {
+        const float *bn = a.packed + (int64_t)s * a.ld_packed + a.bn_off;
+        for (int i = threadIdx.x - 64; i < 2 * a.cout; i += 128) bn_s[i] = __ldg(bn + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const int pass_in = s * a.n_groups_in + n0 / a.g_in, g0 = n0 % a.g_in;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int st = tap % a.stages;
+                const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
+                const int kh = tap / 3, kw = tap - kh * 3;
+                mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[st]);
+                mbar_expect_tx_a(fb, stage_bytes);
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const int mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);      // parity of (kh - 1, kw - 1)
+                tma_load_5d_a(base, &maps.a[mi], 0, (kw - 1) >> 1, h0 + ((kh - 1) >> 1), g0, pass_in, fb);
+                tma_load_3d_a(base + A_BYTES, &maps.b, tap * 2 * CIN, 0, s, fb);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_f16_idesc(128, a.cout);
+            constexpr uint64_t LO_OFF = (uint64_t)((CIN * 2) >> 4);       // lo' half of a row, in 16-byte descriptor units
+            for (int tap = 0; tap < 9; ++tap) {
+                const int st = tap % a.stages;
+                const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
+                mbar_wait_a(smem_u32(&full_bar[st]), ph);
+                tc_fence_after();
+                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                const uint64_t d_a = make_kmajor_desc<ROW_BYTES>(base), d_b = make_kmajor_desc<ROW_BYTES>(base + A_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < CIN / 16; ++ks) {
+                    const uint64_t ko = (uint64_t)(2 * ks);
+                    umma_f16(tmem_base, d_a + ko, d_b + ko, idesc, (tap | ks) != 0);
+                    umma_f16(tmem_base + a.cout, d_a + ko, d_b + LO_OFF + ko, idesc, (tap | ks) != 0);
+                    umma_f16(tmem_base + a.cout, d_a + LO_OFF + ko, d_b + ko, idesc, 1);
+                }
+                umma_commit(smem_u32(&empty_bar[st]));
+            }
+            umma_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
+        const int n = n0 + nl;
+        const bool valid = n < a.n_images;
+        unsigned char *pi_px = nullptr;
+        if (valid) {
+            const int grp = n / a.pi_G, g = n - grp * a.pi_G;
+            pi_px = a.pi_out + ((int64_t)s * a.pi_ngroups + grp) * a.pi_pass_bytes +
+                    (int64_t)((g * (a.hout + 1) + (h0 + h)) * a.pi_pitch + w) * 16;
+        }
+        mbar_wait_a(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.cout; c0 += 16) {
+            uint32_t ra[16], rl[16];
+            tmem_ld<16>(tl + (uint32_t)c0, ra);
+            tmem_ld<16>(tl + (uint32_t)(a.cout + c0), rl);
+            tmem_ld_wait();
+            if (!valid) continue;
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = c0 + i + 2 * jj;
+                    // operands were y / 16: conv = 16 (acc + lo 2^-11); the next planes hold relu(bn2(conv)) / 16
+                    const float v0 = fmaf(__uint_as_float(rl[i + 2 * jj]), kLoUnscale, __uint_as_float(ra[i + 2 * jj])) * kActUp;
+                    const float v1 = fmaf(__uint_as_float(rl[i + 2 * jj + 1]), kLoUnscale, __uint_as_float(ra[i + 2 * jj + 1])) * kActUp;
+                    split_h2(relu_nan(fmaf(bn_s[c], v0, bn_s[a.cout + c])) * kActDown,
+                             relu_nan(fmaf(bn_s[c + 1], v1, bn_s[a.cout + c + 1])) * kActDown, hw[jj], lw[jj]);
+                }
+                const int64_t pl = (int64_t)((c0 + i) >> 3) * a.pi_img_pos * 16;
+                *reinterpret_cast<uint4 *>(pi_px + pl) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(pi_px + (int64_t)a.pi_nplanes * a.pi_img_pos * 16 + pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// a_rows: the producer stage's TMA-stored rows (stage geometry CIN: H = hin, pitch, positions per pass, images per pass)
+template <int CIN>
+static int launch_conv_s2_f16(const void *a_rows, int hin, int pitch_in, int img_pos_in, int g_in, int sc, int nc,
+                              const float *packed, int64_t ld_packed, int64_t w_off, ConvS2Args g, cudaStream_t st) {
+    constexpr int ROWB = CIN * 4;
+    const int hout = hin / 2, cout = 2 * CIN;
+    const int n_groups_in = (nc + g_in - 1) / g_in;
+    const int WT = hout, HT = hout >= 16 ? 128 / hout : hout, NT = 128 / (WT * HT);
+    ConvS2Maps maps;
+    for (int par = 0; par < 4; ++par) {
+        const int hp = par >> 1, wp = par & 1;
+        const unsigned char *base = reinterpret_cast<const unsigned char *>(a_rows) + (size_t)(hp * pitch_in + wp) * ROWB;
+        const uint64_t dims[5] = {(uint64_t)2 * CIN, (uint64_t)(hin / 2), (uint64_t)(hin / 2), (uint64_t)g_in,
+                                  (uint64_t)sc * n_groups_in};
+        const uint64_t sb[4] = {(uint64_t)2 * ROWB, (uint64_t)2 * pitch_in * ROWB, (uint64_t)(hin + 1) * pitch_in * ROWB,
+                                (uint64_t)img_pos_in * ROWB};
+        const uint32_t box[5] = {(uint32_t)2 * CIN, (uint32_t)WT, (uint32_t)HT, (uint32_t)NT, 1};
+        if (int rc = make_tensor_map_t(&maps.a[par], base, 5, dims, sb, box, ROWB, 1)) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)18 * CIN, (uint64_t)cout, (uint64_t)sc};
+        const uint64_t sb[2] = {(uint64_t)18 * CIN * 2, (uint64_t)ld_packed * 4};
+        const uint32_t box[3] = {(uint32_t)2 * CIN, (uint32_t)cout, 1};
+        if (int rc = make_tensor_map_t(&maps.b, packed + w_off, 3, dims, sb, box, ROWB, 1)) return rc;
+    }
+    g.cout = cout; g.hout = hout; g.n_images = nc; g.g_in = g_in; g.n_groups_in = n_groups_in;
+    g.packed = packed; g.ld_packed = ld_packed;
+    const size_t stage_bytes = (size_t)128 * ROWB + (size_t)cout * ROWB;
+    g.stages = 4;                                   // 10-24 KB per stage: several CTAs per SM hide the per-tile latencies
+    const size_t smem = (size_t)g.stages * stage_bytes + 1024;
+    const int tiles = NT == 1 ? nc * ((hout * hout) / 128) : (nc + NT - 1) / NT;
+    URSA_CUDA(cudaFuncSetAttribute(conv3x3s2_f16_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3s2_f16_kernel<CIN><<<dim3(tiles, sc), CTC_THREADS, smem, st>>>(maps, g);
+    URSA_LAUNCH_CHECK("conv3x3s2_f16_kernel");
+    return URSA_OK;
+}
+
 size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C) {
     NetPlan pl;
     if (!build_plan(depth, C, pl, 1)) return 0;
@@ -466,7 +699,7 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
             const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
             // stem: R = conv(x), A1 = split(relu(bn1(R)))
             stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
-                                                           pl.blocks[0][0].bn1, nc, Ra, A1h, A1l);
+                                                           pl.blocks[0][0].bn1, nc, Ra, A1h, A1l, nullptr);
             URSA_LAUNCH_CHECK("stem_nhwc_kernel");
             float *cur = Ra, *nxt = Rb;
             int ch = 16, hw = 32;
@@ -477,7 +710,7 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
                     const int cout = down ? ch * 2 : ch, stride = down ? 2 : 1, hout = hw / stride;
                     const float *res = cur;
                     if (down) {
-                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B.ds, ch, cout, hout, nc, Rs);
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B.ds, ch, cout, hout, nc, Rs, 0);
                         URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
                         res = Rs;
                     }
@@ -515,10 +748,29 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
 // ---- fused-stage path (URSA_ALGO_TCGEN05_FUSED): stem -> [stage kernel] -> (shortcut + stride-2 conv) -> [stage kernel] ...
 // f16 != 0 (URSA_ALGO_TCGEN05_FUSED_F16): FP16-split stage kernels (bma_conv_fused16.cuh), type-6 filters, and the stride-2
 // convs hand their activations over as one plain fp32 plane
+// plane images of the three stages for one chunk (FP16-split path): passes = samples x image groups
+struct PiLayout {
+    size_t off[3], bytes[3], total;
+};
+static PiLayout pi_layout(int sc, int nc) {
+    PiLayout L;
+    const size_t pass_bytes[3] = {(size_t)F16Cfg<16>::PASS_BYTES, (size_t)F16Cfg<32>::PASS_BYTES, (size_t)F16Cfg<64>::PASS_BYTES};
+    const int G[3] = {F16Cfg<16>::G, F16Cfg<32>::G, F16Cfg<64>::G};
+    size_t o = 0;
+    for (int i = 0; i < 3; ++i) {
+        L.off[i] = o;
+        L.bytes[i] = (size_t)sc * ((nc + G[i] - 1) / G[i]) * pass_bytes[i];
+        o += (L.bytes[i] + 1023) & ~(size_t)1023;
+    }
+    L.total = o;
+    return L;
+}
+
 size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C, int f16) {
     NetPlan pl;
     if (!build_plan(depth, C, pl, f16 ? 3 : 2)) return 0;
-    return tc_chunking(S, N, pl).total;
+    const TcChunking ck = tc_chunking(S, N, pl);
+    return ck.total + (f16 ? pi_layout(ck.sc, ck.nc).total + 1024 : 0);
 }
 
 int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
@@ -532,8 +784,12 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
     URSA_REQUIRE(ld_bank >= pl.D, "ursa_bma_preresnet_forward: ld_bank (%lld) < D (%lld)", (long long)ld_bank, (long long)pl.D);
     URSA_REQUIRE(ld_buf >= pl.NB, "ursa_bma_preresnet_forward: ld_buf (%lld) < %lld", (long long)ld_buf, (long long)pl.NB);
     const TcChunking ck = tc_chunking(S, N, pl);
-    URSA_REQUIRE(workspace_bytes >= ck.total, "ursa_bma_preresnet_forward: workspace too small");
+    const PiLayout pil = pi_layout(ck.sc, ck.nc);
+    URSA_REQUIRE(workspace_bytes >= ck.total + (f16 ? pil.total + 1024 : 0), "ursa_bma_preresnet_forward: workspace too small");
     char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    unsigned char *pi_base = reinterpret_cast<unsigned char *>(wsb) + ((ck.total - 2048 + 1023) & ~(size_t)1023);
+    if (f16)   // the producers only write pixel positions: the pad positions of the plane images must read as zero
+        URSA_CUDA(cudaMemsetAsync(pi_base, 0, pil.total, st));
     float *Ra = reinterpret_cast<float *>(wsb);
     float *Rb = reinterpret_cast<float *>(wsb + ck.raw_bytes);
     float *Rs = reinterpret_cast<float *>(wsb + 2 * ck.raw_bytes);
@@ -558,7 +814,8 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
             {
                 ProfScope ps(URSA_PROF_STEM, st);
                 stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
-                                                               pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr);
+                                                               pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr,
+                                                               f16 ? pi_base + pil.off[0] : nullptr);
                 URSA_LAUNCH_CHECK("stem_nhwc_kernel");
             }
             float *cur = Ra, *nxt = Rb;          // residual stream in / out of the current stage
@@ -567,6 +824,7 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 FusedStageArgs g;
                 g.packed = packed; g.ld_packed = pl.packed_floats; g.n_images = nc; g.n_samples = sc;
                 g.n_convs = 0;
+                g.pi_in = f16 ? pi_base + pil.off[stg] : nullptr;
                 if (stg == 0) {
                     g.bn_in_off = pl.blocks[0][0].bn1;
                     g.r_in = cur; g.a_in_hi = g.a_in_lo = nullptr;
@@ -575,16 +833,40 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                     const NetPlan::Block &B0 = pl.blocks[stg][0];
                     {
                         ProfScope ps(URSA_PROF_SHORTCUT, st);
-                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs);
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs, f16 ? 1 : 0);
                         URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
                     }
+                    if (f16) {
+                        // conv1 of the transition block: FP16-split implicit GEMM on the rows the previous stage kernel
+                        // stored by TMA (in the A1h / A1l region), writes this stage kernel's plane image
+                        ConvS2Args c2;
+                        c2.bn_off = B0.bn2;
+                        const int Gn = stg == 1 ? F16Cfg<32>::G : F16Cfg<64>::G;
+                        c2.pi_out = pi_base + pil.off[stg];
+                        c2.pi_G = Gn;
+                        c2.pi_pitch = stg == 1 ? F16Cfg<32>::PITCH : F16Cfg<64>::PITCH;
+                        c2.pi_img_pos = stg == 1 ? F16Cfg<32>::IMG_POS : F16Cfg<64>::IMG_POS;
+                        c2.pi_nplanes = stg == 1 ? F16Cfg<32>::NPLANES : F16Cfg<64>::NPLANES;
+                        c2.pi_ngroups = (nc + Gn - 1) / Gn;
+                        c2.pi_pass_bytes = stg == 1 ? F16Cfg<32>::PASS_BYTES : F16Cfg<64>::PASS_BYTES;
+                        ProfScope ps(URSA_PROF_CONV_S2, st);
+                        int rc;
+                        if (stg == 1)
+                            rc = launch_conv_s2_f16<16>(A1h, 32, F16Cfg<16>::PITCH, F16Cfg<16>::IMG_POS, F16Cfg<16>::G, sc, nc, packed,
+                                                        pl.packed_floats, B0.w1, c2, st);
+                        else
+                            rc = launch_conv_s2_f16<32>(A1h, 16, F16Cfg<32>::PITCH, F16Cfg<32>::IMG_POS, F16Cfg<32>::G, sc, nc, packed,
+                                                        pl.packed_floats, B0.w1, c2, st);
+                        if (rc) return rc;
+                    } else {
                     ConvTcArgs c1;
                     c1.mode = 0; c1.bn_off = B0.bn2; c1.res = nullptr; c1.out_raw = nullptr; c1.out_hi = A2h;
-                    c1.out_lo = f16 ? nullptr : A2l;
+                    c1.out_lo = A2l;
                     {
                         ProfScope ps(URSA_PROF_CONV_S2, st);
                         if (int rc = launch_conv_tc(A1h, A1l, hw, ch, 2 * ch, 2, sc, nc, packed, pl.packed_floats, B0.w1, B0.w1_lo, c1, st))
                             return rc;
+                    }
                     }
                     ch *= 2; hw /= 2;
                     g.bn_in_off = -1;
@@ -601,8 +883,19 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                     g.w_off[g.n_convs] = B.w2; g.mode[g.n_convs] = 1; g.bn_off[g.n_convs] = bn_next; ++g.n_convs;
                 }
                 g.r_out = nxt;
+                g.r_out_compact = (f16 && stg < 2) ? 1 : 0;     // stages 1 / 2: only the shortcut conv reads the raw stream
                 g.a_out_hi = stg < 2 ? A1h : nullptr;
                 g.a_out_lo = stg < 2 ? A1l : nullptr;
+                if (f16 && stg < 2) {
+                    // rows [pass][position][hi(C) | lo'(C)] halves for the next stride-2 conv, as a 2-D fp32 view C x positions
+                    const int Cs = stg == 0 ? 16 : 32, Gs = stg == 0 ? F16Cfg<16>::G : F16Cfg<32>::G;
+                    const int img_pos = stg == 0 ? F16Cfg<16>::IMG_POS : F16Cfg<32>::IMG_POS;
+                    const uint64_t dims[2] = {(uint64_t)Cs, (uint64_t)sc * ((nc + Gs - 1) / Gs) * img_pos};
+                    const uint64_t sb[1] = {(uint64_t)Cs * 4};
+                    const uint32_t box[2] = {(uint32_t)Cs, 128};
+                    if (int rc = make_tensor_map(&g.out_map, A1h, 2, dims, sb, box, Cs * 4)) return rc;
+                    g.has_out_map = 1;
+                }
                 int rc;
                 {
                     ProfScope ps(URSA_PROF_STAGE_C16 + stg, st);

@@ -15,6 +15,8 @@ struct PrepEntry {
                        // 4 conv3x3 -> K-major [co][tap*cin + ci] split into tf32 hi (dst) / lo (dst2) planes
                        // 5 conv3x3 (cin == cout == C) -> fused-stage layout [tap][ci/4][2C rows][4]: rows are
                        //   [hi(co); lo(co)] when buf == 0 and [lo(co); hi(co)] when buf == 1 (see bma_conv_fused.cuh)
+                       // 7 conv3x3 (stride-2 transition, cout = 2 cin) -> K-major FP16-split rows [co][tap][hi(cin) | lo'(cin)]
+                       //   halves (conv3x3s2_f16_kernel); occupies cin*cout*9 floats
                        // 6 conv3x3 (cin == cout == C) -> FP16-split fused-stage layout [tap][ci/8][2C rows][8 halves]:
                        //   rows [hi(co); lo'(co)], w = hi + lo' * 2^-11 (see bma_conv_fused16.cuh); occupies cin*cout*9 floats
     int cin, cout;     // conv: channels; bn: cout = channels; copy: cout = count
@@ -96,6 +98,19 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             const __half h = __float2half_rn(w);
             dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
         }
+    } else if (e.type == 7) {
+        // stride-2 transition conv of the FP16-split path: K-major rows [co][tap][hi(cin) | lo'(cin)] halves
+        __half *dh = reinterpret_cast<__half *>(dst);
+        const int total = e.cout * 9 * 2 * e.cin;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int k = i % (2 * e.cin);
+            const int tap = (i / (2 * e.cin)) % 9;
+            const int co = i / (18 * e.cin);
+            const int ci = k % e.cin;
+            const float w = row[e.src + ((int64_t)co * e.cin + ci) * 9 + tap];
+            const __half h = __float2half_rn(w);
+            dh[i] = k < e.cin ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
+        }
     } else if (e.type == 2) {
         for (int c = threadIdx.x; c < e.cout; c += blockDim.x) {
             const float mean = brow[e.buf + c], var = brow[e.buf + e.cout + c];
@@ -146,7 +161,7 @@ static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
         }
         return d;
     };
-    const int t3 = tc == 0 ? 0 : 4;
+    const int t3 = tc == 0 ? 0 : (tc == 3 ? 7 : 4);       // the two stride-2 transition convs of the tensor-core plans
     auto add_bn = [&](int c) {
         PrepEntry &e = t.e[t.n++];
         e.type = 2; e.cin = 0; e.cout = c; e.src = src; e.src2 = src + c; e.buf = buf; e.dst = dst; e.dst2 = 0;

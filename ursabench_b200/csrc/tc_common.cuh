@@ -219,10 +219,10 @@ inline EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
-// fp32 tensor of `rank` dims (dims[0] innermost, strides in BYTES for dims 1..rank-1), box in elements,
-// swizzle_bytes in {64, 128}; out-of-bounds elements read as zero.
-inline int make_tensor_map(CUtensorMap *tm, const float *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                           const uint32_t *box, int swizzle_bytes) {
+// tensor of `rank` dims (dims[0] innermost, strides in BYTES for dims 1..rank-1), box in elements,
+// swizzle_bytes in {64, 128}; out-of-bounds elements read as zero.  f16 != 0: elements are halves, else fp32.
+inline int make_tensor_map_t(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                             const uint32_t *box, int swizzle_bytes, int f16) {
     EncodeTiledFn fn = tensor_map_encoder();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -236,7 +236,8 @@ inline int make_tensor_map(CUtensorMap *tm, const float *base, int rank, const u
         e[i] = 1;
         if (i + 1 < rank) s[i] = strides_bytes[i];
     }
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(base), d, s, b, e,
+    CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                    const_cast<void *>(base), d, s, b, e,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -248,5 +249,20 @@ inline int make_tensor_map(CUtensorMap *tm, const float *base, int rank, const u
     }
     return URSA_OK;
 }
+inline int make_tensor_map(CUtensorMap *tm, const float *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                           const uint32_t *box, int swizzle_bytes) {
+    return make_tensor_map_t(tm, base, rank, dims, strides_bytes, box, swizzle_bytes, 0);
+}
+
+// ---- TMA tensor STORE (shared -> global) in the bulk async-group ------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, uint32_t src_smem, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem),
+                 "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace ursa
