@@ -17,6 +17,29 @@ import torch.nn as nn
 from .flat import _round_up
 
 
+# Pinned host staging for from_modules(): cudaHostAlloc of ~100 MB costs tens of milliseconds, so the buffers are kept and
+# handed out round-robin; a buffer is reused only after the H2D copy that read it has completed (event).
+_STAGING = {}
+
+
+def _staging(n, ld, ldb, cuda, slots=3):
+    if not cuda:
+        return torch.empty(n, ld), torch.zeros(n, ldb), None
+    key = (ld, ldb)
+    ring = _STAGING.setdefault(key, {"next": 0, "slots": []})
+    if len(ring["slots"]) < slots:
+        cap = max(n, 8)
+        ring["slots"].append([torch.empty(cap, ld).pin_memory(), torch.zeros(cap, ldb).pin_memory(), torch.cuda.Event()])
+        slot = ring["slots"][-1]
+    else:
+        slot = ring["slots"][ring["next"] % slots]
+        ring["next"] += 1
+        slot[2].synchronize()
+        if slot[0].shape[0] < n:
+            slot[0], slot[1] = torch.empty(n, ld).pin_memory(), torch.zeros(n, ldb).pin_memory()
+    return slot[0][:n], slot[1][:n], slot[2]
+
+
 class SampleBank:
     def __init__(self, D, nb, device, capacity=16, skeleton=None):
         self.D, self.nb = D, nb
@@ -76,30 +99,25 @@ class SampleBank:
 
     @classmethod
     def from_modules(cls, models, device):
-        """Pack ordinary modules (e.g. CPU samples from the reference) into a bank: one H2D copy per sample."""
+        """Pack ordinary modules (e.g. CPU samples from the reference) into a bank: one host pass per sample into a
+        pinned staging matrix, then ONE asynchronous H2D copy of the matrix."""
         first = models[0]
         D = sum(p.numel() for p in first.parameters())
-        bufs = [b for b in first.buffers() if b.dtype == torch.float32]
-        nb = sum(b.numel() for b in bufs)
+        nb = sum(b.numel() for b in first.buffers() if b.dtype == torch.float32)
         bank = cls(D, nb, device, capacity=len(models), skeleton=None)
-        stage_w = torch.empty(len(models), bank.ld, dtype=torch.float32).pin_memory() if torch.cuda.is_available() \
-            else torch.empty(len(models), bank.ld, dtype=torch.float32)
-        stage_b = torch.zeros(len(models), bank.ldb, dtype=torch.float32)
+        cuda = bank.device.type == "cuda"
+        stage_w, stage_b, done = _staging(len(models), bank.ld, bank.ldb, cuda)
         for i, m in enumerate(models):
-            off = 0
-            for p in m.parameters():
-                n = p.numel()
-                stage_w[i, off:off + n].copy_(p.detach().reshape(-1))
-                off += n
-            if off != D:
+            ps = [p.detach().reshape(-1) for p in m.parameters()]
+            if sum(p.numel() for p in ps) != D:
                 raise ValueError("models in one ensemble must share an architecture")
-            off = 0
-            for b in m.buffers():
-                if b.dtype == torch.float32:
-                    stage_b[i, off:off + b.numel()].copy_(b.detach().reshape(-1))
-                    off += b.numel()
+            stage_w[i, :D].copy_(torch.cat(ps))
+            if nb:
+                stage_b[i, :nb].copy_(torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]))
         bank.w[:len(models)].copy_(stage_w, non_blocking=True)
-        bank.b[:len(models)].copy_(stage_b)
+        bank.b[:len(models)].copy_(stage_b, non_blocking=True)
+        if cuda:
+            done.record(torch.cuda.current_stream(bank.device))
         bank.count = len(models)
         return bank
 

@@ -33,7 +33,7 @@
 
 namespace ursa {
 
-constexpr int kFusedMaxConvs = 12;
+constexpr int kFusedMaxConvs = 13;
 
 struct FusedStageArgs {
     const float *packed;
@@ -53,6 +53,9 @@ struct FusedStageArgs {
     // (out_map: 2-D fp32 view, C floats x positions, box C x 128, swizzle = row bytes); replaces a_out_hi / a_out_lo
     CUtensorMap out_map;
     int has_out_map = 0;
+    int pi_per_image = 0;              // pi_in holds one plane image per IMAGE GROUP (shared by all samples), not per pass:
+                                       // stage 1, whose input planes carry the test images for the stem conv; r_in == nullptr
+                                       // then starts the residual stream at zero
     int r_out_compact = 0;             // FP16-split stage kernels: r_out holds only the even-row / even-column pixels,
                                        // [S_c][N_c][H/2][W/2][C] -- all the 1x1 stride-2 shortcut of the next stage reads
     int stagger_ns = 0;                // CTA i starts i / gridDim * stagger_ns late (see launch_stage16)

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                         bs[(k + 1) * 2 * C + i] = __ldg(pk + a.bn_off[k] + i) * ((i >= C || a.mode[k] == 1) ? kActDown : 1.f);
         };
         auto load_rows = [&](const float *src, int32_t goff, float *v) {
-            if (goff >= 0) {
+            if (goff >= 0 && src != nullptr) {
                 const float4 *rp = reinterpret_cast<const float4 *>(src + goff);
 #pragma unroll
                 for (int i = 0; i < CPT / 4; ++i) {
@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
         // the planes of tile t <- plane image of `pass`: 2 KB per (part, plane), completion counted on act_ready[t] next
         // to the arrivals of the tile's epilogue threads (which guard the TMEM columns of the tile)
         auto fetch_planes = [&](int pass, int t) {
-            const unsigned char *src = pimg + (int64_t)pass * Cfg::PASS_BYTES + (size_t)t * 2048;
+            const int img = a.pi_per_image ? pass % n_groups : pass;
+            const unsigned char *src = pimg + (int64_t)img * Cfg::PASS_BYTES + (size_t)t * 2048;
             const uint32_t bar = smem_u32(&act_ready[t]);
             mbar_expect_tx_only(bar, Cfg::TILE_TX);
 #pragma unroll
@@ -475,9 +476,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                     // rows are pulled into L2 so that the copies at the pass boundary are short.
                     epi16_bar_sync();
                     load_bn(np, buf ^ 1);
-                    if (etid == 0) bulk_prefetch_l2(pimg + (int64_t)np * Cfg::PASS_BYTES, Cfg::PASS_BYTES);
+                    if (etid == 0)
+                        bulk_prefetch_l2(pimg + (int64_t)(a.pi_per_image ? np % n_groups : np) * Cfg::PASS_BYTES, Cfg::PASS_BYTES);
+                    if (a.r_in != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < TPG; ++j) prefetch_l2(a.r_in, goff_of(np, j));
+                        for (int j = 0; j < TPG; ++j) prefetch_l2(a.r_in, goff_of(np, j));
+                    }
                 }
                 if (has_next) epi16_bar_sync();      // bn_all[buf ^ 1] is complete
 #pragma unroll

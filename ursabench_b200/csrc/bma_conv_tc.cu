@@ -312,6 +312,23 @@ __global__ void __launch_bounds__(256) stem_nhwc_kernel(const float *__restrict_
     }
 }
 
+// test images (NCHW fp32, shared by all samples) -> stage-1 plane images of the FP16-split path: position (h, w) of plane 0
+// holds [x0, x1, x2, 0 x 5] / 16 as FP16 hi and lo'; plane 1 (channels 8..15) stays at the zeros of the workspace memset.
+// With these as its input planes the network's conv1 is simply the first conv of the stage-1 kernel's chain.
+__global__ void __launch_bounds__(256) image_planes_kernel(const float *__restrict__ x, int n_images, unsigned char *__restrict__ pi) {
+    using P16 = F16Cfg<16>;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n_images * 1024) return;
+    const int n = idx >> 10, px = idx & 1023, h = px >> 5, w = px & 31;
+    const float *xp = x + (int64_t)n * 3072 + px;
+    uint32_t h01, l01, h2, l2;
+    split_h2(__ldg(xp) * kActDown, __ldg(xp + 1024) * kActDown, h01, l01);
+    split_h2(__ldg(xp + 2048) * kActDown, 0.f, h2, l2);
+    unsigned char *dst = pi + (int64_t)n * P16::PASS_BYTES + (int64_t)(h * P16::PITCH + w) * 16;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(h01, h2, 0u, 0u);
+    *reinterpret_cast<uint4 *>(dst + (int64_t)2 * P16::IMG_POS * 16) = make_uint4(l01, l2, 0u, 0u);
+}
+
 // 1x1 stride-2 shortcut on the raw NHWC block input
 __global__ void __launch_bounds__(256) shortcut_nhwc_kernel(const float *__restrict__ in, const float *__restrict__ packed,
                                                              int64_t ld_packed, int64_t w_off, int cin, int cout, int hout,
@@ -798,7 +815,7 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
     float *packed = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes);
     float *logits = reinterpret_cast<float *>(wsb + 7 * ck.raw_bytes + ck.packed_bytes);
     const int n = pl.n_blocks;
-    URSA_REQUIRE(2 * n <= kFusedMaxConvs, "ursa_bma_preresnet_forward: depth %d exceeds the fused-stage chain length", depth);
+    URSA_REQUIRE(2 * n + 1 <= kFusedMaxConvs, "ursa_bma_preresnet_forward: depth %d exceeds the fused-stage chain length", depth);
 
     for (int s0 = 0; s0 < S; s0 += ck.sc) {
         const int sc = (S - s0 < ck.sc) ? (S - s0) : ck.sc;
@@ -813,10 +830,14 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
             const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
             {
                 ProfScope ps(URSA_PROF_STEM, st);
-                stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
-                                                               pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr,
-                                                               f16 ? pi_base + pil.off[0] : nullptr);
-                URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+                if (f16) {      // conv1 runs inside the stage-1 kernel: only the images' plane form is prepared here
+                    image_planes_kernel<<<(nc * 1024 + 255) / 256, 256, 0, st>>>(x + i0 * 3 * 32 * 32, nc, pi_base + pil.off[0]);
+                    URSA_LAUNCH_CHECK("image_planes_kernel");
+                } else {
+                    stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w,
+                                                                   pl.blocks[0][0].bn1, nc, Ra, nullptr, nullptr, nullptr);
+                    URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+                }
             }
             float *cur = Ra, *nxt = Rb;          // residual stream in / out of the current stage
             int ch = 16, hw = 32;
@@ -828,6 +849,11 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 if (stg == 0) {
                     g.bn_in_off = pl.blocks[0][0].bn1;
                     g.r_in = cur; g.a_in_hi = g.a_in_lo = nullptr;
+                    if (f16) {  // conv1 (3 -> 16) as conv 0 of the chain: residual update from zero, then bn1 of block 0
+                        g.r_in = nullptr;
+                        g.pi_per_image = 1;
+                        g.w_off[0] = pl.conv1_w16; g.mode[0] = 1; g.bn_off[0] = pl.blocks[0][0].bn1; g.n_convs = 1;
+                    }
                 } else {
                     // transition block: 1x1 stride-2 shortcut on the raw stream, stride-2 conv1 on the layer-wise kernel
                     const NetPlan::Block &B0 = pl.blocks[stg][0];

@@ -98,6 +98,22 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             const __half h = __float2half_rn(w);
             dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
         }
+    } else if (e.type == 9) {
+        // network conv1 (3 -> 16) as a 16 -> 16 conv of the FP16-split stage kernel: type-6 layout with the 13 missing
+        // input channels zero, so the stem is just the first conv of the stage-1 chain (its input planes carry the image)
+        const int C = 16;
+        __half *dh = reinterpret_cast<__half *>(dst);
+        const int total = 9 * (C / 8) * 2 * C * 8;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {       // i over dst [tap][j][n][e8]
+            const int e8 = i & 7;
+            const int n = (i >> 3) % (2 * C);
+            const int j = (i / (16 * C)) % (C / 8);
+            const int tap = i / (2 * C * C);
+            const int co = n % C, ci = 8 * j + e8;
+            const float w = ci < 3 ? row[e.src + ((int64_t)co * 3 + ci) * 9 + tap] : 0.f;
+            const __half h = __float2half_rn(w);
+            dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
+        }
     } else if (e.type == 7) {
         // stride-2 transition conv of the FP16-split path: K-major rows [co][tap][hi(cin) | lo'(cin)] halves
         __half *dh = reinterpret_cast<__half *>(dst);
@@ -129,6 +145,7 @@ struct NetPlan {
     PrepTable table;
     int64_t packed_floats;
     int64_t conv1_w;
+    int64_t conv1_w16;          // tc == 3: conv1 packed as a 16 -> 16 FP16-split stage conv (type 9), else -1
     struct Block { int64_t bn1, w1, bn2, w2, ds, w1_lo, w2_lo; } blocks[3][8];   // w*_lo: tensor-core plan only
     int64_t bn_final, fc;
     int64_t D, NB;              // expected bank / buffer row lengths
@@ -197,6 +214,14 @@ static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
         pl.fc = dst;
         src += C * 64 + C;
         dst += C * 64 + C;
+    }
+    pl.conv1_w16 = -1;
+    if (tc == 3) {
+        dst = (dst + 3) & ~(int64_t)3;          // bulk-copy source: 16-byte aligned
+        PrepEntry &e = t.e[t.n++];
+        e.type = 9; e.cin = 3; e.cout = 16; e.src = 0; e.src2 = 0; e.buf = 0; e.dst = dst; e.dst2 = 0;
+        pl.conv1_w16 = dst;
+        dst += 16 * 16 * 9;
     }
     pl.packed_floats = (dst + 3) & ~(int64_t)3;
     pl.D = src;

@@ -8,6 +8,7 @@ forward otherwise) and accumulates  sum_s softmax_s  and  sum_s entropy(smooth(s
 ``ursa_bma_accumulate``; the tasks derive their own statistics from those two accumulators.
 """
 import copy
+import weakref
 
 import torch
 
@@ -16,10 +17,28 @@ from ..bank import BankedSample, SampleBank
 from ..flat import FlatParams
 
 _LOGIT_CHUNK_BYTES = 256 << 20
+_PACK_BATCH = 8            # = the conv forwards' sample chunk
+
+
+_ARCH_CACHE = weakref.WeakKeyDictionary()
 
 
 def _arch_of(module):
-    """('mlp', in_dim, hidden, C) / ('preresnet', depth, C) / ('wrn', depth, widen, C) / None -- structural match against models.py."""
+    """('mlp', in_dim, hidden, C) / ('preresnet', depth, C) / ('wrn', depth, widen, C) / None -- structural match against
+    models.py (cached per module object: the walk over ~100 tensors is not free when an ensemble has hundreds of members)."""
+    try:
+        return _ARCH_CACHE[module]
+    except (KeyError, TypeError):
+        pass
+    arch = _arch_of_uncached(module)
+    try:
+        _ARCH_CACHE[module] = arch
+    except TypeError:
+        pass
+    return arch
+
+
+def _arch_of_uncached(module):
     name = type(module).__name__
     if name == "MLP" and all(hasattr(module, a) for a in ("fc1", "fc2", "fc3")):
         f1, f2, f3 = module.fc1, module.fc2, module.fc3
@@ -109,6 +128,7 @@ class BMAAccumulator:
         self._proba = torch.zeros(self._n, num_classes, device=self.device)
         self._entropy = torch.zeros(self._n, device=self.device)
         self._workers = {}
+        self._pending = []        # FP16-split forwards of the current accumulate() awaiting the range check
         self.last_engine = None
         self.kernel_launches = 0
 
@@ -144,16 +164,17 @@ class BMAAccumulator:
         with torch.no_grad():
             if pairs is None:
                 self._accumulate(model_list, 0, self._n)
-                return
-            i = 0
-            while i < len(pairs):                       # runs of samples over the same image range go down in one call
-                j = i
-                while j + 1 < len(pairs) and pairs[j + 1][1:] == pairs[i][1:]:
-                    j += 1
-                _, lo, hi = pairs[i]
-                if hi > lo:
-                    self._accumulate([model_list[k] for k, _, _ in pairs[i:j + 1]], lo, hi)
-                i = j + 1
+            else:
+                i = 0
+                while i < len(pairs):                   # runs of samples over the same image range go down in one call
+                    j = i
+                    while j + 1 < len(pairs) and pairs[j + 1][1:] == pairs[i][1:]:
+                        j += 1
+                    _, lo, hi = pairs[i]
+                    if hi > lo:
+                        self._accumulate([model_list[k] for k, _, _ in pairs[i:j + 1]], lo, hi)
+                    i = j + 1
+            self._commit_scratch()
 
     def _accumulate(self, model_list, lo, hi):
         banked = all(isinstance(m, BankedSample) and m.is_pristine() for m in model_list)
@@ -166,9 +187,13 @@ class BMAAccumulator:
         arch = _arch_of(plain[0])
         if self.engine in ("auto", "ffma") and arch is not None and self._fused_available(arch) \
                 and all(_arch_of(m) == arch for m in plain):
-            bank = SampleBank.from_modules(plain, self.device)       # one H2D per sample instead of 2 per batch
-            self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
-            self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
+            # one H2D per sample instead of 2 per batch -- in sub-batches, so that packing sub-batch i + 1 on the host
+            # (a Python walk over ~100 tensors per module) overlaps the forward of sub-batch i on the device
+            step = _PACK_BATCH if len(plain) > 2 * _PACK_BATCH else len(plain)
+            for s0 in range(0, len(plain), step):
+                bank = SampleBank.from_modules(plain[s0:s0 + step], self.device)
+                self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
+                self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
             return
         self._accumulate_generic_modules(plain, lo, hi)
 
@@ -224,16 +249,13 @@ class BMAAccumulator:
                     raise ValueError("PreResNet class dimension does not match the task")
                 if algo == _C.ALGO_TCGEN05_FUSED_F16:
                     # FP16-split operands: activations beyond ~1e6 overflow to inf -> NaN logits (loud by construction).
-                    # The call accumulates into a zeroed scratch pair, ONE flag read decides, then the scratch is added:
-                    # the accumulators never see a NaN and nothing is cloned.
-                    sp, se = self._scratch(hi - lo)
-                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp, se, algo=algo, workspace=self._ws)
-                    if bool(torch.isfinite(sp.sum())):
-                        proba.add_(sp)
-                        entropy.add_(se)
-                    else:                                       # redo on the TF32 engine, which has fp32's range
-                        algo = _C.ALGO_TCGEN05_FUSED
-                        self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=None)
+                    # The calls of one accumulate() go into a zeroed scratch pair; _commit_scratch() reads ONE flag at the
+                    # end and either adds the scratch or redoes the calls on the TF32 engine: the accumulators never see
+                    # a NaN, nothing is cloned and the host does not synchronise between the calls.
+                    sp, se = self._scratch()
+                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp[lo:hi], se[lo:hi], algo=algo,
+                                                        workspace=self._ws)
+                    self._pending.append((w, b, S, depth, C, lo, hi))
                 else:
                     self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_preresnet"
@@ -252,14 +274,30 @@ class BMAAccumulator:
 
         self._accumulate_generic(S, load, None, lo, hi)
 
-    def _scratch(self, n):
+    def _scratch(self):
         if getattr(self, "_scratch_p", None) is None:
             self._scratch_p = torch.empty(self._n, self.num_classes, device=self.device)
             self._scratch_e = torch.empty(self._n, device=self.device)
-        sp, se = self._scratch_p[:n], self._scratch_e[:n]
-        sp.zero_()
-        se.zero_()
-        return sp, se
+        if not self._pending:
+            self._scratch_p.zero_()
+            self._scratch_e.zero_()
+        return self._scratch_p, self._scratch_e
+
+    def _commit_scratch(self):
+        """End of an accumulate(): fold the FP16-split engine's scratch sums into the accumulators, or -- if any logit
+        overflowed -- redo those calls on the TF32 engine, which has fp32's range."""
+        if not self._pending:
+            return
+        pending, self._pending = self._pending, []
+        if bool(torch.isfinite(self._scratch_p.sum())):
+            self._proba.add_(self._scratch_p)
+            self._entropy.add_(self._scratch_e)
+            return
+        self.last_algo = _C.ALGO_TCGEN05_FUSED
+        ws = None
+        for w, b, S, depth, C, lo, hi in pending:
+            ws = _C.bma_preresnet_forward(w, b, S, self._x[lo:hi], depth, C, self._proba[lo:hi], self._entropy[lo:hi],
+                                          algo=_C.ALGO_TCGEN05_FUSED, workspace=ws)
 
     def _inputs_match(self, arch):
         """The fused conv forwards take only (pointer, N): the resident test tensor must be the [N, 3, 32, 32] the

@@ -102,6 +102,7 @@ class Prediction(_Task, BMAAccumulator):
                     w, b = bank.rows([rows[k] for k, _, _ in pairs[i:j + 1]])
                     self._accumulate_rows(w, b, arch, bank.skeleton, lo, hi)
                 i = j + 1
+            self._commit_scratch()
 
     # -- metrics --------------------------------------------------------------------------------------------------
     def _reduced(self):
