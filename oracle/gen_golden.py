@@ -10,6 +10,7 @@ Protocols:
 * identical noise: ``torch.randn_like`` is swapped for a closure that replays
   pre-generated tensors while ``optimSGHMC.step`` runs (optim_sghmc.py:63-64).
 """
+import copy
 import json
 import os
 import re
@@ -368,6 +369,40 @@ def gen_prediction_wrn(R):
     print("prediction_wrn.npz", {k: v for k, v in metric_json.items()})
 
 
+def gen_prediction_preresnet20(R):
+    """Prediction.update_statistics on the reference's PreResNet(depth=20) -- the north-star model -- with logits sharpened to
+    the scale of a trained network (|logit| ~ 20), C = 10 and C = 100.  Weights come from oracle/wrn_fill.py (a seeded
+    stream in flat-layout order), so only x and the reference's outputs are stored."""
+    from oracle.wrn_fill import wrn_fill
+    Prediction = R["tasks"].Prediction
+    out, metric_json = {}, {}
+    for tag, C, S, N, seed, gain in (("c10", 10, 2, 24, 300, 0.4), ("c100", 100, 2, 16, 400, 0.5)):
+        rng = np.random.RandomState(seed + 50)
+        x16 = rng.randn(N, 3, 32, 32).astype(np.float16)
+        x = torch.from_numpy(x16.astype(np.float32))
+        y = torch.from_numpy(rng.randint(0, C, N))
+        ms = [wrn_fill(R["models"].preresnet.PreResNet(num_classes=C, depth=20), seed + s, logit_gain=gain) for s in range(S)]
+        loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=8, shuffle=False)
+        task = Prediction({"in_distribution_test": loader}, C, torch.device("cpu"), "ALL")
+        task.update_statistics(ms, output_performance=False)
+        metric_json[tag] = {k: float(v) for k, v in task.get_performance_metrics().items()}
+        out[tag + "/x"], out[tag + "/y"] = x16, y.numpy()
+        out[tag + "/arch"] = np.array([20, C, S, seed])
+        out[tag + "/gain"] = np.array([gain])
+        out[tag + "/ensemble_proba"] = task.ensemble_proba.numpy().copy()
+        out[tag + "/entropy"] = task.expected_data_uncertainty.numpy().copy()
+        with torch.no_grad():
+            logits = torch.stack([m.eval()(x) for m in ms])
+            out[tag + "/logits"] = logits.numpy()
+            l64 = torch.stack([copy.deepcopy(m).double().eval()(x.double()) for m in ms])
+            # how far the reference's own fp32 forward is from the exact network on these inputs (context for the 1e-5 bar)
+            out[tag + "/fp32_vs_fp64_proba"] = np.array([(torch.softmax(logits.double(), -1) - torch.softmax(l64, -1)).abs().max().item()])
+        print(tag, "max |logit|", float(logits.abs().max()), "fp32 vs fp64 proba", float(out[tag + "/fp32_vs_fp64_proba"][0]))
+    np.savez_compressed(os.path.join(OUT, "prediction_preresnet20.npz"), **out)
+    json.dump(metric_json, open(os.path.join(OUT, "prediction_preresnet20_metrics.json"), "w"), indent=1)
+    print("prediction_preresnet20.npz")
+
+
 def gen_pca_space(R):
     """PCASpace.collect_vector / get_space (inference/subspaces.py:103-156, integer pca_rank) and SubspaceModel.forward
     (inference/projection_model.py:6-14) on the live reference: ring wrap (11 collects into max_rank 8), pca_rank 5; a
@@ -573,7 +608,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, prediction_preresnet20=gen_prediction_preresnet20, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

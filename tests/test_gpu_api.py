@@ -673,3 +673,23 @@ def test_multi_gpu_equals_single_gpu_on_nccl(tmp_path):
     s.close()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(2))
+
+
+def test_handles_survive_update_hyp(U, capsys):
+    """``sample()`` handles must stay independent of later runs (the reference returns deep copies, sghmc.py:99): after
+    ``update_hyp`` + a second ``sample()`` the first run's handles still hold the first run's weights."""
+    ds, loader = _toy()
+    torch.manual_seed(0)
+    hyp = {"lr": 0.1, "prior_std": 1.0, "num_samples": 2, "alpha": 0.3, "burn_in_epochs": 1}
+    inf = U.inference.SGHMC(dict(hyp), U.models.MLP(16, 20, 3), loader, device=DEV)
+    first = inf.sample()
+    rows = [inf.bank.w[h._ursa_row, :inf.flat.D].clone() for h in first]
+    old_bank = inf.bank
+    inf.update_hyp(dict(hyp, lr=0.05))
+    assert inf.bank is not old_bank and getattr(inf, "_graph", None) is None
+    second = inf.sample()
+    for h, w in zip(first, rows):
+        assert h.is_pristine()
+        got = torch.cat([p.detach().reshape(-1) for p in h.parameters()])
+        assert torch.equal(got, w.cpu())
+    assert not torch.equal(_flat(second[0]), _flat(first[0]))

@@ -55,6 +55,12 @@ class SampleBank:
     def capacity(self):
         return self.w.shape[0]
 
+    def fresh(self):
+        """A new, empty bank of the same shape.  Samplers switch to a fresh bank when they restart (``update_hyp``, a new
+        ``HMC.sample()``), so ``BankedSample`` handles returned earlier keep their own storage alive instead of silently
+        aliasing the new run's rows -- the reference hands out independent deep copies (inference/sghmc.py:99)."""
+        return SampleBank(self.D, self.nb, self.device, capacity=min(self.capacity, 8), skeleton=self.skeleton)
+
     def reserve(self, n):
         if n <= self.capacity:
             return

@@ -40,10 +40,12 @@ class cSGHMC(_Inference, SGMCMCLoop):
         self.alpha = h["alpha"]
         self.burn_in_epochs = h["burn_in_epochs"]
         self.num_cycles = h["num_cycles"]
+        self.temperature = h.get("temperature", 1.0)     # optional, not a reference key: sqrt(T) on the noise
 
     def _build_optimizer(self):
         self.optimizer = optimSGHMC(params=self.model.parameters(), lr=self.lr_0, momentum=1 - self.alpha,
-                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2))
+                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2),
+                                    temperature=self.temperature)
         self.burnt_in = False
         self.epochs_run = 0
 
@@ -51,7 +53,9 @@ class cSGHMC(_Inference, SGMCMCLoop):
         self._read_hyp(hyperparameters)
         self.model = reset_model(self.model)
         self._build_optimizer()
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
+        if hasattr(self, "disable_cuda_graph"):
+            self.disable_cuda_graph()             # a captured step reads the OLD optimizer's device scalars
         assert (self.cycle_length - self.burn_in_epochs - self.num_samples_per_cycle) > 0
         # NB the reference does not recompute total_iterations here either (:48-62)
 

@@ -109,7 +109,7 @@ class HMC(_Inference):
     def update_hyp(self, hyperparameters):
         self._read_hyp(hyperparameters)
         self.model = reset_model(self.model)
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
 
     # -- gradient of the data term for all chains ---------------------------------------------------------------------
     def _unflatten(self, row):
@@ -254,17 +254,18 @@ class HMC(_Inference):
         theta[0, :self.D].copy_(torch.cat([p.detach().reshape(-1) for p in self.model.parameters()]))
         if C > 1:
             rank, _ = udist.rank_world()
-            gen_state = torch.random.get_rng_state()
             stage = torch.empty(C - 1, self.D)
             scratch = copy.deepcopy(self._skeleton)
-            for c in range(1, C):
-                torch.manual_seed((self.seed + 7919 * (rank * C + c)) & 0x7FFFFFFF)
-                for m in scratch.modules():
-                    fn = getattr(m, "reset_parameters", None)
-                    if fn is not None:
-                        fn()
-                stage[c - 1].copy_(torch.cat([p.detach().reshape(-1) for p in scratch.parameters()]))
-            torch.random.set_rng_state(gen_state)
+            # reset_parameters() draws from the global CPU generator: fork it (CPU only, devices=[]) so that neither the
+            # caller's CPU stream nor any CUDA generator is reseeded
+            with torch.random.fork_rng(devices=[]):
+                for c in range(1, C):
+                    torch.manual_seed((self.seed + 7919 * (rank * C + c)) & 0x7FFFFFFF)
+                    for m in scratch.modules():
+                        fn = getattr(m, "reset_parameters", None)
+                        if fn is not None:
+                            fn()
+                    stage[c - 1].copy_(torch.cat([p.detach().reshape(-1) for p in scratch.parameters()]))
             theta[1:, :self.D].copy_(stage)
         return theta
 
@@ -278,7 +279,7 @@ class HMC(_Inference):
         chain0 = rank * C
         first_it, use_first = kept_iterations(self.num_samples, L, self.burn)
         n_keep = max(0, self.num_samples - first_it + 1)
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
         self.bank.reserve(max(1, n_keep * C))
         self.model.eval()
         self._grad_fn = self._build_grad_fn()

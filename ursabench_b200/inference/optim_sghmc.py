@@ -9,7 +9,8 @@ Differences that are deliberate:
 * noise is drawn in-register from counter-based Philox (seeded from ``torch.initial_seed()`` unless ``seed`` is
   given) instead of ``torch.randn_like`` (:64); pass ``noise=`` to ``step`` to inject a tensor (parity mode);
 * ``zero_grad`` keeps the gradients as views of the flat buffer (one memset) instead of setting them to None;
-* parameters whose gradient is None are treated as having a zero gradient (the reference skips them, :44-45).
+* parameters whose gradient is None are treated as having a zero gradient (the reference skips them, :44-45);
+* an optional ``temperature`` (default 1 = the reference) scales the injected noise by sqrt(T).
 """
 import math
 
@@ -22,7 +23,7 @@ from ..flat import FlatParams
 
 class optimSGHMC(Optimizer):
     def __init__(self, params, lr=required, momentum=0, dampening=0, weight_decay=0, num_training_samples=None,
-                 nesterov=False, seed=None, elem_offset=0):
+                 nesterov=False, seed=None, elem_offset=0, temperature=1.0):
         if lr is not required and lr < 0.0:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if momentum < 0.0:
@@ -33,8 +34,13 @@ class optimSGHMC(Optimizer):
             raise ValueError("Nesterov momentum requires a momentum and zero dampening")
         if nesterov:
             raise NotImplementedError("the reference never enables nesterov (optim_sghmc.py:57-58); not built")
+        if temperature < 0.0:
+            raise ValueError("Invalid temperature value: {}".format(temperature))
+        # temperature: the noise term becomes z * sqrt(2 (1 - momentum) lr T) / N.  The reference has no such factor
+        # (optim_sghmc.py:63-64) = T = 1, which -- with its mean-loss / N scalings -- samples exp(-N U);
+        # T = N targets the posterior exp(-U) itself.
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov,
-                        num_training_samples=num_training_samples)
+                        num_training_samples=num_training_samples, temperature=temperature)
         super().__init__(params, defaults)
         _C.lib()                                   # fail now, loudly, if the CUDA library is missing
         self._flats = []
@@ -72,7 +78,7 @@ class optimSGHMC(Optimizer):
         if (add_langevin_noise or wd != 0) and not n_train:
             raise ValueError("num_training_samples is required")
         wd_over_n = (wd / n_train) if wd != 0 else 0.0
-        noise_mul = math.sqrt(2 * (1 - momentum) * lr) if add_langevin_noise else 0.0
+        noise_mul = math.sqrt(2 * (1 - momentum) * lr * group.get("temperature", 1.0)) if add_langevin_noise else 0.0
         noise_div = float(n_train) if add_langevin_noise else 1.0
         return lr, momentum, wd_over_n, noise_mul, noise_div
 

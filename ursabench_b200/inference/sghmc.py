@@ -30,10 +30,12 @@ class SGHMC(_Inference, SGMCMCLoop):
         self.num_samples = h["num_samples"]
         self.alpha = h["alpha"]
         self.burn_in_epochs = h["burn_in_epochs"]
+        self.temperature = h.get("temperature", 1.0)     # optional, not a reference key: sqrt(T) on the noise
 
     def _build_optimizer(self, eta_min):
         self.optimizer = optimSGHMC(params=self.model.parameters(), lr=self.lr, momentum=1 - self.alpha,
-                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2))
+                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2),
+                                    temperature=self.temperature)
         self.burnt_in = False
         self.epochs_run = 0
         self.lr_final = self.lr / 2
@@ -44,7 +46,9 @@ class SGHMC(_Inference, SGMCMCLoop):
         self._read_hyp(hyperparameters)
         self.model = reset_model(self.model)
         self._build_optimizer(eta_min=self.lr / 2)           # reference :62-63
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
+        if hasattr(self, "disable_cuda_graph"):
+            self.disable_cuda_graph()             # a captured step reads the OLD optimizer's device scalars
 
     def sample_iterative(self, val_loader=None, debug_val_loss=False, wandb_debug=False):
         if not isinstance(self.model, torch.nn.Module):

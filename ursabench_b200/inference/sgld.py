@@ -22,9 +22,13 @@ class SGLD(SGHMC):
         self.num_samples = hyperparameters["num_samples"]
         self.alpha = 1.0
         self.burn_in_epochs = hyperparameters["burn_in_epochs"]
+        self.temperature = hyperparameters.get("temperature", 1.0)
         self.model = reset_model(self.model)
         self.optimizer = optimSGHMC(params=self.model.parameters(), lr=self.lr, momentum=1 - self.alpha,
-                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2))
+                                    num_training_samples=self.dataset_size, weight_decay=1 / (self.prior_std ** 2),
+                                    temperature=self.temperature)
         self.burnt_in = False
         self.epochs_run = 0
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
+        if hasattr(self, "disable_cuda_graph"):
+            self.disable_cuda_graph()             # a captured step reads the OLD optimizer's device scalars

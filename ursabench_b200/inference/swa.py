@@ -69,7 +69,9 @@ class SWA(_Inference):
         kw.update(subspace_kwargs)
         self.subspace = Subspace.create(self.subspace_type, num_parameters=self.num_parameters, device=self.device,
                                         **kw)
-        self.bank.count = 0
+        self.bank = self.bank.fresh()            # earlier sample() handles keep the old rows
+        if hasattr(self, "disable_cuda_graph"):
+            self.disable_cuda_graph()             # a captured step reads the OLD optimizer's device scalars
 
     @property
     def weight_mean(self):
