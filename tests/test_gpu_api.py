@@ -693,3 +693,47 @@ def test_handles_survive_update_hyp(U, capsys):
         got = torch.cat([p.detach().reshape(-1) for p in h.parameters()])
         assert torch.equal(got, w.cpu())
     assert not torch.equal(_flat(second[0]), _flat(first[0]))
+
+
+def _swag_shard_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import ursabench_b200 as U
+    U.dist.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    try:
+        ds, loader = _toy()
+        torch.manual_seed(5 + rank)                           # ranks start from different weights: only rank 0's fit counts
+        hyp = {"swag_lr": 0.02, "swag_wd": 1e-4, "lr_init": 0.05, "num_samples": 5, "momentum": 0.5, "burn_in_epochs": 2,
+               "num_iterates": 6, "subspace_type": "covariance", "shard_draws": True}
+        inf = U.inference.SWAG(hyp, U.models.MLP(16, 20, 3), loader, device=dev, max_rank=4)
+        out = inf.sample(full_cov=True)
+        assert len(out) == len(range(rank, 5, world))         # draws s = rank (mod world)
+        mean = inf.weight_mean.clone()
+        gathered = [torch.zeros_like(mean) for _ in range(world)]
+        dist.all_gather(gathered, mean)
+        assert all(torch.equal(gathered[0], g) for g in gathered)          # one fit, broadcast
+        assert int(inf.num_models_collected.item()) == 6 and inf.subspace.collected == 6
+        mine = torch.stack([inf.bank.w[h._ursa_row, :inf.flat.D] for h in out])
+        first = [torch.zeros_like(mine[0]) for _ in range(world)]
+        dist.all_gather(first, mine[0].contiguous())
+        assert not torch.equal(first[0], first[1])                          # different substreams on different ranks
+        assert float((mine - mean[None]).abs().max()) > 0 and bool(torch.isfinite(mine).all())
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_swag_draws_sharded_over_ranks_after_one_broadcast(tmp_path):
+    """SURVEY 8e row 2 on real NCCL: rank 0 fits, (mean, second moment, ring) are broadcast once, every rank draws its
+    s = rank (mod world) share from its own substream."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_swag_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(2))

@@ -20,6 +20,7 @@
 #include "tc_common.cuh"
 #include "bma_conv_fused.cuh"
 #include "bma_conv_fused16.cuh"
+#include "bma_epilogue.cuh"
 
 namespace ursa {
 
@@ -401,6 +402,74 @@ __global__ void __launch_bounds__(256) head_nhwc_kernel(const float *__restrict_
         for (int k = 0; k < 64; ++k) acc = fmaf(feat_s[warp][k], __ldg(fw + c * 64 + k), acc);
         logits[(int64_t)pair * C + c] = acc + __ldg(fb + c);
     }
+}
+
+// The same head FUSED with the BMA epilogue: one warp per IMAGE walks the chunk's samples in order -- final BN + ReLU +
+// AvgPool2d(8) + fc leave the logits in registers (class c in lane c % 32), softmax_accumulate_row adds softmax_s and the
+// smoothed entropy to the warp's running sums, and the image's row of proba_sum / entropy_sum is read and written once.
+// No logits round trip, no separate accumulate launch; the per-row sample order (= the reference's list order) is kept.
+template <int PER_LANE>
+__global__ void __launch_bounds__(128) head_bma_kernel(const float *__restrict__ act, const float *__restrict__ packed,
+                                                        int64_t ld_packed, int64_t bn_off, int64_t fc_off, int n_images,
+                                                        int n_samples, int C, float *__restrict__ proba_sum,
+                                                        float *__restrict__ entropy_sum, float one_minus_gamma,
+                                                        float gamma_over_c) {
+    __shared__ float feat_s[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 4 + warp;
+    if (n >= n_images) return;
+    float P[PER_LANE];
+#pragma unroll
+    for (int j = 0; j < PER_LANE; ++j) P[j] = (lane + 32 * j < C) ? proba_sum[(int64_t)n * C + lane + 32 * j] : 0.f;
+    float E = entropy_sum[n];
+    for (int s = 0; s < n_samples; ++s) {
+        const float *pk = packed + (int64_t)s * ld_packed;
+        const float *x = act + ((int64_t)s * n_images + n) * 64 * 64;
+        const float a0 = __ldg(pk + bn_off + lane), b0 = __ldg(pk + bn_off + 64 + lane);
+        const float a1 = __ldg(pk + bn_off + 32 + lane), b1 = __ldg(pk + bn_off + 96 + lane);
+        float f0 = 0.f, f1 = 0.f;
+#pragma unroll 8
+        for (int px = 0; px < 64; ++px) {
+            f0 += relu_nan(fmaf(a0, __ldg(x + px * 64 + lane), b0));
+            f1 += relu_nan(fmaf(a1, __ldg(x + px * 64 + 32 + lane), b1));
+        }
+        __syncwarp();
+        feat_s[warp][lane] = f0 * (1.f / 64.f);
+        feat_s[warp][32 + lane] = f1 * (1.f / 64.f);
+        __syncwarp();
+        const float *fw = pk + fc_off, *fb = pk + fc_off + (int64_t)C * 64;
+        float lg[PER_LANE];
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+            const int c = lane + 32 * j;
+            float acc = 0.f;
+            if (c < C) {
+#pragma unroll 8
+                for (int k = 0; k < 64; ++k) acc = fmaf(feat_s[warp][k], __ldg(fw + c * 64 + k), acc);
+                acc += __ldg(fb + c);
+            }
+            lg[j] = acc;
+        }
+        softmax_accumulate_row<PER_LANE>(lg, C, lane, one_minus_gamma, gamma_over_c, P, E);
+    }
+#pragma unroll
+    for (int j = 0; j < PER_LANE; ++j)
+        if (lane + 32 * j < C) proba_sum[(int64_t)n * C + lane + 32 * j] = P[j];
+    if (lane == 0) entropy_sum[n] = E;
+}
+
+static int launch_head_bma(const float *act, const float *packed, int64_t ld_packed, int64_t bn_off, int64_t fc_off, int nc,
+                           int sc, int C, float *proba_sum, float *entropy_sum, double gamma, cudaStream_t st) {
+    const float omg = (float)(1.0 - gamma), goc = (float)(gamma * 1.0 / C);      // util.py:134: gamma * 1 / C
+    const int grid = (nc + 3) / 4;
+    if (C <= 32)
+        head_bma_kernel<1><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+    else if (C <= 128)
+        head_bma_kernel<4><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+    else
+        head_bma_kernel<32><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+    URSA_LAUNCH_CHECK("head_bma_kernel");
+    return URSA_OK;
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -932,7 +1001,12 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 float *t = cur; cur = nxt; nxt = t;
             }
             const int pairs = sc * nc;
-            {
+            if (logits_out == nullptr) {
+                ProfScope ps(URSA_PROF_HEAD, st);        // head + softmax-average + entropy in ONE kernel, logits stay in registers
+                if (int rc = launch_head_bma(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, sc, C, proba_sum + i0 * C,
+                                             entropy_sum + i0, gamma, st))
+                    return rc;
+            } else {
                 ProfScope ps(URSA_PROF_HEAD, st);
                 head_nhwc_kernel<<<(pairs + 7) / 8, 256, 0, st>>>(cur, packed, pl.packed_floats, pl.bn_final, pl.fc, nc, pairs, C, logits);
                 URSA_LAUNCH_CHECK("head_nhwc_kernel");

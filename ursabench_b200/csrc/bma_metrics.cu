@@ -4,6 +4,7 @@
 // One warp owns one test row; classes are strided over lanes (C <= 1024).  The sample loop is sequential
 // per row, so the fp32 accumulation order equals the reference's list order.  Metric partials are
 // reduced in a fixed order (warp -> block -> second launch) so counters and fp64 sums are reproducible.
+#include "bma_epilogue.cuh"
 #include "common.cuh"
 
 namespace ursa {
@@ -12,48 +13,6 @@ constexpr int kRowThreads = 256;
 constexpr int kRowWarps = kRowThreads / 32;
 constexpr int kMaxPerLane = 32;          // C <= 32 * 32
 constexpr int kMaxBins = 64;
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// softmax-average + smoothed-entropy of one row held as per-lane registers (shared with the fused forwards)
-template <int PER_LANE>
-__device__ __forceinline__ void softmax_accumulate_row(const float (&x)[PER_LANE], int C, int lane, float one_minus_gamma,
-                                                       float gamma_over_c, float (&P)[PER_LANE], float &E) {
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < PER_LANE; ++j)
-        if (lane + 32 * j < C) m = fmaxf(m, x[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < PER_LANE; ++j)
-        if (lane + 32 * j < C) sum += expf(x[j] - m);
-    const float lse = logf(warp_sum(sum));
-    float h = 0.f;
-#pragma unroll
-    for (int j = 0; j < PER_LANE; ++j)
-        if (lane + 32 * j < C) {
-            const float p = expf((x[j] - m) - lse);                                   // log_softmax().exp_()  (:60)
-            P[j] = __fadd_rn(P[j], p);
-            const float q = __fadd_rn(__fmul_rn(one_minus_gamma, p), gamma_over_c);   // util.py:134
-            h = fmaf(q, logf(q), h);                                                  // util.py:144
-        }
-    E = __fadd_rn(E, -warp_sum(h));
-}
 
 template <int PER_LANE>
 __global__ void __launch_bounds__(kRowThreads) bma_accumulate_kernel(const float *__restrict__ logits, int64_t S,

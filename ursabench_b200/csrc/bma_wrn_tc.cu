@@ -38,6 +38,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "bma_epilogue.cuh"
 
 namespace ursa {
 
@@ -498,10 +499,15 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
 }
 
 // ---- head: relu(bn(R)) -> 8x8 average pool -> linear; one CTA per image -------------------------------------------------
+// proba_sum != nullptr: the BMA epilogue is fused -- the image's logits stay in shared memory and warp 0 adds softmax and the
+// smoothed entropy to the image's row of the accumulators (softmax_accumulate_row, the arithmetic of ursa_bma_accumulate).
+template <int PER_LANE>
 __global__ void __launch_bounds__(256) wrn_head_kernel(const float *__restrict__ act, const float *__restrict__ bn, int cf,
                                                        const float *__restrict__ lw, const float *__restrict__ lb, int C,
-                                                       float *__restrict__ logits) {
-    extern __shared__ float feat[];                                    // [cf]
+                                                       float *__restrict__ logits, float *__restrict__ proba_sum,
+                                                       float *__restrict__ entropy_sum, float one_minus_gamma,
+                                                       float gamma_over_c) {
+    extern __shared__ float feat[];                                    // [cf] then [C] logits
     const int n = blockIdx.x;
     const float *xp = act + (int64_t)n * 64 * cf;
     for (int c = threadIdx.x; c < cf; c += 256) {
@@ -517,7 +523,28 @@ __global__ void __launch_bounds__(256) wrn_head_kernel(const float *__restrict__
         for (int k = lane; k < cf; k += 32) acc = fmaf(feat[k], __ldg(lw + (int64_t)c * cf + k), acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) logits[(int64_t)n * C + c] = acc + __ldg(lb + c);
+        if (lane == 0) {
+            const float v = acc + __ldg(lb + c);
+            if (logits != nullptr) logits[(int64_t)n * C + c] = v;
+            feat[cf + c] = v;
+        }
+    }
+    if (proba_sum == nullptr) return;
+    __syncthreads();
+    if (warp == 0) {
+        float lg[PER_LANE], P[PER_LANE];
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+            const int c = lane + 32 * j;
+            lg[j] = c < C ? feat[cf + c] : 0.f;
+            P[j] = c < C ? proba_sum[(int64_t)n * C + c] : 0.f;
+        }
+        float E = entropy_sum[n];
+        softmax_accumulate_row<PER_LANE>(lg, C, lane, one_minus_gamma, gamma_over_c, P, E);
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j)
+            if (lane + 32 * j < C) proba_sum[(int64_t)n * C + lane + 32 * j] = P[j];
+        if (lane == 0) entropy_sum[n] = E;
     }
 }
 
@@ -903,10 +930,19 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
                     if (c2.out_raw) { float *t = cur; cur = nxt; nxt = t; }
                     hw /= B.stride;
                 }
-            wrn_head_kernel<<<nc, 256, cf * sizeof(float), st>>>(cur, packed + pl.p_bnf, cf, row + pl.lin_w, row + pl.lin_b, C, logits);
-            URSA_LAUNCH_CHECK("wrn_head_kernel");
-            if (int rc = ursa_bma_accumulate(logits, 1, nc, C, (int64_t)nc * C, proba_sum + i0 * C, entropy_sum + i0, gamma, (void *)st))
-                return rc;
+            {   // head + softmax-average + entropy in one kernel (samples arrive one per launch: the order is the stream's)
+                const float omg = (float)(1.0 - gamma), goc = (float)(gamma * 1.0 / (double)C);
+                const size_t hsm = (size_t)(cf + C) * sizeof(float);
+                float *lg = logits_out ? logits : nullptr;
+                float *ps = proba_sum + i0 * C, *es = entropy_sum + i0;
+                if (C <= 32)
+                    wrn_head_kernel<1><<<nc, 256, hsm, st>>>(cur, packed + pl.p_bnf, cf, row + pl.lin_w, row + pl.lin_b, C, lg, ps, es, omg, goc);
+                else if (C <= 128)
+                    wrn_head_kernel<4><<<nc, 256, hsm, st>>>(cur, packed + pl.p_bnf, cf, row + pl.lin_w, row + pl.lin_b, C, lg, ps, es, omg, goc);
+                else
+                    wrn_head_kernel<32><<<nc, 256, hsm, st>>>(cur, packed + pl.p_bnf, cf, row + pl.lin_w, row + pl.lin_b, C, lg, ps, es, omg, goc);
+                URSA_LAUNCH_CHECK("wrn_head_kernel");
+            }
             if (logits_out)
                 URSA_CUDA(cudaMemcpyAsync(logits_out + ((int64_t)s * N + i0) * C, logits, (size_t)nc * C * sizeof(float),
                                           cudaMemcpyDeviceToDevice, st));

@@ -7,10 +7,16 @@ Reference quirks (verified on the live reference, tests/golden/swag_compat_facts
 ``hyperparameters['reference_compat'] = True`` reproduces Q5/Q6 bit for bit (Q7 raises the same AttributeError).
 The default is the algorithm the code was written to be (Maddox et al. 2019): n increments after each collect and
 the draw of swag.py:85-97 is returned -- all S draws produced by ONE pass over the deviation ring (K2b).
+
+Multi-GPU: ``hyperparameters['shard_draws'] = True`` under ``torch.distributed`` makes ONE fit serve
+all ranks: rank 0 trains and collects, (mean, second moment, deviation ring, counters) are broadcast once (2.9 GB for
+WRN-28-10 at K = 20: milliseconds over NVLink), and ``sample(num_samples)`` returns on rank r the draws
+s = r, r + G, r + 2G, ... -- each rank draws from its own Philox / generator substream, finishes (BatchNorm
+re-estimation) and keeps its draws in its own bank, where a sample-sharded ``Prediction`` evaluates them.
 """
 import torch
 
-from .. import _C
+from .. import _C, dist as udist
 from ..util import bn_update, check_bn
 from .swa import SWA
 
@@ -24,6 +30,7 @@ class SWAG(SWA):
                          device=device, **subspace_kwargs)
         self.num_samples = hyperparameters["num_samples"]
         self.reference_compat = bool(hyperparameters.get("reference_compat", False))
+        self.shard_draws = bool(hyperparameters.get("shard_draws", False))
         self.weight_variance = None
         self._draw_calls = 0
 
@@ -31,7 +38,39 @@ class SWAG(SWA):
         super().update_hyp(hyperparameters, **subspace_kwargs)
         self.num_samples = hyperparameters["num_samples"]
         self.reference_compat = bool(hyperparameters.get("reference_compat", False))
+        self.shard_draws = bool(hyperparameters.get("shard_draws", False))
         self.weight_variance = None
+
+    # -- one fit for all ranks -------------------------------------------------------------------------------------
+    def _sharded(self):
+        return self.shard_draws and udist.is_distributed()
+
+    def _fit_or_receive(self, val_loader, debug_val_loss, wandb_debug):
+        """Single process: fit.  Sharded draws: rank 0 fits, everybody receives its state by ONE round of broadcasts."""
+        if not self._sharded():
+            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+            return
+        import torch.distributed as dist
+        rank, _ = udist.rank_world()
+        if rank == 0:
+            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+        meta = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if rank == 0:
+            meta[0] = int(self.num_models_collected.item())
+            meta[1] = self.subspace.collected
+            meta[2] = int(self.subspace.rank.item())
+            meta[3] = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        dist.broadcast(meta, 0)
+        dist.broadcast(self._mean, 0)
+        dist.broadcast(self._sq, 0)
+        dist.broadcast(self.subspace.ring, 0)
+        n, collected, srank, seed = (int(v) for v in meta.tolist())
+        self.num_models_collected = torch.full((1,), n, dtype=torch.long)
+        self.subspace.collected = collected
+        self.subspace.rank = torch.full((1,), srank, dtype=torch.long)
+        self._draw_seed = seed
+        self.burnt_in = True
+        _, self.weight_variance = self._get_mean_and_variance()
 
     # -- training + collection (first call only), reference :54-83 ---------------------------------------------
     def _fit_moments(self, val_loader, debug_val_loss, wandb_debug):
@@ -60,6 +99,15 @@ class SWAG(SWA):
         _C.swag_variance(self._mean, self._sq, var_full, self.var_clamp)
         rows = self.subspace.rows() if full_cov else None
         K = 0 if rows is None else rows.shape[0]
+        # sharded draws: one seed for the whole job (broadcast with the fit), one substream per rank
+        rank, world = udist.rank_world() if self._sharded() else (0, 1)
+        seed = getattr(self, "_draw_seed", None) if self._sharded() else None
+        seed = (int(torch.initial_seed()) if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        gen = None
+        if world > 1:
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed((seed + 7919 * (rank + 1)) & 0x7FFFFFFFFFFFFFFF)
+            gen.set_offset(4 * _C.DRAW_MAX_S * _C.DRAW_MAX_K * self._draw_calls)
         done = 0
         while done < num:
             s = min(_C.DRAW_MAX_S, num - done)
@@ -67,10 +115,10 @@ class SWAG(SWA):
             if self.reference_compat:
                 out[:, :D] = self._mean[:D]                    # Q5: the draw is discarded, the mean is returned
             else:
-                z2 = torch.randn(s, K, device=self.device) if K else None
+                z2 = torch.randn(s, K, device=self.device, generator=gen) if K else None
                 _C.swag_draw(out, self._mean, var_full, D, ring=rows if K else None, z2=z2,
                              rank_div=float((self.subspace.max_rank - 1) ** 0.5),          # reference :95
-                             seed=int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, step=self._draw_calls)
+                             seed=seed, step=self._draw_calls * world + rank)
                 self._draw_calls += 1
             done += s
         self.bank.count = first + num
@@ -114,7 +162,7 @@ class SWAG(SWA):
     def sample_iterative(self, update_bn=True, val_loader=None, debug_val_loss=False, wandb_debug=False,
                          full_cov=False):
         if self.burnt_in is False:
-            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+            self._fit_or_receive(val_loader, debug_val_loss, wandb_debug)
         row = self._draw_into_bank(1, full_cov)[0]
         return self._finish_sample(row, update_bn)
 
@@ -122,6 +170,9 @@ class SWAG(SWA):
         if num_samples is None:
             num_samples = self.num_samples
         if self.burnt_in is False:
-            self._fit_moments(val_loader, debug_val_loss, wandb_debug)
+            self._fit_or_receive(val_loader, debug_val_loss, wandb_debug)
+        if self._sharded():
+            rank, world = udist.rank_world()
+            num_samples = len(range(rank, num_samples, world))      # this rank's draws s = rank (mod world)
         rows = self._draw_into_bank(num_samples, full_cov)     # all draws: one pass over the ring
         return [self._finish_sample(r, True) for r in rows]
