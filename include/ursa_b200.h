@@ -129,7 +129,8 @@ int ursa_swag_variance(const float *mean, const float *sq_mean, float *var, int6
  * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox (key = seed, counter =
  * (s*D + d)/4 .. as in K1 with elem index s*D+d, step).  All S draws are produced in ONE pass over the
  * ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  Rows (ring, out, z1) must be 16-byte aligned:
- * ld_* % 4 == 0.  S <= URSA_DRAW_MAX_S, K <= URSA_DRAW_MAX_K.
+ * ld_* % 4 == 0.  K <= URSA_DRAW_MAX_K; any S >= 1 (draws are processed URSA_DRAW_MAX_S per launch, so the ring is
+ * read once per group of 32 draws; the Philox stream does not depend on the grouping).
  * ---------------------------------------------------------------------- */
 #define URSA_DRAW_MAX_S 32
 #define URSA_DRAW_MAX_K 24

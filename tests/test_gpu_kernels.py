@@ -183,7 +183,7 @@ def test_k2_collect_matches_reference_golden(C, mode):
 
 
 @pytest.mark.parametrize("D,K,S", [(1000, 0, 1), (1000, 5, 4), (4099, 20, 30), (1024 * 3 + 1, 24, 32), (2_050_001, 20, 8),
-                                   (513, 3, 16)])
+                                   (513, 3, 16), (4099, 20, 70), (1000, 0, 33)])      # S > 32: grouped launches, same stream
 def test_k2_draw_matches_oracle(C, D, K, S):
     rng = np.random.RandomState(D % 97)
     ld = (D + 3) // 4 * 4

@@ -10,6 +10,7 @@ rows in place, anything else sees an ordinary CPU module materialised on first
 use.
 """
 import copy
+from contextlib import nullcontext as _nullcontext
 
 import torch
 import torch.nn as nn
@@ -25,7 +26,7 @@ _STAGING = {}
 def _staging(n, ld, ldb, cuda, slots=3):
     if not cuda:
         return torch.empty(n, ld), torch.zeros(n, ldb), None
-    key = (ld, ldb)
+    key = (ld, ldb, torch.cuda.current_device() if cuda is True else cuda)
     ring = _STAGING.setdefault(key, {"next": 0, "slots": []})
     if len(ring["slots"]) < slots:
         cap = max(n, 8)
@@ -112,7 +113,9 @@ class SampleBank:
         nb = sum(b.numel() for b in first.buffers() if b.dtype == torch.float32)
         bank = cls(D, nb, device, capacity=len(models), skeleton=None)
         cuda = bank.device.type == "cuda"
-        stage_w, stage_b, done = _staging(len(models), bank.ld, bank.ldb, cuda)
+        dev_index = bank.device.index if bank.device.index is not None else (torch.cuda.current_device() if cuda else 0)
+        with torch.cuda.device(dev_index) if cuda else _nullcontext():
+            stage_w, stage_b, done = _staging(len(models), bank.ld, bank.ldb, cuda)
         for i, m in enumerate(models):
             ps = [p.detach().reshape(-1) for p in m.parameters()]
             if sum(p.numel() for p in ps) != D:
@@ -123,7 +126,8 @@ class SampleBank:
         bank.w[:len(models)].copy_(stage_w, non_blocking=True)
         bank.b[:len(models)].copy_(stage_b, non_blocking=True)
         if cuda:
-            done.record(torch.cuda.current_stream(bank.device))
+            with torch.cuda.device(dev_index):
+                done.record(torch.cuda.current_stream(bank.device))
         bank.count = len(models)
         return bank
 

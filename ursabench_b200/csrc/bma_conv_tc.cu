@@ -414,15 +414,13 @@ __global__ void __launch_bounds__(128) head_bma_kernel(const float *__restrict__
                                                         int n_samples, int C, float *__restrict__ proba_sum,
                                                         float *__restrict__ entropy_sum, float one_minus_gamma,
                                                         float gamma_over_c) {
+    // one CTA per image; warp w computes the logits of samples s = w, w + 4, .. into shared memory, then warp 0 folds
+    // them into the image's row in sample order
+    extern __shared__ float lg_s[];                       // [n_samples][C]
     __shared__ float feat_s[4][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 4 + warp;
-    if (n >= n_images) return;
-    float P[PER_LANE];
-#pragma unroll
-    for (int j = 0; j < PER_LANE; ++j) P[j] = (lane + 32 * j < C) ? proba_sum[(int64_t)n * C + lane + 32 * j] : 0.f;
-    float E = entropy_sum[n];
-    for (int s = 0; s < n_samples; ++s) {
+    const int n = blockIdx.x;
+    for (int s = warp; s < n_samples; s += 4) {
         const float *pk = packed + (int64_t)s * ld_packed;
         const float *x = act + ((int64_t)s * n_images + n) * 64 * 64;
         const float a0 = __ldg(pk + bn_off + lane), b0 = __ldg(pk + bn_off + 64 + lane);
@@ -438,18 +436,23 @@ __global__ void __launch_bounds__(128) head_bma_kernel(const float *__restrict__
         feat_s[warp][32 + lane] = f1 * (1.f / 64.f);
         __syncwarp();
         const float *fw = pk + fc_off, *fb = pk + fc_off + (int64_t)C * 64;
+        for (int c = lane; c < C; c += 32) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) acc = fmaf(feat_s[warp][k], __ldg(fw + c * 64 + k), acc);
+            lg_s[s * C + c] = acc + __ldg(fb + c);
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    float P[PER_LANE];
+#pragma unroll
+    for (int j = 0; j < PER_LANE; ++j) P[j] = (lane + 32 * j < C) ? proba_sum[(int64_t)n * C + lane + 32 * j] : 0.f;
+    float E = entropy_sum[n];
+    for (int s = 0; s < n_samples; ++s) {
         float lg[PER_LANE];
 #pragma unroll
-        for (int j = 0; j < PER_LANE; ++j) {
-            const int c = lane + 32 * j;
-            float acc = 0.f;
-            if (c < C) {
-#pragma unroll 8
-                for (int k = 0; k < 64; ++k) acc = fmaf(feat_s[warp][k], __ldg(fw + c * 64 + k), acc);
-                acc += __ldg(fb + c);
-            }
-            lg[j] = acc;
-        }
+        for (int j = 0; j < PER_LANE; ++j) lg[j] = (lane + 32 * j < C) ? lg_s[s * C + lane + 32 * j] : 0.f;
         softmax_accumulate_row<PER_LANE>(lg, C, lane, one_minus_gamma, gamma_over_c, P, E);
     }
 #pragma unroll
@@ -461,13 +464,13 @@ __global__ void __launch_bounds__(128) head_bma_kernel(const float *__restrict__
 static int launch_head_bma(const float *act, const float *packed, int64_t ld_packed, int64_t bn_off, int64_t fc_off, int nc,
                            int sc, int C, float *proba_sum, float *entropy_sum, double gamma, cudaStream_t st) {
     const float omg = (float)(1.0 - gamma), goc = (float)(gamma * 1.0 / C);      // util.py:134: gamma * 1 / C
-    const int grid = (nc + 3) / 4;
+    const size_t sm = (size_t)sc * C * sizeof(float);
     if (C <= 32)
-        head_bma_kernel<1><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+        head_bma_kernel<1><<<nc, 128, sm, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
     else if (C <= 128)
-        head_bma_kernel<4><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+        head_bma_kernel<4><<<nc, 128, sm, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
     else
-        head_bma_kernel<32><<<grid, 128, 0, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
+        head_bma_kernel<32><<<nc, 128, sm, st>>>(act, packed, ld_packed, bn_off, fc_off, nc, sc, C, proba_sum, entropy_sum, omg, goc);
     URSA_LAUNCH_CHECK("head_bma_kernel");
     return URSA_OK;
 }

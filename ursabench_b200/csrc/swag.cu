@@ -85,6 +85,7 @@ struct DrawArgs {
     const float *mean, *var, *ring, *z2, *z1;
     int64_t ld_out, ld_ring, ld_z1, D;
     int K, S;
+    int s0;                 // index of the launch's first draw within the call: Philox block base (s0 + s) * ceil(D / 4)
     float rank_div;
     uint2 key;
     uint64_t step;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawAr
     for (int i = 0; i < NI; ++i) {
         const int s = (i >> 1) * 16 + (i & 1) * 8 + nrow;
         act[i] = s < S;
-        ctr_base[i] = (uint64_t)s * (uint64_t)Dp4;
+        ctr_base[i] = (uint64_t)(a.s0 + s) * (uint64_t)Dp4;
         out_row[i] = a.out + (int64_t)s * a.ld_out;
     }
     const bool dense = S > 16 * MT - 8 && a.z1 == nullptr;                      // (nearly) all fragment rows are real draws
@@ -449,7 +450,7 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
                               int64_t ld_ring, int K, const float *z2, const float *z1, int64_t ld_z1, int S,
                               int64_t D, float rank_div, uint64_t seed, uint64_t step, void *stream) {
     URSA_REQUIRE(out && mean && var && D >= 0, "ursa_swag_draw: bad arguments");
-    URSA_REQUIRE(S >= 1 && S <= URSA_DRAW_MAX_S, "ursa_swag_draw: S must be in [1, %d]", URSA_DRAW_MAX_S);
+    URSA_REQUIRE(S >= 1, "ursa_swag_draw: S must be positive");
     URSA_REQUIRE(K >= 0 && K <= URSA_DRAW_MAX_K, "ursa_swag_draw: K must be in [0, %d]", URSA_DRAW_MAX_K);
     URSA_REQUIRE(K == 0 || (ring && z2 && rank_div != 0.f), "ursa_swag_draw: ring, z2 and rank_div are required when K > 0");
     const int64_t d4 = (D + 3) & ~(int64_t)3;
@@ -458,15 +459,25 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
     URSA_REQUIRE(!z1 || (ld_z1 % 4 == 0 && ld_z1 >= d4 && aligned16(z1)), "ursa_swag_draw: z1 rows must be 16-byte aligned");
     URSA_REQUIRE(aligned16(mean) && aligned16(var), "ursa_swag_draw: mean/var must be 16-byte aligned");
     if (D == 0) return URSA_OK;
-    DrawArgs a;
-    a.out = out; a.mean = mean; a.var = var; a.ring = ring; a.z2 = z2; a.z1 = z1;
-    a.ld_out = ld_out; a.ld_ring = ld_ring; a.ld_z1 = ld_z1; a.D = D; a.K = K; a.S = S;
-    a.rank_div = rank_div;
-    a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    a.step = step;
     cudaStream_t st = (cudaStream_t)stream;
-    if (K == 0) return S <= 16 ? launch_draw<1, false>(a, st) : launch_draw<2, false>(a, st);
-    return S <= 16 ? launch_draw<1, true>(a, st) : launch_draw<2, true>(a, st);
+    // One launch holds the fragments of up to URSA_DRAW_MAX_S draws; more draws go out in groups (the ring is re-read once
+    // per group of 32).  The Philox stream is indexed by the draw's position in the CALL, so grouping does not change it.
+    for (int g0 = 0; g0 < S; g0 += URSA_DRAW_MAX_S) {
+        const int sg = S - g0 < URSA_DRAW_MAX_S ? S - g0 : URSA_DRAW_MAX_S;
+        DrawArgs a;
+        a.out = out + (int64_t)g0 * ld_out; a.mean = mean; a.var = var; a.ring = ring;
+        a.z2 = z2 ? z2 + (int64_t)g0 * K : nullptr;
+        a.z1 = z1 ? z1 + (int64_t)g0 * ld_z1 : nullptr;
+        a.ld_out = ld_out; a.ld_ring = ld_ring; a.ld_z1 = ld_z1; a.D = D; a.K = K; a.S = sg; a.s0 = g0;
+        a.rank_div = rank_div;
+        a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        a.step = step;
+        int rc;
+        if (K == 0) rc = sg <= 16 ? launch_draw<1, false>(a, st) : launch_draw<2, false>(a, st);
+        else rc = sg <= 16 ? launch_draw<1, true>(a, st) : launch_draw<2, true>(a, st);
+        if (rc) return rc;
+    }
+    return URSA_OK;
 }
 
 extern "C" int ursa_swag_gram(const float *ring, int64_t ld_ring, int K, int64_t D, double *gram, void *stream) {

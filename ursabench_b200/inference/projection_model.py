@@ -42,8 +42,6 @@ class SubspaceModel(torch.nn.Module):
         """t: [rank] -> theta [D]; t: [S, rank] (S <= 32 proposals) -> [S, D] in the same single pass over the factor."""
         single = t.dim() == 1
         z2 = t.reshape(-1, self.rank).to(device=self._mean_pad.device, dtype=torch.float32).contiguous()
-        if z2.shape[0] > _C.DRAW_MAX_S:
-            raise ValueError("at most %d projections per call" % _C.DRAW_MAX_S)
         out = torch.empty(z2.shape[0], self._mean_pad.numel(), dtype=torch.float32, device=self._mean_pad.device)
         _C.swag_draw(out, self._mean_pad, self._zero_var, self.num_parameters, ring=self._factor_pad, z2=z2, rank_div=1.0)
         out = out[:, :self.num_parameters]

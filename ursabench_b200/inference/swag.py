@@ -88,7 +88,7 @@ class SWAG(SWA):
 
     # -- K2b -----------------------------------------------------------------------------------------------------
     def _draw_into_bank(self, num, full_cov):
-        """Draw ``num`` weight vectors into fresh bank rows with one kernel launch per <= 32 draws."""
+        """Draw ``num`` weight vectors into fresh bank rows with ONE ``ursa_swag_draw`` call (one pass over the ring per 32 draws)."""
         if full_cov and self.reference_compat:
             # reference :90 dereferences self.swag_model.subspace, which does not exist (Q7)
             raise AttributeError("'%s' object has no attribute 'subspace'" % type(self.swag_model).__name__)
@@ -107,20 +107,16 @@ class SWAG(SWA):
         if world > 1:
             gen = torch.Generator(device=self.device)
             gen.manual_seed((seed + 7919 * (rank + 1)) & 0x7FFFFFFFFFFFFFFF)
-            gen.set_offset(4 * _C.DRAW_MAX_S * _C.DRAW_MAX_K * self._draw_calls)
-        done = 0
-        while done < num:
-            s = min(_C.DRAW_MAX_S, num - done)
-            out = self.bank.w[first + done:first + done + s]
-            if self.reference_compat:
-                out[:, :D] = self._mean[:D]                    # Q5: the draw is discarded, the mean is returned
-            else:
-                z2 = torch.randn(s, K, device=self.device, generator=gen) if K else None
-                _C.swag_draw(out, self._mean, var_full, D, ring=rows if K else None, z2=z2,
-                             rank_div=float((self.subspace.max_rank - 1) ** 0.5),          # reference :95
-                             seed=seed, step=self._draw_calls * world + rank)
-                self._draw_calls += 1
-            done += s
+            gen.set_offset(4 * 4096 * _C.DRAW_MAX_K * self._draw_calls)
+        out = self.bank.w[first:first + num]
+        if self.reference_compat:
+            out[:, :D] = self._mean[:D]                        # Q5: the draw is discarded, the mean is returned
+        else:
+            z2 = torch.randn(num, K, device=self.device, generator=gen) if K else None
+            _C.swag_draw(out, self._mean, var_full, D, ring=rows if K else None, z2=z2,
+                         rank_div=float((self.subspace.max_rank - 1) ** 0.5),              # reference :95
+                         seed=seed, step=self._draw_calls * world + rank)
+            self._draw_calls += 1
         self.bank.count = first + num
         return list(range(first, first + num))
 
