@@ -61,11 +61,12 @@ struct F16Cfg {
     static constexpr int IMG_POS = T * 128;
     static constexpr int PASS_BYTES = 2 * NPLANES * IMG_POS * 16;
     static constexpr int TILE_TX = 2 * NPLANES * 2048;
-    // output staging (C <= 32, the stages that feed a stride-2 conv): one 128-row tile of [hi(C) | lo'(C)] halves per tile
-    // group, 64- / 128-byte swizzled so that row-per-lane 16-byte stores are conflict free and one TMA tensor store drains it
+    // output staging (C <= 32, the stages that feed a stride-2 conv): every epilogue warp owns a 32-row x 64-byte tile --
+    // its rows' [hi(16 ch) | lo'(16 ch)] halves -- 64-byte swizzled so that row-per-lane 16-byte stores are conflict free,
+    // drained by one TMA tensor store per warp and tile.  A global row is OUT_ROW_BYTES = 64 B per 16-channel group.
     static constexpr int OUT_ROW_BYTES = 4 * C;
-    static constexpr int STG_BYTES = C <= 32 ? 128 * OUT_ROW_BYTES : 0;
-    static constexpr size_t SMEM = (size_t)NGT * STG_BYTES + (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES +
+    static constexpr int STG_BYTES = C <= 32 ? 16 * 2048 : 0;                   // 16 epilogue warps x 2 KB
+    static constexpr size_t SMEM = (size_t)STG_BYTES + (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES +
                                    2 * BN_FLOATS * 4 + 1024;
     static_assert(T * TILE_COLS <= 512, "TMEM columns");
     static_assert(SMEM <= 227 * 1024, "shared memory");
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
     __shared__ uint32_t tmem_base_s;
 
     const uint32_t smem_base0 = (smem_u32(smem_raw) + 1023u) & ~1023u;       // staging tiles first (swizzle atoms: 1 KB aligned)
-    const uint32_t smem_base = smem_base0 + NGT * Cfg::STG_BYTES;
+    const uint32_t smem_base = smem_base0 + Cfg::STG_BYTES;
     const uint32_t planes_hi = smem_base;
     const uint32_t planes_lo = smem_base + NPL * PLANE;
     const uint32_t ring = smem_base + 2 * NPL * PLANE;
@@ -553,14 +554,15 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                             for (int i = 0; i < CPT; i += 4) op[i >> 2] = make_float4(R[j][i], R[j][i + 1], R[j][i + 2], R[j][i + 3]);
                         }
                         if (Cfg::STG_BYTES > 0 && to_global && !(DBG && (a.dbg_skip & 1))) {
-                            // y / 16 = relu(bn_next(R)) / 16, split like the planes, leaves through the tile group's staging
-                            // tile and ONE asynchronous TMA tensor store: no thread waits on a global store (round 1: 8
+                            // y / 16 = relu(bn_next(R)) / 16, split like the planes, leaves through the warp's own staging tile
+                            // and ONE asynchronous TMA tensor store per warp: no thread waits on a global store (round 1: 8
                             // STG.128 per row held every thread in the store queue for ~5 k clk per tile at the pass boundary)
-                            unsigned char *slot = stg_base + gt * Cfg::STG_BYTES;
-                            if (copier) bulk_wait_group_read0();                    // the previous store has read the slot
-                            asm volatile("bar.sync %0, %1;" ::"r"(2 + gt), "r"(128 * NGC) : "memory");
+                            // and no warp waits for another (a tile-wide staging slot with group barriers cost ~6 k clk/pass)
+                            unsigned char *slot = stg_base + (warp - 2) * 2048;
+                            if (lane == 0) bulk_wait_group_read0();                 // this warp's previous store has read the slot
+                            __syncwarp();
                             if (goff[j] >= 0) {
-                                const int sw = C == 16 ? ((m >> 1) & 3) : (m & 7);
+                                const int sw = (lane >> 1) & 3;
 #pragma unroll
                                 for (int i = 0; i < 16; i += 8) {
                                     uint32_t hw[4], lw[4];
@@ -570,15 +572,15 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                         split_h2(relu_nan(fmaf(bn[ch0 + c], R[j][c], bn[C + ch0 + c])),
                                                  relu_nan(fmaf(bn[ch0 + c + 1], R[j][c + 1], bn[C + ch0 + c + 1])), hw[jj], lw[jj]);
                                     }
-                                    const int ck = (ch0 + i) >> 3;                 // 16-byte chunk of the hi half of the row
-                                    *reinterpret_cast<uint4 *>(slot + m * Cfg::OUT_ROW_BYTES + ((ck ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                    *reinterpret_cast<uint4 *>(slot + m * Cfg::OUT_ROW_BYTES + (((C / 8 + ck) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                                    const int ck = i >> 3;                         // 16-byte chunk: hi {0, 1}, lo' {2, 3}
+                                    *reinterpret_cast<uint4 *>(slot + lane * 64 + ((ck ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                    *reinterpret_cast<uint4 *>(slot + lane * 64 + (((2 + ck) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                                 }
                             }
                             fence_proxy_async();
-                            asm volatile("bar.sync %0, %1;" ::"r"(2 + gt), "r"(128 * NGC) : "memory");
-                            if (copier) {
-                                tma_store_2d(&a.out_map, smem_u32(slot), 0, pass * Cfg::IMG_POS + 128 * t);
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, pass * Cfg::IMG_POS + 128 * t + 32 * q);
                                 bulk_commit_group();
                             }
                         }
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                 if (has_next) buf ^= 1;
             }
         }
-        if (copier) bulk_wait_group0();              // the CTA's last tensor stores have left shared memory
+        if (lane == 0) bulk_wait_group0();           // the warp's last tensor store has left shared memory
         if (dbg_me) {
             if (gt == 0) {
                 a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)d_wait_acc;

@@ -567,7 +567,7 @@ static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin
 // ---- stride-2 transition conv of the FP16-split path ------------------------------------------------------------------
 // conv1 of layer2.0 / layer3.0 (3x3, stride 2, Cin -> 2 Cin) as an implicit GEMM like conv3x3_tc_kernel, but on the FP16-split
 // operands the stage kernels use: the input is what the previous stage kernel's last epilogue stored by TMA -- rows
-// [pass][position][hi(Cin) | lo'(Cin)] halves of relu(bn1(R)) / 16 in the padded-pitch position space of that stage -- so a
+// [pass][position][hi(16 ch) | lo'(16 ch)] x (Cin / 16) halves of relu(bn1(R)) / 16 in the padded-pitch position space of that stage -- so a
 // tap's A tile is ONE 5-D TMA box (64- / 128-byte rows: hi and lo' of a pixel travel together; parity-split maps make the
 // stride-2 taps dense; out-of-bounds fill = zero padding) and the filters are K-major rows [co][tap][hi | lo'] (prep type 7).
 // Three kind::f16 MMAs per 16 channels: hi x hi -> ACC, hi x lo' -> LO, lo' x hi -> LO (the operands of the second and third
@@ -647,7 +647,7 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = make_f16_idesc(128, a.cout);
-            constexpr uint64_t LO_OFF = (uint64_t)((CIN * 2) >> 4);       // lo' half of a row, in 16-byte descriptor units
+            // a row = [hi(16 ch) | lo'(16 ch)] per 16-channel group: hi of K step ks at 64 ks bytes, lo' 32 bytes further
             for (int tap = 0; tap < 9; ++tap) {
                 const int st = tap % a.stages;
                 const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
@@ -657,10 +657,10 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
                 const uint64_t d_a = make_kmajor_desc<ROW_BYTES>(base), d_b = make_kmajor_desc<ROW_BYTES>(base + A_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < CIN / 16; ++ks) {
-                    const uint64_t ko = (uint64_t)(2 * ks);
-                    umma_f16(tmem_base, d_a + ko, d_b + ko, idesc, (tap | ks) != 0);
-                    umma_f16(tmem_base + a.cout, d_a + ko, d_b + LO_OFF + ko, idesc, (tap | ks) != 0);
-                    umma_f16(tmem_base + a.cout, d_a + LO_OFF + ko, d_b + ko, idesc, 1);
+                    const uint64_t kh = (uint64_t)(4 * ks), kl = kh + 2;          // 16-byte descriptor units
+                    umma_f16(tmem_base, d_a + kh, d_b + kh, idesc, (tap | ks) != 0);
+                    umma_f16(tmem_base + a.cout, d_a + kh, d_b + kl, idesc, (tap | ks) != 0);
+                    umma_f16(tmem_base + a.cout, d_a + kl, d_b + kh, idesc, 1);
                 }
                 umma_commit(smem_u32(&empty_bar[st]));
             }
@@ -990,8 +990,8 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                     const int img_pos = stg == 0 ? F16Cfg<16>::IMG_POS : F16Cfg<32>::IMG_POS;
                     const uint64_t dims[2] = {(uint64_t)Cs, (uint64_t)sc * ((nc + Gs - 1) / Gs) * img_pos};
                     const uint64_t sb[1] = {(uint64_t)Cs * 4};
-                    const uint32_t box[2] = {(uint32_t)Cs, 128};
-                    if (int rc = make_tensor_map(&g.out_map, A1h, 2, dims, sb, box, Cs * 4)) return rc;
+                    const uint32_t box[2] = {16, 32};               // one warp's rows x one 16-channel group's [hi | lo'] = 64 B
+                    if (int rc = make_tensor_map(&g.out_map, A1h, 2, dims, sb, box, 64)) return rc;
                     g.has_out_map = 1;
                 }
                 int rc;

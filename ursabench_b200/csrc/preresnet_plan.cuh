@@ -115,17 +115,18 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
         }
     } else if (e.type == 7) {
-        // stride-2 transition conv of the FP16-split path: K-major rows [co][tap][hi(cin) | lo'(cin)] halves
+        // stride-2 transition conv of the FP16-split path: K-major rows [co][tap][ [hi(16 ch) | lo'(16 ch)] x cin / 16 ] halves
         __half *dh = reinterpret_cast<__half *>(dst);
         const int total = e.cout * 9 * 2 * e.cin;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int k = i % (2 * e.cin);
             const int tap = (i / (2 * e.cin)) % 9;
             const int co = i / (18 * e.cin);
-            const int ci = k % e.cin;
+            const int seg = k >> 4;                                   // 16-half segments: (channel group, hi / lo')
+            const int ci = (seg >> 1) * 16 + (k & 15);
             const float w = row[e.src + ((int64_t)co * e.cin + ci) * 9 + tap];
             const __half h = __float2half_rn(w);
-            dh[i] = k < e.cin ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
+            dh[i] = (seg & 1) == 0 ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
         }
     } else if (e.type == 2) {
         for (int c = threadIdx.x; c < e.cout; c += blockDim.x) {
