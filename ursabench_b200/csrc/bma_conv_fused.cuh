@@ -53,6 +53,10 @@ struct FusedStageArgs {
     // (out_map: 2-D fp32 view, C floats x positions, box C x 128, swizzle = row bytes); replaces a_out_hi / a_out_lo
     CUtensorMap out_map;
     int has_out_map = 0;
+    // same row format for the RAW residual R / 16 (what the next stage's 1x1 stride-2 shortcut reads as a tenth K block of
+    // conv3x3s2_f16_kernel); when set, r_out is not written at all
+    CUtensorMap rrow_map;
+    int has_rrow_map = 0;
     int pi_per_image = 0;              // pi_in holds one plane image per IMAGE GROUP (shared by all samples), not per pass:
                                        // stage 1, whose input planes carry the test images for the stem conv; r_in == nullptr
                                        // then starts the residual stream at zero

@@ -65,7 +65,8 @@ struct F16Cfg {
     // its rows' [hi(16 ch) | lo'(16 ch)] halves -- 64-byte swizzled so that row-per-lane 16-byte stores are conflict free,
     // drained by one TMA tensor store per warp and tile.  A global row is OUT_ROW_BYTES = 64 B per 16-channel group.
     static constexpr int OUT_ROW_BYTES = 4 * C;
-    static constexpr int STG_BYTES = C <= 32 ? 16 * 2048 : 0;                   // 16 epilogue warps x 2 KB
+    static constexpr int STG_SLOTS = C == 16 ? 2 : 1;                           // per warp: y and R tiles (C = 32: one, reused)
+    static constexpr int STG_BYTES = C <= 32 ? 16 * 2048 * STG_SLOTS : 0;       // 16 epilogue warps x 2 KB x slots
     static constexpr size_t SMEM = (size_t)STG_BYTES + (size_t)2 * NPLANES * PLANE_BYTES + (size_t)NSLOT * SLOT_BYTES +
                                    2 * BN_FLOATS * 4 + 1024;
     static_assert(T * TILE_COLS <= 512, "TMEM columns");
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                     for (int j = 0; j < TPG; ++j) {
                         const int t = gt + j * NGT;
                         if (t >= T) continue;                       // warp-uniform
-                        const int32_t my_r = rout_of(pass, j);
+                        const int32_t my_r = (Cfg::STG_BYTES > 0 && a.has_rrow_map) ? -1 : rout_of(pass, j);
                         if (my_r >= 0 && !(DBG && (a.dbg_skip & 2))) {
                             float4 *op = reinterpret_cast<float4 *>(a.r_out + my_r);
 #pragma unroll
@@ -558,11 +559,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                             // and ONE asynchronous TMA tensor store per warp: no thread waits on a global store (round 1: 8
                             // STG.128 per row held every thread in the store queue for ~5 k clk per tile at the pass boundary)
                             // and no warp waits for another (a tile-wide staging slot with group barriers cost ~6 k clk/pass)
-                            unsigned char *slot = stg_base + (warp - 2) * 2048;
-                            if (lane == 0) bulk_wait_group_read0();                 // this warp's previous store has read the slot
+                            unsigned char *slot = stg_base + (warp - 2) * (2048 * Cfg::STG_SLOTS);
+                            const int sw = (lane >> 1) & 3;
+                            const int yrow = pass * Cfg::IMG_POS + 128 * t + 32 * q;
+                            if (lane == 0) bulk_wait_group_read0();                 // this warp's previous stores have read the slots
                             __syncwarp();
                             if (goff[j] >= 0) {
-                                const int sw = (lane >> 1) & 3;
 #pragma unroll
                                 for (int i = 0; i < 16; i += 8) {
                                     uint32_t hw[4], lw[4];
@@ -580,8 +582,34 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                             fence_proxy_async();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, pass * Cfg::IMG_POS + 128 * t + 32 * q);
+                                tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, yrow);
                                 bulk_commit_group();
+                            }
+                            if (a.has_rrow_map) {
+                                // the raw residual R / 16 in the same row format (the next stage's shortcut conv reads it)
+                                unsigned char *rslot = slot + (Cfg::STG_SLOTS == 2 ? 2048 : 0);
+                                if (Cfg::STG_SLOTS == 1) {
+                                    if (lane == 0) bulk_wait_group_read0();
+                                    __syncwarp();
+                                }
+                                if (goff[j] >= 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; i += 8) {
+                                        uint32_t hw[4], lw[4];
+#pragma unroll
+                                        for (int jj = 0; jj < 4; ++jj)
+                                            split_h2(R[j][i + 2 * jj] * kActDown, R[j][i + 2 * jj + 1] * kActDown, hw[jj], lw[jj]);
+                                        const int ck = i >> 3;
+                                        *reinterpret_cast<uint4 *>(rslot + lane * 64 + ((ck ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                        *reinterpret_cast<uint4 *>(rslot + lane * 64 + (((2 + ck) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                                    }
+                                }
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&a.rrow_map, smem_u32(rslot), gc * 16, yrow);
+                                    bulk_commit_group();
+                                }
                             }
                         }
                         if (has_next) {

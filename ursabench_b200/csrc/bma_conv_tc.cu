@@ -575,6 +575,7 @@ static int launch_conv_tc(const float *a_hi, const float *a_lo, int hin, int cin
 struct ConvS2Maps {
     CUtensorMap a[4];                  // index = h-parity * 2 + w-parity of (kh - 1, kw - 1)
     CUtensorMap b;
+    CUtensorMap r, bsc;                // shortcut: even-pixel view of the raw residual rows, 1x1 filters (has_sc)
 };
 struct ConvS2Args {
     int cout, hout, n_images, stages;
@@ -584,6 +585,10 @@ struct ConvS2Args {
     unsigned char *pi_out;             // plane image of the consumer stage (bma_conv_fused16.cuh)
     int pi_G, pi_pitch, pi_img_pos, pi_nplanes, pi_ngroups;
     int64_t pi_pass_bytes;
+    // the block's 1x1 stride-2 shortcut (reference models/preresnet.py:122-128, applied to the RAW block input) as a tenth
+    // K block into its own accumulator columns: Rs = W_ds * R, written NHWC fp32 for the stage kernel's residual registers
+    int has_sc;
+    float *rs_out;
 };
 
 template <int CIN>
@@ -608,7 +613,8 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     const uint32_t b_bytes = (uint32_t)a.cout * ROW_BYTES;
     const uint32_t stage_bytes = A_BYTES + b_bytes;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_cols = 2 * a.cout;                      // [ACC | LO]: 64 or 128 columns
+    const uint32_t tmem_cols = (a.has_sc ? 4 : 2) * a.cout;     // [ACC | LO | SC_ACC | SC_LO]: 64 .. 256 columns
+    const int n_kb = a.has_sc ? 10 : 9;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -631,7 +637,7 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     if (warp == 0) {
         if (elect_one()) {
             const int pass_in = s * a.n_groups_in + n0 / a.g_in, g0 = n0 % a.g_in;
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < n_kb; ++tap) {
                 const int st = tap % a.stages;
                 const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
                 const int kh = tap / 3, kw = tap - kh * 3;
@@ -639,6 +645,11 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
                 const uint32_t fb = smem_u32(&full_bar[st]);
                 mbar_expect_tx_a(fb, stage_bytes);
                 const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+                if (tap == 9) {                                          // shortcut: pixels (2 oh, 2 ow) of the raw rows
+                    tma_load_5d_a(base, &maps.r, 0, 0, h0, g0, pass_in, fb);
+                    tma_load_3d_a(base + A_BYTES, &maps.bsc, 0, 0, s, fb);
+                    continue;
+                }
                 const int mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);      // parity of (kh - 1, kw - 1)
                 tma_load_5d_a(base, &maps.a[mi], 0, (kw - 1) >> 1, h0 + ((kh - 1) >> 1), g0, pass_in, fb);
                 tma_load_3d_a(base + A_BYTES, &maps.b, tap * 2 * CIN, 0, s, fb);
@@ -648,19 +659,21 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
         if (elect_one()) {
             const uint32_t idesc = make_f16_idesc(128, a.cout);
             // a row = [hi(16 ch) | lo'(16 ch)] per 16-channel group: hi of K step ks at 64 ks bytes, lo' 32 bytes further
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < n_kb; ++tap) {
                 const int st = tap % a.stages;
                 const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
                 mbar_wait_a(smem_u32(&full_bar[st]), ph);
                 tc_fence_after();
                 const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
                 const uint64_t d_a = make_kmajor_desc<ROW_BYTES>(base), d_b = make_kmajor_desc<ROW_BYTES>(base + A_BYTES);
+                const uint32_t d0 = tmem_base + (tap == 9 ? 2 * a.cout : 0);      // shortcut block: its own accumulators
+                const int first = tap == 9 ? 9 : 0;
 #pragma unroll
                 for (int ks = 0; ks < CIN / 16; ++ks) {
                     const uint64_t kh = (uint64_t)(4 * ks), kl = kh + 2;          // 16-byte descriptor units
-                    umma_f16(tmem_base, d_a + kh, d_b + kh, idesc, (tap | ks) != 0);
-                    umma_f16(tmem_base + a.cout, d_a + kh, d_b + kl, idesc, (tap | ks) != 0);
-                    umma_f16(tmem_base + a.cout, d_a + kl, d_b + kh, idesc, 1);
+                    umma_f16(d0, d_a + kh, d_b + kh, idesc, (tap != first) || ks != 0);
+                    umma_f16(d0 + a.cout, d_a + kh, d_b + kl, idesc, (tap != first) || ks != 0);
+                    umma_f16(d0 + a.cout, d_a + kl, d_b + kh, idesc, 1);
                 }
                 umma_commit(smem_u32(&empty_bar[st]));
             }
@@ -704,6 +717,24 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
                 *reinterpret_cast<uint4 *>(pi_px + (int64_t)a.pi_nplanes * a.pi_img_pos * 16 + pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
+        if (a.has_sc) {
+            float *rp = a.rs_out + ((((int64_t)s * a.n_images + n) * a.hout + (h0 + h)) * a.hout + w) * a.cout;
+            for (int c0 = 0; c0 < a.cout; c0 += 16) {
+                uint32_t ra[16], rl[16];
+                tmem_ld<16>(tl + (uint32_t)(2 * a.cout + c0), ra);
+                tmem_ld<16>(tl + (uint32_t)(3 * a.cout + c0), rl);
+                tmem_ld_wait();
+                if (!valid) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)                   // operand rows were R / 16
+                        v[e] = fmaf(__uint_as_float(rl[i + e]), kLoUnscale, __uint_as_float(ra[i + e])) * kActUp;
+                    *reinterpret_cast<float4 *>(rp + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -715,8 +746,9 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
 
 // a_rows: the producer stage's TMA-stored rows (stage geometry CIN: H = hin, pitch, positions per pass, images per pass)
 template <int CIN>
-static int launch_conv_s2_f16(const void *a_rows, int hin, int pitch_in, int img_pos_in, int g_in, int sc, int nc,
-                              const float *packed, int64_t ld_packed, int64_t w_off, ConvS2Args g, cudaStream_t st) {
+static int launch_conv_s2_f16(const void *a_rows, const void *r_rows, int hin, int pitch_in, int img_pos_in, int g_in, int sc,
+                              int nc, const float *packed, int64_t ld_packed, int64_t w_off, int64_t ds_off, ConvS2Args g,
+                              cudaStream_t st) {
     constexpr int ROWB = CIN * 4;
     const int hout = hin / 2, cout = 2 * CIN;
     const int n_groups_in = (nc + g_in - 1) / g_in;
@@ -731,6 +763,18 @@ static int launch_conv_s2_f16(const void *a_rows, int hin, int pitch_in, int img
                                 (uint64_t)img_pos_in * ROWB};
         const uint32_t box[5] = {(uint32_t)2 * CIN, (uint32_t)WT, (uint32_t)HT, (uint32_t)NT, 1};
         if (int rc = make_tensor_map_t(&maps.a[par], base, 5, dims, sb, box, ROWB, 1)) return rc;
+        if (par == 0 && r_rows != nullptr)
+            if (int rc = make_tensor_map_t(&maps.r, r_rows, 5, dims, sb, box, ROWB, 1)) return rc;
+    }
+    g.has_sc = r_rows != nullptr ? 1 : 0;
+    if (g.has_sc) {
+        const uint64_t dims[3] = {(uint64_t)2 * CIN, (uint64_t)cout, (uint64_t)sc};
+        const uint64_t sb[2] = {(uint64_t)2 * CIN * 2, (uint64_t)ld_packed * 4};
+        const uint32_t box[3] = {(uint32_t)2 * CIN, (uint32_t)cout, 1};
+        if (int rc = make_tensor_map_t(&maps.bsc, packed + ds_off, 3, dims, sb, box, ROWB, 1)) return rc;
+    } else {
+        maps.r = maps.a[0];
+        maps.bsc = maps.a[0];
     }
     {
         const uint64_t dims[3] = {(uint64_t)18 * CIN, (uint64_t)cout, (uint64_t)sc};
@@ -929,9 +973,9 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                 } else {
                     // transition block: 1x1 stride-2 shortcut on the raw stream, stride-2 conv1 on the layer-wise kernel
                     const NetPlan::Block &B0 = pl.blocks[stg][0];
-                    {
+                    if (!f16) {     // FP16-split path: the shortcut is a tenth K block of conv3x3s2_f16_kernel (below)
                         ProfScope ps(URSA_PROF_SHORTCUT, st);
-                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs, f16 ? 1 : 0);
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B0.ds, ch, 2 * ch, hw / 2, nc, Rs, 0);
                         URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
                     }
                     if (f16) {
@@ -947,14 +991,15 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                         c2.pi_nplanes = stg == 1 ? F16Cfg<32>::NPLANES : F16Cfg<64>::NPLANES;
                         c2.pi_ngroups = (nc + Gn - 1) / Gn;
                         c2.pi_pass_bytes = stg == 1 ? F16Cfg<32>::PASS_BYTES : F16Cfg<64>::PASS_BYTES;
+                        c2.rs_out = Rs;                     // + the block's 1x1 shortcut on the raw rows (A2h region)
                         ProfScope ps(URSA_PROF_CONV_S2, st);
                         int rc;
                         if (stg == 1)
-                            rc = launch_conv_s2_f16<16>(A1h, 32, F16Cfg<16>::PITCH, F16Cfg<16>::IMG_POS, F16Cfg<16>::G, sc, nc, packed,
-                                                        pl.packed_floats, B0.w1, c2, st);
+                            rc = launch_conv_s2_f16<16>(A1h, A2h, 32, F16Cfg<16>::PITCH, F16Cfg<16>::IMG_POS, F16Cfg<16>::G, sc, nc,
+                                                        packed, pl.packed_floats, B0.w1, B0.ds16, c2, st);
                         else
-                            rc = launch_conv_s2_f16<32>(A1h, 16, F16Cfg<32>::PITCH, F16Cfg<32>::IMG_POS, F16Cfg<32>::G, sc, nc, packed,
-                                                        pl.packed_floats, B0.w1, c2, st);
+                            rc = launch_conv_s2_f16<32>(A1h, A2h, 16, F16Cfg<32>::PITCH, F16Cfg<32>::IMG_POS, F16Cfg<32>::G, sc, nc,
+                                                        packed, pl.packed_floats, B0.w1, B0.ds16, c2, st);
                         if (rc) return rc;
                     } else {
                     ConvTcArgs c1;
@@ -993,6 +1038,8 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
                     const uint32_t box[2] = {16, 32};               // one warp's rows x one 16-channel group's [hi | lo'] = 64 B
                     if (int rc = make_tensor_map(&g.out_map, A1h, 2, dims, sb, box, 64)) return rc;
                     g.has_out_map = 1;
+                    if (int rc = make_tensor_map(&g.rrow_map, A2h, 2, dims, sb, box, 64)) return rc;   // raw residual rows
+                    g.has_rrow_map = 1;
                 }
                 int rc;
                 {

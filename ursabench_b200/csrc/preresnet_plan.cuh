@@ -98,6 +98,20 @@ static __global__ void __launch_bounds__(256) preresnet_prep_kernel(const PrepTa
             const __half h = __float2half_rn(w);
             dh[i] = n < C ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
         }
+    } else if (e.type == 10) {
+        // 1x1 stride-2 shortcut of the FP16-split path: K-major rows [co][ [hi(16 ch) | lo'(16 ch)] x cin / 16 ] halves, the
+        // layout of one tap of type 7 (it runs as a tenth K block of conv3x3s2_f16_kernel on the raw residual rows)
+        __half *dh = reinterpret_cast<__half *>(dst);
+        const int total = e.cout * 2 * e.cin;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int k = i % (2 * e.cin);
+            const int co = i / (2 * e.cin);
+            const int seg = k >> 4;
+            const int ci = (seg >> 1) * 16 + (k & 15);
+            const float w = row[e.src + (int64_t)co * e.cin + ci];          // PyTorch [co][ci][1][1]
+            const __half h = __float2half_rn(w);
+            dh[i] = (seg & 1) == 0 ? h : __float2half_rn((w - __half2float(h)) * 2048.f);
+        }
     } else if (e.type == 9) {
         // network conv1 (3 -> 16) as a 16 -> 16 conv of the FP16-split stage kernel: type-6 layout with the 13 missing
         // input channels zero, so the stem is just the first conv of the stage-1 chain (its input planes carry the image)
@@ -147,7 +161,8 @@ struct NetPlan {
     int64_t packed_floats;
     int64_t conv1_w;
     int64_t conv1_w16;          // tc == 3: conv1 packed as a 16 -> 16 FP16-split stage conv (type 9), else -1
-    struct Block { int64_t bn1, w1, bn2, w2, ds, w1_lo, w2_lo; } blocks[3][8];   // w*_lo: tensor-core plan only
+    struct Block { int64_t bn1, w1, bn2, w2, ds, w1_lo, w2_lo, ds16; } blocks[3][8];   // w*_lo: tensor-core plan only;
+                                                                                       // ds16: type-10 shortcut (tc == 3)
     int64_t bn_final, fc;
     int64_t D, NB;              // expected bank / buffer row lengths
 };
@@ -205,6 +220,14 @@ static bool build_plan(int depth, int C, NetPlan &pl, int tc = 0) {
             B.w2 = tc == 2 ? add_conv(5, w, w, 1) : (tc == 3 ? add_conv(6, w, w, 0) : add_conv(t3, w, w));
             B.w2_lo = last_lo;
             B.ds = (b == 0 && st > 0) ? add_conv(1, inpl, w) : -1;
+            B.ds16 = -1;
+            if (tc == 3 && B.ds >= 0) {                 // second packing of the same weights (src was advanced by add_conv)
+                dst = (dst + 3) & ~(int64_t)3;
+                PrepEntry &e = t.e[t.n++];
+                e.type = 10; e.cin = inpl; e.cout = w; e.src = src - (int64_t)inpl * w; e.src2 = 0; e.buf = 0; e.dst = dst; e.dst2 = 0;
+                B.ds16 = dst;
+                dst += (int64_t)inpl * w;               // cout * 2 cin halves
+            }
             inpl = w;
         }
     }
