@@ -403,6 +403,51 @@ def gen_prediction_preresnet20(R):
     print("prediction_preresnet20.npz")
 
 
+def gen_ess(R):
+    """util.elliptical_slice (util.py:287-354) and util.log_pdf (:260-274) of the live reference: (a) 25 chained ESS updates
+    of a 5-d correlated-Gaussian log density with seeded ``np.random`` (thetas, log densities, number of density calls),
+    (b) ``log_pdf`` of three subspace points for an MLP(16, 20, 3) over a 3-batch loader at temperature 7."""
+    util = R["util"]
+    from URSABench.inference.projection_model import SubspaceModel
+    out = {}
+    rng = np.random.RandomState(5)
+    A = rng.randn(5, 5)
+    prec = A @ A.T + 0.5 * np.eye(5)
+    mu = rng.randn(5)
+    calls = [0]
+
+    def lnpdf(th, subspace):
+        calls[0] += 1
+        d = th - mu
+        return float(-0.5 * d @ prec @ d)
+
+    np.random.seed(123)
+    theta = np.zeros(5)
+    thetas, lps, ncalls = [], [], []
+    for _ in range(25):
+        prior = np.random.normal(loc=0.0, scale=2.0, size=5)
+        theta, lp = util.elliptical_slice(initial_theta=theta.copy(), prior=prior, lnpdf=lnpdf, subspace=None)
+        thetas.append(theta.copy()); lps.append(lp); ncalls.append(calls[0])
+    out["ess/prec"], out["ess/mu"] = prec, mu
+    out["ess/thetas"], out["ess/lps"], out["ess/ncalls"] = np.stack(thetas), np.array(lps), np.array(ncalls)
+    # (b) log_pdf
+    torch.manual_seed(9)
+    model = R["models"].mlp.MLP(16, 20, 3)
+    D = sum(p.numel() for p in model.parameters())
+    mean = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    factor = torch.randn(4, D) * 0.05
+    x = torch.randn(70, 1, 4, 5)
+    y = torch.randint(0, 3, (70,))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=32, shuffle=False)
+    sub = SubspaceModel(mean, factor)
+    ts = np.array([[0.0, 0.0, 0.0, 0.0], [0.5, -1.0, 0.25, 2.0], [-3.0, 1.5, 0.0, 0.7]])
+    out["logpdf/mean"], out["logpdf/factor"] = mean.numpy(), factor.numpy()
+    out["logpdf/x"], out["logpdf/y"], out["logpdf/t"] = x.numpy(), y.numpy(), ts
+    out["logpdf/value"] = np.array([util.log_pdf(t, sub, model, loader, util.cross_entropy, 7.0, torch.device("cpu")) for t in ts])
+    np.savez_compressed(os.path.join(OUT, "ess.npz"), **out)
+    print("ess.npz", out["ess/ncalls"][-1], out["logpdf/value"])
+
+
 def gen_pca_space(R):
     """PCASpace.collect_vector / get_space (inference/subspaces.py:103-156, integer pca_rank) and SubspaceModel.forward
     (inference/projection_model.py:6-14) on the live reference: ring wrap (11 collects into max_rank 8), pca_rank 5; a
@@ -608,7 +653,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, prediction_preresnet20=gen_prediction_preresnet20, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, prediction_preresnet20=gen_prediction_preresnet20, ess=gen_ess, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

@@ -4,6 +4,7 @@ from .csgld import cSGLD
 from .hmc import HMC
 from .inference_base import _Inference
 from .optim_sghmc import optimSGHMC
+from .pca_subspace import PCASubspaceSampler
 from .sghmc import SGHMC
 from .sgld import SGLD
 from .projection_model import SubspaceModel
@@ -12,4 +13,4 @@ from .swa import SWA
 from .swag import SWAG
 
 __all__ = ["_Inference", "optimSGHMC", "SGHMC", "SGLD", "cSGHMC", "cSGLD", "SWA", "SWAG", "HMC", "Subspace",
-           "CovarianceSpace", "PCASpace", "SubspaceModel"]
+           "CovarianceSpace", "PCASpace", "SubspaceModel", "PCASubspaceSampler"]
