@@ -181,7 +181,8 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
  * K3  sample-batched BMA forward, MLP  (replaces S x ceil(N/B) calls of model(x) + the accumulation above
  *     for models/mlp.py:8-23).  bank: [S, ld_bank] flat weight vectors in model.parameters() order
  *     (fc1.weight[h,in], fc1.bias[h], fc2.weight[h,h], fc2.bias[h], fc3.weight[C,h], fc3.bias[C]).
- *     x: [N, in_dim].  Accumulates into proba_sum [N, C] / entropy_sum [N] in sample order.
+ *     x: [N, in_dim].  Accumulates into proba_sum [N, C] / entropy_sum [N] in sample order (layer 3 writes logits to
+ *     the workspace, then ONE ursa_bma_accumulate launch per chunk: tiles of different samples finish in any order).
  *     logits_out (nullable): [S, N, C].
  *     algo: URSA_ALGO_FFMA (fp32 CUDA cores) or URSA_ALGO_TCGEN05 (3xTF32 on tcgen05 + TMA).
  * ---------------------------------------------------------------------- */
@@ -216,6 +217,11 @@ int ursa_gemm_nt_3xtf32(const float *A, int64_t lda, int64_t a_batch_stride, con
  *     bank: [S, ld_bank] parameters; bufbank: [S, ld_buf] BatchNorm running stats in named_buffers()
  *     order with the int64 num_batches_tracked entries dropped (mean, var per BN layer);
  *     x: [N, 3, 32, 32] NCHW.  Eval-mode BN (eps 1e-5) + ReLU are folded into the consuming conv.
+ *     URSA_ALGO_TCGEN05_FUSED_F16 (the product path): conv1 + stage 1, stage 2 and stage 3 each run as ONE persistent
+ *     tcgen05 kernel with the activations resident in shared memory (inputs arrive as TMA-copied plane images, outputs
+ *     leave by TMA tensor stores), the two stride-2 convs with their 1x1 shortcuts as one FP16-split implicit GEMM each,
+ *     and -- when logits_out is NULL -- the head kernel ends in the softmax-average / entropy epilogue (no logits round
+ *     trip).  Other algos write logits to the workspace and call the ursa_bma_accumulate kernel.
  * ---------------------------------------------------------------------- */
 size_t ursa_bma_preresnet_workspace(int S, int64_t N, int depth, int C, int algo);
 int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf,
@@ -228,7 +234,8 @@ int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *
  *     models/wideresnet.py:78-120 -- BASELINE.json configs[2] is WRN-28-10 with C = 100).
  *     depth = 6n+4 (n <= 8), widen even in [2, 16].  bank / bufbank / x as for the PreResNet entry point.
  *     One posterior sample at a time over chunks of images; every 3x3 conv (and the 1x1 shortcut convs,
- *     folded into conv2's K loop) runs as a persistent 3xTF32 tcgen05 implicit GEMM.  algo must be
+ *     folded into conv2's K loop) runs as a persistent 3xTF32 tcgen05 implicit GEMM; the head kernel (BN + ReLU +
+ *     pool + linear) ends in the softmax-average / entropy epilogue.  algo must be
  *     URSA_ALGO_TCGEN05; the workspace query returns 0 for an unsupported shape.
  * ---------------------------------------------------------------------- */
 size_t ursa_bma_wrn_workspace(int S, int64_t N, int depth, int widen, int C, int algo);
