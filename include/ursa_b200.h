@@ -213,6 +213,19 @@ int ursa_gemm_nt_3xtf32(const float *A, int64_t lda, int64_t a_batch_stride, con
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * K5' chain-batched likelihood gradient of the 3-layer MLP for HMC (replaces the per-chain autograd pass hamiltorch runs
+ *     per leapfrog step, inference/hmc.py:71-75; BASELINE.json configs[3]).  theta: [C, ld] chain states in the MLP's flat
+ *     layout (fc1.weight[h,in], fc1.bias, fc2.weight[h,h], fc2.bias, fc3.weight[k,h], fc3.bias); x: [N, in] shared by all
+ *     chains; y: [N] int64 labels.  grad[c, :D] = d/dtheta sum_n CE(f_theta_c(x_n), y_n), ce[c] = that sum (fp32, fixed
+ *     reduction order).  Eight 3xTF32 tcgen05 GEMMs; every operand is produced in split form by the epilogue of the GEMM
+ *     before it, activations also transposed for the weight-gradient GEMMs.  in % 4 == 0, h % 4 == 0, k <= 128.
+ * ---------------------------------------------------------------------- */
+size_t ursa_hmc_mlp_grad_workspace(int C, int64_t N, int in_dim, int hidden, int n_classes);
+int ursa_hmc_mlp_grad(const float *theta, int64_t ld, int C, const float *x, const int64_t *y, int64_t N,
+                      int in_dim, int hidden, int n_classes, float *grad, float *ce,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * K3  sample-batched BMA forward, PreResNet (BasicBlock, depth = 6n+2 < 44; models/preresnet.py:90-151)
  *     bank: [S, ld_bank] parameters; bufbank: [S, ld_buf] BatchNorm running stats in named_buffers()
  *     order with the int64 num_batches_tracked entries dropped (mean, var per BN layer);

@@ -242,7 +242,15 @@ def test_hmc_mlp_gemm_gradient_matches_vmap_grad():
     hyp = {"step_size": 1e-3, "num_samples": 1, "L": 2, "tau": 10.0, "burn": 0, "mass": 1.0, "num_chains": 5}
     inf = inference.HMC(hyperparameters=dict(hyp), model=models.MLP(40, 36, 7), train_loader=loader, device=DEV)
     inf.sample()
-    assert inf.grad_engine == "mlp_gemm"                    # fp32 GEMM formulation (the faster of the two fast paths)
+    assert inf.grad_engine == "mlp_tcgen05_fused"           # the hand-written chain-batched forward + backward is the default
+    th = torch.randn(5, inf.ld, device=DEV) * 0.2
+    g0, ce0 = torch.zeros_like(th), torch.zeros(5, device=DEV)
+    inf._grad(th, g0, ce0)                                   # ursa_hmc_mlp_grad
+    inf._grad_fn = inf._build_grad_fn()                      # vmap(grad) of the module
+    gv, cev = torch.zeros_like(th), torch.zeros(5, device=DEV)
+    inf._grad(th, gv, cev)
+    assert (g0 - gv)[:, :inf.D].abs().max().item() < 2e-5 * gv.abs().max().item()
+    assert torch.allclose(ce0, cev, rtol=2e-6, atol=1e-4)
     from ursabench_b200.tasks._engine import _arch_of
     theta = torch.randn(5, inf.ld, device=DEV) * 0.2
     inf._grad_fn = inf._build_grad_fn_mlp_tc(_arch_of(inf.model))        # the same GEMMs on ursa_gemm_nt_3xtf32
@@ -302,3 +310,39 @@ def test_hmc_trajectory_graph_replay_equals_eager():
         outs.append((torch.stack([inf.bank.w[h._ursa_row, :inf.D] for h in handles]).clone(), inf.acceptance_rate.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert float(outs[0][1].mean()) > 0.2
+
+
+@pytest.mark.parametrize("C,N,in_dim,hid,ncls", [(3, 70, 36, 40, 7), (2, 257, 784, 200, 10), (1, 1000, 16, 8, 3), (4, 33, 20, 132, 100)])
+def test_hmc_mlp_fused_gradient_matches_autograd(C, N, in_dim, hid, ncls):
+    """``ursa_hmc_mlp_grad`` (eight 3xTF32 tcgen05 GEMMs with split / transposed operands handed from epilogue to epilogue)
+    against fp64 autograd of the same MLP: gradient of the summed cross entropy per chain, and its value; ragged point
+    counts, hidden widths that are not a multiple of the N tile, more classes than one 16-column chunk."""
+    from ursabench_b200 import _C
+    torch.manual_seed(C * 1000 + N)
+    D = hid * in_dim + hid + hid * hid + hid + ncls * hid + ncls
+    ld = (D + 3) // 4 * 4
+    theta = torch.zeros(C, ld, device=DEV)
+    theta[:, :D] = torch.randn(C, D, device=DEV) * (1.5 / in_dim ** 0.5)
+    x = torch.randn(N, in_dim, device=DEV)
+    y = torch.randint(0, ncls, (N,), device=DEV)
+    g = torch.full((C, ld), 7.0, device=DEV)
+    ce = torch.zeros(C, device=DEV)
+    ws = _C.hmc_mlp_grad(theta, x, y, in_dim, hid, ncls, g, ce)
+    assert ws is not None
+    o = [0, hid * in_dim, hid * in_dim + hid, hid * in_dim + hid + hid * hid, hid * in_dim + 2 * hid + hid * hid,
+         hid * in_dim + 2 * hid + hid * hid + ncls * hid, D]
+    for c in range(C):
+        t = theta[c, :D].double().clone().requires_grad_(True)
+        W1, b1, W2, b2, W3, b3 = (t[o[i]:o[i + 1]] for i in range(6))
+        h1 = torch.relu(x.double() @ W1.view(hid, in_dim).t() + b1)
+        h2 = torch.relu(h1 @ W2.view(hid, hid).t() + b2)
+        loss = torch.nn.functional.cross_entropy(h2 @ W3.view(ncls, hid).t() + b3, y, reduction="sum")
+        loss.backward()
+        scale = t.grad.abs().max().item()
+        assert (g[c, :D].double() - t.grad).abs().max().item() < 2e-5 * scale, (c, scale)
+        assert abs(ce[c].item() - loss.item()) < 2e-6 * abs(loss.item()) + 1e-4
+    if ld > D:
+        assert (g[:, D:] == 7.0).all()                        # padding untouched
+    with pytest.raises(ValueError):
+        _C.hmc_mlp_grad(theta, x, y.int(), in_dim, hid, ncls, g, ce)
+    assert _C.lib().ursa_hmc_mlp_grad_workspace(2, 10, 30, 40, 5) == 0      # in_dim % 4 != 0: not covered

@@ -48,6 +48,8 @@ SIGNATURES = {
     "ursa_gemm_nt_3xtf32_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_gemm_nt_3xtf32": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _i64, _i32, _i32,
                                    _vp, _sz, _vp]),
+    "ursa_hmc_mlp_grad_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
+    "ursa_hmc_mlp_grad": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
     "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                     _sz, _i32, _vp]),
@@ -336,6 +338,28 @@ def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
     rc = lib().ursa_wrn_bn_update(_ptr(bank_row), _ptr(buf_row), _ptr(x), N, batch, depth, widen, C, _ptr(workspace),
                                   workspace.numel() * workspace.element_size(), _stream(x))
     _check(rc, "ursa_wrn_bn_update")
+    return workspace
+
+
+@_on_device
+def hmc_mlp_grad(theta, x, y, in_dim, hidden, n_classes, grad, ce, workspace=None):
+    """Chain-batched MLP likelihood gradient on tcgen05 (see ursa_hmc_mlp_grad).  theta, grad: [C, ld]; x: [N, in];
+    y: [N] int64; ce: [C].  Returns the workspace (None if the shape is not covered)."""
+    _dev_f32(theta, "theta"), _dev_f32(x, "x"), _dev_f32(grad, "grad"), _dev_f32(ce, "ce")
+    if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous():
+        raise ValueError("y must be a contiguous CUDA int64 tensor")
+    C, ld = theta.shape
+    N = x.shape[0]
+    if tuple(grad.shape) != (C, ld) or ce.numel() < C or x.shape[1] != in_dim or y.numel() != N:
+        raise ValueError("hmc_mlp_grad: shape mismatch")
+    need = lib().ursa_hmc_mlp_grad_workspace(C, N, in_dim, hidden, n_classes)
+    if need == 0:
+        return None
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_hmc_mlp_grad(_ptr(theta), ld, C, _ptr(x), y.data_ptr(), N, in_dim, hidden, n_classes, _ptr(grad), _ptr(ce),
+                                 _ptr(workspace), workspace.numel() * workspace.element_size(), _stream(theta))
+    _check(rc, "ursa_hmc_mlp_grad")
     return workspace
 
 

@@ -39,10 +39,19 @@ struct TcGemmArgs {
     int BN;                       // N tile (multiple of 16, <= 256)
     int k_blocks;                 // Kp / 32
     int a_batched;                // 0: A shared by all samples (layer 1 input)
+    int b_shared = 0;             // 1: B shared by all samples (the data matrix of the MLP weight-gradient GEMM)
     int relu;
     int stages;                   // smem ring depth (<= TC_STAGES)
     uint32_t tmem_cols;
     int seg, ntbuf;               // K blocks per TMEM accumulation segment; rotating accumulators (column pitch BN)
+    // chain-batched MLP gradient (ursa_hmc_mlp_grad): optional extras of the epilogue
+    const float *mask = nullptr;  // [S][M][ld_mask]: v *= (mask > 0)  (ReLU derivative of the layer's forward activation)
+    int ld_mask = 0;
+    int64_t mask_batch_stride = 0;
+    float *outT_hi = nullptr, *outT_lo = nullptr;   // TRANSPOSED copy [S][features][ld_t] (lo null: plain fp32): the operand of
+    int ld_t = 0;                                   // the weight-gradient GEMMs, which contract over the rows of this one;
+    int64_t outT_batch_stride = 0;                  // rows M .. ld_t of it are written as zeros
+    int t_valid = 0;                                // plain transposed store: features [0, t_valid) only
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -99,8 +108,8 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const int k0 = kb * TC_BK;
                 tma_load_3d_a(base, &tm_a_hi, k0, m_blk * TC_BM, a_b, fb);
                 tma_load_3d_a(base + TC_A_BYTES, &tm_a_lo, k0, m_blk * TC_BM, a_b, fb);
-                tma_load_3d_a(base + 2 * TC_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, s, fb);
-                tma_load_3d_a(base + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, s, fb);
+                tma_load_3d_a(base + 2 * TC_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, a.b_shared ? 0 : s, fb);
+                tma_load_3d_a(base + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, a.b_shared ? 0 : s, fb);
                 if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
             }
         }
@@ -169,8 +178,11 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
         const float *bias = a.bias + (int64_t)s * a.bias_stride;
         const bool split = a.out_lo != nullptr;
-        float *ohi = a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out;
+        float *ohi = a.out_hi ? a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
         float *olo = split ? a.out_lo + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+        const float *mrow = a.mask ? a.mask + (int64_t)s * a.mask_batch_stride + row * a.ld_mask : nullptr;
+        float *thi = a.outT_hi ? a.outT_hi + (int64_t)s * a.outT_batch_stride + row : nullptr;
+        float *tlo = a.outT_lo ? a.outT_lo + (int64_t)s * a.outT_batch_stride + row : nullptr;
 #pragma unroll
         for (int j = 0; j < TC_EPI_CHUNKS; ++j) {
             const int c0 = j * 16;
@@ -185,7 +197,12 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 if (a.relu) x = fmaxf(x, 0.f);
                 v[i] = x;
             }
-            if (row < a.M) {
+            if (mrow != nullptr && row < a.M) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (col0 + i < a.n_valid && !(__ldg(mrow + col0 + i) > 0.f)) v[i] = 0.f;
+            }
+            if (row < a.M && ohi != nullptr) {
                 if (split) {
                     if (col0 + 16 <= a.ld_out) {
 #pragma unroll
@@ -202,6 +219,22 @@ mlp_tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (col0 + i < a.n_valid) ohi[col0 + i] = v[i];
+                }
+            }
+            if (thi != nullptr && row < a.ld_t) {
+                // transposed copy: lanes are consecutive rows, so every store of a warp is one contiguous 128-byte segment
+                const bool live = row < a.M;
+                if (tlo != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x = live ? v[i] : 0.f, h = rn_tf32(x);
+                        thi[(int64_t)(col0 + i) * a.ld_t] = h;
+                        tlo[(int64_t)(col0 + i) * a.ld_t] = rn_tf32(x - h);
+                    }
+                } else if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (col0 + i < a.t_valid) thi[(int64_t)(col0 + i) * a.ld_t] = v[i];
                 }
             }
         }
@@ -291,8 +324,8 @@ static int launch_tc_gemm(const float *a_hi, const float *a_lo, int64_t a_rows, 
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (int rc = make_tmap(&ta_hi, a_hi, Kp, a_rows, a_batch, TC_BM)) return rc;
     if (int rc = make_tmap(&ta_lo, a_lo, Kp, a_rows, a_batch, TC_BM)) return rc;
-    if (int rc = make_tmap(&tb_hi, b_hi, Kp, Np, batch, BN)) return rc;
-    if (int rc = make_tmap(&tb_lo, b_lo, Kp, Np, batch, BN)) return rc;
+    if (int rc = make_tmap(&tb_hi, b_hi, Kp, Np, g.b_shared ? 1 : batch, BN)) return rc;
+    if (int rc = make_tmap(&tb_lo, b_lo, Kp, Np, g.b_shared ? 1 : batch, BN)) return rc;
     g.BN = BN;
     g.k_blocks = Kp / TC_BK;
     g.a_batched = a_batch > 1 ? 1 : 0;
@@ -384,6 +417,253 @@ int mlp_forward_tcgen05(const float *bank, int64_t ld_bank, int S, const float *
 }
 
 }  // namespace ursa
+
+
+// ---- chain-batched likelihood gradient of the 3-layer MLP (HMC, BASELINE.json configs[3]) -------------------------------------
+// What hamiltorch does per leapfrog step and chain -- one autograd pass of the module over the full batch
+// (reference inference/hmc.py:71-75) -- for ALL chains as eight tcgen05 GEMMs on the 3xTF32 kernel above, with every operand
+// produced in split (hi / lo) form by the epilogue of the GEMM before it:
+//   forward   a1 = relu(X W1^T + b1), a2 = relu(a1 W2^T + b2), logits = a2 W3^T + b3       (a1, a2 also stored TRANSPOSED)
+//   loss      ce[c] = sum_n -log softmax(logits)[y_n];  dlo = softmax - onehot              (point- and feature-major)
+//   backward  da2 = (dlo W3) . [a2 > 0]   dW3 = dlo^T a2   dW2 = da2^T a1   da1 = (da2 W2) . [a1 > 0]   dW1 = da1^T X
+// The weight-gradient GEMMs contract over the data points, i.e. over the ROWS of the activations: their operands are the
+// transposed copies the producing epilogues wrote next to the point-major ones (a warp's lanes are consecutive points, so
+// those stores are contiguous) -- no transpose kernels, no per-call operand split passes over the activations.
+namespace ursa {
+
+struct HmcGradPlan {
+    int K1p, K2p, K3p, Kq, BNh, Nph, BNc, Npc, BNi, Npi;
+    size_t x, xt, w1, w2, w3, w3t, act, actT, dlo, dloT, logits;     // floats per plane
+    size_t total_bytes;
+};
+
+static HmcGradPlan hmc_grad_plan(int C, int64_t Npts, int in_dim, int hid, int ncls) {
+    HmcGradPlan p;
+    p.K1p = round_up_i(in_dim, TC_BK);
+    p.K2p = round_up_i(hid, TC_BK);
+    p.K3p = round_up_i(ncls, TC_BK);
+    p.Kq = round_up_i((int)Npts, TC_BK);
+    p.BNh = pick_bn(hid);   p.Nph = round_up_i(round_up_i(hid, 16), p.BNh);
+    p.BNc = pick_bn(ncls);  p.Npc = round_up_i(round_up_i(ncls, 16), p.BNc);
+    p.BNi = pick_bn(in_dim); p.Npi = round_up_i(round_up_i(in_dim, 16), p.BNi);
+    p.x = (size_t)Npts * p.K1p;
+    p.xt = (size_t)p.Npi * p.Kq;
+    p.w1 = (size_t)C * p.Nph * p.K1p;
+    p.w2 = (size_t)C * p.Nph * p.K2p;
+    p.w3 = (size_t)C * p.Npc * p.K2p;
+    p.w3t = (size_t)C * p.Nph * p.K3p;
+    p.act = (size_t)C * Npts * p.K2p;
+    p.actT = (size_t)C * p.Nph * p.Kq;
+    p.dlo = (size_t)C * Npts * p.K3p;
+    p.dloT = (size_t)C * p.Npc * p.Kq;
+    p.logits = ((size_t)C * Npts * ncls + 3) & ~(size_t)3;
+    // hi / lo pairs: X, XT, W1, W2, W2T, W3, W3T, a1, a2, da2, a1T, a2T, da2T, da1T, dlo, dloT ; plain: logits, zero bias
+    const size_t fl = 2 * (p.x + p.xt + p.w1 + 2 * p.w2 + p.w3 + p.w3t + 3 * p.act + 4 * p.actT + p.dlo + p.dloT) + p.logits +
+                      (size_t)(p.Nph > p.Npi ? p.Nph : p.Npi);
+    p.total_bytes = fl * sizeof(float) + 4096;
+    return p;
+}
+
+// theta rows -> split filter planes: W1 [h][in], W2 [h][h], W2^T, W3 [C][h], W3^T  (zero padded to the plane shapes)
+__global__ void __launch_bounds__(256) hmc_mlp_prep_kernel(const float *__restrict__ theta, int64_t ld, int in_dim, int hid, int ncls,
+                                                           HmcGradPlan p, float *w1h, float *w1l, float *w2h, float *w2l, float *w2th,
+                                                           float *w2tl, float *w3h, float *w3l, float *w3th, float *w3tl) {
+    const int c = blockIdx.y;
+    const float *row = theta + (int64_t)c * ld;
+    const int64_t oW1 = 0, oW2 = (int64_t)hid * in_dim + hid, oW3 = oW2 + (int64_t)hid * hid + hid;
+    const int64_t n1 = (int64_t)p.Nph * p.K1p, n2 = (int64_t)p.Nph * p.K2p, n3 = (int64_t)p.Npc * p.K2p, n3t = (int64_t)p.Nph * p.K3p;
+    const int64_t total = n1 + 2 * n2 + n3 + n3t;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        float x = 0.f, *dh, *dl;
+        int64_t j = i;
+        if (j < n1) {
+            const int r = (int)(j / p.K1p), k = (int)(j % p.K1p);
+            if (r < hid && k < in_dim) x = __ldg(row + oW1 + (int64_t)r * in_dim + k);
+            dh = w1h + c * n1 + j; dl = w1l + c * n1 + j;
+        } else if ((j -= n1) < n2) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);
+            if (r < hid && k < hid) x = __ldg(row + oW2 + (int64_t)r * hid + k);
+            dh = w2h + c * n2 + j; dl = w2l + c * n2 + j;
+        } else if ((j -= n2) < n2) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);                      // W2^T[r = in-feature][k = out-feature]
+            if (r < hid && k < hid) x = __ldg(row + oW2 + (int64_t)k * hid + r);
+            dh = w2th + c * n2 + j; dl = w2tl + c * n2 + j;
+        } else if ((j -= n2) < n3) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);
+            if (r < ncls && k < hid) x = __ldg(row + oW3 + (int64_t)r * hid + k);
+            dh = w3h + c * n3 + j; dl = w3l + c * n3 + j;
+        } else {
+            j -= n3;
+            const int r = (int)(j / p.K3p), k = (int)(j % p.K3p);                      // W3^T[r = hidden][k = class]
+            if (r < hid && k < ncls) x = __ldg(row + oW3 + (int64_t)k * hid + r);
+            dh = w3th + c * n3t + j; dl = w3tl + c * n3t + j;
+        }
+        const float h = rn_tf32(x);
+        *dh = h;
+        *dl = rn_tf32(x - h);
+    }
+}
+
+// X [N][in] -> X planes [N][K1p] and X^T planes [Npi][Kq]
+__global__ void __launch_bounds__(256) hmc_mlp_xprep_kernel(const float *__restrict__ x, int64_t Npts, int in_dim, HmcGradPlan p,
+                                                            float *xh, float *xl, float *xth, float *xtl) {
+    const int64_t n1 = (int64_t)Npts * p.K1p, n2 = (int64_t)p.Npi * p.Kq;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * 256) {
+        float v = 0.f, *dh, *dl;
+        if (i < n1) {
+            const int64_t r = i / p.K1p; const int k = (int)(i % p.K1p);
+            if (k < in_dim) v = __ldg(x + r * in_dim + k);
+            dh = xh + i; dl = xl + i;
+        } else {
+            const int64_t j = i - n1;
+            const int r = (int)(j / p.Kq); const int64_t k = j % p.Kq;
+            if (r < in_dim && k < Npts) v = __ldg(x + k * in_dim + r);
+            dh = xth + j; dl = xtl + j;
+        }
+        const float h = rn_tf32(v);
+        *dh = h;
+        *dl = rn_tf32(v - h);
+    }
+}
+
+// one CTA per chain: ce[c] (fixed reduction order) and dlo = softmax - onehot in both layouts (pads stay at the memset zeros)
+__global__ void __launch_bounds__(256) hmc_mlp_loss_kernel(const float *__restrict__ logits, const int64_t *__restrict__ y, int64_t Npts,
+                                                           int ncls, HmcGradPlan p, float *dh, float *dl, float *dth, float *dtl,
+                                                           float *__restrict__ ce) {
+    __shared__ float red[256];
+    const int c = blockIdx.x;
+    const float *lg = logits + (int64_t)c * Npts * ncls;
+    float acc = 0.f;
+    for (int64_t n = threadIdx.x; n < Npts; n += 256) {
+        const float *l = lg + n * ncls;
+        float m = -INFINITY;
+        for (int k = 0; k < ncls; ++k) m = fmaxf(m, l[k]);
+        float sum = 0.f;
+        for (int k = 0; k < ncls; ++k) sum += expf(l[k] - m);
+        const float lse = logf(sum);
+        const int yy = (int)y[n];
+        acc += -((l[yy] - m) - lse);
+        for (int k = 0; k < ncls; ++k) {
+            const float d = expf((l[k] - m) - lse) - (k == yy ? 1.f : 0.f);
+            const float h = rn_tf32(d), lo = rn_tf32(d - h);
+            const int64_t a = ((int64_t)c * Npts + n) * p.K3p + k, b = ((int64_t)c * p.Npc + k) * p.Kq + n;
+            dh[a] = h; dl[a] = lo; dth[b] = h; dtl[b] = lo;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ce[c] = red[0];
+}
+
+// bias gradients: db[c][f] = sum_n (hi + lo)[c][f][n] over the transposed planes; one warp per (chain, feature)
+__global__ void __launch_bounds__(256) hmc_mlp_bias_kernel(const float *__restrict__ th, const float *__restrict__ tl, int rows_p, int Kq,
+                                                           int n_feat, int C, float *__restrict__ grad, int64_t ld, int64_t off) {
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= C * n_feat) return;
+    const int c = w / n_feat, f = w - c * n_feat;
+    const float *ph = th + ((int64_t)c * rows_p + f) * Kq, *pl = tl + ((int64_t)c * rows_p + f) * Kq;
+    float s = 0.f;
+    for (int k = lane; k < Kq; k += 32) s += ph[k] + pl[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) grad[(int64_t)c * ld + off + f] = s;
+}
+
+}  // namespace ursa
+
+extern "C" size_t ursa_hmc_mlp_grad_workspace(int C, int64_t Npts, int in_dim, int hidden, int ncls) {
+    if (C < 1 || Npts < 1 || in_dim < 1 || hidden < 1 || ncls < 1 || in_dim % 4 != 0 || hidden % 4 != 0 || ncls > 128) return 0;
+    return ursa::hmc_grad_plan(C, Npts, in_dim, hidden, ncls).total_bytes;
+}
+
+extern "C" int ursa_hmc_mlp_grad(const float *theta, int64_t ld, int C, const float *x, const int64_t *y, int64_t Npts, int in_dim,
+                                 int hidden, int ncls, float *grad, float *ce, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+    using namespace ursa;
+    URSA_REQUIRE(theta && x && y && grad && ce && workspace, "ursa_hmc_mlp_grad: null pointer");
+    URSA_REQUIRE(ursa_hmc_mlp_grad_workspace(C, Npts, in_dim, hidden, ncls) != 0,
+                 "ursa_hmc_mlp_grad: unsupported shape (in_dim %% 4, hidden %% 4, classes <= 128)");
+    const int64_t D = (int64_t)hidden * in_dim + hidden + (int64_t)hidden * hidden + hidden + (int64_t)ncls * hidden + ncls;
+    URSA_REQUIRE(ld >= D, "ursa_hmc_mlp_grad: ld (%lld) < D (%lld)", (long long)ld, (long long)D);
+    const HmcGradPlan p = hmc_grad_plan(C, Npts, in_dim, hidden, ncls);
+    URSA_REQUIRE(workspace_bytes >= p.total_bytes, "ursa_hmc_mlp_grad: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *w = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    auto take = [&](size_t n) { float *r = w; w += n; return r; };
+    float *xh = take(p.x), *xl = take(p.x), *xth = take(p.xt), *xtl = take(p.xt);
+    float *w1h = take(p.w1), *w1l = take(p.w1), *w2h = take(p.w2), *w2l = take(p.w2), *w2th = take(p.w2), *w2tl = take(p.w2);
+    float *w3h = take(p.w3), *w3l = take(p.w3), *w3th = take(p.w3t), *w3tl = take(p.w3t);
+    float *a1h = take(p.act), *a1l = take(p.act), *a2h = take(p.act), *a2l = take(p.act), *d2h = take(p.act), *d2l = take(p.act);
+    float *a1th = take(p.actT), *a1tl = take(p.actT), *a2th = take(p.actT), *a2tl = take(p.actT);
+    float *d2th = take(p.actT), *d2tl = take(p.actT), *d1th = take(p.actT), *d1tl = take(p.actT);
+    float *dlh = take(p.dlo), *dll = take(p.dlo), *dlth = take(p.dloT), *dltl = take(p.dloT);
+    float *logits = take(p.logits);
+    float *zero_bias = take((size_t)(p.Nph > p.Npi ? p.Nph : p.Npi));
+    const int64_t oW1 = 0, ob1 = (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)hidden * hidden, oW3 = ob2 + hidden,
+                  ob3 = oW3 + (int64_t)ncls * hidden;
+
+    // pads: K2p - hidden columns of the point-major activations, the class pads of dlo / dloT, zero bias
+    if (p.Nph < p.K2p)      // otherwise the N tiles of the producing GEMMs cover every column (zeros beyond `hidden`)
+        URSA_CUDA(cudaMemsetAsync(a1h, 0, 6 * p.act * sizeof(float), st));
+    URSA_CUDA(cudaMemsetAsync(dlh, 0, (2 * p.dlo + 2 * p.dloT) * sizeof(float), st));
+    URSA_CUDA(cudaMemsetAsync(zero_bias, 0, (size_t)(p.Nph > p.Npi ? p.Nph : p.Npi) * sizeof(float), st));
+    hmc_mlp_xprep_kernel<<<148 * 4, 256, 0, st>>>(x, Npts, in_dim, p, xh, xl, xth, xtl);
+    URSA_LAUNCH_CHECK("hmc_mlp_xprep_kernel");
+    hmc_mlp_prep_kernel<<<dim3(148, C), 256, 0, st>>>(theta, ld, in_dim, hidden, ncls, p, w1h, w1l, w2h, w2l, w2th, w2tl, w3h, w3l, w3th,
+                                                      w3tl);
+    URSA_LAUNCH_CHECK("hmc_mlp_prep_kernel");
+
+    const int64_t act_bs = (int64_t)Npts * p.K2p, actT_bs = (int64_t)p.Nph * p.Kq;
+    TcGemmArgs g;
+    // ---- forward
+    g = TcGemmArgs(); g.M = Npts; g.bias = theta + ob1; g.bias_stride = ld; g.relu = 1; g.n_valid = hidden;
+    g.out_hi = a1h; g.out_lo = a1l; g.out_batch_stride = act_bs; g.ld_out = p.K2p;
+    g.outT_hi = a1th; g.outT_lo = a1tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    if (int rc = launch_tc_gemm(xh, xl, Npts, 1, p.K1p, w1h, w1l, p.Nph, p.BNh, C, g, st)) return rc;
+    g.bias = theta + ob2; g.out_hi = a2h; g.out_lo = a2l; g.outT_hi = a2th; g.outT_lo = a2tl;
+    if (int rc = launch_tc_gemm(a1h, a1l, Npts, C, p.K2p, w2h, w2l, p.Nph, p.BNh, C, g, st)) return rc;
+    g = TcGemmArgs(); g.M = Npts; g.bias = theta + ob3; g.bias_stride = ld; g.relu = 0; g.n_valid = ncls;
+    g.out_hi = logits; g.out_lo = nullptr; g.out_batch_stride = (int64_t)Npts * ncls; g.ld_out = ncls;
+    if (int rc = launch_tc_gemm(a2h, a2l, Npts, C, p.K2p, w3h, w3l, p.Npc, p.BNc, C, g, st)) return rc;
+    // ---- loss
+    hmc_mlp_loss_kernel<<<C, 256, 0, st>>>(logits, y, Npts, ncls, p, dlh, dll, dlth, dltl, ce);
+    URSA_LAUNCH_CHECK("hmc_mlp_loss_kernel");
+    // ---- backward
+    // da2 = (dlo W3) . [a2 > 0]  -> point-major (A of the da1 GEMM) and transposed (A of the dW2 GEMM)
+    g = TcGemmArgs(); g.M = Npts; g.bias = zero_bias; g.bias_stride = 0; g.relu = 0; g.n_valid = hidden;
+    g.out_hi = d2h; g.out_lo = d2l; g.out_batch_stride = act_bs; g.ld_out = p.K2p;
+    g.outT_hi = d2th; g.outT_lo = d2tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    g.mask = a2h; g.ld_mask = p.K2p; g.mask_batch_stride = act_bs;
+    if (int rc = launch_tc_gemm(dlh, dll, Npts, C, p.K3p, w3th, w3tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // dW3^T[h][k] = sum_n a2T[h][n] dloT[k][n]  -> stored transposed = W3's own [k][h] layout
+    g = TcGemmArgs(); g.M = hidden; g.bias = zero_bias; g.bias_stride = 0; g.relu = 0; g.n_valid = ncls;
+    g.out_hi = nullptr; g.outT_hi = grad + oW3; g.outT_lo = nullptr; g.outT_batch_stride = ld; g.ld_t = hidden; g.t_valid = ncls;
+    if (int rc = launch_tc_gemm(a2th, a2tl, p.Nph, C, p.Kq, dlth, dltl, p.Npc, p.BNc, C, g, st)) return rc;
+    // dW2[o][i] = sum_n da2T[o][n] a1T[i][n]
+    g = TcGemmArgs(); g.M = hidden; g.bias = zero_bias; g.bias_stride = 0; g.relu = 0; g.n_valid = hidden;
+    g.out_hi = grad + oW2; g.out_lo = nullptr; g.out_batch_stride = ld; g.ld_out = hidden;
+    if (int rc = launch_tc_gemm(d2th, d2tl, p.Nph, C, p.Kq, a1th, a1tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // da1 = (da2 W2) . [a1 > 0]  -> only its transposed form is needed
+    g = TcGemmArgs(); g.M = Npts; g.bias = zero_bias; g.bias_stride = 0; g.relu = 0; g.n_valid = hidden;
+    g.out_hi = nullptr; g.outT_hi = d1th; g.outT_lo = d1tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    g.mask = a1h; g.ld_mask = p.K2p; g.mask_batch_stride = act_bs;
+    if (int rc = launch_tc_gemm(d2h, d2l, Npts, C, p.K2p, w2th, w2tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // dW1[o][k] = sum_n da1T[o][n] XT[k][n]   (XT shared by all chains)
+    g = TcGemmArgs(); g.M = hidden; g.bias = zero_bias; g.bias_stride = 0; g.relu = 0; g.n_valid = in_dim; g.b_shared = 1;
+    g.out_hi = grad + oW1; g.out_lo = nullptr; g.out_batch_stride = ld; g.ld_out = in_dim;
+    if (int rc = launch_tc_gemm(d1th, d1tl, p.Nph, C, p.Kq, xth, xtl, p.Npi, p.BNi, C, g, st)) return rc;
+    // bias gradients = row sums of the transposed planes
+    const int gb1 = (C * hidden + 7) / 8, gb3 = (C * ncls + 7) / 8;
+    hmc_mlp_bias_kernel<<<gb1, 256, 0, st>>>(d1th, d1tl, p.Nph, p.Kq, hidden, C, grad, ld, ob1);
+    hmc_mlp_bias_kernel<<<gb1, 256, 0, st>>>(d2th, d2tl, p.Nph, p.Kq, hidden, C, grad, ld, ob2);
+    hmc_mlp_bias_kernel<<<gb3, 256, 0, st>>>(dlth, dltl, p.Npc, p.Kq, ncls, C, grad, ld, ob3);
+    URSA_LAUNCH_CHECK("hmc_mlp_bias_kernel");
+    return URSA_OK;
+}
 
 // ---- generic entry: batched  out[b] = A[b or shared] B[b]^T (+ bias[b]) (ReLU)  on the same 3xTF32 kernel ----------------------
 // (the chain-batched HMC likelihood gradient of the MLPs runs its nine GEMMs through this; SURVEY 8(d) cfg 4)

@@ -220,8 +220,28 @@ class HMC(_Inference):
 
         return fn
 
+    def _build_grad_fn_mlp_fused(self, arch):
+        """``ursa_hmc_mlp_grad``: forward, loss and backward of all chains as eight hand-written tcgen05 GEMMs whose operands
+        are produced in split form by the previous GEMM's epilogue (csrc/bma_mlp_tc.cu).  Writes straight into the [C, ld]
+        gradient / energy buffers: ``fn(theta, g, ce)``."""
+        _, in_dim, hid, ncls = arch
+        x2 = self.x.reshape(self.x.shape[0], -1).contiguous().float()
+        y = self.y.long().contiguous()
+        ws = [None]
+
+        def fn(theta, g, ce):
+            ws[0] = _C.hmc_mlp_grad(theta, x2, y, in_dim, hid, ncls, g, ce, workspace=ws[0])
+            if ws[0] is None:
+                raise RuntimeError("ursa_hmc_mlp_grad does not cover this MLP shape")
+
+        fn.in_place = True
+        return fn
+
     def _grad(self, theta, g, ce):
         """g[c, :D] = d/dtheta sum_i loss_i(theta_c) ; ce[c] = sum_i loss_i(theta_c)   (fp32 forward/backward)."""
+        if getattr(self._grad_fn, "in_place", False):
+            self._grad_fn(theta, g, ce)
+            return
         C = theta.shape[0]
         chunk = self.chain_chunk if self.chain_chunk > 0 else C
         tf32 = torch.backends.cuda.matmul.allow_tf32
@@ -289,15 +309,23 @@ class HMC(_Inference):
         if arch is not None and arch[0] == "mlp" and self.model_loss == "multi_class_linear_output" \
                 and getattr(self, "force_vmap_grad", False) is False and self.D == arch[2] * arch[1] + arch[2] \
                 + arch[2] * arch[2] + arch[2] + arch[3] * arch[2] + arch[3]:
-            # measured at 128 chains x 1000 points, MLP 784-200-200-10, ms per HMC iteration (L = 10): vmap(grad) 102.9,
-            # fp32 GEMM formulation on cuBLAS 92.3, the same GEMMs on ursa_gemm_nt_3xtf32 102.8 (its TF32 split passes and the
-            # feature-major copies eat what the tensor cores gain on K = 200 / 784 problems) -> cuBLAS is the default
+            # round 1, ms per HMC iteration at 128 chains x 1000 points, MLP 784-200-200-10, L = 10 (eager loop): vmap(grad)
+            # 102.9, fp32 GEMMs on cuBLAS 92.3, the same GEMMs one by one on ursa_gemm_nt_3xtf32 102.8 (split passes and
+            # feature-major copies per call).  Round 2: ursa_hmc_mlp_grad keeps every operand in split form between GEMMs
+            engine = getattr(self, "grad_engine_request", None)          # None = the default below; tests / benches pin one
+            fused_ok = self.chain_chunk <= 0 and _C.lib().ursa_hmc_mlp_grad_workspace(self.num_chains, self.x.shape[0], arch[1],
+                                                                                      arch[2], arch[3]) > 0
+            if engine is None:
+                engine = "mlp_tcgen05_fused" if fused_ok else "mlp_gemm"
             if getattr(self, "force_tc_grad", False):
-                self._grad_fn = self._build_grad_fn_mlp_tc(arch)
-                self.grad_engine = "mlp_tcgen05"
+                engine = "mlp_tcgen05"
+            if engine == "mlp_tcgen05_fused":
+                self._grad_fn = self._build_grad_fn_mlp_fused(arch)      # hand-written tcgen05 forward + backward (default)
+            elif engine == "mlp_tcgen05":
+                self._grad_fn = self._build_grad_fn_mlp_tc(arch)         # the same GEMMs one by one through ursa_gemm_nt_3xtf32
             else:
-                self._grad_fn = self._build_grad_fn_mlp(arch)
-                self.grad_engine = "mlp_gemm"
+                self._grad_fn = self._build_grad_fn_mlp(arch)            # fp32 GEMM formulation on cuBLAS (comparison engine)
+            self.grad_engine = engine
         self._sums, self._energy_ws = None, None
         with torch.no_grad():
             theta = self._initial_state()
@@ -339,7 +367,10 @@ class HMC(_Inference):
             graph = None
             want_graph = bool(getattr(self, "use_cuda_graph", True)) and self.grad_engine != "vmap" and self.num_samples >= 3
             self.graph_replays = 0
+            ev_mid, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for n in range(1, self.num_samples + 1):
+                if n == 3:
+                    ev_mid.record()                             # iterations 1-2 warm up / capture: steady state from here
                 inj = self._inject
                 _C.hmc_momentum(r, math.sqrt(self.mass), noise=None if inj is None else inj[0][n - 1], seed=self.seed,
                                 step=n, elem_offset=chain0 * ld)
@@ -365,6 +396,11 @@ class HMC(_Inference):
                 if debug:
                     print("HMC iteration %d: accepted %d / %d chains, H_old[0] = %.4f, H_new[0] = %.4f"
                           % (n, int(accept.sum().item()), C, float(h_old[0].item()), float(h_new[0].item())))
+            self.ms_per_iteration = None                        # device time per iteration, iterations 3 .. num_samples
+            if self.num_samples >= 3:
+                ev_end.record()
+                ev_end.synchronize()
+                self.ms_per_iteration = ev_mid.elapsed_time(ev_end) / (self.num_samples - 2)
             self.acceptance_rate = (n_accept.double() / max(1, self.num_samples)).cpu()
             self.theta = theta
         # leave the live model on chain 0's final state, like hamiltorch leaves `params`
