@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                         // ok_a / ok_b: act_ready[0] / act_ready[1] of this conv were seen complete by the previous conv's tail
                         if (!ok_a) DBG_T(d_wait_act0, mbar_wait_a(smem_u32(&act_ready[0]), iph));
                         bool ok_next = ok_b;
-#pragma unroll 1
+#pragma unroll
                         for (int t = 0; t < T; ++t) {
                             // tile t reads the planes of tiles t-1 .. t+1 (halo); tile groups publish independently
                             if (t + 1 < T && !ok_next) { if (k == 0) DBG_T(d_wait_act0, mbar_wait_a(smem_u32(&act_ready[t + 1]), iph)); else DBG_T(d_wait_act, mbar_wait_a(smem_u32(&act_ready[t + 1]), iph)); }
