@@ -579,11 +579,14 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                     *reinterpret_cast<uint4 *>(slot + lane * 64 + (((2 + ck) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                                 }
                             }
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) {
-                                tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, yrow);
-                                bulk_commit_group();
+                            const bool both = Cfg::STG_SLOTS == 2 && a.has_rrow_map;     // two slots: one fence, two stores
+                            if (!both) {
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, yrow);
+                                    bulk_commit_group();
+                                }
                             }
                             if (a.has_rrow_map) {
                                 // the raw residual R / 16 in the same row format (the next stage's shortcut conv reads it)
@@ -607,6 +610,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) preresnet_stage16_kernel(const
                                 fence_proxy_async();
                                 __syncwarp();
                                 if (lane == 0) {
+                                    if (both) tma_store_2d(&a.out_map, smem_u32(slot), gc * 16, yrow);
                                     tma_store_2d(&a.rrow_map, smem_u32(rslot), gc * 16, yrow);
                                     bulk_commit_group();
                                 }
