@@ -728,6 +728,31 @@ def run_extras(dev, rank, world, peak):
         out["bma_preresnet20_S100_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
                                                          "img_samples_per_s": N * S_all / ms * 1e3,
                                                          "TFLOPs": 81.63e6 * N * S_all / ms / 1e9, "n_gpus": world}
+    # K3b for the north-star model: BatchNorm re-estimation (util.bn_update, once per SWAG sample) of 8 draws, sample-batched,
+    # on a bounded sample of the 50 000-image pass; beside it the PyTorch / cuDNN fp32 train-mode pass it replaces
+    Nbn, Bbn, Sbn = 2048, 128, min(8, ns) if ns > 0 else 0
+    if Sbn > 0:
+        from ursabench_b200.util import bn_update as torch_bn_update
+        bn_ws = [None]
+        bn_fn = lambda: bn_ws.__setitem__(0, _C.preresnet_bn_update(bankp[:Sbn], bufp[:Sbn].clone(), xi[:Nbn], Bbn, 20, 10, workspace=bn_ws[0]))  # noqa: E731
+        bn_fn()
+        torch.cuda.synchronize()
+        ms, _ = _event_time_ms(bn_fn, 3)
+        out["k3b_bn_update_preresnet20_S%d_N2048_b128" % Sbn] = {"ms": ms, "img_samples_per_s": Sbn * Nbn / ms * 1e3,
+                                                                 "full_pass_50k_images_per_sample_s": ms * 50_000 / Nbn / Sbn / 1e3}
+        if rank == 0:
+            mt = m.to(dev)
+            tf32c, tf32m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                ld_bn = [(xi[i:i + Bbn], None) for i in range(0, Nbn, Bbn)]
+                torch_bn_update(ld_bn, mt, device=dev)
+                tms, _ = _event_time_ms(lambda: torch_bn_update(ld_bn, mt, device=dev), 2)
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32c, tf32m
+            out["k3b_bn_update_preresnet20_torch_cudnn_fp32"] = {"sample": "1 sample x 2048 images, batch 128", "ms": tms,
+                                                                 "img_samples_per_s": Nbn / tms * 1e3}
+            m.cpu()
     # BASELINE.json configs[4]: the S = 10 / 100 / 1000 sweep on the product engine (S = 100 is the line above)
     for S_sw in (10, 1000):
         lo_s, hi_s = udist.shard_range(S_sw, rank, world)

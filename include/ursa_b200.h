@@ -269,6 +269,16 @@ size_t ursa_wrn_bn_update_workspace(int64_t N, int batch, int depth, int widen, 
 int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch,
                        int depth, int widen, int C, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same for PreResNets (the north-star model), SAMPLE-BATCHED: S posterior samples (rows of bank / bufbank) take the
+ * train-mode pass together, 8 per launch.  Layer by layer on the 3xTF32 tcgen05 conv kernel with a statistics epilogue
+ * (batch statistics need the whole batch's conv output, so the fused stage kernels cannot be used): per conv
+ * conv -> finalize (this batch's (a, b), running statistics) -> apply.  bufbank rows [S, ld_buf] are overwritten
+ * (running_mean, running_var of every BatchNorm in named_buffers() order).  depth = 6n+2 in 8..38; batch even, 2..512. */
+size_t ursa_preresnet_bn_update_workspace(int S, int64_t N, int batch, int depth, int C);
+int ursa_preresnet_bn_update(const float *bank, int64_t ld_bank, float *bufbank, int64_t ld_buf, int S,
+                             const float *x, int64_t N, int batch, int depth, int C,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * K5  chain-batched HMC  (replaces the call into hamiltorch.sample_model made by HMC.sample,
  *     inference/hmc.py:62-85.  hamiltorch is a third-party dependency that is NOT vendored in the reference

@@ -503,6 +503,32 @@ def gen_bn_update(R):
     print("bn_update.npz", out["buffers"].shape, out["momentum_after"][:3])
 
 
+def gen_bn_update_preresnet(R):
+    """util.bn_update (util.py:212-247) of the LIVE reference on its own PreResNet(depth=8) and PreResNet(depth=20), CPU (the
+    hard-coded ``input.cuda()`` of util.py:236 patched out harness-side).  Weights from oracle/wrn_fill.py (seeded), ragged last
+    batch."""
+    from oracle.wrn_fill import wrn_fill
+    out = {}
+    for tag, depth, C, N, batch, seed in (("d8", 8, 10, 44, 16, 500), ("d20", 20, 10, 40, 16, 600)):
+        rng = np.random.RandomState(seed + 1)
+        x16 = rng.randn(N, 3, 32, 32).astype(np.float16)
+        x = torch.from_numpy(x16.astype(np.float32))
+        loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, torch.zeros(N, dtype=torch.long)), batch_size=batch,
+                                             shuffle=False)
+        m = wrn_fill(R["models"].preresnet.PreResNet(num_classes=C, depth=depth), seed, logit_gain=0.4)
+        orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self          # harness-side: no GPU in this container
+        try:
+            R["util"].bn_update(loader, m)
+        finally:
+            torch.Tensor.cuda = orig
+        out[tag + "/x"] = x16
+        out[tag + "/cfg"] = np.array([depth, C, N, batch, seed])
+        out[tag + "/buffers"] = _flat_buffers(m)
+    np.savez_compressed(os.path.join(OUT, "bn_update_preresnet.npz"), **out)
+    print("bn_update_preresnet.npz", {k: v.shape for k, v in out.items() if k.endswith("buffers")})
+
+
 def gen_metrics_edge(R):
     """get_performance_metrics / _get_ece / _get_brier on crafted probabilities: confidences exactly on bin
     edges, argmax ties, one-hot rows, C = 2..100."""
@@ -653,7 +679,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = _ref()
     gens = dict(sgmcmc_step=gen_sgmcmc_step, csghmc_schedule=gen_csghmc_schedule, swa_collect=gen_swa_collect,
-                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, prediction_preresnet20=gen_prediction_preresnet20, ess=gen_ess, pca_space=gen_pca_space, bn_update=gen_bn_update, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
+                swag_compat=gen_swag_compat, prediction=gen_prediction, prediction_wrn=gen_prediction_wrn, prediction_preresnet20=gen_prediction_preresnet20, ess=gen_ess, pca_space=gen_pca_space, bn_update=gen_bn_update, bn_update_preresnet=gen_bn_update_preresnet, metrics_edge=gen_metrics_edge, layouts=gen_layouts,
                 ood_decision=gen_ood_decision)
     for name in (sys.argv[1:] or list(gens)):        # `python -m oracle.gen_golden ood_decision` regenerates one fixture
         gens[name](R)

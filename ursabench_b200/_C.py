@@ -56,6 +56,8 @@ SIGNATURES = {
     "ursa_swag_gram": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "ursa_wrn_bn_update_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "ursa_wrn_bn_update": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "ursa_preresnet_bn_update_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
+    "ursa_preresnet_bn_update": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
     "ursa_hmc_leapfrog": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
     "ursa_hmc_energy_workspace": (_sz, [_i64, _i64]),
@@ -338,6 +340,25 @@ def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
     rc = lib().ursa_wrn_bn_update(_ptr(bank_row), _ptr(buf_row), _ptr(x), N, batch, depth, widen, C, _ptr(workspace),
                                   workspace.numel() * workspace.element_size(), _stream(x))
     _check(rc, "ursa_wrn_bn_update")
+    return workspace
+
+
+@_on_device
+def preresnet_bn_update(bank_rows, buf_rows, x, batch, depth, C, workspace=None):
+    """Re-estimate the BatchNorm running statistics of S PreResNet samples (rows of ``bank_rows`` [S, ld]) with ONE
+    sample-batched train-mode pass over ``x``; ``buf_rows`` [S, ldb] is overwritten.  Returns the workspace (None if the
+    shape is not covered)."""
+    _dev_f32(bank_rows, "bank_rows"), _dev_f32(buf_rows, "buf_rows"), _dev_f32(x, "x")
+    S, N = bank_rows.shape[0], x.shape[0]
+    need = lib().ursa_preresnet_bn_update_workspace(S, N, batch, depth, C)
+    if need == 0:
+        return None
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    rc = lib().ursa_preresnet_bn_update(_ptr(bank_rows), bank_rows.stride(0), _ptr(buf_rows), buf_rows.stride(0), S, _ptr(x), N,
+                                        batch, depth, C, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                        _stream(x))
+    _check(rc, "ursa_preresnet_bn_update")
     return workspace
 
 

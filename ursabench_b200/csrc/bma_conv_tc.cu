@@ -44,6 +44,10 @@ struct ConvTcArgs {
     unsigned char *pi_out = nullptr;   // nullable
     int pi_G = 1, pi_pitch = 0, pi_img_pos = 0, pi_nplanes = 0, pi_ngroups = 0;
     int64_t pi_pass_bytes = 0;
+    // mode 2 (train-mode BatchNorm pass, ursa_preresnet_bn_update): out_raw = acc (+ res) and the per-(sample, batch,
+    // channel) sums of v and v^2 over the batch's pixels go to stats [S_c][n_batches][2][cout] (fp64 atomics)
+    double *stats = nullptr;
+    int batch = 0, n_batches = 0;
 };
 
 constexpr int CTC_THREADS = 192, CTC_MAX_STAGES = 8;
@@ -162,6 +166,49 @@ conv3x3_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs a) {
         for (int c0 = 0; c0 < a.cout; c0 += 16) {
             uint32_t rr[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
+            if (a.mode == 2) {
+                // raw output (+ residual) and batch statistics.  The 32 pixels of a warp belong to one image (or to two images
+                // of one batch): a transposing butterfly leaves lane l with the warp's sum of value l of
+                // [v_0 .. v_15, v_0^2 .. v_15^2] after 31 shuffles, then one fp64 atomic per lane.
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(rr[i]) : 0.f;
+                if (valid) {
+                    if (a.res != nullptr) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(a.res + off + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 t = __ldg(rp + i);
+                            v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                        }
+                    }
+                    float4 *op = reinterpret_cast<float4 *>(a.out_raw + off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                float w32[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { w32[i] = v[i]; w32[16 + i] = v[i] * v[i]; }
+#pragma unroll
+                for (int half = 16; half >= 1; half >>= 1) {
+                    const bool up = (lane & half) != 0;
+#pragma unroll
+                    for (int i = 0; i < half; ++i) {
+                        const float send = up ? w32[i] : w32[i + half];
+                        const float got = __shfl_xor_sync(0xffffffffu, send, half);
+                        w32[i] = (up ? w32[i + half] : w32[i]) + got;
+                    }
+                }
+                // lane l now holds value index bit-reversed-free mapping: after the steps lane l owns index l (bits taken MSB first)
+                const int n_first = n0 + (NT == 1 ? 0 : (q * 32) / (WT * HT));      // image of this warp's first pixel
+                if (n_first < a.n_images) {
+                    const int j = n_first / a.batch;
+                    const int idx = lane;                                          // [0,16): sum v_c ; [16,32): sum v_c^2
+                    double *sp = a.stats + (((int64_t)s * a.n_batches + j) * 2 + (idx >> 4)) * a.cout + c0 + (idx & 15);
+                    atomicAdd(sp, (double)w32[0]);
+                }
+                continue;
+            }
             if (!valid) continue;
             float v[16];
 #pragma unroll
@@ -878,6 +925,223 @@ int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *b
     return URSA_OK;
 }
 
+}  // namespace ursa
+
+// ---- train-mode BatchNorm pass: re-estimation of the running statistics ---------------------------------
+// util.bn_update (reference util.py:212-247, called once per SWAG / ESS sample at inference/swag.py:123-124 and
+// pca_subspace.py:137) = ONE train-mode forward of the sample over the training set: every BatchNorm normalises with the
+// statistics of the current batch and folds them into its running statistics with the cumulative momentum b / (n + b).
+// Batch statistics need the whole batch's conv output before the next conv can start, so the fused stage kernels cannot be
+// used; the pass runs layer by layer on conv3x3_tc_kernel (3xTF32 tcgen05, mode 2: raw output + a statistics epilogue),
+// SAMPLE-BATCHED (grid.y = sample): per conv  conv -> finalize (sums -> this batch's (a, b), running statistics) -> apply
+// (split(relu(a v + b)) = the next conv's TMA planes).
+namespace ursa {
+
+// per-(sample, batch, channel) sums of v and v^2 of a raw NHWC tensor [S_c][nc][hw][C] (the stem output)
+__global__ void __launch_bounds__(256) bn_stats_nhwc_kernel(const float *__restrict__ raw, int C, int hw, int nc, int batch,
+                                                            int n_batches, double *__restrict__ stats) {
+    // one CTA per (image, sample); thread = (pixel lane, channel): 256 threads = 256 / C pixel lanes
+    const int n = blockIdx.x, s = blockIdx.y;
+    const int c = threadIdx.x % C, pl = threadIdx.x / C, npl = 256 / C;
+    const float *p = raw + ((int64_t)s * nc + n) * hw * C;
+    double s1 = 0.0, s2 = 0.0;
+    for (int px = pl; px < hw; px += npl) {
+        const float v = __ldg(p + (int64_t)px * C + c);
+        s1 += v;
+        s2 += (double)v * v;
+    }
+    __shared__ double r1[256], r2[256];
+    r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+    __syncthreads();
+    if (pl == 0) {
+        for (int k = 1; k < npl; ++k) { s1 += r1[k * C + c]; s2 += r2[k * C + c]; }
+        double *sp = stats + (((int64_t)s * n_batches + n / batch) * 2) * C + c;
+        atomicAdd(sp, s1);
+        atomicAdd(sp + C, s2);
+    }
+}
+
+// sums -> (a, b) of every batch of the chunk and the running statistics (in the sample's buffer row); clears the sums
+__global__ void bn_finalize_kernel(double *__restrict__ stats, const float *__restrict__ bank, int64_t ld_bank, int64_t w_off,
+                                   int64_t b_off, float *__restrict__ bufbank, int64_t ld_buf, int64_t buf_off, int C, int hw, int nc,
+                                   int batch, int n_batches, int64_t n_before, float *__restrict__ ab) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+    if (c >= C) return;
+    const float gamma = bank[(int64_t)s * ld_bank + w_off + c], beta = bank[(int64_t)s * ld_bank + b_off + c];
+    float *rmp = bufbank + (int64_t)s * ld_buf + buf_off + c, *rvp = rmp + C;
+    float rm = *rmp, rv = *rvp;
+    int64_t n = n_before;
+    if (n == 0) { rm = 0.f; rv = 1.f; }                    // reset_bn (util.py:196-199)
+    for (int j = 0; j < n_batches; ++j) {
+        const int bj = nc - j * batch < batch ? nc - j * batch : batch;
+        if (bj <= 0) break;
+        const double cnt = (double)bj * hw;
+        double *sp = stats + (((int64_t)s * n_batches + j) * 2) * C;
+        const double mean = sp[c] / cnt;
+        double var = sp[C + c] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        sp[c] = 0.0;
+        sp[C + c] = 0.0;
+        const float av = gamma / sqrtf((float)var + 1e-5f);
+        float *abp = ab + (((int64_t)s * n_batches + j) * 2) * C;
+        abp[c] = av;
+        abp[C + c] = beta - (float)mean * av;
+        const float mom = (float)((double)bj / (double)(n + bj));          // util.py:239-241
+        const float unbiased = (float)(cnt > 1.0 ? var * cnt / (cnt - 1.0) : var);
+        rm = (1.f - mom) * rm + mom * (float)mean;
+        rv = (1.f - mom) * rv + mom * unbiased;
+        n += bj;
+    }
+    *rmp = rm;
+    *rvp = rv;
+}
+
+// raw [S_c][nc][hw][C] -> TF32 planes split(relu(a v + b)) with the (a, b) of the pixel's (sample, batch)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float *__restrict__ raw, const float *__restrict__ ab, int C, int hw, int nc,
+                                                       int batch, int n_batches, int64_t total4, float *__restrict__ a_hi,
+                                                       float *__restrict__ a_lo) {
+    const int c4n = C >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % c4n) * 4;
+        const int64_t px = i / c4n;
+        const int64_t img = px / hw;                       // s * nc + n
+        const int s = (int)(img / nc), n = (int)(img - (int64_t)s * nc);
+        const float *abp = ab + (((int64_t)s * n_batches + n / batch) * 2) * C;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(raw + px * C + c));
+        const float4 a4 = __ldg(reinterpret_cast<const float4 *>(abp + c)), b4 = __ldg(reinterpret_cast<const float4 *>(abp + C + c));
+        const float y0 = relu_nan(fmaf(a4.x, v.x, b4.x)), y1 = relu_nan(fmaf(a4.y, v.y, b4.y));
+        const float y2 = relu_nan(fmaf(a4.z, v.z, b4.z)), y3 = relu_nan(fmaf(a4.w, v.w, b4.w));
+        float4 hv, lv;
+        hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
+        lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
+        *reinterpret_cast<float4 *>(a_hi + px * C + c) = hv;
+        *reinterpret_cast<float4 *>(a_lo + px * C + c) = lv;
+    }
+}
+
+struct BnTrainLayout {
+    int sc, nc, nb;
+    size_t raw_bytes, packed_bytes, stats_bytes, ab_bytes, total;
+};
+static bool bn_train_layout(int S, int64_t N, int batch, const NetPlan &pl, BnTrainLayout &L) {
+    if (batch < 2 || (batch & 1) || batch > kTcChunkImages || N < 1 || S < 1) return false;      // 8 x 8 tiles pair two images of a batch
+    L.sc = S < kTcChunkSamples ? S : kTcChunkSamples;
+    int64_t nc = (int64_t)batch * (kTcChunkImages / batch);
+    if (N < nc) nc = N;
+    L.nc = (int)nc;
+    L.nb = (int)((nc + batch - 1) / batch);
+    L.raw_bytes = (size_t)L.sc * L.nc * 16 * 32 * 32 * sizeof(float);
+    L.packed_bytes = (((size_t)L.sc * pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
+    L.stats_bytes = (((size_t)L.sc * L.nb * 2 * 64 * sizeof(double)) + 1023) & ~(size_t)1023;
+    L.ab_bytes = (((size_t)L.sc * L.nb * 2 * 64 * sizeof(float)) + 1023) & ~(size_t)1023;
+    L.total = 6 * L.raw_bytes + L.packed_bytes + L.stats_bytes + L.ab_bytes + 2048;     // Ra, Rb, Rs, Craw, A hi / lo
+    return true;
+}
+
+}  // namespace ursa
+
+extern "C" size_t ursa_preresnet_bn_update_workspace(int S, int64_t N, int batch, int depth, int C) {
+    using namespace ursa;
+    NetPlan pl;
+    BnTrainLayout L;
+    if (!build_plan(depth, C, pl, 1) || !bn_train_layout(S, N, batch, pl, L)) return 0;
+    return L.total;
+}
+
+extern "C" int ursa_preresnet_bn_update(const float *bank, int64_t ld_bank, float *bufbank, int64_t ld_buf, int S, const float *x,
+                                        int64_t N, int batch, int depth, int C, void *workspace, size_t workspace_bytes,
+                                        void *stream) {
+    using namespace ursa;
+    URSA_REQUIRE(bank && bufbank && x && workspace, "ursa_preresnet_bn_update: null pointer");
+    static thread_local NetPlan pl;
+    BnTrainLayout L;
+    if (!build_plan(depth, C, pl, 1) || !bn_train_layout(S, N, batch, pl, L)) {
+        set_error("ursa_preresnet_bn_update: unsupported depth %d / batch %d (depth = 6n+2 in 8..38, even batch 2..%d)", depth, batch,
+                  kTcChunkImages);
+        return URSA_ERR_UNSUPPORTED;
+    }
+    URSA_REQUIRE(ld_bank >= pl.D && ld_buf >= pl.NB, "ursa_preresnet_bn_update: ld_bank / ld_buf too small");
+    URSA_REQUIRE(workspace_bytes >= L.total, "ursa_preresnet_bn_update: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    float *Ra = reinterpret_cast<float *>(wsb), *Rb = reinterpret_cast<float *>(wsb + L.raw_bytes);
+    float *Rs = reinterpret_cast<float *>(wsb + 2 * L.raw_bytes), *Cr = reinterpret_cast<float *>(wsb + 3 * L.raw_bytes);
+    float *Ah = reinterpret_cast<float *>(wsb + 4 * L.raw_bytes), *Al = reinterpret_cast<float *>(wsb + 5 * L.raw_bytes);
+    float *packed = reinterpret_cast<float *>(wsb + 6 * L.raw_bytes);
+    double *stats = reinterpret_cast<double *>(wsb + 6 * L.raw_bytes + L.packed_bytes);
+    float *ab = reinterpret_cast<float *>(wsb + 6 * L.raw_bytes + L.packed_bytes + L.stats_bytes);
+    // BatchNorm layers in forward order = the type-2 entries of the prep table (bank offsets of gamma / beta, buffer offset)
+    int bn_idx[kMaxLayers], n_bn = 0;
+    for (int i = 0; i < pl.table.n; ++i)
+        if (pl.table.e[i].type == 2) bn_idx[n_bn++] = i;
+    const int n = pl.n_blocks;
+    URSA_REQUIRE(n_bn == 6 * n + 1, "ursa_preresnet_bn_update: plan mismatch");
+
+    for (int s0 = 0; s0 < S; s0 += L.sc) {
+        const int sc = (S - s0 < L.sc) ? (S - s0) : L.sc;
+        const float *bk = bank + (int64_t)s0 * ld_bank;
+        float *bf = bufbank + (int64_t)s0 * ld_buf;
+        preresnet_prep_kernel<<<dim3(pl.table.n, sc), 256, 0, st>>>(pl.table, bk, ld_bank, bf, ld_buf, packed, pl.packed_floats);
+        URSA_LAUNCH_CHECK("preresnet_prep_kernel");
+        URSA_CUDA(cudaMemsetAsync(stats, 0, L.stats_bytes, st));
+        for (int64_t i0 = 0; i0 < N; i0 += L.nc) {
+            const int nc = (int)((N - i0 < L.nc) ? (N - i0) : L.nc);
+            const int nb = (nc + batch - 1) / batch;
+            int bn_pos = 0;
+            auto finalize = [&](int Cc, int hw) -> int {
+                const PrepEntry &e = pl.table.e[bn_idx[bn_pos++]];
+                bn_finalize_kernel<<<dim3((Cc + 63) / 64, sc), 64, 0, st>>>(stats, bk, ld_bank, e.src, e.src2, bf, ld_buf, e.buf, Cc, hw, nc,
+                                                                            batch, L.nb, i0, ab);
+                URSA_LAUNCH_CHECK("bn_finalize_kernel");
+                return URSA_OK;
+            };
+            auto apply = [&](const float *raw, int Cc, int hw) -> int {
+                const int64_t total4 = (int64_t)sc * nc * hw * Cc / 4;
+                int gx = (int)((total4 + 255) / 256);
+                if (gx > 148 * 16) gx = 148 * 16;
+                bn_apply_kernel<<<gx, 256, 0, st>>>(raw, ab, Cc, hw, nc, batch, L.nb, total4, Ah, Al);
+                URSA_LAUNCH_CHECK("bn_apply_kernel");
+                return URSA_OK;
+            };
+            stem_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(x + i0 * 3 * 32 * 32, packed, pl.packed_floats, pl.conv1_w, pl.blocks[0][0].bn1, nc,
+                                                           Ra, nullptr, nullptr, nullptr);
+            URSA_LAUNCH_CHECK("stem_nhwc_kernel");
+            bn_stats_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(Ra, 16, 1024, nc, batch, L.nb, stats);
+            URSA_LAUNCH_CHECK("bn_stats_nhwc_kernel");
+            float *cur = Ra, *nxt = Rb;
+            int ch = 16, hw = 32;
+            for (int stg = 0; stg < 3; ++stg)
+                for (int b = 0; b < n; ++b) {
+                    const NetPlan::Block &B = pl.blocks[stg][b];
+                    const bool down = B.ds >= 0;
+                    const int cout = down ? ch * 2 : ch, stride = down ? 2 : 1, hout = hw / stride;
+                    if (int rc = finalize(ch, hw * hw)) return rc;                      // bn1: statistics of the block input
+                    if (int rc = apply(cur, ch, hw * hw)) return rc;
+                    const float *res = cur;
+                    if (down) {
+                        shortcut_nhwc_kernel<<<dim3(nc, sc), 256, 0, st>>>(cur, packed, pl.packed_floats, B.ds, ch, cout, hout, nc, Rs, 0);
+                        URSA_LAUNCH_CHECK("shortcut_nhwc_kernel");
+                        res = Rs;
+                    }
+                    ConvTcArgs g;
+                    g.mode = 2; g.bn_off = -1; g.res = nullptr; g.out_raw = Cr; g.out_hi = nullptr; g.out_lo = nullptr;
+                    g.stats = stats; g.batch = batch; g.n_batches = L.nb;
+                    if (int rc = launch_conv_tc(Ah, Al, hw, ch, cout, stride, sc, nc, packed, pl.packed_floats, B.w1, B.w1_lo, g, st)) return rc;
+                    if (int rc = finalize(cout, hout * hout)) return rc;                // bn2: statistics of conv1's output
+                    if (int rc = apply(Cr, cout, hout * hout)) return rc;
+                    g.res = res; g.out_raw = nxt;                                       // conv2 + shortcut -> next block input (+ its statistics)
+                    if (int rc = launch_conv_tc(Ah, Al, hout, cout, cout, 1, sc, nc, packed, pl.packed_floats, B.w2, B.w2_lo, g, st)) return rc;
+                    float *t = cur; cur = nxt; nxt = t;
+                    ch = cout; hw = hout;
+                }
+            if (int rc = finalize(64, 64)) return rc;                                   // the final bn (no apply: only its statistics matter)
+            (void)nb;
+        }
+    }
+    return URSA_OK;
+}
+
+namespace ursa {
 // ---- fused-stage path (URSA_ALGO_TCGEN05_FUSED): stem -> [stage kernel] -> (shortcut + stride-2 conv) -> [stage kernel] ...
 // f16 != 0 (URSA_ALGO_TCGEN05_FUSED_F16): FP16-split stage kernels (bma_conv_fused16.cuh), type-6 filters, and the stride-2
 // convs hand their activations over as one plain fp32 plane

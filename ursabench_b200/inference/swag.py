@@ -144,11 +144,40 @@ class SWAG(SWA):
                                        workspace=self._bn_ws)
         return self._bn_ws is not None
 
+    def _engine_bn_update_rows(self, rows):
+        """PreResNets: ONE sample-batched train-mode pass for all ``rows`` (``ursa_preresnet_bn_update``, 8 samples per launch
+        on the tcgen05 layer kernel with a statistics epilogue) instead of one PyTorch pass over the train set per sample
+        (util.py:212-247, swag.py:123-124).  Returns False when the model / loader shape is not covered."""
+        from ..tasks._engine import _arch_of
+        arch = _arch_of(self.swag_model)
+        batch = getattr(self.train_loader, "batch_size", None)
+        if arch is None or arch[0] != "preresnet" or not batch or getattr(self.train_loader, "drop_last", False) or not rows:
+            return False
+        _, depth, C = arch
+        n_train = max(len(self.train_loader.dataset), 1)
+        if _C.lib().ursa_preresnet_bn_update_workspace(len(rows), n_train, batch, depth, C) == 0:
+            return False
+        if getattr(self, "_bn_x", None) is None:
+            xs = [xb for xb, _ in self.train_loader]
+            if any(len(xb) != batch for xb in xs[:-1]) or xs[0].dim() != 4 or tuple(xs[0].shape[1:]) != (3, 32, 32):
+                return False
+            self._bn_x = torch.cat(xs).to(self.device, non_blocking=True).float().contiguous()
+            self._bn_ws = None
+        w, b = self.bank.rows(list(rows))
+        contiguous = b.data_ptr() == self.bank.b[rows[0]].data_ptr()        # a view of the bank: written in place
+        self._bn_ws = _C.preresnet_bn_update(w, b, self._bn_x, batch, depth, C, workspace=self._bn_ws)
+        if self._bn_ws is None:
+            return False
+        if not contiguous:
+            for i, r in enumerate(rows):
+                self.bank.b[r].copy_(b[i])
+        return True
+
     def _finish_sample(self, row, update_bn):
         """Load the draw into ``swag_model``, re-estimate BatchNorm statistics (reference :99-102,:123-124 -- one full
         pass over the train set per sample) and store them with the row."""
         if update_bn and check_bn(self.swag_model):
-            if self._engine_bn_update(row):
+            if self._engine_bn_update(row) or self._engine_bn_update_rows([row]):
                 return self.bank.handle(row)
             self.swag_flat.load_vector(self.bank.w[row])
             bn_update(self.train_loader, self.swag_model, device=self.device)
@@ -171,4 +200,6 @@ class SWAG(SWA):
             rank, world = udist.rank_world()
             num_samples = len(range(rank, num_samples, world))      # this rank's draws s = rank (mod world)
         rows = self._draw_into_bank(num_samples, full_cov)     # all draws: one pass over the ring
+        if check_bn(self.swag_model) and self._engine_bn_update_rows(rows):
+            return [self.bank.handle(r) for r in rows]         # BatchNorm statistics of all draws: one sample-batched pass
         return [self._finish_sample(r, True) for r in rows]
