@@ -533,7 +533,12 @@ struct TcChunking {
 static TcChunking tc_chunking(int S, int64_t N, const NetPlan &pl) {
     TcChunking c;
     c.sc = S < kTcChunkSamples ? S : kTcChunkSamples;
-    c.nc = (int)(N < kTcChunkImages ? N : kTcChunkImages);
+    static const int chunk_images = [] {            // URSA_CHUNK_IMAGES: images per launch of the conv forwards (experiments)
+        const char *e = getenv("URSA_CHUNK_IMAGES");
+        const int v = e ? atoi(e) : 0;
+        return v >= 64 && v <= 16384 ? v : kTcChunkImages;
+    }();
+    c.nc = (int)(N < chunk_images ? N : chunk_images);
     const size_t pairs = (size_t)c.sc * c.nc;
     c.raw_bytes = pairs * 16 * 32 * 32 * sizeof(float);               // largest activation: 64 KB per pair
     c.packed_bytes = (((size_t)c.sc * pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
