@@ -126,11 +126,13 @@ int ursa_swag_variance(const float *mean, const float *sq_mean, float *var, int6
  *     its low-rank branch raises -- see DESIGN.md "reference quirks")
  *   out[s, :] = mean + sqrt(var) * z1[s, :] + (ring^T z2[s, :]) / rank_div        s = 0..S-1
  * ring: [K, ld_ring] deviation rows (K == 0 -> diagonal draw); z2: [S, K] device, row-major;
- * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox (key = seed, counter =
- * (s*D + d)/4 .. as in K1 with elem index s*D+d, step).  All S draws are produced in ONE pass over the
- * ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  Rows (ring, out, z1) must be 16-byte aligned:
- * ld_* % 4 == 0.  K <= URSA_DRAW_MAX_K; any S >= 1 (draws are processed URSA_DRAW_MAX_S per launch, so the ring is
- * read once per group of 32 draws; the Philox stream does not depend on the grouping).
+ * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox4x32-10 (key = seed, counter = (block, step)):
+ * element (s, d) is normal (s & 3) of block (s >> 2) * D + d, i.e. element 4 * ((s >> 2) * D + d) + (s & 3) of the K1 stream
+ * (ursa_philox_normal) -- a block serves four consecutive draws of one column.  All S draws are produced in ONE pass over the
+ * ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  The K x S contraction runs on tcgen05 (3xTF32, fp32 accumulate in
+ * TMEM).  Rows (ring, out, z1) must be 16-byte aligned: ld_* % 4 == 0.  K <= URSA_DRAW_MAX_K; any S >= 1 (draws are processed
+ * URSA_DRAW_MAX_S per launch, so the ring is read once per group of 32 draws; the Philox stream does not depend on the
+ * grouping).
  * ---------------------------------------------------------------------- */
 #define URSA_DRAW_MAX_S 32
 #define URSA_DRAW_MAX_K 24

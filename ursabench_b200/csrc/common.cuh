@@ -64,6 +64,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// lg2.approx.ftz: MUFU.LG2 alone -- __log2f adds a denormal rescue (compare, scale, fix-up) around it; the arguments here are
+// >= 2^-33, where both give the same bits
+__device__ __forceinline__ float fast_log2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -77,8 +85,8 @@ __device__ __forceinline__ float4 box_muller4(uint4 r) {
     const float kTwoPi2m32 = 1.4629180792671596e-9f;          // 2*pi * 2^-32
     const float u1a = fmaf(__uint2float_rn(r.x), k2m32, k2m33);
     const float u1b = fmaf(__uint2float_rn(r.z), k2m32, k2m33);
-    const float ra = fast_sqrt(-1.3862943611198906f * __log2f(u1a));   // sqrt(-2 ln u)
-    const float rb = fast_sqrt(-1.3862943611198906f * __log2f(u1b));
+    const float ra = fast_sqrt(-1.3862943611198906f * fast_log2(u1a));   // sqrt(-2 ln u)
+    const float rb = fast_sqrt(-1.3862943611198906f * fast_log2(u1b));
     const float ta = fmaf(__uint2float_rn(r.y), kTwoPi2m32, 0.5f * kTwoPi2m32);
     const float tb = fmaf(__uint2float_rn(r.w), kTwoPi2m32, 0.5f * kTwoPi2m32);
     float sa, ca, sb, cb;

@@ -9,6 +9,7 @@
 // memory in parity mode).
 #include "async.cuh"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ursa {
 
@@ -61,252 +62,282 @@ __global__ void __launch_bounds__(kEwThreads) swag_variance_kernel(const float *
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2b.  CTA = 16 warps, tile = 1024 columns of the ring, double buffered in shared memory by the TMA engine.
-// A warp owns 16-column blocks of the tile.  The K x S contraction  acc[s, d] = sum_k z2[s, k] ring[k, d]  runs on
-// the warp-level tensor-core MMA (m16n8k8, 3xTF32: operands split hi + lo, lo*lo dropped, fp32 accumulate) because
-// its accumulator fragments stay in the registers of the thread that also draws the Gaussians for the same (s, d):
-//   A = z2 / rank_div  [16 draws x 8 ring rows]   constant per launch -> loaded once into registers (hi / lo)
-//   B = ring tile      [8 ring rows x 8 columns]  LDS.64 from the staged tile (row pitch = 1032 floats: conflict free)
-//   C                  [16 draws x 8 columns]     MMA column c of n-tile j <-> column 4*(c/2) + 2*(c%2) + j of the block,
-//                                                 so a thread ends up with 4 CONSECUTIVE columns of 4 draws
-// = one Philox4x32-10 block (4 normals along d) and one 16-byte store per (draw, thread).  Before this, the contraction
-// was K*S FFMAs per column and the kernel was issue bound at 44 % of HBM peak.
-constexpr int kDrawThreads = 512;
-constexpr int kDrawWarps = kDrawThreads / 32;
-constexpr int kTileCols = 1024;
-constexpr int kPitch = kTileCols + 8;           // floats; pitch % 32 == 8
+// K2b.  out[s, d] = mean[d] + sd[d] z1[s, d] + sum_k (z2[s, k] / rank_div) ring[k, d]      (swag.py:85-97)
+// One persistent CTA per SM, tile = 512 columns d of the ring, all S <= 32 draws of the tile per pass, so the ring crosses
+// HBM once.  Round 2 rebuilt the kernel around tcgen05: the round-1 version ran the K x S contraction on the warp-level
+// mma.sync and spent 45 issue slots per Gaussian (17 of them on fragment loads / splits / moves around the HMMAs; ncu r04,
+// r2s15: IPC 2.15, no pipe above 45 %) -- it was bound by instruction issue at 0.47 of the HBM roofline.
+//   warp 16  (one lane) = producer: K + 2 row copies (ring rows, mean, var) per tile into a 2-stage ring by the TMA engine
+//            (cp.async.bulk + mbarrier), and the tile's 36 tcgen05.mma: D[128 columns x 32 draws] (+)= A[128 x 8] * B[32 x 8]^T,
+//            kind::tf32, three products per k-step (lo*hi, hi*lo, hi*hi), four 128-column row tiles, into one of two TMEM
+//            buffers; B = z2 / rank_div, split once per launch
+//   warps 0..15, thread = column:
+//     split  its K ring values become the rows of the A operand, split x = hi + lo (3xTF32), written in the NO-SWIZZLE
+//            K-major UMMA layout (row d at 16 B stride, one 4-k chunk per 8 KB plane: 6 STS.128 per part, conflict free);
+//            the same thread takes sqrt(var) once -- no lane recomputes another lane's value
+//     Gauss  TMEM lane = column: tcgen05.ld hands the thread its 32 low-rank terms; ceil(S / 4) Philox4x32-10 blocks, two at
+//            a time in straight-line code -> Box-Muller -> mean + (sd z + lr), one coalesced 128-byte store per warp and draw
+// No CTA-wide barrier in the loop: split(i + 1) -> a_ready (mbarrier, 512 arrivals) -> MMA(i + 1) -> mma_bar -> Gauss(i + 1);
+// the MMAs of tile i + 1 and the copies of tiles i + 2, i + 3 run under the Gaussian generation of tile i.
+// Philox stream: element (s, d) of a call is normal (s & 3) of block (s >> 2) * D + d at `step` -- a block serves four
+// consecutive DRAWS of one column, so a thread never needs another thread's normals.
+constexpr int kDrawThreads = 512;               // compute threads (the ring kernel adds one producer warp)
+constexpr int kTileCols = 512;
 constexpr int kKP = 24;                         // ring rows padded to 3 k-steps of 8 (URSA_DRAW_MAX_K)
 constexpr int kRows = kKP + 2;                  // + the mean and var rows of the tile (staged by the same bulk copies)
 constexpr int kStages = 2;
-static_assert(URSA_DRAW_MAX_K <= kKP && URSA_DRAW_MAX_S <= 32, "fragment shapes");
+constexpr int kDrawN = 32;                      // draws per launch = MMA N (URSA_DRAW_MAX_S)
+constexpr uint32_t kAPlane = kTileCols * 16;    // bytes between two 4-k chunks of the A operand (LBO)
+constexpr uint32_t kABytes = (kKP / 4) * kAPlane;            // 48 KB per part (hi / lo)
+constexpr uint32_t kBPlane = kDrawN * 16;       // LBO of the B operand
+constexpr uint32_t kBBytes = (kKP / 4) * kBPlane;            // 3 KB per part
+constexpr uint32_t kTmemCols = 2 * (kTileCols / 128) * kDrawN;   // two buffers of four 32-column accumulators
+constexpr uint32_t kStageBytes = kRows * kTileCols * 4;
+constexpr uint32_t kAOff = kStages * kStageBytes, kBOff = kAOff + 2 * kABytes, kDrawSmem = kBOff + 2 * kBBytes;
+static_assert(URSA_DRAW_MAX_K <= kKP && URSA_DRAW_MAX_S == kDrawN, "operand shapes");
+static_assert(kTileCols == kDrawThreads, "thread = column");
+static_assert(kTmemCols == 256, "power-of-two TMEM allocation");
+static_assert(kDrawSmem <= 227 * 1024 - 1024, "shared memory");
 
 struct DrawArgs {
     float *out;
     const float *mean, *var, *ring, *z2, *z1;
     int64_t ld_out, ld_ring, ld_z1, D;
     int K, S;
-    int s0;                 // index of the launch's first draw within the call: Philox block base (s0 + s) * ceil(D / 4)
+    int s0;                 // index of the launch's first draw within the call (a multiple of 32): Philox block row (s0 + s) >> 2
     float rank_div;
     uint2 key;
     uint64_t step;
 };
 
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// no-swizzle K-major UMMA descriptor: start | LBO = stride between two 16-byte K chunks | SBO = 128 B between 8-row groups
+__device__ __forceinline__ uint64_t draw_desc(uint32_t addr, uint32_t lbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           ((uint64_t)1 << 46);
 }
 
-// MT = 16-draw row tiles (1: S <= 16, 2: S <= 32); RING = low-rank term present (K > 0)
-template <int MT, bool RING>
-__global__ void __launch_bounds__(kDrawThreads, 1) swag_draw_kernel(const DrawArgs a) {
-    constexpr int NI = 2 * MT;                                                  // draws per thread: rows nrow + 8 i
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int TR = RING ? kRows : 2;                                        // staged rows per tile
-    constexpr int MROW = RING ? kKP : 0;                                        // row index of the mean (var = MROW + 1)
-    float *ring_s = reinterpret_cast<float *>(smem_raw);                       // [kStages][TR][kPitch]
-    __shared__ __align__(16) uint4 afrag[2][3][MT][32];                         // [hi / lo][k-step][row tile][lane]
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = lane & 3, nrow = lane >> 2;
-    const int K = a.K, S = a.S;
-    const int KT = (K + 7) >> 3;
-
-    if (RING) {
-        // A fragments (z2 / rank_div, split hi + lo): a0 = (row nrow, col q), a1 = (row nrow + 8, col q),
-        // a2 = (row nrow, col q + 4), a3 = (row nrow + 8, col q + 4); one uint4 per lane, conflict-free LDS.128
-        const float inv_div = 1.0f / a.rank_div;                               // 1/sqrt(max_rank-1) folded in (swag.py:95)
-        for (int e = threadIdx.x; e < 3 * MT * 32; e += kDrawThreads) {
-            const int ln = e & 31, mt = (e >> 5) % MT, kt = (e >> 5) / MT;
-            uint32_t h[4], l[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int s = mt * 16 + (ln >> 2) + (i & 1) * 8, k = kt * 8 + (ln & 3) + (i >> 1) * 4;
-                const float z = (s < S && k < K) ? __ldg(a.z2 + (int64_t)s * K + k) * inv_div : 0.f;
-                h[i] = __float_as_uint(z) & 0xFFFFE000u;
-                l[i] = __float_as_uint(z - __uint_as_float(h[i]));
-            }
-            afrag[0][kt][mt][ln] = make_uint4(h[0], h[1], h[2], h[3]);
-            afrag[1][kt][mt][ln] = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-        // rows K .. 8*KT-1 of both stages are never written by the bulk copies: zero them once
-        const int zr = 8 * KT - K;
-        for (int i = threadIdx.x; i < kStages * zr * kPitch; i += kDrawThreads) {
-            const int st = i / (zr * kPitch), r = i - st * zr * kPitch;
-            ring_s[(st * TR + K) * kPitch + r] = 0.f;
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
-    const int64_t Dp4 = (a.D + 3) >> 2;                                        // Philox blocks per draw row
-    // per-thread draw rows: Philox block base and output row of draw i
-    uint64_t ctr_base[NI];
-    float *out_row[NI];
-    bool act[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const int s = (i >> 1) * 16 + (i & 1) * 8 + nrow;
-        act[i] = s < S;
-        ctr_base[i] = (uint64_t)(a.s0 + s) * (uint64_t)Dp4;
-        out_row[i] = a.out + (int64_t)s * a.ld_out;
-    }
-    const bool dense = S > 16 * MT - 8 && a.z1 == nullptr;                      // (nearly) all fragment rows are real draws
-
-    auto issue = [&](int64_t tile, int stage) {                                 // one thread: K bulk copies
-        const int64_t c0 = tile * kTileCols;
-        const int64_t rem = a.D - c0;
-        const uint32_t cols = (uint32_t)(rem >= kTileCols ? kTileCols : ((rem + 3) & ~(int64_t)3));
-        const uint32_t bytes = cols * 4u;
-        // mean / var are only guaranteed D elements: copy whole quads, the ragged last quad is read directly
-        const uint32_t mv_bytes = (uint32_t)(rem >= kTileCols ? kTileCols : (rem & ~(int64_t)3)) * 4u;
-        mbar_arrive_expect_tx(&full_bar[stage], bytes * (uint32_t)K + 2u * mv_bytes);
-        float *dst = ring_s + stage * TR * kPitch;
-        for (int k = 0; k < K; ++k)
-            bulk_g2s(dst + k * kPitch, a.ring + (int64_t)k * a.ld_ring + c0, bytes, &full_bar[stage]);
-        if (mv_bytes) {
-            bulk_g2s(dst + MROW * kPitch, a.mean + c0, mv_bytes, &full_bar[stage]);
-            bulk_g2s(dst + (MROW + 1) * kPitch, a.var + c0, mv_bytes, &full_bar[stage]);
-        }
+// The S draws of column c (c < D): groups of four draws share a Philox block; two groups at a time run as straight-line code so
+// that the two Philox / Box-Muller chains interleave (a single chain leaves the 4 warps of a scheduler waiting on IMAD.WIDE).
+template <bool RING, bool EXTZ>
+__device__ __forceinline__ void emit_draws(const DrawArgs &a, int64_t c, float m, float sd, const uint32_t (&lr)[kDrawN]) {
+    const int S = a.S;
+    float *o = a.out + c;
+    const float *zp = EXTZ ? a.z1 + c : nullptr;
+    uint64_t blk = (uint64_t)(a.s0 >> 2) * (uint64_t)a.D + (uint64_t)c;
+    auto apply = [&](float z, int s) {
+        float r = __fmul_rn(sd, z);                                                        // swag.py:88-89
+        if (RING) r = __fadd_rn(r, __uint_as_float(lr[s]));                                // swag.py:95-96 (scale folded)
+        *o = __fadd_rn(m, r);                                                              // swag.py:97
+        o += a.ld_out;
     };
-    if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
-
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const float *rs = ring_s + stage * TR * kPitch;
-        const float *bfrag = rs + q * kPitch + 2 * nrow;                        // B fragment base of this lane
-        {
-            const int64_t next = tile + gridDim.x;
-            if (threadIdx.x == 0 && next < ntiles) issue(next, stage ^ 1);
-            mbar_wait(&full_bar[stage], (uint32_t)(it >> 1) & 1u);
-        }
-#pragma unroll 1
-        for (int blk = warp; blk < kTileCols / 16; blk += kDrawWarps) {
-            const int cb = blk * 16;
-            const int64_t cblk = tile * kTileCols + cb;
-            if (cblk >= a.D) break;                                             // warp-uniform
-            const int64_t c0 = cblk + 4 * q;                                    // this thread's 4 columns
-            const bool whole = cblk + 16 <= a.D;                                // warp-uniform: no ragged edge in this block
-            const bool live = c0 < a.D, full4 = c0 + 4 <= a.D;
-            float m[4], sd[4];
-            if (full4) {
-                const float4 mv = *reinterpret_cast<const float4 *>(rs + MROW * kPitch + cb + 4 * q);
-                const float4 vv = *reinterpret_cast<const float4 *>(rs + (MROW + 1) * kPitch + cb + 4 * q);
-                m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-                sd[0] = sqrtf(vv.x); sd[1] = sqrtf(vv.y); sd[2] = sqrtf(vv.z); sd[3] = sqrtf(vv.w);
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool ok = c0 + j < a.D;
-                    m[j] = ok ? a.mean[c0 + j] : 0.f;
-                    sd[j] = ok ? sqrtf(a.var[c0 + j]) : 0.f;
+    for (int gp = 0; gp < kDrawN / 8; ++gp) {
+        if (8 * gp + 8 <= S) {                                                             // uniform: eight draws, no predicates
+            float z[8];
+            if (EXTZ) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { z[e] = __ldg(zp); zp += a.ld_z1; }
+            } else {
+                const float4 za = philox_normal4(blk, a.step, a.key), zb = philox_normal4(blk + (uint64_t)a.D, a.step, a.key);
+                blk += 2 * (uint64_t)a.D;
+                z[0] = za.x; z[1] = za.y; z[2] = za.z; z[3] = za.w; z[4] = zb.x; z[5] = zb.y; z[6] = zb.z; z[7] = zb.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) apply(z[e], 8 * gp + e);
+        } else if (8 * gp < S) {                                                           // the ragged last pair of groups
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (8 * gp + 4 * h < S) {
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (EXTZ) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (8 * gp + 4 * h + e < S) { z[e] = __ldg(zp); zp += a.ld_z1; }
+                    } else {
+                        const float4 zv = philox_normal4(blk, a.step, a.key);
+                        blk += (uint64_t)a.D;
+                        z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (8 * gp + 4 * h + e < S) apply(z[e], 8 * gp + 4 * h + e);
                 }
             }
-            float acc[MT][2][4];                                                // [row tile][n-tile j][c0..c3]
+        }
+    }
+}
+
+// K = 0 (diagonal draw): nothing to stage or contract -- thread = column, 8 B read and 4 S bytes written per column
+template <bool EXTZ>
+__global__ void __launch_bounds__(kDrawThreads, 2) swag_draw_diag_kernel(const DrawArgs a) {
+    const int64_t stride = (int64_t)gridDim.x * kDrawThreads;
+    int64_t c = (int64_t)blockIdx.x * kDrawThreads + threadIdx.x;
+    float m_next = 0.f, v_next = 0.f;
+    if (c < a.D) { m_next = __ldg(a.mean + c); v_next = __ldg(a.var + c); }
+    for (; c < a.D; c += stride) {
+        const float m = m_next, sd = sqrtf(v_next);                                        // swag.py:88 var.sqrt()
+        if (c + stride < a.D) { m_next = __ldg(a.mean + c + stride); v_next = __ldg(a.var + c + stride); }   // one column ahead
+        uint32_t none[kDrawN];
+        emit_draws<false, EXTZ>(a, c, m, sd, none);
+    }
+}
+
+template <bool EXTZ>
+__global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const DrawArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int MROW = kKP;                                                   // row index of the mean (var = MROW + 1)
+    float *raw = reinterpret_cast<float *>(smem_raw);                          // [kStages][kRows][kTileCols]
+    __shared__ __align__(8) uint64_t full_bar[kStages], mma_bar[2], a_ready;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool producer = warp == kDrawThreads / 32;
+    const int K = a.K, S = a.S;
+    const int KS = (K + 7) >> 3, KC = 2 * KS;                                   // 8-k MMA steps / 4-k chunks in use
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t a_hi = sbase + kAOff, a_lo = a_hi + kABytes, b_hi = sbase + kBOff, b_lo = b_hi + kBBytes;
+
+    if (!producer) {
+        // B operand: z2 / rank_div (swag.py:95), split hi + lo; element (s, k) at chunk (k / 4) * kBPlane + s * 16 + (k % 4) * 4
+        const float inv_div = 1.0f / a.rank_div;
+        for (int e = tid; e < kDrawN * kKP; e += kDrawThreads) {
+            const int s = e & (kDrawN - 1), k = e / kDrawN;
+            const float z = (s < S && k < K) ? __ldg(a.z2 + (int64_t)s * K + k) * inv_div : 0.f;
+            const uint32_t h = __float_as_uint(z) & 0xFFFFE000u;
+            const uint32_t off = (uint32_t)(k >> 2) * kBPlane + (uint32_t)s * 16u + (uint32_t)(k & 3) * 4u;
+            *reinterpret_cast<uint32_t *>(smem_raw + kBOff + off) = h;
+            *reinterpret_cast<float *>(smem_raw + kBOff + kBBytes + off) = z - __uint_as_float(h);
+        }
+        // ring rows K .. 8 KS - 1 of both stages are never written by the bulk copies: zero them once
+        for (int st = 0; st < kStages; ++st)
+            for (int r = K; r < 8 * KS; ++r) raw[(st * kRows + r) * kTileCols + tid] = 0.f;
+        fence_proxy_async();
+        if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+    } else if (tid == kDrawThreads) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        mbar_init(&a_ready, kDrawThreads);
+        fence_barrier_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
+    const int n_my = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles blockIdx.x + i * gridDim.x, i < n_my
+
+    if (producer) {
+        if (tid == kDrawThreads) {
+            auto issue = [&](int i) {                                           // K + 2 bulk copies of local tile i
+                const int stage = i & 1;
+                const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols;
+                const int64_t rem = a.D - c0;
+                const uint32_t bytes = (uint32_t)(rem >= kTileCols ? kTileCols : ((rem + 3) & ~(int64_t)3)) * 4u;
+                // mean / var are only guaranteed D elements: copy whole quads, the ragged last quad is read directly
+                const uint32_t mv_bytes = (uint32_t)(rem >= kTileCols ? kTileCols : (rem & ~(int64_t)3)) * 4u;
+                mbar_arrive_expect_tx(&full_bar[stage], bytes * (uint32_t)K + 2u * mv_bytes);
+                float *dst = raw + stage * kRows * kTileCols;
+                const float *src = a.ring + c0;
+                for (int k = 0; k < K; ++k, src += a.ld_ring, dst += kTileCols) bulk_g2s(dst, src, bytes, &full_bar[stage]);
+                if (mv_bytes) {
+                    dst = raw + (stage * kRows + MROW) * kTileCols;
+                    bulk_g2s(dst, a.mean + c0, mv_bytes, &full_bar[stage]);
+                    bulk_g2s(dst + kTileCols, a.var + c0, mv_bytes, &full_bar[stage]);
+                }
+            };
+            if (n_my > 0) issue(0);
+            if (n_my > 1) issue(1);
+            const uint32_t idesc = make_tf32_idesc(128, kDrawN);
+            // descriptors differ only in the start-address field (bits 0-13, 16-byte units): one 32-bit add per operand and MMA.
+            // The loop is straight-line code -- this lane shares its scheduler with four busy compute warps, and every
+            // instruction it spends between a_ready and the commit delays the tile's Gaussians.
+            const uint64_t ah0 = draw_desc(a_hi, kAPlane), al0 = draw_desc(a_lo, kAPlane);
+            const uint64_t bh0 = draw_desc(b_hi, kBPlane), bl0 = draw_desc(b_lo, kBPlane);
+            for (int i = 0; i < n_my; ++i) {
+                mbar_wait(&a_ready, (uint32_t)i & 1u);                          // A operand of tile i written, raw stage i & 1 consumed
+                tc_fence_after();
+                const uint32_t dbase = tmem + (uint32_t)(i & 1) * (kTmemCols / 2);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+                for (int ks = 0; ks < kKP / 8; ++ks) {
+                    if (ks < KS) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
-            if (RING) {
-#pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
-                    if (kt < KT) {
-                        // B fragments of both n-tiles: b0 = (k = q, n = nrow), b1 = (k = q + 4, n = nrow); columns cb + 2n + j
-                        const float2 r0 = *reinterpret_cast<const float2 *>(bfrag + kt * 8 * kPitch + cb);
-                        const float2 r1 = *reinterpret_cast<const float2 *>(bfrag + (kt * 8 + 4) * kPitch + cb);
-                        const float bv[2][2] = {{r0.x, r1.x}, {r0.y, r1.y}};    // [j][b0 / b1]
-                        uint32_t bh[2][2], bl[2][2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                bh[j][e] = __float_as_uint(bv[j][e]) & 0xFFFFE000u;
-                                bl[j][e] = __float_as_uint(bv[j][e] - __uint_as_float(bh[j][e]));
-                            }
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint4 ah4 = afrag[0][kt][mt][lane], al4 = afrag[1][kt][mt][lane];
-                            const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                mma_tf32_16x8x8(acc[mt][j], al, bh[j][0], bh[j][1]);
-                                mma_tf32_16x8x8(acc[mt][j], ah, bl[j][0], bl[j][1]);
-                                mma_tf32_16x8x8(acc[mt][j], ah, bh[j][0], bh[j][1]);
-                            }
+                        for (int t = 0; t < kTileCols / 128; ++t) {
+                            const uint32_t d = dbase + (uint32_t)t * kDrawN;
+                            const uint32_t ao = ((uint32_t)(2 * ks) * kAPlane + (uint32_t)t * 2048u) >> 4;
+                            const uint32_t bo = ((uint32_t)(2 * ks) * kBPlane) >> 4;
+                            umma_tf32(d, al0 + ao, bh0 + bo, idesc, ks > 0);
+                            umma_tf32(d, ah0 + ao, bl0 + bo, idesc, 1);
+                            umma_tf32(d, ah0 + ao, bh0 + bo, idesc, 1);
                         }
                     }
                 }
-            }
-            // draw i covers row s = 16 (i / 2) + 8 (i % 2) + nrow; column 4q + e of the block is C element
-            // (n-tile e & 1, c = 2 (i % 2) + (e >> 1))
-            if (dense && whole) {
-                // straight-line path: the NI Philox / Box-Muller chains are independent and interleave
-                const uint64_t blk4 = (uint64_t)(c0 >> 2);
-                float4 zv[NI];
-#pragma unroll
-                for (int i = 0; i < NI; ++i) zv[i] = philox_normal4(ctr_base[i] + blk4, a.step, a.key);
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int mt = i >> 1, h = i & 1;
-                    const float z[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
-                    const float lr[4] = {acc[mt][0][2 * h], acc[mt][1][2 * h], acc[mt][0][2 * h + 1], acc[mt][1][2 * h + 1]};
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float r = __fmul_rn(sd[j], z[j]);                                  // swag.py:88-89
-                        if (RING) r = __fadd_rn(r, lr[j]);                                 // swag.py:95-96 (scale folded)
-                        o[j] = __fadd_rn(m[j], r);                                         // swag.py:97
-                    }
-                    if (act[i]) *reinterpret_cast<float4 *>(out_row[i] + c0) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                continue;
-            }
-            if (!live) continue;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                if (!act[i]) continue;
-                const int mt = i >> 1, h = i & 1;
-                float z[4];
-                if (a.z1) {
-                    const float *zr = a.z1 + (int64_t)((i >> 1) * 16 + (i & 1) * 8 + nrow) * a.ld_z1 + c0;
-                    if (full4) {
-                        const float4 zv = __ldg(reinterpret_cast<const float4 *>(zr));
-                        z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) z[j] = (c0 + j < a.D) ? zr[j] : 0.f;
-                    }
-                } else {
-                    const float4 zv = philox_normal4(ctr_base[i] + (uint64_t)(c0 >> 2), a.step, a.key);
-                    z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
-                }
-                const float lr[4] = {acc[mt][0][2 * h], acc[mt][1][2 * h], acc[mt][0][2 * h + 1], acc[mt][1][2 * h + 1]};
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float r = __fmul_rn(sd[j], z[j]);                                      // swag.py:88-89
-                    if (RING) r = __fadd_rn(r, lr[j]);                                     // swag.py:95-96 (scale folded)
-                    o[j] = __fadd_rn(m[j], r);                                             // swag.py:97
-                }
-                float *orow = out_row[i] + c0;
-                if (full4) {
-                    *reinterpret_cast<float4 *>(orow) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (c0 + j < a.D) orow[j] = o[j];
-                }
+                umma_commit(smem_u32(&mma_bar[i & 1]));
+                if (i + 2 < n_my) issue(i + 2);
             }
         }
-        __syncthreads();   // everyone is done with ring_s[stage] before it is refilled
+    } else {
+        float m_next = 0.f, sd_next = 0.f;
+        // local tile i has landed: this thread's column -> (mean, sd) registers and its rows of the A operand
+        auto split = [&](int i) {
+            const int stage = i & 1;
+            mbar_wait(&full_bar[stage], (uint32_t)(i >> 1) & 1u);
+            const float *rs = raw + stage * kRows * kTileCols + tid;
+            const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols;
+            const int64_t c = c0 + tid, rem = a.D - c0;
+            if (c < a.D) {
+                const bool staged = tid < (rem >= kTileCols ? kTileCols : (int)(rem & ~(int64_t)3));
+                m_next = staged ? rs[MROW * kTileCols] : a.mean[c];
+                sd_next = sqrtf(staged ? rs[(MROW + 1) * kTileCols] : a.var[c]);   // swag.py:88 var.sqrt()
+            }
+            float x[kKP];                                                       // all loads first: their latencies overlap
+#pragma unroll
+            for (int r = 0; r < kKP; ++r) x[r] = (r >> 2) < KC ? rs[r * kTileCols] : 0.f;
+#pragma unroll
+            for (int kc = 0; kc < kKP / 4; ++kc) {
+                if (kc < KC) {
+                    uint32_t h[4];
+                    float l[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        h[e] = __float_as_uint(x[4 * kc + e]) & 0xFFFFE000u;
+                        l[e] = x[4 * kc + e] - __uint_as_float(h[e]);
+                    }
+                    const uint32_t off = kAOff + (uint32_t)kc * kAPlane + (uint32_t)tid * 16u;
+                    *reinterpret_cast<uint4 *>(smem_raw + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4 *>(smem_raw + off + kABytes) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+            }
+            fence_proxy_async();                                                // generic writes -> tensor-core (async proxy) reads
+            tc_fence_before();                                                  // this thread's tcgen05.ld of tile i - 2 (same TMEM buffer) precede the MMAs
+            mbar_arrive(&a_ready);
+        };
+        if (n_my > 0) split(0);
+        for (int i = 0; i < n_my; ++i) {
+            const float m = m_next, sd = sd_next;
+            mbar_wait(&mma_bar[i & 1], (uint32_t)(i >> 1) & 1u);                // tile i's MMAs done: A is free, TMEM buffer full
+            if (i + 1 < n_my) split(i + 1);
+            tc_fence_after();
+            // TMEM lane = row of the 128-column accumulator tile = 32 (warp % 4) + lane; tile warp / 4 at columns 32 (warp / 4)
+            const uint32_t taddr = tmem + (uint32_t)(i & 1) * (kTmemCols / 2) + (uint32_t)(warp >> 2) * kDrawN +
+                                   ((uint32_t)((warp & 3) * 32) << 16);
+            uint32_t lr[kDrawN];
+            {
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(taddr, r0);
+                tmem_ld16_nowait(taddr + 16, r1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { lr[e] = r0[e]; lr[16 + e] = r1[e]; }
+            }
+            const int64_t c = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols + tid;
+            if (c < a.D) emit_draws<true, EXTZ>(a, c, m, sd, lr);
+        }
+        tc_fence_before();
     }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -409,13 +440,19 @@ static int ew_grid(int64_t work_items) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-template <int MT, bool RING>
+template <bool EXTZ>
 static int launch_draw(const DrawArgs &a, cudaStream_t st) {
-    const size_t smem = (size_t)kStages * (RING ? kRows : 2) * kPitch * sizeof(float);
-    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<MT, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
+    if (a.K == 0) {
+        const int64_t cap = (int64_t)sm_count() * 2;
+        swag_draw_diag_kernel<EXTZ><<<(int)(ntiles < cap ? ntiles : cap), kDrawThreads, 0, st>>>(a);
+        URSA_LAUNCH_CHECK("swag_draw_diag_kernel");
+        return URSA_OK;
+    }
+    const size_t smem = kDrawSmem + 1024;                                      // + slack for the 1 KB alignment
+    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<EXTZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    swag_draw_kernel<MT, RING><<<grid, kDrawThreads, smem, st>>>(a);
+    swag_draw_kernel<EXTZ><<<grid, kDrawThreads + 32, smem, st>>>(a);
     URSA_LAUNCH_CHECK("swag_draw_kernel");
     return URSA_OK;
 }
@@ -472,9 +509,7 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
         a.rank_div = rank_div;
         a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         a.step = step;
-        int rc;
-        if (K == 0) rc = sg <= 16 ? launch_draw<1, false>(a, st) : launch_draw<2, false>(a, st);
-        else rc = sg <= 16 ? launch_draw<1, true>(a, st) : launch_draw<2, true>(a, st);
+        const int rc = z1 ? launch_draw<true>(a, st) : launch_draw<false>(a, st);
         if (rc) return rc;
     }
     return URSA_OK;
