@@ -126,15 +126,16 @@ int ursa_swag_variance(const float *mean, const float *sq_mean, float *var, int6
  *     its low-rank branch raises -- see DESIGN.md "reference quirks")
  *   out[s, :] = mean + sqrt(var) * z1[s, :] + (ring^T z2[s, :]) / rank_div        s = 0..S-1
  * ring: [K, ld_ring] deviation rows (K == 0 -> diagonal draw); z2: [S, K] device, row-major;
- * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox4x32-10 (key = seed, counter = (block, step)):
- * element (s, d) is normal (s & 3) of block (s >> 2) * D + d, i.e. element 4 * ((s >> 2) * D + d) + (s & 3) of the K1 stream
- * (ursa_philox_normal) -- a block serves four consecutive draws of one column.  All S draws are produced in ONE pass over the
- * ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  The K x S contraction runs on tcgen05 (3xTF32, fp32 accumulate in
- * TMEM).  Rows (ring, out, z1) must be 16-byte aligned: ld_* % 4 == 0.  K <= URSA_DRAW_MAX_K; any S >= 1 (draws are processed
- * URSA_DRAW_MAX_S per launch, so the ring is read once per group of 32 draws; the Philox stream does not depend on the
- * grouping).
+ * z1: [S, ld_z1] device, or NULL to draw z1 in-register from Philox4x32-10 (key = seed, counter = (block, step)): element
+ * (s, d) is normal s % 6 of block (s / 6) * D + d -- a block serves SIX consecutive draws of one column; its 128 bits are cut
+ * into three (24-bit radius uniform, 18-bit angle) Box-Muller pairs (csrc/common.cuh::box_muller6; oracle/restate.py::
+ * draw_normals restates it).  A diagonal draw with mean = 0, var = 1 returns exactly this stream.  All S draws are produced in
+ * ONE pass over the ring: (K + 2 + S) * 4 B/param instead of S * (K + 3) * 4.  The K x S contraction runs on tcgen05 (3xTF32,
+ * fp32 accumulate in TMEM).  Rows (ring, out, z1) must be 16-byte aligned: ld_* % 4 == 0.  K <= URSA_DRAW_MAX_K; any S >= 1
+ * (draws are processed URSA_DRAW_MAX_S per launch, so the ring is read once per group of 30 draws; the Philox stream does not
+ * depend on the grouping).
  * ---------------------------------------------------------------------- */
-#define URSA_DRAW_MAX_S 32
+#define URSA_DRAW_MAX_S 30
 #define URSA_DRAW_MAX_K 24
 
 int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, const float *var,

@@ -314,6 +314,43 @@ def box_muller(r):
     return np.stack([ra * np.cos(ta), ra * np.sin(ta), rb * np.cos(tb), rb * np.sin(tb)], axis=-1)
 
 
+def draw_normals(S, D, seed, step):
+    """The N(0, 1) stream of ``ursa_swag_draw`` in Philox mode (csrc/common.cuh::box_muller6): element (s, d) is normal
+    s % 6 of the block with counter ((s // 6) * D + d, step), key = seed; the block's 128 bits x:y:z:w are cut from the top
+    into three (24-bit radius uniform a, 18-bit angle t) pairs.  Returns float64 [S, D]."""
+    G = (S + 5) // 6
+    blk = (np.arange(G, dtype=np.uint64)[:, None] * np.uint64(D) + np.arange(D, dtype=np.uint64)[None, :]).reshape(-1)
+    ctr = np.zeros((blk.shape[0], 4), np.uint32)
+    ctr[:, 0] = (blk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (blk >> np.uint64(32)).astype(np.uint32)
+    ctr[:, 2] = np.uint32(step & 0xFFFFFFFF)
+    ctr[:, 3] = np.uint32((step >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).astype(np.uint64)
+    bits = (r[:, 0] << np.uint64(32) | r[:, 1]), (r[:, 2] << np.uint64(32) | r[:, 3])      # (x:y, z:w)
+
+    def field(top, width):                                    # `width` bits whose MSB is bit `top` of the 128-bit string (127 = MSB of x)
+        lo = top - width + 1
+        if lo >= 64:
+            v = bits[0] >> np.uint64(lo - 64)
+        elif top < 64:
+            v = bits[1] >> np.uint64(lo)
+        else:
+            v = (bits[0] << np.uint64(64 - lo)) | (bits[1] >> np.uint64(lo))
+        return (v & np.uint64((1 << width) - 1)).astype(np.float64)
+
+    z = np.empty((G, 6, D))
+    top = 127
+    for j in range(3):
+        a, t = field(top, 24), field(top - 24, 18)
+        top -= 42
+        u = ((a + 0.5) * 2.0 ** -24).astype(np.float32).astype(np.float64)       # the device rounds u to fp32 (a = 2^24 - 1 -> 1.0)
+        rad = np.sqrt(-2.0 * np.log(u))
+        th = 2.0 * np.pi * (t + 0.5) * 2.0 ** -18
+        z[:, 2 * j] = (rad * np.cos(th)).reshape(G, D)
+        z[:, 2 * j + 1] = (rad * np.sin(th)).reshape(G, D)
+    return z.reshape(6 * G, D)[:S]
+
+
 # --------------------------------------------------------------------------
 # a15  HMC                        inference/hmc.py:62-85  ->  hamiltorch.sample_model
 #

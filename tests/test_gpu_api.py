@@ -265,9 +265,7 @@ def test_swag_textbook_moments_and_draws(U):
     # Philox z1 stream (swag.py:88-97 without the :98 overwrite)
     draws = torch.stack([_flat(m) for m in samples])            # [32, D] (CPU handles)
     D = W.shape[1]
-    z1 = torch.empty(32 * seen["ld"], device=DEV)
-    _C.philox_normal(z1, seen["seed"], seen["step"])
-    z1 = z1.view(32, seen["ld"])[:, :D].cpu().numpy()
+    z1 = _C.swag_draw_noise(32, D, seen["seed"], seen["step"], DEV)[:, :D].cpu().numpy()
     expect = R.swag_draw(mean.numpy(), var.numpy(), z1, seen["ring"][:, :D].cpu().numpy(), seen["z2"].cpu().numpy(),
                          max_rank=4)
     np.testing.assert_allclose(draws.numpy(), expect, rtol=2e-5, atol=2e-6)

@@ -82,13 +82,18 @@ def test_k2_full_size_collect_fixed_point_and_draw_contraction(C):
         ref = mean[:D].double() + ring[s % K, :D].double() * ((1.0 + s) / rd)
         worst = max(worst, (out[s, :D].double() - ref).abs().max().item())
     assert worst < 1e-6, worst                                            # fp32-level: |term| <= 4 sigma * 0.02 * 30 / 4.4
-    # Philox z1 with K = 0 and unit variance: out - mean is the documented N(0,1) stream, row s starts at block s*ld/4
+    # Philox z1 with K = 0 and unit variance: out - mean is the documented N(0,1) stream (six normals per block, block
+    # (s // 6) * D + d; test_gpu_kernels.py pins it against the oracle's restatement); moments over the full size
     var.fill_(1.0)
-    out2 = torch.empty(2, ld, device="cuda")
+    out2 = torch.empty(8, ld, device="cuda")
     C.swag_draw(out2, mean, var, D, seed=9, step=4)
-    zs = torch.empty(2 * ld, device="cuda")
-    C.philox_normal(zs, 9, 4)
-    assert (out2[:, :D] - mean[None, :D] - zs.view(2, ld)[:, :D]).abs().max().item() < 1e-6
+    zs = C.swag_draw_noise(8, D, 9, 4, "cuda")
+    assert (out2[:, :D] - mean[None, :D] - zs[:, :D]).abs().max().item() < 1e-6
+    zz = zs[:, :D].double()
+    assert abs(zz.mean().item()) < 4 / math.sqrt(zz.numel()) and abs(zz.var().item() - 1) < 6 * math.sqrt(2 / zz.numel())
+    assert abs((zz ** 4).mean().item() - 3) < 6 * math.sqrt(96 / zz.numel())
+    c = torch.corrcoef(zz[:, :: 7])                                                          # draws of one block are uncorrelated
+    assert (c - torch.eye(8, device="cuda", dtype=torch.float64)).abs().max().item() < 6 / math.sqrt(D / 7)
 
 
 def test_k3_k4_full_size_bma_sharding_and_counters(C):

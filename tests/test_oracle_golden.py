@@ -178,6 +178,24 @@ def test_philox_known_answers():
     assert [hex(int(v)) for v in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
 
 
+def test_draw_normals_stream():
+    # the SWAG draw's six-normals-per-block stream (oracle restatement of csrc/common.cuh::box_muller6)
+    z = R.draw_normals(13, 20000, seed=77, step=3)
+    assert z.shape == (13, 20000) and abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.01 and abs((z ** 4).mean() - 3) < 0.06
+    assert np.abs(np.corrcoef(z) - np.eye(13)).max() < 0.04                      # the six draws of a block are uncorrelated
+    assert np.array_equal(R.draw_normals(6, 20000, 77, 3), z[:6]) and np.abs(z).max() < 5.9
+    # bit layout: block 0 of (seed 0, step 0) is the Random123 known answer 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    x, y, zz, w = 0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8
+    a = [x >> 8, ((y << 2) | (zz >> 30)) & 0xFFFFFF, ((zz << 12) | (w >> 20)) & 0xFFFFFF]
+    t = [((x << 10) | (y >> 22)) & 0x3FFFF, (zz >> 12) & 0x3FFFF, (w >> 2) & 0x3FFFF]
+    exp = []
+    for aj, tj in zip(a, t):
+        rad = np.sqrt(-2 * np.log(float(np.float32((aj + 0.5) * 2.0 ** -24))))
+        th = 2 * np.pi * (tj + 0.5) * 2.0 ** -18
+        exp += [rad * np.cos(th), rad * np.sin(th)]
+    np.testing.assert_allclose(R.draw_normals(6, 1, 0, 0)[:, 0], exp, rtol=1e-12)
+
+
 def test_philox_normals_moments():
     z, _ = R.philox_normals(200000, seed=1234, step=7)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01

@@ -16,7 +16,7 @@ reps = int(os.environ.get("REPS", "20"))
 mean = torch.randn(ld, device=dev) * 0.05
 var = torch.rand(ld, device=dev) * 1e-4 + 1e-6
 ring = torch.randn(20, ld, device=dev) * 0.01
-for S, K in [(30, 20), (30, 0), (32, 20), (16, 20), (100, 20)]:
+for S, K in [(30, 20), (30, 0), (24, 20), (16, 20), (100, 20)]:
     bank = torch.empty(S, ld, device=dev)
     z2 = torch.randn(S, max(K, 1), device=dev)
 

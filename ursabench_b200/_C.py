@@ -211,6 +211,14 @@ def swag_draw(out, mean, var, D, ring=None, z2=None, z1=None, rank_div=1.0, seed
     return out
 
 
+def swag_draw_noise(S, D, seed, step, device):
+    """The [S, roundup4(D)] N(0, 1) stream ``swag_draw`` uses when z1 is None: a diagonal draw with mean 0 and variance 1
+    returns it exactly (0 + 1 * z)."""
+    ld = (D + 3) // 4 * 4
+    out = torch.zeros(S, ld, device=device)
+    return swag_draw(out, torch.zeros(ld, device=device), torch.ones(ld, device=device), D, seed=seed, step=step)
+
+
 @_on_device
 def swag_gram(ring, D):
     """ring: [K, ld] device fp32 -> [K, K] float64 device tensor R R^T over the first D columns."""

@@ -101,6 +101,36 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t blk, uint64_t step, ui
     return box_muller4(philox4x32_10(ctr, key));
 }
 
+// The SWAG draw's stream (K2b): SIX normals per Philox block.  The 32-bit generator work (20 IMAD.WIDE + 20 LOP3, four and two
+// issue cycles each on this SM) is what bounds that kernel, and a float carries 24 bits: the block's 128 bits are cut, from the
+// top of x to the bottom of w, into three (24-bit radius uniform, 18-bit angle) pairs (2 bits unused):
+//   a0 = x[31:8]              t0 = x[7:0] : y[31:22]
+//   a1 = y[21:0] : z[31:30]   t1 = z[29:12]
+//   a2 = z[11:0] : w[31:20]   t2 = w[19:2]
+//   u = (a + 1/2) 2^-24 (rounded to fp32, in (0, 1]),  theta = 2 pi (t + 1/2) 2^-18,  z[2j] = r cos(theta), z[2j+1] = r sin(theta),
+//   r = sqrt(-2 ln u) <= 5.89 (torch's CPU float normal has the same 24-bit radius resolution).
+__device__ __forceinline__ void box_muller6(uint4 r, float (&z)[6]) {
+    const uint32_t a[3] = {r.x >> 8, __funnelshift_l(r.z, r.y, 2) & 0xFFFFFFu, __funnelshift_l(r.w, r.z, 12) & 0xFFFFFFu};
+    const uint32_t t[3] = {__funnelshift_l(r.y, r.x, 10) & 0x3FFFFu, (r.z >> 12) & 0x3FFFFu, (r.w >> 2) & 0x3FFFFu};
+    const float k2m24 = 5.9604644775390625e-08f, k2m25 = 2.98023223876953125e-08f;
+    const float kTwoPi2m18 = 2.3968449810247229e-05f;         // 2*pi * 2^-18
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float u = fmaf(__uint2float_rn(a[j]), k2m24, k2m25);
+        const float rad = fast_sqrt(-1.3862943611198906f * fast_log2(u));
+        const float th = fmaf(__uint2float_rn(t[j]), kTwoPi2m18, 0.5f * kTwoPi2m18);
+        float sn, cs;
+        __sincosf(th, &sn, &cs);
+        z[2 * j] = rad * cs;
+        z[2 * j + 1] = rad * sn;
+    }
+}
+
+__device__ __forceinline__ void philox_normal6(uint64_t blk, uint64_t step, uint2 key, float (&z)[6]) {
+    const uint4 ctr = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)step, (uint32_t)(step >> 32));
+    box_muller6(philox4x32_10(ctr, key), z);
+}
+
 __device__ __forceinline__ float f4_get(const float4 &v, int i) {
     return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }

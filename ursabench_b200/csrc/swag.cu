@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kEwThreads) swag_variance_kernel(const float *
 
 // ---------------------------------------------------------------------------------------------
 // K2b.  out[s, d] = mean[d] + sd[d] z1[s, d] + sum_k (z2[s, k] / rank_div) ring[k, d]      (swag.py:85-97)
-// One persistent CTA per SM, tile = 512 columns d of the ring, all S <= 32 draws of the tile per pass, so the ring crosses
+// One persistent CTA per SM, tile = 512 columns d of the ring, all S <= 30 draws of the tile per pass, so the ring crosses
 // HBM once.  Round 2 rebuilt the kernel around tcgen05: the round-1 version ran the K x S contraction on the warp-level
 // mma.sync and spent 45 issue slots per Gaussian (17 of them on fragment loads / splits / moves around the HMMAs; ncu r04,
 // r2s15: IPC 2.15, no pipe above 45 %) -- it was bound by instruction issue at 0.47 of the HBM roofline.
@@ -75,18 +75,20 @@ __global__ void __launch_bounds__(kEwThreads) swag_variance_kernel(const float *
 //     split  its K ring values become the rows of the A operand, split x = hi + lo (3xTF32), written in the NO-SWIZZLE
 //            K-major UMMA layout (row d at 16 B stride, one 4-k chunk per 8 KB plane: 6 STS.128 per part, conflict free);
 //            the same thread takes sqrt(var) once -- no lane recomputes another lane's value
-//     Gauss  TMEM lane = column: tcgen05.ld hands the thread its 32 low-rank terms; ceil(S / 4) Philox4x32-10 blocks, two at
+//     Gauss  TMEM lane = column: tcgen05.ld hands the thread its 32 low-rank terms; ceil(S / 6) Philox4x32-10 blocks, two at
 //            a time in straight-line code -> Box-Muller -> mean + (sd z + lr), one coalesced 128-byte store per warp and draw
 // No CTA-wide barrier in the loop: split(i + 1) -> a_ready (mbarrier, 512 arrivals) -> MMA(i + 1) -> mma_bar -> Gauss(i + 1);
 // the MMAs of tile i + 1 and the copies of tiles i + 2, i + 3 run under the Gaussian generation of tile i.
-// Philox stream: element (s, d) of a call is normal (s & 3) of block (s >> 2) * D + d at `step` -- a block serves four
-// consecutive DRAWS of one column, so a thread never needs another thread's normals.
+// Philox stream: element (s, d) of a call is normal s % 6 of block (s / 6) * D + d at `step` (common.cuh::box_muller6) -- a block
+// serves six consecutive DRAWS of one column, so a thread never needs another thread's normals, and the generator work per
+// Gaussian is 2/3 of the K1 stream's.
 constexpr int kDrawThreads = 512;               // compute threads (the ring kernel adds one producer warp)
 constexpr int kTileCols = 512;
 constexpr int kKP = 24;                         // ring rows padded to 3 k-steps of 8 (URSA_DRAW_MAX_K)
 constexpr int kRows = kKP + 2;                  // + the mean and var rows of the tile (staged by the same bulk copies)
 constexpr int kStages = 2;
-constexpr int kDrawN = 32;                      // draws per launch = MMA N (URSA_DRAW_MAX_S)
+constexpr int kDrawN = 32;                      // MMA N: TMEM columns per accumulator tile
+constexpr int kDrawGroup = URSA_DRAW_MAX_S;     // draws per launch: five Philox blocks of six normals
 constexpr uint32_t kAPlane = kTileCols * 16;    // bytes between two 4-k chunks of the A operand (LBO)
 constexpr uint32_t kABytes = (kKP / 4) * kAPlane;            // 48 KB per part (hi / lo)
 constexpr uint32_t kBPlane = kDrawN * 16;       // LBO of the B operand
@@ -94,7 +96,7 @@ constexpr uint32_t kBBytes = (kKP / 4) * kBPlane;            // 3 KB per part
 constexpr uint32_t kTmemCols = 2 * (kTileCols / 128) * kDrawN;   // two buffers of four 32-column accumulators
 constexpr uint32_t kStageBytes = kRows * kTileCols * 4;
 constexpr uint32_t kAOff = kStages * kStageBytes, kBOff = kAOff + 2 * kABytes, kDrawSmem = kBOff + 2 * kBBytes;
-static_assert(URSA_DRAW_MAX_K <= kKP && URSA_DRAW_MAX_S == kDrawN, "operand shapes");
+static_assert(URSA_DRAW_MAX_K <= kKP && kDrawGroup <= kDrawN && kDrawGroup == 30, "operand shapes");
 static_assert(kTileCols == kDrawThreads, "thread = column");
 static_assert(kTmemCols == 256, "power-of-two TMEM allocation");
 static_assert(kDrawSmem <= 227 * 1024 - 1024, "shared memory");
@@ -104,7 +106,7 @@ struct DrawArgs {
     const float *mean, *var, *ring, *z2, *z1;
     int64_t ld_out, ld_ring, ld_z1, D;
     int K, S;
-    int s0;                 // index of the launch's first draw within the call (a multiple of 32): Philox block row (s0 + s) >> 2
+    int s0;                 // index of the launch's first draw within the call (a multiple of 30): Philox block row (s0 + s) / 6
     float rank_div;
     uint2 key;
     uint64_t step;
@@ -116,14 +118,14 @@ __device__ __forceinline__ uint64_t draw_desc(uint32_t addr, uint32_t lbo_bytes)
            ((uint64_t)1 << 46);
 }
 
-// The S draws of column c (c < D): groups of four draws share a Philox block; two groups at a time run as straight-line code so
-// that the two Philox / Box-Muller chains interleave (a single chain leaves the 4 warps of a scheduler waiting on IMAD.WIDE).
+// The S <= 30 draws of column c (c < D): groups of SIX draws share a Philox block (box_muller6); two groups at a time run as
+// straight-line code so that the two Philox / Box-Muller chains interleave.
 template <bool RING, bool EXTZ>
 __device__ __forceinline__ void emit_draws(const DrawArgs &a, int64_t c, float m, float sd, const uint32_t (&lr)[kDrawN]) {
     const int S = a.S;
     float *o = a.out + c;
     const float *zp = EXTZ ? a.z1 + c : nullptr;
-    uint64_t blk = (uint64_t)(a.s0 >> 2) * (uint64_t)a.D + (uint64_t)c;
+    uint64_t blk = (uint64_t)(a.s0 / 6) * (uint64_t)a.D + (uint64_t)c;
     auto apply = [&](float z, int s) {
         float r = __fmul_rn(sd, z);                                                        // swag.py:88-89
         if (RING) r = __fadd_rn(r, __uint_as_float(lr[s]));                                // swag.py:95-96 (scale folded)
@@ -131,36 +133,40 @@ __device__ __forceinline__ void emit_draws(const DrawArgs &a, int64_t c, float m
         o += a.ld_out;
     };
 #pragma unroll
-    for (int gp = 0; gp < kDrawN / 8; ++gp) {
-        if (8 * gp + 8 <= S) {                                                             // uniform: eight draws, no predicates
-            float z[8];
+    for (int gp = 0; gp < 3; ++gp) {                                                       // groups 2 gp, 2 gp + 1 (there is no group 5)
+        if (gp < 2 && 12 * gp + 12 <= S) {                                                 // uniform: twelve draws, no predicates
+            float za[6], zb[6];
             if (EXTZ) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { z[e] = __ldg(zp); zp += a.ld_z1; }
+                for (int e = 0; e < 6; ++e) { za[e] = __ldg(zp); zp += a.ld_z1; }
+#pragma unroll
+                for (int e = 0; e < 6; ++e) { zb[e] = __ldg(zp); zp += a.ld_z1; }
             } else {
-                const float4 za = philox_normal4(blk, a.step, a.key), zb = philox_normal4(blk + (uint64_t)a.D, a.step, a.key);
+                philox_normal6(blk, a.step, a.key, za);
+                philox_normal6(blk + (uint64_t)a.D, a.step, a.key, zb);
                 blk += 2 * (uint64_t)a.D;
-                z[0] = za.x; z[1] = za.y; z[2] = za.z; z[3] = za.w; z[4] = zb.x; z[5] = zb.y; z[6] = zb.z; z[7] = zb.w;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) apply(z[e], 8 * gp + e);
-        } else if (8 * gp < S) {                                                           // the ragged last pair of groups
+            for (int e = 0; e < 6; ++e) apply(za[e], 12 * gp + e);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) apply(zb[e], 12 * gp + 6 + e);
+        } else {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (8 * gp + 4 * h < S) {
-                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                const int s0 = 12 * gp + 6 * h;
+                if (s0 < kDrawGroup && s0 < S) {                                           // uniform; the last group may be ragged
+                    float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     if (EXTZ) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (8 * gp + 4 * h + e < S) { z[e] = __ldg(zp); zp += a.ld_z1; }
+                        for (int e = 0; e < 6; ++e)
+                            if (s0 + e < S) { z[e] = __ldg(zp); zp += a.ld_z1; }
                     } else {
-                        const float4 zv = philox_normal4(blk, a.step, a.key);
+                        philox_normal6(blk, a.step, a.key, z);
                         blk += (uint64_t)a.D;
-                        z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
                     }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (8 * gp + 4 * h + e < S) apply(z[e], 8 * gp + 4 * h + e);
+                    for (int e = 0; e < 6; ++e)
+                        if (s0 + e < S) apply(z[e], s0 + e);
                 }
             }
         }
