@@ -62,6 +62,16 @@ def test_swag_gram_matches_fp64_numpy(K, D):
     ref = ring[:, :D].astype(np.float64) @ ring[:, :D].astype(np.float64).T
     np.testing.assert_allclose(gram, ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max())
     np.testing.assert_array_equal(gram, gram.T)
+    # fixed reduction order: a second call returns the same bits
+    assert np.array_equal(gram, _C.swag_gram(torch.from_numpy(ring).cuda(), D).cpu().numpy())
+    # rows that are not 16-byte aligned take the CUDA-core path (the tensor-core kernel streams rows with bulk copies)
+    if D > 1:
+        buf = torch.empty(K * ld + 1, device="cuda")
+        odd = buf[1:].view(K, ld)                                          # contiguous, base 4 bytes off a 16-byte boundary
+        odd.copy_(torch.from_numpy(ring))
+        g2 = _C.swag_gram(odd, D).cpu().numpy()
+        np.testing.assert_allclose(g2, ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max())
+        np.testing.assert_array_equal(g2, g2.T)
 
 
 @pytest.mark.gpu

@@ -347,17 +347,160 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
 }
 
 // ---------------------------------------------------------------------------------------------
-// Gram matrix of the deviation ring, G = R R^T (K x K, fp64), one streaming pass over [K, D]: the first half of the PCA
+// K2c.  Gram matrix of the deviation ring, G = R R^T (K x K, fp64), one streaming pass over [K, D]: the first half of the PCA
 // subspace (reference inference/subspaces.py:116-131 runs sklearn's randomized SVD on the K x D matrix on the host; with
 // K <= 24 rows the SVD is the eigen-decomposition of G, and s V^T = U^T R is one more K2b-shaped pass).
-// CTA = 8 warps, slab = 128 columns staged [24][128] in shared memory (coalesced float4 loads, double buffered through
-// registers); warp w owns up to three 4 x 4 blocks (ib <= jb) of G, its lanes own columns -- conflict-free LDS along a row,
-// 16 FMAs per 8 LDS.  fp32 partial sums per lane, shuffle reduce, fp64 atomicAdd per entry.
-constexpr int kGramCols = 128, kGramRows = URSA_DRAW_MAX_K, kGramThreads = 256;
-static_assert(kGramRows == 24, "6 x 6 blocks of 4 rows");
+// Round 2: the contraction moved from FFMA (0.35 of the HBM roofline, issue bound) to the warp-level tensor-core MMA
+// (m16n8k8, 3xTF32: x = hi + lo, lo*lo dropped) -- the accumulators must come back to registers every few steps anyway
+// (below), so the TMEM round trip of tcgen05 has nothing to offer here -- and the reduction order is FIXED (no atomics).
+//   producer warp (one lane): ONE 2-D TMA tensor copy per slab -- box = 248 columns x K rows (<= 23 KB) -- into a 6-stage
+//            ring; columns beyond D are zero-filled by the TMA engine.  (Row-by-row bulk copies, 20 per slab, kept the
+//            producer lane busier than the slab's HBM time: 0.38 of the roofline, 28 % of all samples waiting for data.)
+//   16 MMA warps: warp w owns k-steps w, w + 16 of a slab (8 columns each; the order of the contraction index is free, so
+//            k = t is column 2 t and k = t + 4 column 2 t + 1).  Per k-step a lane loads three float2 R[g + 8 r][c + 2 t ..]
+//            (LDS.64, bank-conflict free at the box's row pitch of 248 floats); they are BOTH the A fragments of the row
+//            tiles {0-15, 16-31} and the B fragments of the column tiles {0-7, 8-15, 16-23}, because A = B^T = R.
+//            12 mma.sync per k-step: tiles (0-15) x {0-7, 8-15, 16-23} and (16-23) x (16-23); the rest is the transpose.
+//   accumulation: the tensor core adds into its accumulator with truncation (a bias that grows with the chain), so a chain
+//            covers 16 k-steps = 128 columns, then goes into per-lane fp64 sums; warps -> CTA in warp order through shared
+//            memory, CTAs -> G in CTA order by gram_finish_kernel: bit-reproducible.
+constexpr int kGramSlab = 248, kGramKSteps = kGramSlab / 8, kGramRows = URSA_DRAW_MAX_K, kGramStages = 6;
+constexpr int kGramWarps = 16, kGramThreads = (kGramWarps + 1) * 32;
+constexpr int kGramFrag = 16 * 32;                                           // doubles per warp / CTA partial (fragment layout)
+constexpr uint32_t kGramStageBytes = kGramRows * kGramSlab * 4;
+static_assert(kGramRows == 24, "two 16-row tiles (the second half padded), three 8-column tiles");
+static_assert(kGramSlab % 32 == 24 || kGramSlab % 32 == 8, "LDS.64 fragment loads: rows g = 0..3 of a half-warp on distinct bank groups");
+static_assert(kGramSlab <= 256 && kGramSlab % 8 == 0, "TMA box");
+static_assert(kGramStages * kGramStageBytes + kGramWarps * kGramFrag * 8 <= 227 * 1024 - 1024, "shared memory");
 
-__global__ void __launch_bounds__(kGramThreads) ring_gram_kernel(const float *__restrict__ ring, int64_t ld, int K, int64_t D,
-                                                                 int vec_ok, double *__restrict__ gram) {
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kGramThreads, 1) ring_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, int K, int64_t D,
+                                                                        double *__restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // TMA destinations: 128-byte aligned
+    float *stage_s = reinterpret_cast<float *>(base);                         // [kGramStages][kGramRows][kGramSlab]
+    double *red = reinterpret_cast<double *>(base + kGramStages * kGramStageBytes);       // [kGramWarps][kGramFrag]
+    __shared__ __align__(8) uint64_t full_bar[kGramStages], empty_bar[kGramStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t nslab = (D + kGramSlab - 1) / kGramSlab;
+    const int n_my = (int)((nslab - blockIdx.x + gridDim.x - 1) / gridDim.x);  // slabs blockIdx.x + i * gridDim.x
+
+    // rows K .. 23 are never written by the copies: zero them once in every stage
+    for (int i = tid; i < kGramStages * (kGramRows - K) * kGramSlab; i += kGramThreads) {
+        const int st = i / ((kGramRows - K) * kGramSlab), r = i - st * (kGramRows - K) * kGramSlab;
+        stage_s[(st * kGramRows + K) * kGramSlab + r] = 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kGramStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kGramWarps); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kGramWarps) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            for (int i = 0; i < n_my; ++i) {
+                const int st = i % kGramStages;
+                if (i >= kGramStages) mbar_wait(&empty_bar[st], (uint32_t)(i / kGramStages - 1) & 1u);
+                const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kGramSlab;
+                mbar_arrive_expect_tx(&full_bar[st], (uint32_t)K * kGramSlab * 4u);   // the whole box, zero fill included
+                tma_load_2d(stage_s + st * kGramRows * kGramSlab, &tmap, (int)c0, 0, &full_bar[st]);
+            }
+        }
+        return;
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+    double sum[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sum[e] = 0.0;
+    float acc[4][4];                                                           // tiles (m0,n0) (m0,n1) (m0,n2) (m1,n2)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    auto drain = [&]() {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { sum[4 * q + e] += (double)acc[q][e]; acc[q][e] = 0.f; }
+    };
+    for (int i = 0; i < n_my; ++i) {
+        const int st = i % kGramStages;
+        mbar_wait(&full_bar[st], (uint32_t)(i / kGramStages) & 1u);
+        const float *rs = stage_s + st * kGramRows * kGramSlab + g * kGramSlab + 2 * t;
+#pragma unroll
+        for (int j = 0; j < (kGramKSteps + kGramWarps - 1) / kGramWarps; ++j) {
+            const int ks = warp + kGramWarps * j;
+            if (ks < kGramKSteps) {                                            // warp-uniform
+                uint32_t hi[3][2], lo[3][2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float2 x = *reinterpret_cast<const float2 *>(rs + r * 8 * kGramSlab + 8 * ks);
+                    hi[r][0] = __float_as_uint(x.x) & 0xFFFFE000u;
+                    hi[r][1] = __float_as_uint(x.y) & 0xFFFFE000u;
+                    lo[r][0] = __float_as_uint(x.x - __uint_as_float(hi[r][0]));
+                    lo[r][1] = __float_as_uint(x.y - __uint_as_float(hi[r][1]));
+                }
+                const uint32_t a0h[4] = {hi[0][0], hi[1][0], hi[0][1], hi[1][1]}, a0l[4] = {lo[0][0], lo[1][0], lo[0][1], lo[1][1]};
+                const uint32_t a1h[4] = {hi[2][0], 0u, hi[2][1], 0u}, a1l[4] = {lo[2][0], 0u, lo[2][1], 0u};
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    mma_tf32_16x8x8(acc[n], a0l, hi[n][0], hi[n][1]);
+                    mma_tf32_16x8x8(acc[n], a0h, lo[n][0], lo[n][1]);
+                    mma_tf32_16x8x8(acc[n], a0h, hi[n][0], hi[n][1]);
+                }
+                mma_tf32_16x8x8(acc[3], a1l, hi[2][0], hi[2][1]);
+                mma_tf32_16x8x8(acc[3], a1h, lo[2][0], lo[2][1]);
+                mma_tf32_16x8x8(acc[3], a1h, hi[2][0], hi[2][1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if ((i & 7) == 7) drain();                                             // 8 slabs x <= 2 k-steps per accumulation chain
+    }
+    drain();
+    // warps -> CTA in warp order (fragment layout: entry e of lane l at e * 32 + l), then one coalesced row of the partials
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[warp * kGramFrag + e * 32 + lane] = sum[e];
+    asm volatile("bar.sync 1, %0;" ::"n"(kGramWarps * 32) : "memory");       // the producer warp has left
+    for (int e = tid; e < kGramFrag; e += kGramWarps * 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kGramWarps; ++w) v += red[w * kGramFrag + e];
+        partial[(int64_t)blockIdx.x * kGramFrag + e] = v;
+    }
+}
+
+// CTA partials -> G in CTA order.  Fragment entry (q, e) of lane (g, t): tile q = (m0,n0) (m0,n1) (m0,n2) (m1,n2),
+// row = 16 (q == 3) + g + 8 (e >> 1), column = 8 min(q, 2) + 2 t + (e & 1); rows 24..31 of tile m1 are padding.
+__global__ void __launch_bounds__(kGramFrag) gram_finish_kernel(const double *__restrict__ partial, int nparts, int K,
+                                                                double *__restrict__ gram) {
+    const int idx = threadIdx.x, lane = idx & 31, qe = idx >> 5;
+    const int q = qe >> 2, e = qe & 3, g = lane >> 2, t = lane & 3;
+    double v = 0.0;
+    for (int p = 0; p < nparts; ++p) v += partial[(int64_t)p * kGramFrag + idx];
+    const int row = (q == 3 ? 16 : 0) + g + 8 * (e >> 1), col = 8 * (q < 2 ? q : 2) + 2 * t + (e & 1);
+    if (q == 3 && (e >> 1)) return;
+    // the tiles hold some entries twice, as (i, j) and (j, i), summed in a different order: the upper triangle is the one kept,
+    // so that the result is exactly symmetric
+    if (row <= col && col < K) {
+        gram[(int64_t)row * K + col] = v;
+        gram[(int64_t)col * K + row] = v;
+    }
+}
+
+// Fallback for rings that are not 16-byte aligned (bulk copies need it): CUDA cores, same fixed-order reduction.
+// CTA = 8 warps, slab = 128 columns staged [24][128] in shared memory (double buffered through registers); warp w owns up to
+// three 4 x 4 blocks (ib <= jb) of G, its lanes own columns -- conflict-free LDS along a row, 16 FMAs per 8 LDS.
+constexpr int kGramCols = 128, kGramFmaThreads = 256;
+
+__global__ void __launch_bounds__(kGramFmaThreads) ring_gram_kernel(const float *__restrict__ ring, int64_t ld, int K, int64_t D,
+                                                                    double *__restrict__ partial) {
     __shared__ __align__(16) float sm[kGramRows][kGramCols];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the 21 upper-triangular 4 x 4 blocks, dealt round-robin to the 8 warps
@@ -374,35 +517,24 @@ __global__ void __launch_bounds__(kGramThreads) ring_gram_kernel(const float *__
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[b][e] = 0.f;
     const int64_t nslab = (D + kGramCols - 1) / kGramCols;
-    auto load = [&](int64_t slab, float4 (&r)[3]) {                       // 24 rows x 32 float4 = 768 = 3 per thread
+    auto load = [&](int64_t slab, float (&r)[12]) {                       // 24 rows x 128 columns = 3072 = 12 per thread
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int idx = threadIdx.x + u * kGramThreads;
-            const int row = idx >> 5, c4 = (idx & 31) * 4;
-            const int64_t c = slab * kGramCols + c4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < K && c < D) {
-                const float *src = ring + (int64_t)row * ld + c;
-                if (vec_ok && c + 4 <= D) v = __ldg(reinterpret_cast<const float4 *>(src));
-                else {
-                    v.x = __ldg(src);
-                    if (c + 1 < D) v.y = __ldg(src + 1);
-                    if (c + 2 < D) v.z = __ldg(src + 2);
-                    if (c + 3 < D) v.w = __ldg(src + 3);
-                }
-            }
-            r[u] = v;
+        for (int u = 0; u < 12; ++u) {
+            const int idx = threadIdx.x + u * kGramFmaThreads;
+            const int row = idx >> 7;
+            const int64_t c = slab * kGramCols + (idx & 127);
+            r[u] = (row < K && c < D) ? __ldg(ring + (int64_t)row * ld + c) : 0.f;
         }
     };
-    float4 regs[3];
+    float regs[12];
     int64_t slab = blockIdx.x;
     if (slab < nslab) load(slab, regs);
     for (; slab < nslab; slab += gridDim.x) {
         __syncthreads();                                                   // previous slab consumed
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int idx = threadIdx.x + u * kGramThreads;
-            *reinterpret_cast<float4 *>(&sm[idx >> 5][(idx & 31) * 4]) = regs[u];
+        for (int u = 0; u < 12; ++u) {
+            const int idx = threadIdx.x + u * kGramFmaThreads;
+            sm[idx >> 7][idx & 127] = regs[u];
         }
         __syncthreads();
         if (slab + gridDim.x < nslab) load(slab + gridDim.x, regs);        // next slab's loads fly during the FMAs
@@ -423,21 +555,29 @@ __global__ void __launch_bounds__(kGramThreads) ring_gram_kernel(const float *__
             }
         }
     }
-#pragma unroll
+    // per-CTA partial in matrix layout [24][24] (upper blocks; lanes in butterfly order: deterministic)
     for (int b = 0; b < 3; ++b) {
         if (b >= nblk) continue;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            float v = acc[b][e];
+            double v = (double)acc[b][e];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             const int i = ib[b] * 4 + (e >> 2), j = jb[b] * 4 + (e & 3);
-            if (lane == 0 && i < K && j < K) {
-                atomicAdd(gram + (int64_t)i * K + j, (double)v);
-                if (ib[b] != jb[b]) atomicAdd(gram + (int64_t)j * K + i, (double)v);
-            }
+            if (lane == 0) partial[(int64_t)blockIdx.x * (kGramRows * kGramRows) + i * kGramRows + j] = v;
         }
     }
+}
+
+__global__ void __launch_bounds__(kGramRows * kGramRows) gram_finish_fma_kernel(const double *__restrict__ partial, int nparts,
+                                                                               int K, double *__restrict__ gram) {
+    const int i = threadIdx.x / kGramRows, j = threadIdx.x % kGramRows;
+    if (i > j || j >= K) return;                                           // blocks with ib <= jb: element (i, j), i <= j within the diagonal blocks too
+    double v = 0.0;
+    const int src = (i / 4 <= j / 4) ? i * kGramRows + j : j * kGramRows + i;
+    for (int p = 0; p < nparts; ++p) v += partial[(int64_t)p * (kGramRows * kGramRows) + src];
+    gram[(int64_t)i * K + j] = v;
+    gram[(int64_t)j * K + i] = v;
 }
 
 static int ew_grid(int64_t work_items) {
@@ -526,12 +666,61 @@ extern "C" int ursa_swag_gram(const float *ring, int64_t ld_ring, int K, int64_t
     URSA_REQUIRE(K >= 1 && K <= URSA_DRAW_MAX_K, "ursa_swag_gram: K must be in [1, %d]", URSA_DRAW_MAX_K);
     URSA_REQUIRE(ld_ring >= D, "ursa_swag_gram: ld_ring < D");
     cudaStream_t st = (cudaStream_t)stream;
-    URSA_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * K * K, st));
-    if (D == 0) return URSA_OK;
-    const int64_t nslab = (D + kGramCols - 1) / kGramCols;
-    const int64_t cap = (int64_t)sm_count() * 4;
-    const int vec_ok = aligned16(ring) && (ld_ring & 3) == 0;
-    ring_gram_kernel<<<(int)(nslab < cap ? nslab : cap), kGramThreads, 0, st>>>(ring, ld_ring, K, D, vec_ok, gram);
-    URSA_LAUNCH_CHECK("ring_gram_kernel");
-    return URSA_OK;
+    if (D == 0) {
+        URSA_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * K * K, st));
+        return URSA_OK;
+    }
+    // per-CTA partial sums live in stream-ordered scratch, so that the reduction order is fixed and concurrent calls on
+    // different streams do not share state
+    const bool tc = aligned16(ring) && (ld_ring & 3) == 0;
+    const int64_t nslab = tc ? (D + kGramSlab - 1) / kGramSlab : (D + kGramCols - 1) / kGramCols;
+    const int64_t cap = tc ? (int64_t)sm_count() : (int64_t)sm_count() * 4;
+    const int grid = (int)(nslab < cap ? nslab : cap);
+    const size_t per = tc ? (size_t)kGramFrag : (size_t)kGramRows * kGramRows;
+    double *partial = nullptr;
+    {
+        // keep the default pool's memory across synchronisations (its default is to hand everything back to the OS)
+        static bool pool_set[64] = {};
+        int dev = 0;
+        URSA_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && !pool_set[dev]) {
+            cudaMemPool_t pool;
+            uint64_t keep = 64ull << 20;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_set[dev] = true;
+        }
+    }
+    URSA_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partial), sizeof(double) * per * grid, st));
+    int rc = URSA_OK;
+    if (tc) {
+        const size_t smem = kGramStages * kGramStageBytes + kGramWarps * kGramFrag * sizeof(double) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(ring_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(ring_gram_tc_kernel)");
+        CUtensorMap tm;
+        if (!rc) {
+            // ring as a [K rows, D columns] tensor: columns >= D (the padding up to ld_ring included) are out of bounds = zero
+            const uint64_t dims[2] = {(uint64_t)D, (uint64_t)K}, strides[1] = {(uint64_t)ld_ring * 4};
+            const uint32_t box[2] = {(uint32_t)kGramSlab, (uint32_t)K};
+            rc = make_tensor_map(&tm, ring, 2, dims, strides, box, 0);
+        }
+        if (!rc) {
+            ring_gram_tc_kernel<<<grid, kGramThreads, smem, st>>>(tm, K, D, partial);
+            count_launch();
+            gram_finish_kernel<<<1, kGramFrag, 0, st>>>(partial, grid, K, gram);
+            count_launch();
+        }
+    } else {
+        URSA_CUDA(cudaMemsetAsync(partial, 0, sizeof(double) * per * grid, st));
+        ring_gram_kernel<<<grid, kGramFmaThreads, 0, st>>>(ring, ld_ring, K, D, partial);
+        count_launch();
+        gram_finish_fma_kernel<<<1, kGramRows * kGramRows, 0, st>>>(partial, grid, K, gram);
+        count_launch();
+    }
+    if (!rc) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "ring_gram_kernel");
+    }
+    cudaFreeAsync(partial, st);
+    return rc;
 }

@@ -220,7 +220,7 @@ inline EncodeTiledFn tensor_map_encoder() {
 }
 
 // tensor of `rank` dims (dims[0] innermost, strides in BYTES for dims 1..rank-1), box in elements,
-// swizzle_bytes in {64, 128}; out-of-bounds elements read as zero.  f16 != 0: elements are halves, else fp32.
+// swizzle_bytes in {0 (none), 64, 128}; out-of-bounds elements read as zero.  f16 != 0: elements are halves, else fp32.
 inline int make_tensor_map_t(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                              const uint32_t *box, int swizzle_bytes, int f16) {
     EncodeTiledFn fn = tensor_map_encoder();
@@ -239,7 +239,8 @@ inline int make_tensor_map_t(CUtensorMap *tm, const void *base, int rank, const 
     CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                     const_cast<void *>(base), d, s, b, e,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu ..] box [%u %u %u ..]", (int)r, rank,
