@@ -669,7 +669,7 @@ def run_extras(dev, rank, world, peak):
     P, E = torch.zeros(N, 10, device=dev), torch.zeros(N, device=dev)
     ws = [None]
 
-    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05)):
+    for algo_name, algo in (("ffma", _C.ALGO_FFMA), ("tcgen05", _C.ALGO_TCGEN05), ("f16", _C.ALGO_TCGEN05_F16)):
         def bma():
             P.zero_()
             E.zero_()

@@ -187,11 +187,15 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
  *     x: [N, in_dim].  Accumulates into proba_sum [N, C] / entropy_sum [N] in sample order (layer 3 writes logits to
  *     the workspace, then ONE ursa_bma_accumulate launch per chunk: tiles of different samples finish in any order).
  *     logits_out (nullable): [S, N, C].
- *     algo: URSA_ALGO_FFMA (fp32 CUDA cores) or URSA_ALGO_TCGEN05 (3xTF32 on tcgen05 + TMA).
+ *     algo: URSA_ALGO_FFMA (fp32 CUDA cores), URSA_ALGO_TCGEN05 (3xTF32 on tcgen05 + TMA, one tile per CTA) or
+ *     URSA_ALGO_TCGEN05_F16 (the product path: 2xFP16-split operands -- half the operand bytes and twice the K per MMA of
+ *     3xTF32 at the same 22 significant bits -- on a persistent tcgen05 kernel whose MMAs run under the previous tile's
+ *     epilogue; operands beyond fp16's range, |x| > 65 504, surface as NaN logits, never as finite wrong values).
  * ---------------------------------------------------------------------- */
 #define URSA_ALGO_FFMA    0
 #define URSA_ALGO_TCGEN05 1
 #define URSA_ALGO_TCGEN05_FUSED 2   /* PreResNet only: stage-fused 3xTF32 kernel, activations in shared memory, residual in TMEM */
+#define URSA_ALGO_TCGEN05_F16 4     /* MLP only: persistent 2xFP16-split GEMM kernel (csrc/bma_mlp_f16.cu) */
 #define URSA_ALGO_TCGEN05_FUSED_F16 3 /* PreResNet only: stage-fused kernel on 2xFP16-split operands (22 significant bits, fp32
                                        * accumulate), MMA / epilogue wavefront per 128-position tile.  Activations above ~1e6
                                        * overflow FP16 and surface as NaN logits (never as finite wrong values). */

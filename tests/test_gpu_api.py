@@ -309,7 +309,7 @@ def test_prediction_matches_reference_golden_mlp(U, engine):
     assert task.num_samples_collected == 5
     assert task.last_engine == ("generic" if engine == "generic" else "fused_mlp")
     if engine != "generic":                                             # the product path is the tcgen05 kernel
-        assert task.last_algo == (U._C.ALGO_TCGEN05 if engine == "auto" else U._C.ALGO_FFMA)
+        assert task.last_algo == (U._C.ALGO_TCGEN05_F16 if engine == "auto" else U._C.ALGO_FFMA)
     np.testing.assert_allclose(task.ensemble_proba.numpy(), g["mlp/ensemble_proba"], atol=1e-5, rtol=0)
     np.testing.assert_allclose(task.expected_data_uncertainty.numpy(), g["mlp/entropy"], atol=1e-5, rtol=1e-5)
     m = task.get_performance_metrics()
@@ -436,6 +436,29 @@ def test_prediction_fp16_range_overflow_is_loud_and_falls_back(U):
     with torch.no_grad():
         ref = torch.stack([torch.softmax(m.double()(x.double()), -1) for m in ms]).sum(0)
     assert (proba.argmax(1) == ref.argmax(1)).float().mean().item() >= 0.95
+
+
+def test_prediction_mlp_fp16_range_overflow_falls_back(U):
+    """The MLP product path (2xFP16-split) sees an input beyond fp16's range: NaN, never finite-but-wrong, and Prediction
+    redoes the evaluation on the 3xTF32 engine."""
+    torch.manual_seed(5)
+    ms = [U.models.MLP(200, 784, 10).eval() for _ in range(3)]
+    x = torch.randn(64, 1, 28, 28)
+    x[3, 0, 2, 2] = 3e5
+    y = torch.randint(0, 10, (64,))
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=16, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate"])
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_engine == "fused_mlp" and task.last_algo == U._C.ALGO_TCGEN05
+    with torch.no_grad():
+        ref = torch.stack([torch.softmax(m.double()(x.double().view(64, -1)), -1) for m in ms]).sum(0)
+    assert (task.ensemble_proba.double() - ref).abs().max().item() < 1e-5
+    # in range: the FP16-split engine answers
+    x[3, 0, 2, 2] = 1.0
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=16, shuffle=False)
+    task = U.tasks.Prediction({"in_distribution_test": loader}, 10, DEV, ["error_rate"])
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_algo == U._C.ALGO_TCGEN05_F16
 
 
 def test_cuda_graph_step_matches_eager(U, capsys):

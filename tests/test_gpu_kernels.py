@@ -373,9 +373,10 @@ def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc, algo):
     assert (P.double() / S - pbar).abs().max().item() < 1e-5
 
 
-# ----------------------------------------------------------------------------- K3 forward, MLP on tcgen05 (3xTF32)
+# ----------------------------------------------------------------------------- K3 forward, MLP on tcgen05 (3xTF32, 2xFP16-split)
+@pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
 @pytest.mark.parametrize("name,S", [("mlp", 5), ("mlp_c100", 3)])
-def test_k3_mlp_tcgen05_matches_reference_golden(C, name, S):
+def test_k3_mlp_tcgen05_matches_reference_golden(C, name, S, engine):
     g = _npz("prediction.npz")
     hidden, in_dim, Cc = (int(v) for v in g[name + "/arch"])
     bank = dev(g[name + "/bank"])
@@ -383,7 +384,7 @@ def test_k3_mlp_tcgen05_matches_reference_golden(C, name, S):
     N = x.shape[0]
     P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
     logits = torch.empty(S, N, Cc, device="cuda")
-    C.bma_mlp_forward(bank, S, x, in_dim, hidden, Cc, P, E, logits_out=logits, algo=C.ALGO_TCGEN05)
+    C.bma_mlp_forward(bank, S, x, in_dim, hidden, Cc, P, E, logits_out=logits, algo=getattr(C, engine))
     torch.cuda.synchronize()
     if name + "/logits" in g:
         np.testing.assert_allclose(logits.cpu().numpy(), g[name + "/logits"], atol=3e-5, rtol=1e-5)
@@ -391,10 +392,11 @@ def test_k3_mlp_tcgen05_matches_reference_golden(C, name, S):
     np.testing.assert_allclose(E.cpu().numpy(), g[name + "/entropy"], atol=2e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("hidden,S,N", [(400, 6, 1000), (200, 3, 333), (600, 2, 129)])
+@pytest.mark.parametrize("hidden,S,N", [(400, 6, 1000), (200, 3, 333), (600, 2, 129), (400, 40, 700)])
 def test_k3_mlp_tcgen05_vs_ffma_config1_shapes(C, hidden, S, N):
-    """MLP 784-h-h-10 (config 1 and its siblings): the tensor-core path against the fp32 CUDA-core path and a
-    float64 forward -- 3xTF32 must stay at fp32-level accuracy (single-pass TF32 would be ~1e-3)."""
+    """MLP 784-h-h-10 (config 1 and its siblings): the tensor-core paths against the fp32 CUDA-core path and a
+    float64 forward -- 3xTF32 and 2xFP16-split must stay at fp32-level accuracy (a single TF32 / FP16 pass would be ~1e-3).
+    S = 40 spans two sample chunks of the persistent FP16-split kernel (tiles of many samples per CTA)."""
     from ursabench_b200.models import MLP
     torch.manual_seed(hidden)
     ms = [MLP(hidden, 784, 10).cuda() for _ in range(S)]
@@ -404,7 +406,7 @@ def test_k3_mlp_tcgen05_vs_ffma_config1_shapes(C, hidden, S, N):
     bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms])
     x = torch.randn(N, 784, device="cuda")
     outs = {}
-    for algo in (C.ALGO_FFMA, C.ALGO_TCGEN05):
+    for algo in (C.ALGO_FFMA, C.ALGO_TCGEN05, C.ALGO_TCGEN05_F16):
         P, E = torch.zeros(N, 10, device="cuda"), torch.zeros(N, device="cuda")
         logits = torch.empty(S, N, 10, device="cuda")
         C.bma_mlp_forward(bank, S, x, 784, hidden, 10, P, E, logits_out=logits, algo=algo)
@@ -417,6 +419,28 @@ def test_k3_mlp_tcgen05_vs_ffma_config1_shapes(C, hidden, S, N):
     e_tc = (outs[C.ALGO_TCGEN05][0].double() - ref).abs().max().item()
     assert e_ffma < 2e-5 * scale
     assert e_tc < 4e-5 * scale, (e_tc, e_ffma)
+    e_f16 = (outs[C.ALGO_TCGEN05_F16][0].double() - ref).abs().max().item()
+    assert e_f16 < 4e-5 * scale, (e_f16, e_tc, e_ffma)
     pbar_ref = torch.softmax(ref, -1).mean(0)                       # the BMA probabilities (north star: 1e-5)
     assert (outs[C.ALGO_TCGEN05][1].double() / S - pbar_ref).abs().max().item() < 5e-6
+    assert (outs[C.ALGO_TCGEN05_F16][1].double() / S - pbar_ref).abs().max().item() < 5e-6
     assert (outs[C.ALGO_FFMA][1].double() / S - pbar_ref).abs().max().item() < 5e-6
+
+
+def test_k3_mlp_f16_range_overflow_is_loud(C):
+    """An input beyond fp16's range must come out as NaN probabilities for that image (never finite-but-wrong); the other
+    images are untouched."""
+    from ursabench_b200.models import MLP
+    torch.manual_seed(3)
+    m = MLP(200, 784, 10).cuda()
+    bank = torch.cat([p.detach().reshape(-1) for p in m.parameters()])[None].contiguous()
+    x = torch.randn(300, 784, device="cuda")
+    x[7, 5] = 1e6
+    P, E = torch.zeros(300, 10, device="cuda"), torch.zeros(300, device="cuda")
+    C.bma_mlp_forward(bank, 1, x, 784, 200, 10, P, E, algo=C.ALGO_TCGEN05_F16)
+    assert not torch.isfinite(P[7]).all()
+    keep = torch.ones(300, dtype=torch.bool, device="cuda")
+    keep[7] = False
+    with torch.no_grad():
+        ref = torch.softmax(m.double()(x.double()), -1)
+    assert (P[keep].double() - ref[keep]).abs().max().item() < 1e-5

@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("URSA_B200_LIB") or os.path.join(_HERE, "libursa_b200.so")   # env override: debug builds
 
 STEP_FIRST, STEP_NOISE, STEP_ZERO_GRAD = 1, 2, 4
-ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED, ALGO_TCGEN05_FUSED_F16 = 0, 1, 2, 3
-DRAW_MAX_S, DRAW_MAX_K = 32, 24
+ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED, ALGO_TCGEN05_FUSED_F16, ALGO_TCGEN05_F16 = 0, 1, 2, 3, 4
+DRAW_MAX_S, DRAW_MAX_K = 30, 24
 
 _c = ctypes
 _vp, _i64, _i32, _u32, _u64, _f32, _f64, _sz = (_c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32, _c.c_uint64,

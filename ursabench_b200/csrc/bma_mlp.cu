@@ -13,6 +13,10 @@ int mlp_forward_tcgen05(const float *bank, int64_t ld_bank, int S, const float *
                         int C, float *proba_sum, float *entropy_sum, float *logits_out, double gamma, void *workspace,
                         size_t workspace_bytes, cudaStream_t st);
 size_t mlp_workspace_tcgen05(int S, int64_t N, int in_dim, int hidden, int C);
+int mlp_forward_f16(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N, int in_dim, int hidden, int C,
+                    float *proba_sum, float *entropy_sum, float *logits_out, double gamma, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+size_t mlp_workspace_f16(int S, int64_t N, int in_dim, int hidden, int C);
 
 constexpr int BM = 128, BN = 64, BK = 16, kGemmThreads = 256;
 
@@ -143,6 +147,8 @@ using namespace ursa;
 extern "C" size_t ursa_bma_mlp_workspace(int S, int64_t N, int in_dim, int hidden, int C, int algo) {
     if (S < 1 || N < 1 || in_dim < 1 || hidden < 1 || C < 1) return 0;
     if (algo == URSA_ALGO_TCGEN05) return mlp_workspace_tcgen05(S, N, in_dim, hidden, C);
+    if (algo == URSA_ALGO_TCGEN05_F16) return mlp_workspace_f16(S, N, in_dim, hidden, C);
+    if (algo != URSA_ALGO_FFMA) return 0;
     const int sc = ffma_chunk(S, N, hidden);
     return (size_t)sc * (size_t)N * (size_t)(2 * hidden + C) * sizeof(float);
 }
@@ -159,6 +165,9 @@ extern "C" int ursa_bma_mlp_forward(const float *bank, int64_t ld_bank, int S, c
     if (algo == URSA_ALGO_TCGEN05)
         return mlp_forward_tcgen05(bank, ld_bank, S, x, N, in_dim, hidden, C, proba_sum, entropy_sum, logits_out, gamma,
                                    workspace, workspace_bytes, st);
+    if (algo == URSA_ALGO_TCGEN05_F16)
+        return mlp_forward_f16(bank, ld_bank, S, x, N, in_dim, hidden, C, proba_sum, entropy_sum, logits_out, gamma, workspace,
+                               workspace_bytes, st);
     URSA_REQUIRE(algo == URSA_ALGO_FFMA, "ursa_bma_mlp_forward: unknown algo %d", algo);
 
     const int64_t oW1 = 0, ob1 = oW1 + (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)hidden * hidden,

@@ -1,0 +1,413 @@
+// K3 (MLP), product path: sample-batched GEMM on 2xFP16-split operands, PERSISTENT CTAs, TMA-fed, accumulators in TMEM.
+//
+// Why a second tensor-core engine.  The 3xTF32 kernel (bma_mlp_tc.cu) streams fp32 hi / lo planes: 8 bytes per operand element
+// and K = 8 per MMA.  At S = 100 x N = 10 000 its CTAs pull 80 GB through the L2 -> SM path per evaluation -- 7 TB/s of the
+// ~12 TB/s the L2 slices deliver -- and every CTA ran prologue, main loop and epilogue back to back (one tile per CTA).
+// Here an operand element is 4 bytes and one MMA covers K = 16:
+//     x = hi + lo' 2^-11,   hi = rn_f16(x),   lo' = rn_f16((x - hi) 2^11)              (22 significant bits, as 3xTF32)
+//     ACC += A_hi B_hi                      LO += A_hi B_lo' + A_lo' B_hi               (lo' lo' ~ 2^-22 dropped)
+//     result = ACC + LO 2^-11                                                           (fp32, in the epilogue registers)
+// as TWO tcgen05.mma.kind::f16 per K = 16: A_hi x [B_hi ; B_lo'] (N = 2 BN: the two B tiles are adjacent in shared memory, so
+// one descriptor covers both and the accumulator columns come out as [ACC | LO]) and A_lo' x B_hi (N = BN) into the LO columns.
+// Range: fp16 overflows beyond 65 504 -> inf -> NaN logits (the ReLU here propagates NaN): loud by construction; the class
+// layer (tasks/_engine.py) redoes such an evaluation on the 3xTF32 engine, which has fp32's range.
+//
+// Kernel anatomy (192 threads, one CTA per SM, static tile schedule t = blockIdx.x + i gridDim.x over (sample, m, n), n fastest):
+//   warp 0      TMA producer: per k-block (64 halves = one 128-byte swizzle row) four 3-D tiled loads into a 4-stage ring
+//   warp 1      MMA issuer: 4 (K = 16) x 2 MMAs per stage; a chain covers F_SEG k-blocks (two-level accumulation: the tensor
+//               core adds into TMEM with truncation, a bias that grows with the chain), then moves to the next of the rotating
+//               TMEM accumulators -- across tile boundaries too, so the MMAs of tile i + 1 run under the epilogue of tile i
+//   warps 2-5   epilogue: drain each finished segment (tcgen05.ld ACC and LO chunks -> acc + lo 2^-11 -> fp32 registers), after a
+//               tile's last segment + bias -> ReLU -> split -> global (the next layer's TMA source), or plain fp32 logits
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace ursa {
+
+constexpr int F_BM = 128, F_BK = 64, F_MAX_STAGES = 6, F_THREADS = 192;
+constexpr int F_SEG = 4, F_MAX_TBUF = 4, F_EPI_CHUNKS = 8;             // BN <= 128 = 8 chunks of 16 columns
+constexpr uint32_t F_A_BYTES = F_BM * F_BK * 2;                          // 16 KB per A tile
+constexpr float kF16LoScale = 2048.f, kF16LoUnscale = 1.f / 2048.f;    // 2^11
+
+struct F16GemmArgs {
+    const float *bias;            // per-sample bias vector: bias + s * bias_stride
+    int64_t bias_stride;
+    __half *out_hi, *out_lo;      // split outputs [S][M][ld_out] (next layer's operand planes), or null
+    float *out_f32;               // plain fp32 output [S][M][ld_out] (the logits), or null
+    int64_t out_batch_stride;
+    int ld_out;
+    int64_t M;
+    int n_valid;                  // real output features
+    int BN, k_blocks, a_batched, relu, stages;
+    uint32_t tmem_cols;
+    int seg, ntbuf;
+    int m_blocks, n_blocks, tiles;
+};
+
+__device__ __forceinline__ uint32_t make_f16_idesc_mlp(int m, int n) {     // D = F32, A = B = F16, K-major both
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_mlp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const F16GemmArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[F_MAX_TBUF];
+    __shared__ __align__(8) uint64_t tempty_bar[F_MAX_TBUF];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ntbuf = (uint32_t)a.ntbuf;
+    const uint32_t b_bytes = (uint32_t)a.BN * F_BK * 2;
+    const uint32_t stage_bytes = 2 * F_A_BYTES + 2 * b_bytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle-128B tiles need 1024-byte alignment
+    const int tiles_per_sample = a.m_blocks * a.n_blocks;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < F_MAX_TBUF; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);                                    // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi);
+        tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane) =====
+        if (elect_one()) {
+            uint32_t st = 0, ph = 0;                                         // ring position / phase, carried across tiles
+            for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+                const int s = t / tiles_per_sample, r = t - s * tiles_per_sample;
+                const int m_blk = r / a.n_blocks, n_blk = r - m_blk * a.n_blocks;
+                const int a_b = a.a_batched ? s : 0;
+                for (int kb = 0; kb < a.k_blocks; ++kb) {
+                    mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);          // slot free (first pass: passes at once)
+                    const uint32_t fb = smem_u32(&full_bar[st]);
+                    mbar_expect_tx_a(fb, stage_bytes);
+                    const uint32_t base = smem_base + st * stage_bytes;
+                    const int k0 = kb * F_BK;
+                    tma_load_3d_a(base, &tm_a_hi, k0, m_blk * F_BM, a_b, fb);
+                    tma_load_3d_a(base + F_A_BYTES, &tm_a_lo, k0, m_blk * F_BM, a_b, fb);
+                    tma_load_3d_a(base + 2 * F_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, s, fb);
+                    tma_load_3d_a(base + 2 * F_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, s, fb);
+                    if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (elect_one()) {
+            const uint32_t idesc_cat = make_f16_idesc_mlp(F_BM, 2 * a.BN), idesc_lo = make_f16_idesc_mlp(F_BM, a.BN);
+            uint32_t buf = 0, bph = 0, st = 0, ph = 0;
+            for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < a.k_blocks; kb0 += a.seg) {
+                    mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);       // the epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)(2 * a.BN);
+                    const int kb1 = kb0 + a.seg < a.k_blocks ? kb0 + a.seg : a.k_blocks;
+                    uint32_t acc = 0;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait_a(smem_u32(&full_bar[st]), ph);            // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t base = smem_base + st * stage_bytes;
+                        const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + F_A_BYTES);
+                        const uint64_t d_b = make_kmajor_desc<128>(base + 2 * F_A_BYTES);     // [B_hi ; B_lo'] rows
+#pragma unroll
+                        for (int k = 0; k < F_BK / 16; ++k) {
+                            const uint64_t koff = (uint64_t)((k * 32) >> 4);  // advance 32 bytes inside the swizzle row
+                            umma_f16_mlp(d_tmem, d_ahi + koff, d_b + koff, idesc_cat, acc);
+                            acc = 1;
+                            umma_f16_mlp(d_tmem + (uint32_t)a.BN, d_alo + koff, d_b + koff, idesc_lo, 1);
+                        }
+                        umma_commit(smem_u32(&empty_bar[st]));               // frees the smem slot when the MMAs retire
+                        if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
+                    }
+                    umma_commit(smem_u32(&tfull_bar[buf]));                  // segment complete -> epilogue drains it
+                    if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        uint32_t buf = 0, bph = 0;
+        for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+            const int s = t / tiles_per_sample, r = t - s * tiles_per_sample;
+            const int m_blk = r / a.n_blocks, n_blk = r - m_blk * a.n_blocks;
+            float accr[F_EPI_CHUNKS][16];
+#pragma unroll
+            for (int j = 0; j < F_EPI_CHUNKS; ++j)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) accr[j][e] = 0.f;
+            for (int kb0 = 0; kb0 < a.k_blocks; kb0 += a.seg) {
+                mbar_wait_a(smem_u32(&tfull_bar[buf]), bph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(2 * a.BN);
+#pragma unroll
+                for (int j = 0; j < F_EPI_CHUNKS; ++j) {
+                    if (j * 16 < a.BN) {
+                        uint32_t ra[16], rl[16];
+                        tmem_ld16_nowait(taddr + (uint32_t)(j * 16), ra);
+                        tmem_ld16_nowait(taddr + (uint32_t)(a.BN + j * 16), rl);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            accr[j][e] += fmaf(__uint_as_float(rl[e]), kF16LoUnscale, __uint_as_float(ra[e]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
+            }
+            const int64_t row = (int64_t)m_blk * F_BM + q * 32 + lane;
+            if (row >= a.M) continue;
+            const float *bias = a.bias + (int64_t)s * a.bias_stride;
+            __half *ohi = a.out_hi ? a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+            __half *olo = a.out_hi ? a.out_lo + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+            float *of = a.out_f32 ? a.out_f32 + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+#pragma unroll
+            for (int j = 0; j < F_EPI_CHUNKS; ++j) {
+                const int c0 = j * 16;
+                if (c0 >= a.BN) continue;
+                const int col0 = n_blk * a.BN + c0;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = col0 + i;
+                    float x = accr[j][i] + (col < a.n_valid ? __ldg(bias + col) : 0.f);
+                    if (a.relu) x = relu_nan(x);
+                    v[i] = x;
+                }
+                if (ohi != nullptr) {
+                    if (col0 + 16 <= a.ld_out) {
+                        uint32_t h[8], l[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn((v[2 * i] - hf.x) * kF16LoScale, (v[2 * i + 1] - hf.y) * kF16LoScale);
+                            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                        }
+                        uint4 *ph4 = reinterpret_cast<uint4 *>(ohi + col0), *pl4 = reinterpret_cast<uint4 *>(olo + col0);
+                        ph4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        ph4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                        pl4[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                        pl4[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                    }
+                } else if (of != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (col0 + i < a.n_valid) of[col0 + i] = v[i];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// fp32 [rows, cols] (ld, per-batch stride) -> zero-padded hi / lo' half planes [batch][rows_p][cols_p]
+__global__ void __launch_bounds__(256) split_f16_kernel(const float *__restrict__ src, int64_t ld_src, int64_t src_batch_stride,
+                                                        int rows, int cols, __half *__restrict__ hi, __half *__restrict__ lo,
+                                                        int rows_p, int cols_p) {
+    const int b = blockIdx.y;
+    const int64_t total = (int64_t)rows_p * cols_p;
+    const float *sb = src + (int64_t)b * src_batch_stride;
+    __half *hb = hi + (int64_t)b * total, *lb = lo + (int64_t)b * total;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)(i % cols_p);
+        const int64_t r = i / cols_p;
+        float x = 0.f;
+        if (r < rows && c < cols) x = __ldg(sb + r * ld_src + c);
+        const __half h = __float2half_rn(x);
+        hb[i] = h;
+        lb[i] = __float2half_rn((x - __half2float(h)) * kF16LoScale);
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+// 3-D half tensor [batch][rows][cols_p] (cols innermost), box = [1][box_rows][64], 128-byte swizzle
+static int make_tmap_h(CUtensorMap *tm, const __half *base, int64_t cols_p, int64_t rows, int64_t batch, int box_rows) {
+    const uint64_t dims[3] = {(uint64_t)cols_p, (uint64_t)rows, (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)cols_p * 2, (uint64_t)cols_p * 2 * (uint64_t)rows};
+    const uint32_t box[3] = {F_BK, (uint32_t)box_rows, 1};
+    return make_tensor_map_t(tm, base, 3, dims, strides, box, 128, 1);
+}
+
+static int round_up_f(int v, int m) { return (v + m - 1) / m * m; }
+
+// N tile: multiple of 16, <= 128 (the concatenated [B_hi ; B_lo'] operand has N = 2 BN <= 256), minimal padding (ties -> larger)
+static int pick_bn_f16(int n_out) {
+    const int nr = round_up_f(n_out, 16);
+    if (nr <= 128) return nr;
+    int best = 128, best_waste = round_up_f(nr, 128) - nr;
+    for (int bn = 112; bn >= 64; bn -= 16) {
+        const int w = round_up_f(nr, bn) - nr;
+        if (w < best_waste) { best = bn; best_waste = w; }
+    }
+    return best;
+}
+
+struct F16Plan {
+    int K1p, K2p, BN1, BN3, Np1, Np3, sc;
+    size_t x_plane, w1_plane, w2_plane, w3_plane, h_plane, logit_plane;   // elements per (sample) plane
+    size_t total_bytes;
+};
+
+static F16Plan f16_plan(int S, int64_t N, int in_dim, int hidden, int C) {
+    F16Plan p;
+    p.K1p = round_up_f(in_dim, F_BK);
+    p.K2p = round_up_f(hidden, F_BK);
+    p.BN1 = pick_bn_f16(hidden);
+    p.BN3 = pick_bn_f16(C);
+    p.Np1 = round_up_f(round_up_f(hidden, 16), p.BN1);
+    p.Np3 = round_up_f(round_up_f(C, 16), p.BN3);
+    p.x_plane = ((size_t)N * p.K1p + 511) & ~(size_t)511;
+    p.w1_plane = (size_t)p.Np1 * p.K1p;
+    p.w2_plane = (size_t)p.Np1 * p.K2p;
+    p.w3_plane = (size_t)p.Np3 * p.K2p;
+    p.h_plane = (size_t)N * p.K2p;
+    p.logit_plane = ((size_t)N * C + 3) & ~(size_t)3;
+    const size_t per_sample_bytes = 2 * 2 * (p.w1_plane + p.w2_plane + p.w3_plane) + 2 * 4 * p.h_plane + 4 * p.logit_plane;
+    size_t sc = (size_t)(768ull << 20) / (per_sample_bytes + 1);
+    if (sc < 1) sc = 1;
+    if (sc > (size_t)S) sc = S;
+    if (sc > 32) sc = 32;
+    p.sc = (int)sc;
+    p.total_bytes = 2 * 2 * p.x_plane + (size_t)p.sc * per_sample_bytes + 4096;
+    return p;
+}
+
+static int launch_f16_gemm(const __half *a_hi, const __half *a_lo, int64_t a_rows, int64_t a_batch, int Kp, const __half *b_hi,
+                           const __half *b_lo, int Np, int BN, int batch, F16GemmArgs g, cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (int rc = make_tmap_h(&ta_hi, a_hi, Kp, a_rows, a_batch, F_BM)) return rc;
+    if (int rc = make_tmap_h(&ta_lo, a_lo, Kp, a_rows, a_batch, F_BM)) return rc;
+    if (int rc = make_tmap_h(&tb_hi, b_hi, Kp, Np, batch, BN)) return rc;
+    if (int rc = make_tmap_h(&tb_lo, b_lo, Kp, Np, batch, BN)) return rc;
+    g.BN = BN;
+    g.k_blocks = Kp / F_BK;
+    g.a_batched = a_batch > 1 ? 1 : 0;
+    g.seg = F_SEG;
+    if (const char *e = getenv("URSA_MLP_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }   // accuracy / speed experiments
+    g.ntbuf = 512 / (2 * BN) < F_MAX_TBUF ? 512 / (2 * BN) : F_MAX_TBUF;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(g.ntbuf * 2 * BN)) cols <<= 1;
+    g.tmem_cols = cols;
+    const size_t stage_bytes = 2 * F_A_BYTES + 2 * (size_t)BN * F_BK * 2;
+    int stages = (int)((size_t)(225 << 10) / stage_bytes);
+    if (stages > F_MAX_STAGES) stages = F_MAX_STAGES;
+    URSA_REQUIRE(stages >= 2, "mlp_f16_gemm: tile does not fit in shared memory");
+    g.stages = stages;
+    g.m_blocks = (int)((g.M + F_BM - 1) / F_BM);
+    g.n_blocks = Np / BN;
+    g.tiles = batch * g.m_blocks * g.n_blocks;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    URSA_CUDA(cudaFuncSetAttribute(mlp_f16_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = g.tiles < sm_count() ? g.tiles : sm_count();
+    mlp_f16_gemm_kernel<<<grid, F_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    URSA_LAUNCH_CHECK("mlp_f16_gemm_kernel");
+    return URSA_OK;
+}
+
+size_t mlp_workspace_f16(int S, int64_t N, int in_dim, int hidden, int C) {
+    if (in_dim % 4 != 0 || hidden % 4 != 0 || C > 128) return 0;
+    return f16_plan(S, N, in_dim, hidden, C).total_bytes;
+}
+
+int mlp_forward_f16(const float *bank, int64_t ld_bank, int S, const float *x, int64_t N, int in_dim, int hidden, int C,
+                    float *proba_sum, float *entropy_sum, float *logits_out, double gamma, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+    if (mlp_workspace_f16(S, N, in_dim, hidden, C) == 0) {
+        set_error("URSA_ALGO_TCGEN05_F16 does not cover this MLP shape; use URSA_ALGO_TCGEN05 or URSA_ALGO_FFMA");
+        return URSA_ERR_UNSUPPORTED;
+    }
+    const F16Plan p = f16_plan(S, N, in_dim, hidden, C);
+    URSA_REQUIRE(workspace_bytes >= p.total_bytes, "ursa_bma_mlp_forward: workspace too small");
+    __half *ws = reinterpret_cast<__half *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    __half *x_hi = ws, *x_lo = x_hi + p.x_plane;
+    __half *w1_hi = x_lo + p.x_plane, *w1_lo = w1_hi + p.sc * p.w1_plane;
+    __half *w2_hi = w1_lo + p.sc * p.w1_plane, *w2_lo = w2_hi + p.sc * p.w2_plane;
+    __half *w3_hi = w2_lo + p.sc * p.w2_plane, *w3_lo = w3_hi + p.sc * p.w3_plane;
+    __half *h1_hi = w3_lo + p.sc * p.w3_plane, *h1_lo = h1_hi + p.sc * p.h_plane;
+    __half *h2_hi = h1_lo + p.sc * p.h_plane, *h2_lo = h2_hi + p.sc * p.h_plane;
+    float *lg = reinterpret_cast<float *>(h2_lo + p.sc * p.h_plane);
+
+    const int64_t oW1 = 0, ob1 = oW1 + (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)hidden * hidden,
+                  oW3 = ob2 + hidden, ob3 = oW3 + (int64_t)C * hidden;
+    auto split = [&](const float *src, int64_t ld, int64_t bstride, int rows, int cols, __half *hi, __half *lo, int rows_p,
+                     int cols_p, int batch) -> int {
+        const int64_t total = (int64_t)rows_p * cols_p;
+        int gx = (int)((total + 255) / 256);
+        if (gx > 148 * 8) gx = 148 * 8;
+        split_f16_kernel<<<dim3(gx, batch), 256, 0, st>>>(src, ld, bstride, rows, cols, hi, lo, rows_p, cols_p);
+        URSA_LAUNCH_CHECK("split_f16_kernel");
+        return URSA_OK;
+    };
+    if (int rc = split(x, in_dim, 0, (int)N, in_dim, x_hi, x_lo, (int)N, p.K1p, 1)) return rc;
+    // hidden-activation padding columns (hidden..K2p) are never written by a tile: zero them once
+    URSA_CUDA(cudaMemsetAsync(h1_hi, 0, 4 * (size_t)p.sc * p.h_plane * sizeof(__half), st));
+
+    for (int s0 = 0; s0 < S; s0 += p.sc) {
+        const int nb = (S - s0 < p.sc) ? (S - s0) : p.sc;
+        const float *bk = bank + (int64_t)s0 * ld_bank;
+        if (int rc = split(bk + oW1, in_dim, ld_bank, hidden, in_dim, w1_hi, w1_lo, p.Np1, p.K1p, nb)) return rc;
+        if (int rc = split(bk + oW2, hidden, ld_bank, hidden, hidden, w2_hi, w2_lo, p.Np1, p.K2p, nb)) return rc;
+        if (int rc = split(bk + oW3, hidden, ld_bank, C, hidden, w3_hi, w3_lo, p.Np3, p.K2p, nb)) return rc;
+        F16GemmArgs g;
+        g.M = N; g.bias_stride = ld_bank;
+        // layer 1: relu(x W1^T + b1) -> h1 (split)
+        g.bias = bk + ob1; g.out_hi = h1_hi; g.out_lo = h1_lo; g.out_f32 = nullptr; g.out_batch_stride = (int64_t)p.h_plane;
+        g.ld_out = p.K2p; g.n_valid = hidden; g.relu = 1;
+        if (int rc = launch_f16_gemm(x_hi, x_lo, N, 1, p.K1p, w1_hi, w1_lo, p.Np1, p.BN1, nb, g, st)) return rc;
+        // layer 2: relu(h1 W2^T + b2) -> h2 (split)
+        g.bias = bk + ob2; g.out_hi = h2_hi; g.out_lo = h2_lo;
+        if (int rc = launch_f16_gemm(h1_hi, h1_lo, N, nb, p.K2p, w2_hi, w2_lo, p.Np1, p.BN1, nb, g, st)) return rc;
+        // layer 3: logits = h2 W3^T + b3 (plain fp32)
+        g.bias = bk + ob3; g.out_hi = nullptr; g.out_lo = nullptr; g.out_f32 = lg; g.out_batch_stride = (int64_t)p.logit_plane;
+        g.ld_out = C; g.n_valid = C; g.relu = 0;
+        if (int rc = launch_f16_gemm(h2_hi, h2_lo, N, nb, p.K2p, w3_hi, w3_lo, p.Np3, p.BN3, nb, g, st)) return rc;
+        if (int rc = ursa_bma_accumulate(lg, nb, N, C, (int64_t)p.logit_plane, proba_sum, entropy_sum, gamma, (void *)st))
+            return rc;
+        if (logits_out)
+            URSA_CUDA(cudaMemcpy2DAsync(logits_out + (size_t)s0 * N * C, (size_t)N * C * sizeof(float), lg,
+                                        p.logit_plane * sizeof(float), (size_t)N * C * sizeof(float), nb,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    return URSA_OK;
+}
+
+}  // namespace ursa

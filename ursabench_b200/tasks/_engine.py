@@ -206,7 +206,7 @@ class BMAAccumulator:
         (e.g. an MLP width that is not a multiple of 4).  ``engine='ffma'`` pins the CUDA-core kernels."""
         lib = _C.lib()
         if arch[0] == "mlp":
-            order = (_C.ALGO_FFMA,) if self.engine == "ffma" else (_C.ALGO_TCGEN05, _C.ALGO_FFMA)
+            order = (_C.ALGO_FFMA,) if self.engine == "ffma" else (_C.ALGO_TCGEN05_F16, _C.ALGO_TCGEN05, _C.ALGO_FFMA)
             for algo in order:
                 if lib.ursa_bma_mlp_workspace(1, 1, arch[1], arch[2], arch[3], algo) > 0:
                     return algo
@@ -235,7 +235,14 @@ class BMAAccumulator:
                     raise ValueError("MLP input / class dimensions do not match the task")
                 if w.shape[1] < (in_dim + 1) * hidden + (hidden + 1) * hidden + (hidden + 1) * C:
                     raise ValueError("bank rows are shorter than the MLP's parameter vector")
-                self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, proba, entropy, algo=algo, workspace=self._ws)
+                if algo == _C.ALGO_TCGEN05_F16:
+                    # FP16-split operands: inputs / activations beyond 65 504 overflow to inf -> NaN logits (loud by
+                    # construction); same scratch-and-commit protocol as the PreResNet FP16-split engine below
+                    sp, se = self._scratch()
+                    self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, sp[lo:hi], se[lo:hi], algo=algo, workspace=self._ws)
+                    self._pending.append(("mlp", w, S, in_dim, hidden, C, lo, hi))
+                else:
+                    self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_mlp"
             elif arch[0] == "wrn":
                 _, depth, widen, C = arch
@@ -255,7 +262,7 @@ class BMAAccumulator:
                     sp, se = self._scratch()
                     self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp[lo:hi], se[lo:hi], algo=algo,
                                                         workspace=self._ws)
-                    self._pending.append((w, b, S, depth, C, lo, hi))
+                    self._pending.append(("preresnet", w, b, S, depth, C, lo, hi))
                 else:
                     self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=self._ws)
                 self.last_engine = "fused_preresnet"
@@ -293,11 +300,18 @@ class BMAAccumulator:
             self._proba.add_(self._scratch_p)
             self._entropy.add_(self._scratch_e)
             return
-        self.last_algo = _C.ALGO_TCGEN05_FUSED
         ws = None
-        for w, b, S, depth, C, lo, hi in pending:
-            ws = _C.bma_preresnet_forward(w, b, S, self._x[lo:hi], depth, C, self._proba[lo:hi], self._entropy[lo:hi],
-                                          algo=_C.ALGO_TCGEN05_FUSED, workspace=ws)
+        for job in pending:
+            if job[0] == "mlp":
+                _, w, S, in_dim, hidden, C, lo, hi = job
+                self.last_algo = _C.ALGO_TCGEN05
+                ws = _C.bma_mlp_forward(w, S, self._x.view(self._n, -1)[lo:hi], in_dim, hidden, C, self._proba[lo:hi],
+                                        self._entropy[lo:hi], algo=_C.ALGO_TCGEN05, workspace=ws)
+            else:
+                _, w, b, S, depth, C, lo, hi = job
+                self.last_algo = _C.ALGO_TCGEN05_FUSED
+                ws = _C.bma_preresnet_forward(w, b, S, self._x[lo:hi], depth, C, self._proba[lo:hi], self._entropy[lo:hi],
+                                              algo=_C.ALGO_TCGEN05_FUSED, workspace=ws)
 
     def _inputs_match(self, arch):
         """The fused conv forwards take only (pointer, N): the resident test tensor must be the [N, 3, 32, 32] the
