@@ -12,13 +12,14 @@
 // Range: fp16 overflows beyond 65 504 -> inf -> NaN logits (the ReLU here propagates NaN): loud by construction; the class
 // layer (tasks/_engine.py) redoes such an evaluation on the 3xTF32 engine, which has fp32's range.
 //
-// Kernel anatomy (192 threads, one CTA per SM, static tile schedule t = blockIdx.x + i gridDim.x over (sample, m, n), n fastest):
+// Kernel anatomy (320 threads, one CTA per SM, static tile schedule t = blockIdx.x + i gridDim.x over (sample, m, n), n fastest):
 //   warp 0      TMA producer: per k-block (64 halves = one 128-byte swizzle row) four 3-D tiled loads into a 4-stage ring
 //   warp 1      MMA issuer: 4 (K = 16) x 2 MMAs per stage; a chain covers F_SEG k-blocks (two-level accumulation: the tensor
 //               core adds into TMEM with truncation, a bias that grows with the chain), then moves to the next of the rotating
 //               TMEM accumulators -- across tile boundaries too, so the MMAs of tile i + 1 run under the epilogue of tile i
-//   warps 2-5   epilogue: drain each finished segment (tcgen05.ld ACC and LO chunks -> acc + lo 2^-11 -> fp32 registers), after a
-//               tile's last segment + bias -> ReLU -> split -> global (the next layer's TMA source), or plain fp32 logits
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, alternating 16-column chunks; with four warps layer 2, K = 448, was
+//               epilogue bound): drain each finished segment (tcgen05.ld ACC and LO chunks -> acc + lo 2^-11 -> fp32 registers),
+//               after a tile's last segment + bias -> ReLU -> split -> global (the next layer's TMA source), or fp32 logits
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -26,8 +27,8 @@
 
 namespace ursa {
 
-constexpr int F_BM = 128, F_BK = 64, F_MAX_STAGES = 6, F_THREADS = 192;
-constexpr int F_SEG = 4, F_MAX_TBUF = 4, F_EPI_CHUNKS = 8;             // BN <= 128 = 8 chunks of 16 columns
+constexpr int F_BM = 128, F_BK = 64, F_MAX_STAGES = 6, F_EPI_WARPS = 8, F_THREADS = 64 + 32 * F_EPI_WARPS;
+constexpr int F_SEG = 4, F_MAX_TBUF = 4, F_EPI_CHUNKS = 4;             // BN <= 128 = 8 chunks of 16 columns, 4 per epilogue warp
 constexpr uint32_t F_A_BYTES = F_BM * F_BK * 2;                          // 16 KB per A tile
 constexpr float kF16LoScale = 2048.f, kF16LoUnscale = 1.f / 2048.f;    // 2^11
 
@@ -83,7 +84,7 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
         for (int i = 0; i < F_MAX_TBUF; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);                                    // one arrival per epilogue warp
+            mbar_init(&tempty_bar[i], F_EPI_WARPS);                          // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -155,8 +156,8 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
+        // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4; warps 2-5 take the even 16-column chunks, 6-9 the odd ones =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
         uint32_t buf = 0, bph = 0;
         for (int t = blockIdx.x; t < a.tiles; t += gridDim.x) {
             const int s = t / tiles_per_sample, r = t - s * tiles_per_sample;
@@ -172,10 +173,11 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(2 * a.BN);
 #pragma unroll
                 for (int j = 0; j < F_EPI_CHUNKS; ++j) {
-                    if (j * 16 < a.BN) {
+                    const int c0 = (2 * j + half) * 16;
+                    if (c0 < a.BN) {
                         uint32_t ra[16], rl[16];
-                        tmem_ld16_nowait(taddr + (uint32_t)(j * 16), ra);
-                        tmem_ld16_nowait(taddr + (uint32_t)(a.BN + j * 16), rl);
+                        tmem_ld16_nowait(taddr + (uint32_t)c0, ra);
+                        tmem_ld16_nowait(taddr + (uint32_t)(a.BN + c0), rl);
                         tmem_wait_ld();
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
@@ -195,7 +197,7 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             float *of = a.out_f32 ? a.out_f32 + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
 #pragma unroll
             for (int j = 0; j < F_EPI_CHUNKS; ++j) {
-                const int c0 = j * 16;
+                const int c0 = (2 * j + half) * 16;
                 if (c0 >= a.BN) continue;
                 const int col0 = n_blk * a.BN + c0;
                 float v[16];
