@@ -195,6 +195,9 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
 #define URSA_ALGO_FFMA    0
 #define URSA_ALGO_TCGEN05 1
 #define URSA_ALGO_TCGEN05_FUSED 2   /* PreResNet only: stage-fused 3xTF32 kernel, activations in shared memory, residual in TMEM */
+#define URSA_ALGO_FLAG_WS_KEPT 0x100 /* OR-ed into `algo` of ursa_bma_preresnet_forward: the workspace is the one the caller's PREVIOUS
+                                      * call of this entry used, with the same min(S, 8), N, depth and C, and nothing else has written
+                                      * to it since -- the FP16-split engine then skips re-zeroing the pad positions of its plane images */
 #define URSA_ALGO_TCGEN05_F16 4     /* MLP only: persistent 2xFP16-split GEMM kernel (csrc/bma_mlp_f16.cu) */
 #define URSA_ALGO_TCGEN05_FUSED_F16 3 /* PreResNet only: stage-fused kernel on 2xFP16-split operands (22 significant bits, fp32
                                        * accumulate), MMA / epilogue wavefront per 128-position tile.  Activations above ~1e6

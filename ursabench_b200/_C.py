@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("URSA_B200_LIB") or os.path.join(_HERE, "libursa_b200.
 
 STEP_FIRST, STEP_NOISE, STEP_ZERO_GRAD = 1, 2, 4
 ALGO_FFMA, ALGO_TCGEN05, ALGO_TCGEN05_FUSED, ALGO_TCGEN05_FUSED_F16, ALGO_TCGEN05_F16 = 0, 1, 2, 3, 4
+ALGO_FLAG_WS_KEPT = 0x100      # ursa_bma_preresnet_forward: workspace untouched since this caller's previous identical-shape call
 DRAW_MAX_S, DRAW_MAX_K = 30, 24
 
 _c = ctypes

@@ -22,7 +22,7 @@ size_t preresnet_workspace_tcgen05(int S, int64_t N, int depth, int C);
 size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C, int f16);
 int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                             int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
-                            double gamma, void *workspace, size_t workspace_bytes, int f16, cudaStream_t st);
+                            double gamma, void *workspace, size_t workspace_bytes, int f16, int ws_kept, cudaStream_t st);
 int preresnet_forward_tcgen05(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                               int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
                               double gamma, void *workspace, size_t workspace_bytes, cudaStream_t st);
@@ -234,6 +234,7 @@ static int launch_conv(ConvArgs a, int sc, cudaStream_t st) {
 using namespace ursa;
 
 extern "C" size_t ursa_bma_preresnet_workspace(int S, int64_t N, int depth, int C, int algo) {
+    algo &= ~URSA_ALGO_FLAG_WS_KEPT;
     NetPlan pl;
     if (S < 1 || N < 1) return 0;
     if (algo == URSA_ALGO_TCGEN05) return preresnet_workspace_tcgen05(S, N, depth, C);
@@ -249,13 +250,15 @@ extern "C" int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, co
                                           size_t workspace_bytes, int algo, void *stream) {
     URSA_REQUIRE(bank && bufbank && x && proba_sum && entropy_sum && workspace, "ursa_bma_preresnet_forward: null pointer");
     URSA_REQUIRE(S >= 1 && N >= 1, "ursa_bma_preresnet_forward: bad shape");
+    const int ws_kept = (algo & URSA_ALGO_FLAG_WS_KEPT) != 0;
+    algo &= ~URSA_ALGO_FLAG_WS_KEPT;
     if (algo == URSA_ALGO_TCGEN05)
         return preresnet_forward_tcgen05(bank, ld_bank, bufbank, ld_buf, S, x, N, depth, C, proba_sum, entropy_sum,
                                          logits_out, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
     if (algo == URSA_ALGO_TCGEN05_FUSED || algo == URSA_ALGO_TCGEN05_FUSED_F16)
         return preresnet_forward_fused(bank, ld_bank, bufbank, ld_buf, S, x, N, depth, C, proba_sum, entropy_sum,
                                        logits_out, gamma, workspace, workspace_bytes, algo == URSA_ALGO_TCGEN05_FUSED_F16,
-                                       (cudaStream_t)stream);
+                                       ws_kept, (cudaStream_t)stream);
     if (algo != URSA_ALGO_FFMA) {
         set_error("ursa_bma_preresnet_forward: unknown algo %d", algo);
         return URSA_ERR_UNSUPPORTED;

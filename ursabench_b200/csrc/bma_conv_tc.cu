@@ -523,22 +523,27 @@ static int launch_head_bma(const float *act, const float *packed, int64_t ld_pac
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
-constexpr int kTcChunkSamples = 8, kTcChunkImages = 512;
+constexpr int kTcChunkSamples = 8, kTcChunkImages = 512;      // images per launch: layer-by-layer engine and bn_update batches
+// images per launch of the fused stage engines: a launch is 8 samples x 2 500 images = 20 000 passes over 148 persistent CTAs, so the
+// ragged last round and the launch gaps of the 7-kernel chain are 1/5 of what 512-image launches pay (490 -> 465 ms at
+// S = 100 x N = 10 000); 9.2 GB of workspace on a 180 GB part
+constexpr int kFusedChunkImages = 2500;
 
 struct TcChunking {
     int sc, nc;
     size_t raw_bytes, packed_bytes, logit_bytes, total;
 };
 
-static TcChunking tc_chunking(int S, int64_t N, const NetPlan &pl) {
+static TcChunking tc_chunking(int S, int64_t N, const NetPlan &pl, bool fused = false) {
     TcChunking c;
     c.sc = S < kTcChunkSamples ? S : kTcChunkSamples;
     static const int chunk_images = [] {            // URSA_CHUNK_IMAGES: images per launch of the conv forwards (experiments)
         const char *e = getenv("URSA_CHUNK_IMAGES");
         const int v = e ? atoi(e) : 0;
-        return v >= 64 && v <= 16384 ? v : kTcChunkImages;
+        return v >= 64 && v <= 16384 ? v : 0;
     }();
-    c.nc = (int)(N < chunk_images ? N : chunk_images);
+    const int ci = chunk_images ? chunk_images : (fused ? kFusedChunkImages : kTcChunkImages);
+    c.nc = (int)(N < ci ? N : ci);
     const size_t pairs = (size_t)c.sc * c.nc;
     c.raw_bytes = pairs * 16 * 32 * 32 * sizeof(float);               // largest activation: 64 KB per pair
     c.packed_bytes = (((size_t)c.sc * pl.packed_floats * sizeof(float)) + 1023) & ~(size_t)1023;
@@ -1171,13 +1176,13 @@ static PiLayout pi_layout(int sc, int nc) {
 size_t preresnet_workspace_fused(int S, int64_t N, int depth, int C, int f16) {
     NetPlan pl;
     if (!build_plan(depth, C, pl, f16 ? 3 : 2)) return 0;
-    const TcChunking ck = tc_chunking(S, N, pl);
+    const TcChunking ck = tc_chunking(S, N, pl, true);
     return ck.total + (f16 ? pi_layout(ck.sc, ck.nc).total + 1024 : 0);
 }
 
 int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf, int S, const float *x,
                             int64_t N, int depth, int C, float *proba_sum, float *entropy_sum, float *logits_out,
-                            double gamma, void *workspace, size_t workspace_bytes, int f16, cudaStream_t st) {
+                            double gamma, void *workspace, size_t workspace_bytes, int f16, int ws_kept, cudaStream_t st) {
     static thread_local NetPlan pl;
     if (!build_plan(depth, C, pl, f16 ? 3 : 2)) {
         set_error("ursa_bma_preresnet_forward: unsupported depth %d (BasicBlock PreResNet: depth = 6n+2, 8..38)", depth);
@@ -1185,13 +1190,15 @@ int preresnet_forward_fused(const float *bank, int64_t ld_bank, const float *buf
     }
     URSA_REQUIRE(ld_bank >= pl.D, "ursa_bma_preresnet_forward: ld_bank (%lld) < D (%lld)", (long long)ld_bank, (long long)pl.D);
     URSA_REQUIRE(ld_buf >= pl.NB, "ursa_bma_preresnet_forward: ld_buf (%lld) < %lld", (long long)ld_buf, (long long)pl.NB);
-    const TcChunking ck = tc_chunking(S, N, pl);
+    const TcChunking ck = tc_chunking(S, N, pl, true);
     const PiLayout pil = pi_layout(ck.sc, ck.nc);
     URSA_REQUIRE(workspace_bytes >= ck.total + (f16 ? pil.total + 1024 : 0), "ursa_bma_preresnet_forward: workspace too small");
     char *wsb = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     unsigned char *pi_base = reinterpret_cast<unsigned char *>(wsb) + ((ck.total - 2048 + 1023) & ~(size_t)1023);
-    if (f16)   // the producers only write pixel positions: the pad positions of the plane images must read as zero
-        URSA_CUDA(cudaMemsetAsync(pi_base, 0, pil.total, st));
+    // The producers only write pixel positions: the pad positions of the plane images must read as zero.  With
+    // URSA_ALGO_FLAG_WS_KEPT the caller vouches that they still do (same workspace, same S-chunk and N as its previous call,
+    // nothing else wrote to it): 2.7 GB of memset per call at the default chunking.
+    if (f16 && !ws_kept) URSA_CUDA(cudaMemsetAsync(pi_base, 0, pil.total, st));
     float *Ra = reinterpret_cast<float *>(wsb);
     float *Rb = reinterpret_cast<float *>(wsb + ck.raw_bytes);
     float *Rs = reinterpret_cast<float *>(wsb + 2 * ck.raw_bytes);

@@ -129,6 +129,7 @@ class BMAAccumulator:
         self._entropy = torch.zeros(self._n, device=self.device)
         self._workers = {}
         self._pending = []        # FP16-split forwards of the current accumulate() awaiting the range check
+        self._ws_key = None       # launch shape + address of the workspace whose plane-image pads are known to be zero
         self.last_engine = None
         self.kernel_launches = 0
 
@@ -189,11 +190,15 @@ class BMAAccumulator:
                 and all(_arch_of(m) == arch for m in plain):
             # one H2D per sample instead of 2 per batch -- in sub-batches, so that packing sub-batch i + 1 on the host
             # (a Python walk over ~100 tensors per module) overlaps the forward of sub-batch i on the device
+            # The first sub-batch is small: nothing runs on the device while it is being packed.
             step = _PACK_BATCH if len(plain) > 2 * _PACK_BATCH else len(plain)
-            for s0 in range(0, len(plain), step):
-                bank = SampleBank.from_modules(plain[s0:s0 + step], self.device)
+            s0 = 0
+            while s0 < len(plain):
+                n = min(2, step) if s0 == 0 and len(plain) > step else step
+                bank = SampleBank.from_modules(plain[s0:s0 + n], self.device)
                 self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
                 self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
+                s0 += n
             return
         self._accumulate_generic_modules(plain, lo, hi)
 
@@ -243,12 +248,14 @@ class BMAAccumulator:
                     self._pending.append(("mlp", w, S, in_dim, hidden, C, lo, hi))
                 else:
                     self._ws = _C.bma_mlp_forward(w, S, x2, in_dim, hidden, C, proba, entropy, algo=algo, workspace=self._ws)
+                self._ws_key = None
                 self.last_engine = "fused_mlp"
             elif arch[0] == "wrn":
                 _, depth, widen, C = arch
                 if C != self.num_classes:
                     raise ValueError("WideResNet class dimension does not match the task")
                 self._ws = _C.bma_wrn_forward(w, b, S, x, depth, widen, C, proba, entropy, algo=algo, workspace=self._ws)
+                self._ws_key = None
                 self.last_engine = "fused_wrn"
             else:
                 _, depth, C = arch
@@ -260,11 +267,17 @@ class BMAAccumulator:
                     # end and either adds the scratch or redoes the calls on the TF32 engine: the accumulators never see
                     # a NaN, nothing is cloned and the host does not synchronise between the calls.
                     sp, se = self._scratch()
-                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp[lo:hi], se[lo:hi], algo=algo,
+                    # the engine's plane images need zeroed pad positions (2.7 GB of memset per call at the default chunking):
+                    # skipped when this object's previous call left them so -- same private workspace, same launch shape
+                    key = (min(S, 8), hi - lo, depth, C, None if self._ws is None else self._ws.data_ptr())
+                    kept = _C.ALGO_FLAG_WS_KEPT if key == self._ws_key else 0
+                    self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, sp[lo:hi], se[lo:hi], algo=algo | kept,
                                                         workspace=self._ws)
+                    self._ws_key = key[:4] + (self._ws.data_ptr(),)
                     self._pending.append(("preresnet", w, b, S, depth, C, lo, hi))
                 else:
                     self._ws = _C.bma_preresnet_forward(w, b, S, x, depth, C, proba, entropy, algo=algo, workspace=self._ws)
+                    self._ws_key = None
                 self.last_engine = "fused_preresnet"
             self.last_algo = algo
             self.kernel_launches += 1
