@@ -1,6 +1,6 @@
-"""One launch of each HBM-bound / GEMM kernel at its bench size, for `ncu --set full` (profiles/r2s14_*):
-K1 sgmcmc_step (WRN size), K2a swag_collect, K2b swag_draw (S = 30, K = 20), K2c ring_gram, K5 hmc_leapfrog, the MLP tcgen05 GEMM
-(BMA forward S = 16 x N = 10 000) and the chain-batched HMC gradient GEMMs."""
+"""One launch of each HBM-bound / GEMM kernel at its bench size, for `ncu --set full` (profiles/r2s14_*, r2s23_*):
+K1 sgmcmc_step (WRN size), K2a swag_collect, K2b swag_draw (S = 30, K = 20 and the diagonal K = 0), K2c ring_gram_tc, K5 hmc_leapfrog,
+the MLP GEMMs of both tensor-core engines (BMA forward S = 16 x N = 10 000) and the chain-batched HMC gradient GEMMs."""
 import math
 import os
 import sys
@@ -27,6 +27,7 @@ bank = torch.empty(S, ld, device=dev)
 z2 = torch.randn(S, K, device=dev)
 for rep in range(2):
     _C.swag_draw(bank, mean, var, D, ring=ring, z2=z2, rank_div=math.sqrt(K - 1.0), seed=5, step=rep)
+    _C.swag_draw(bank, mean, var, D, seed=5, step=rep)
     _C.swag_gram(ring, D)
 del bank, ring, p, g, v, mean, sq, var
 Dh = 199_210
@@ -47,5 +48,8 @@ P, E = torch.zeros(10_000, 10, device=dev), torch.zeros(10_000, device=dev)
 ws = None
 for rep in range(2):
     ws = _C.bma_mlp_forward(bankm, 16, xm, 784, 400, 10, P, E, algo=_C.ALGO_TCGEN05, workspace=ws)
+ws = None
+for rep in range(2):
+    ws = _C.bma_mlp_forward(bankm, 16, xm, 784, 400, 10, P, E, algo=_C.ALGO_TCGEN05_F16, workspace=ws)
 torch.cuda.synchronize()
 print("done")
