@@ -607,6 +607,41 @@ def cpu_extras():
         opt.step(add_langevin_noise=True)
     t = timeit(sgmcmc_step, 20, warm=2)
     out["csghmc_preresnet20_b128"] = {"steps_per_s": 1 / t, "sample": "20 steps (csghmc.py:80-93 loop body), one chain"}
+    # config 3: Prediction on WideResNet-28-10 (C = 100), bounded S = 1 x N = 64 (11.9 GFLOP per image)
+    try:
+        from URSABench.models import wideresnet as rwrn
+        wrn, wkind = rwrn.WideResNet(num_classes=100, depth=28, widen_factor=10), kind
+    except Exception:  # noqa: BLE001
+        wrn, wkind = M.WideResNet(num_classes=100, depth=28, widen_factor=10), "port"
+    wrn.eval()
+    xw, yw = torch.randn(64, 3, 32, 32, generator=g), torch.randint(0, 100, (64,), generator=g)
+    lw = {"in_distribution_test": torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xw, yw), batch_size=64)}
+
+    def wrn_eval():
+        tk = Pred(lw, 100, torch.device("cpu"), METRICS)
+        tk.update_statistics([wrn], output_performance=False)
+        return tk.get_performance_metrics()
+    t = timeit(wrn_eval, 2)
+    out["bma_wrn28x10"] = {"img_samples_per_s": 64 / t, "ms_for_S30_N10k_extrapolated": 30 * 10_000 / 64 * t * 1e3, "kind": wkind,
+                           "sample": "2 x (S = 1 x N = 64) through tasks.Prediction"}
+    # config 4: one HMC leapfrog step of ONE chain = autograd gradient of the MLP-200 log-likelihood over 1 000 points + the
+    # kick / drift updates (what hamiltorch.sample does L times per iteration and chain, inference/hmc.py:71-75; hamiltorch is
+    # not vendored, so this is the restated loop body on torch CPU: kind "port")
+    mlp = M.MLP(200, 784, 10)
+    xh, yh = torch.randn(1000, 784, generator=g), torch.randint(0, 10, (1000,), generator=g)
+    params = list(mlp.parameters())
+    mom = [torch.randn_like(q) for q in params]
+    ce = torch.nn.CrossEntropyLoss(reduction="sum")
+
+    def leapfrog():
+        grads = torch.autograd.grad(ce(mlp(xh), yh), params)
+        with torch.no_grad():
+            for q, r, gq in zip(params, mom, grads):
+                r.add_(gq + 100.0 * q, alpha=-2.09e-4)
+                q.add_(r, alpha=2.09e-4 / 0.192)
+    t = timeit(leapfrog, 50, warm=3)
+    out["hmc_mlp200_N1000"] = {"chain_leapfrog_steps_per_s": 1 / t, "kind": "port",
+                               "sample": "50 leapfrog steps of one chain (gradient over 1 000 points + kick / drift), torch CPU"}
     return out
 
 
