@@ -234,6 +234,13 @@ size_t ursa_hmc_mlp_grad_workspace(int C, int64_t N, int in_dim, int hidden, int
 int ursa_hmc_mlp_grad(const float *theta, int64_t ld, int C, const float *x, const int64_t *y, int64_t N,
                       int in_dim, int hidden, int n_classes, float *grad, float *ce,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* The same gradient on the persistent 2xFP16-split GEMM kernel (csrc/bma_mlp_f16.cu; planes are halves, x = hi + lo' 2^-11):
+ * the product path of inference.HMC for the reference's MLPs.  Operands beyond fp16's range (|x| > 65 504) make grad / ce
+ * non-finite -- never finite-but-wrong; callers fall back to ursa_hmc_mlp_grad, which has fp32's range. */
+size_t ursa_hmc_mlp_grad_f16_workspace(int C, int64_t N, int in_dim, int hidden, int n_classes);
+int ursa_hmc_mlp_grad_f16(const float *theta, int64_t ld, int C, const float *x, const int64_t *y, int64_t N,
+                          int in_dim, int hidden, int n_classes, float *grad, float *ce,
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * K3  sample-batched BMA forward, PreResNet (BasicBlock, depth = 6n+2 < 44; models/preresnet.py:90-151)

@@ -242,7 +242,7 @@ def test_hmc_mlp_gemm_gradient_matches_vmap_grad():
     hyp = {"step_size": 1e-3, "num_samples": 1, "L": 2, "tau": 10.0, "burn": 0, "mass": 1.0, "num_chains": 5}
     inf = inference.HMC(hyperparameters=dict(hyp), model=models.MLP(40, 36, 7), train_loader=loader, device=DEV)
     inf.sample()
-    assert inf.grad_engine == "mlp_tcgen05_fused"           # the hand-written chain-batched forward + backward is the default
+    assert inf.grad_engine == "mlp_tcgen05_fused_f16"       # the hand-written chain-batched forward + backward (FP16-split) is the default
     th = torch.randn(5, inf.ld, device=DEV) * 0.2
     g0, ce0 = torch.zeros_like(th), torch.zeros(5, device=DEV)
     inf._grad(th, g0, ce0)                                   # ursa_hmc_mlp_grad
@@ -312,9 +312,10 @@ def test_hmc_trajectory_graph_replay_equals_eager():
     assert float(outs[0][1].mean()) > 0.2
 
 
+@pytest.mark.parametrize("engine", ["tf32", "f16"])
 @pytest.mark.parametrize("C,N,in_dim,hid,ncls", [(3, 70, 36, 40, 7), (2, 257, 784, 200, 10), (1, 1000, 16, 8, 3), (4, 33, 20, 132, 100)])
-def test_hmc_mlp_fused_gradient_matches_autograd(C, N, in_dim, hid, ncls):
-    """``ursa_hmc_mlp_grad`` (eight 3xTF32 tcgen05 GEMMs with split / transposed operands handed from epilogue to epilogue)
+def test_hmc_mlp_fused_gradient_matches_autograd(C, N, in_dim, hid, ncls, engine):
+    """``ursa_hmc_mlp_grad`` / ``ursa_hmc_mlp_grad_f16`` (eight tcgen05 GEMMs, 3xTF32 or persistent 2xFP16-split, with split / transposed operands handed from epilogue to epilogue)
     against fp64 autograd of the same MLP: gradient of the summed cross entropy per chain, and its value; ragged point
     counts, hidden widths that are not a multiple of the N tile, more classes than one 16-column chunk."""
     from ursabench_b200 import _C
@@ -327,7 +328,7 @@ def test_hmc_mlp_fused_gradient_matches_autograd(C, N, in_dim, hid, ncls):
     y = torch.randint(0, ncls, (N,), device=DEV)
     g = torch.full((C, ld), 7.0, device=DEV)
     ce = torch.zeros(C, device=DEV)
-    ws = _C.hmc_mlp_grad(theta, x, y, in_dim, hid, ncls, g, ce)
+    ws = _C.hmc_mlp_grad(theta, x, y, in_dim, hid, ncls, g, ce, engine=engine)
     assert ws is not None
     o = [0, hid * in_dim, hid * in_dim + hid, hid * in_dim + hid + hid * hid, hid * in_dim + 2 * hid + hid * hid,
          hid * in_dim + 2 * hid + hid * hid + ncls * hid, D]

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ursabench_b200 import inference, models  # noqa: E402
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-engines = sys.argv[2:] or ["mlp_tcgen05_fused", "mlp_gemm"]
+engines = sys.argv[2:] or ["mlp_tcgen05_fused_f16", "mlp_tcgen05_fused", "mlp_gemm"]
 dev = torch.device("cuda")
 g = torch.Generator().manual_seed(5)
 xs, ys = torch.randn(1000, 1, 28, 28, generator=g), torch.randint(0, 10, (1000,), generator=g)

@@ -51,6 +51,8 @@ SIGNATURES = {
                                    _vp, _sz, _vp]),
     "ursa_hmc_mlp_grad_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_hmc_mlp_grad": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "ursa_hmc_mlp_grad_f16_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
+    "ursa_hmc_mlp_grad_f16": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ursa_bma_wrn_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32]),
     "ursa_bma_wrn_forward": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _f64, _vp,
                                     _sz, _i32, _vp]),
@@ -372,24 +374,29 @@ def preresnet_bn_update(bank_rows, buf_rows, x, batch, depth, C, workspace=None)
 
 
 @_on_device
-def hmc_mlp_grad(theta, x, y, in_dim, hidden, n_classes, grad, ce, workspace=None):
-    """Chain-batched MLP likelihood gradient on tcgen05 (see ursa_hmc_mlp_grad).  theta, grad: [C, ld]; x: [N, in];
-    y: [N] int64; ce: [C].  Returns the workspace (None if the shape is not covered)."""
+def hmc_mlp_grad(theta, x, y, in_dim, hidden, n_classes, grad, ce, workspace=None, engine="tf32"):
+    """Chain-batched MLP likelihood gradient on tcgen05 (see ursa_hmc_mlp_grad / ursa_hmc_mlp_grad_f16).  theta, grad: [C, ld];
+    x: [N, in]; y: [N] int64; ce: [C].  ``engine``: "tf32" (3xTF32 kernel) or "f16" (persistent 2xFP16-split kernel).  Returns
+    the workspace (None if the shape is not covered)."""
     _dev_f32(theta, "theta"), _dev_f32(x, "x"), _dev_f32(grad, "grad"), _dev_f32(ce, "ce")
     if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous():
         raise ValueError("y must be a contiguous CUDA int64 tensor")
+    if engine not in ("tf32", "f16"):
+        raise ValueError("hmc_mlp_grad: engine must be 'tf32' or 'f16'")
     C, ld = theta.shape
     N = x.shape[0]
     if tuple(grad.shape) != (C, ld) or ce.numel() < C or x.shape[1] != in_dim or y.numel() != N:
         raise ValueError("hmc_mlp_grad: shape mismatch")
-    need = lib().ursa_hmc_mlp_grad_workspace(C, N, in_dim, hidden, n_classes)
+    ws_fn, fn = ((lib().ursa_hmc_mlp_grad_f16_workspace, lib().ursa_hmc_mlp_grad_f16) if engine == "f16"
+                 else (lib().ursa_hmc_mlp_grad_workspace, lib().ursa_hmc_mlp_grad))
+    need = ws_fn(C, N, in_dim, hidden, n_classes)
     if need == 0:
         return None
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
-    rc = lib().ursa_hmc_mlp_grad(_ptr(theta), ld, C, _ptr(x), y.data_ptr(), N, in_dim, hidden, n_classes, _ptr(grad), _ptr(ce),
-                                 _ptr(workspace), workspace.numel() * workspace.element_size(), _stream(theta))
-    _check(rc, "ursa_hmc_mlp_grad")
+    rc = fn(_ptr(theta), ld, C, _ptr(x), y.data_ptr(), N, in_dim, hidden, n_classes, _ptr(grad), _ptr(ce),
+            _ptr(workspace), workspace.numel() * workspace.element_size(), _stream(theta))
+    _check(rc, "ursa_hmc_mlp_grad" + ("_f16" if engine == "f16" else ""))
     return workspace
 
 

@@ -45,6 +45,16 @@ struct F16GemmArgs {
     uint32_t tmem_cols;
     int seg, ntbuf;
     int m_blocks, n_blocks, tiles;
+    // chain-batched MLP gradient (ursa_hmc_mlp_grad_f16): optional extras of the epilogue
+    int b_shared = 0;                               // B shared by all samples (the data matrix of the dW1 GEMM)
+    const __half *mask_hi = nullptr, *mask_lo = nullptr;   // [S][M][ld_mask] planes of a forward activation: v *= (act > 0)
+    int ld_mask = 0;
+    int64_t mask_batch_stride = 0;
+    __half *outT_hi = nullptr, *outT_lo = nullptr;  // TRANSPOSED split copy [S][features][ld_t]: the operand of the weight-gradient
+    float *outT_f32 = nullptr;                      // GEMMs (they contract over the rows of this one); or a plain fp32 transposed
+    int ld_t = 0;                                   // store of features [0, t_valid).  Rows M .. ld_t of the split copy are written
+    int64_t outT_batch_stride = 0;                  // as zeros.
+    int t_valid = 0;
 };
 
 __device__ __forceinline__ uint32_t make_f16_idesc_mlp(int m, int n) {     // D = F32, A = B = F16, K-major both
@@ -116,8 +126,8 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     const int k0 = kb * F_BK;
                     tma_load_3d_a(base, &tm_a_hi, k0, m_blk * F_BM, a_b, fb);
                     tma_load_3d_a(base + F_A_BYTES, &tm_a_lo, k0, m_blk * F_BM, a_b, fb);
-                    tma_load_3d_a(base + 2 * F_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, s, fb);
-                    tma_load_3d_a(base + 2 * F_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, s, fb);
+                    tma_load_3d_a(base + 2 * F_A_BYTES, &tm_b_hi, k0, n_blk * a.BN, a.b_shared ? 0 : s, fb);
+                    tma_load_3d_a(base + 2 * F_A_BYTES + b_bytes, &tm_b_lo, k0, n_blk * a.BN, a.b_shared ? 0 : s, fb);
                     if (++st == (uint32_t)a.stages) { st = 0; ph ^= 1u; }
                 }
             }
@@ -190,11 +200,18 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
             }
             const int64_t row = (int64_t)m_blk * F_BM + q * 32 + lane;
-            if (row >= a.M) continue;
-            const float *bias = a.bias + (int64_t)s * a.bias_stride;
+            const bool live = row < a.M;
+            const bool tlive = (a.outT_hi != nullptr || a.outT_f32 != nullptr) && row < a.ld_t;
+            if (!live && !tlive) continue;
+            const float *bias = a.bias ? a.bias + (int64_t)s * a.bias_stride : nullptr;
             __half *ohi = a.out_hi ? a.out_hi + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
             __half *olo = a.out_hi ? a.out_lo + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
             float *of = a.out_f32 ? a.out_f32 + (int64_t)s * a.out_batch_stride + row * a.ld_out : nullptr;
+            const __half *mh = a.mask_hi ? a.mask_hi + (int64_t)s * a.mask_batch_stride + row * a.ld_mask : nullptr;
+            const __half *ml = a.mask_hi ? a.mask_lo + (int64_t)s * a.mask_batch_stride + row * a.ld_mask : nullptr;
+            __half *thi = a.outT_hi ? a.outT_hi + (int64_t)s * a.outT_batch_stride + row : nullptr;
+            __half *tlo = a.outT_hi ? a.outT_lo + (int64_t)s * a.outT_batch_stride + row : nullptr;
+            float *tf = a.outT_f32 ? a.outT_f32 + (int64_t)s * a.outT_batch_stride + row : nullptr;
 #pragma unroll
             for (int j = 0; j < F_EPI_CHUNKS; ++j) {
                 const int c0 = (2 * j + half) * 16;
@@ -204,31 +221,64 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int col = col0 + i;
-                    float x = accr[j][i] + (col < a.n_valid ? __ldg(bias + col) : 0.f);
+                    float x = accr[j][i] + ((bias != nullptr && col < a.n_valid) ? __ldg(bias + col) : 0.f);
                     if (a.relu) x = relu_nan(x);
-                    v[i] = x;
+                    v[i] = live ? x : 0.f;
                 }
-                if (ohi != nullptr) {
-                    if (col0 + 16 <= a.ld_out) {
-                        uint32_t h[8], l[8];
+                if (mh != nullptr && live) {
+                    // ReLU derivative of the forward activation: act > 0 <=> one of its split parts is positive (act >= 0)
+                    const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(mh + col0)), m1 = __ldg(reinterpret_cast<const uint4 *>(mh + col0) + 1);
+                    const uint4 l0 = __ldg(reinterpret_cast<const uint4 *>(ml + col0)), l1 = __ldg(reinterpret_cast<const uint4 *>(ml + col0) + 1);
+                    const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                    const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                            const float2 hf = __half22float2(hh);
-                            const __half2 ll = __floats2half2_rn((v[2 * i] - hf.x) * kF16LoScale, (v[2 * i + 1] - hf.y) * kF16LoScale);
-                            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-                            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 am = __half22float2(*reinterpret_cast<const __half2 *>(&mw[i]));
+                        const float2 al = __half22float2(*reinterpret_cast<const __half2 *>(&lw[i]));
+                        if (!(am.x > 0.f || al.x > 0.f)) v[2 * i] = 0.f;
+                        if (!(am.y > 0.f || al.y > 0.f)) v[2 * i + 1] = 0.f;
+                    }
+                }
+                uint32_t h[8], l[8];
+                if (ohi != nullptr || thi != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn((v[2 * i] - hf.x) * kF16LoScale, (v[2 * i + 1] - hf.y) * kF16LoScale);
+                        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                        l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                    }
+                }
+                if (live && ohi != nullptr) {
+                    if (col0 + 16 <= a.ld_out) {
                         uint4 *ph4 = reinterpret_cast<uint4 *>(ohi + col0), *pl4 = reinterpret_cast<uint4 *>(olo + col0);
                         ph4[0] = make_uint4(h[0], h[1], h[2], h[3]);
                         ph4[1] = make_uint4(h[4], h[5], h[6], h[7]);
                         pl4[0] = make_uint4(l[0], l[1], l[2], l[3]);
                         pl4[1] = make_uint4(l[4], l[5], l[6], l[7]);
                     }
-                } else if (of != nullptr) {
+                } else if (live && of != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (col0 + i < a.n_valid) of[col0 + i] = v[i];
+                }
+                if (tlive) {
+                    // transposed copy: lanes are consecutive rows, so every store of a warp is one contiguous segment
+                    if (thi != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 hh = *reinterpret_cast<const __half2 *>(&h[i]), ll = *reinterpret_cast<const __half2 *>(&l[i]);
+                            thi[(int64_t)(col0 + 2 * i) * a.ld_t] = __low2half(hh);
+                            thi[(int64_t)(col0 + 2 * i + 1) * a.ld_t] = __high2half(hh);
+                            tlo[(int64_t)(col0 + 2 * i) * a.ld_t] = __low2half(ll);
+                            tlo[(int64_t)(col0 + 2 * i + 1) * a.ld_t] = __high2half(ll);
+                        }
+                    } else if (live) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (col0 + i < a.t_valid) tf[(int64_t)(col0 + i) * a.ld_t] = v[i];
+                    }
                 }
             }
         }
@@ -318,8 +368,8 @@ static int launch_f16_gemm(const __half *a_hi, const __half *a_lo, int64_t a_row
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (int rc = make_tmap_h(&ta_hi, a_hi, Kp, a_rows, a_batch, F_BM)) return rc;
     if (int rc = make_tmap_h(&ta_lo, a_lo, Kp, a_rows, a_batch, F_BM)) return rc;
-    if (int rc = make_tmap_h(&tb_hi, b_hi, Kp, Np, batch, BN)) return rc;
-    if (int rc = make_tmap_h(&tb_lo, b_lo, Kp, Np, batch, BN)) return rc;
+    if (int rc = make_tmap_h(&tb_hi, b_hi, Kp, Np, g.b_shared ? 1 : batch, BN)) return rc;
+    if (int rc = make_tmap_h(&tb_lo, b_lo, Kp, Np, g.b_shared ? 1 : batch, BN)) return rc;
     g.BN = BN;
     g.k_blocks = Kp / F_BK;
     g.a_batched = a_batch > 1 ? 1 : 0;
@@ -412,4 +462,254 @@ int mlp_forward_f16(const float *bank, int64_t ld_bank, int S, const float *x, i
     return URSA_OK;
 }
 
+
+// ---- chain-batched likelihood gradient of the 3-layer MLP on the FP16-split kernel (HMC, BASELINE.json configs[3]) -----------
+// Same dataflow as ursa_hmc_mlp_grad (bma_mlp_tc.cu): forward, loss and backward of ALL chains as eight GEMMs whose operands are
+// produced in split form by the epilogue of the GEMM before them, activations additionally stored TRANSPOSED because the
+// weight-gradient GEMMs contract over the data points.  Here the planes are halves (x = hi + lo' 2^-11) and the GEMMs run on the
+// persistent kernel above: the 3xTF32 version spent most of a gradient in the epilogues of one-tile CTAs (K = 224 / 32: a few
+// MMAs per tile, then 4 planes of stores with nothing to overlap them).
+struct HmcF16Plan {
+    int K1p, K2p, K3p, Kq, BNh, Nph, BNc, Npc, BNi, Npi;
+    size_t x, xt, w1, w2, w3, w3t, act, actT, dlo, dloT, logits;     // elements per plane
+    size_t total_bytes;
+};
+
+static HmcF16Plan hmc_f16_plan(int C, int64_t Npts, int in_dim, int hid, int ncls) {
+    HmcF16Plan p;
+    p.K1p = round_up_f(in_dim, F_BK);
+    p.K2p = round_up_f(hid, F_BK);
+    p.K3p = round_up_f(ncls, F_BK);
+    p.Kq = round_up_f((int)Npts, F_BK);
+    p.BNh = pick_bn_f16(hid);    p.Nph = round_up_f(round_up_f(hid, 16), p.BNh);
+    p.BNc = pick_bn_f16(ncls);   p.Npc = round_up_f(round_up_f(ncls, 16), p.BNc);
+    p.BNi = pick_bn_f16(in_dim); p.Npi = round_up_f(round_up_f(in_dim, 16), p.BNi);
+    p.x = (size_t)Npts * p.K1p;
+    p.xt = (size_t)p.Npi * p.Kq;
+    p.w1 = (size_t)C * p.Nph * p.K1p;
+    p.w2 = (size_t)C * p.Nph * p.K2p;
+    p.w3 = (size_t)C * p.Npc * p.K2p;
+    p.w3t = (size_t)C * p.Nph * p.K3p;
+    p.act = (size_t)C * Npts * p.K2p;
+    p.actT = (size_t)C * p.Nph * p.Kq;
+    p.dlo = (size_t)C * Npts * p.K3p;
+    p.dloT = (size_t)C * p.Npc * p.Kq;
+    p.logits = ((size_t)C * Npts * ncls + 3) & ~(size_t)3;
+    // hi / lo' pairs: X, XT, W1, W2, W2T, W3, W3T, a1, a2, da2, a1T, a2T, da2T, da1T, dlo, dloT (halves) ; plain fp32: logits
+    const size_t halves = 2 * (p.x + p.xt + p.w1 + 2 * p.w2 + p.w3 + p.w3t + 3 * p.act + 4 * p.actT + p.dlo + p.dloT);
+    p.total_bytes = halves * sizeof(__half) + p.logits * sizeof(float) + 4096 + 40 * 1024;   // planes are padded to 1 KB
+    return p;
+}
+
+__device__ __forceinline__ void put_split_h(__half *h, __half *l, float x) {
+    const __half hh = __float2half_rn(x);
+    *h = hh;
+    *l = __float2half_rn((x - __half2float(hh)) * kF16LoScale);
+}
+
+// theta rows -> split filter planes: W1 [h][in], W2 [h][h], W2^T, W3 [C][h], W3^T  (zero padded to the plane shapes)
+__global__ void __launch_bounds__(256) hmc_f16_prep_kernel(const float *__restrict__ theta, int64_t ld, int in_dim, int hid, int ncls,
+                                                           HmcF16Plan p, __half *w1h, __half *w1l, __half *w2h, __half *w2l,
+                                                           __half *w2th, __half *w2tl, __half *w3h, __half *w3l, __half *w3th,
+                                                           __half *w3tl) {
+    const int c = blockIdx.y;
+    const float *row = theta + (int64_t)c * ld;
+    const int64_t oW1 = 0, oW2 = (int64_t)hid * in_dim + hid, oW3 = oW2 + (int64_t)hid * hid + hid;
+    const int64_t n1 = (int64_t)p.Nph * p.K1p, n2 = (int64_t)p.Nph * p.K2p, n3 = (int64_t)p.Npc * p.K2p, n3t = (int64_t)p.Nph * p.K3p;
+    const int64_t total = n1 + 2 * n2 + n3 + n3t;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        float x = 0.f;
+        __half *dh, *dl;
+        int64_t j = i;
+        if (j < n1) {
+            const int r = (int)(j / p.K1p), k = (int)(j % p.K1p);
+            if (r < hid && k < in_dim) x = __ldg(row + oW1 + (int64_t)r * in_dim + k);
+            dh = w1h + c * n1 + j; dl = w1l + c * n1 + j;
+        } else if ((j -= n1) < n2) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);
+            if (r < hid && k < hid) x = __ldg(row + oW2 + (int64_t)r * hid + k);
+            dh = w2h + c * n2 + j; dl = w2l + c * n2 + j;
+        } else if ((j -= n2) < n2) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);                      // W2^T[r = in-feature][k = out-feature]
+            if (r < hid && k < hid) x = __ldg(row + oW2 + (int64_t)k * hid + r);
+            dh = w2th + c * n2 + j; dl = w2tl + c * n2 + j;
+        } else if ((j -= n2) < n3) {
+            const int r = (int)(j / p.K2p), k = (int)(j % p.K2p);
+            if (r < ncls && k < hid) x = __ldg(row + oW3 + (int64_t)r * hid + k);
+            dh = w3h + c * n3 + j; dl = w3l + c * n3 + j;
+        } else {
+            j -= n3;
+            const int r = (int)(j / p.K3p), k = (int)(j % p.K3p);                      // W3^T[r = hidden][k = class]
+            if (r < hid && k < ncls) x = __ldg(row + oW3 + (int64_t)k * hid + r);
+            dh = w3th + c * n3t + j; dl = w3tl + c * n3t + j;
+        }
+        put_split_h(dh, dl, x);
+    }
+}
+
+// X [N][in] -> X planes [N][K1p] and X^T planes [Npi][Kq]
+__global__ void __launch_bounds__(256) hmc_f16_xprep_kernel(const float *__restrict__ x, int64_t Npts, int in_dim, HmcF16Plan p,
+                                                            __half *xh, __half *xl, __half *xth, __half *xtl) {
+    const int64_t n1 = (int64_t)Npts * p.K1p, n2 = (int64_t)p.Npi * p.Kq;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * 256) {
+        float v = 0.f;
+        __half *dh, *dl;
+        if (i < n1) {
+            const int64_t r = i / p.K1p; const int k = (int)(i % p.K1p);
+            if (k < in_dim) v = __ldg(x + r * in_dim + k);
+            dh = xh + i; dl = xl + i;
+        } else {
+            const int64_t j = i - n1;
+            const int r = (int)(j / p.Kq); const int64_t k = j % p.Kq;
+            if (r < in_dim && k < Npts) v = __ldg(x + k * in_dim + r);
+            dh = xth + j; dl = xtl + j;
+        }
+        put_split_h(dh, dl, v);
+    }
+}
+
+// one CTA per chain: ce[c] (fixed reduction order) and dlo = softmax - onehot in both layouts (pads stay at the memset zeros)
+__global__ void __launch_bounds__(256) hmc_f16_loss_kernel(const float *__restrict__ logits, const int64_t *__restrict__ y, int64_t Npts,
+                                                           int ncls, HmcF16Plan p, __half *dh, __half *dl, __half *dth, __half *dtl,
+                                                           float *__restrict__ ce) {
+    __shared__ float red[256];
+    const int c = blockIdx.x;
+    const float *lg = logits + (int64_t)c * Npts * ncls;
+    float acc = 0.f;
+    for (int64_t n = threadIdx.x; n < Npts; n += 256) {
+        const float *l = lg + n * ncls;
+        float m = -INFINITY;
+        for (int k = 0; k < ncls; ++k) m = fmaxf(m, l[k]);
+        float sum = 0.f;
+        for (int k = 0; k < ncls; ++k) sum += expf(l[k] - m);
+        const float lse = logf(sum);
+        const int yy = (int)y[n];
+        acc += -((l[yy] - m) - lse);
+        for (int k = 0; k < ncls; ++k) {
+            const float d = expf((l[k] - m) - lse) - (k == yy ? 1.f : 0.f);
+            const int64_t a = ((int64_t)c * Npts + n) * p.K3p + k, b = ((int64_t)c * p.Npc + k) * p.Kq + n;
+            put_split_h(dh + a, dl + a, d);
+            dth[b] = dh[a];
+            dtl[b] = dl[a];
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ce[c] = red[0];
+}
+
+// bias gradients: db[c][f] = sum_n (hi + lo' 2^-11)[c][f][n] over the transposed planes; one warp per (chain, feature)
+__global__ void __launch_bounds__(256) hmc_f16_bias_kernel(const __half *__restrict__ th, const __half *__restrict__ tl, int rows_p, int Kq,
+                                                           int n_feat, int C, float *__restrict__ grad, int64_t ld, int64_t off) {
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= C * n_feat) return;
+    const int c = w / n_feat, f = w - c * n_feat;
+    const __half *ph = th + ((int64_t)c * rows_p + f) * Kq, *pl = tl + ((int64_t)c * rows_p + f) * Kq;
+    float sh = 0.f, sl = 0.f;
+    for (int k = lane; k < Kq; k += 32) { sh += __half2float(ph[k]); sl += __half2float(pl[k]); }
+    float s = fmaf(sl, kF16LoUnscale, sh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) grad[(int64_t)c * ld + off + f] = s;
+}
+
 }  // namespace ursa
+
+extern "C" size_t ursa_hmc_mlp_grad_f16_workspace(int C, int64_t Npts, int in_dim, int hidden, int ncls) {
+    if (C < 1 || Npts < 1 || in_dim < 1 || hidden < 1 || ncls < 1 || in_dim % 4 != 0 || hidden % 4 != 0 || ncls > 128) return 0;
+    return ursa::hmc_f16_plan(C, Npts, in_dim, hidden, ncls).total_bytes;
+}
+
+extern "C" int ursa_hmc_mlp_grad_f16(const float *theta, int64_t ld, int C, const float *x, const int64_t *y, int64_t Npts,
+                                     int in_dim, int hidden, int ncls, float *grad, float *ce, void *workspace,
+                                     size_t workspace_bytes, void *stream) {
+    using namespace ursa;
+    URSA_REQUIRE(theta && x && y && grad && ce && workspace, "ursa_hmc_mlp_grad_f16: null pointer");
+    URSA_REQUIRE(ursa_hmc_mlp_grad_f16_workspace(C, Npts, in_dim, hidden, ncls) != 0,
+                 "ursa_hmc_mlp_grad_f16: unsupported shape (in_dim %% 4, hidden %% 4, classes <= 128)");
+    const int64_t D = (int64_t)hidden * in_dim + hidden + (int64_t)hidden * hidden + hidden + (int64_t)ncls * hidden + ncls;
+    URSA_REQUIRE(ld >= D, "ursa_hmc_mlp_grad_f16: ld (%lld) < D (%lld)", (long long)ld, (long long)D);
+    const HmcF16Plan p = hmc_f16_plan(C, Npts, in_dim, hidden, ncls);
+    URSA_REQUIRE(workspace_bytes >= p.total_bytes, "ursa_hmc_mlp_grad_f16: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    __half *w = reinterpret_cast<__half *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    auto take = [&](size_t n) { __half *r = w; w += (n + 511) & ~(size_t)511; return r; };     // planes stay 1 KB aligned
+    __half *xh = take(p.x), *xl = take(p.x), *xth = take(p.xt), *xtl = take(p.xt);
+    __half *w1h = take(p.w1), *w1l = take(p.w1), *w2h = take(p.w2), *w2l = take(p.w2), *w2th = take(p.w2), *w2tl = take(p.w2);
+    __half *w3h = take(p.w3), *w3l = take(p.w3), *w3th = take(p.w3t), *w3tl = take(p.w3t);
+    __half *a1h = take(p.act), *a1l = take(p.act), *a2h = take(p.act), *a2l = take(p.act), *d2h = take(p.act), *d2l = take(p.act);
+    __half *a1th = take(p.actT), *a1tl = take(p.actT), *a2th = take(p.actT), *a2tl = take(p.actT);
+    __half *d2th = take(p.actT), *d2tl = take(p.actT), *d1th = take(p.actT), *d1tl = take(p.actT);
+    __half *dlh = take(p.dlo), *dll = take(p.dlo), *dlth = take(p.dloT), *dltl = take(p.dloT);
+    float *logits = reinterpret_cast<float *>(w);
+    const int64_t oW1 = 0, ob1 = (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)hidden * hidden, oW3 = ob2 + hidden,
+                  ob3 = oW3 + (int64_t)ncls * hidden;
+
+    // pads: K2p - Nph columns of the point-major activations (the N tiles cover the rest), the class pads of dlo / dloT
+    if (p.Nph < p.K2p) {
+        URSA_CUDA(cudaMemsetAsync(a1h, 0, (size_t)((char *)a1th - (char *)a1h), st));
+    }
+    URSA_CUDA(cudaMemsetAsync(dlh, 0, (size_t)((char *)logits - (char *)dlh), st));
+    hmc_f16_xprep_kernel<<<148 * 4, 256, 0, st>>>(x, Npts, in_dim, p, xh, xl, xth, xtl);
+    URSA_LAUNCH_CHECK("hmc_f16_xprep_kernel");
+    hmc_f16_prep_kernel<<<dim3(148, C), 256, 0, st>>>(theta, ld, in_dim, hidden, ncls, p, w1h, w1l, w2h, w2l, w2th, w2tl, w3h, w3l, w3th,
+                                                      w3tl);
+    URSA_LAUNCH_CHECK("hmc_f16_prep_kernel");
+
+    const int64_t act_bs = (int64_t)Npts * p.K2p, actT_bs = (int64_t)p.Nph * p.Kq;
+    F16GemmArgs g;
+    auto fresh = [&]() {
+        F16GemmArgs z;
+        z.bias = nullptr; z.bias_stride = 0; z.out_hi = z.out_lo = nullptr; z.out_f32 = nullptr; z.out_batch_stride = 0; z.ld_out = 0;
+        z.M = 0; z.n_valid = 0; z.relu = 0;
+        return z;
+    };
+    // ---- forward
+    g = fresh(); g.M = Npts; g.bias = theta + ob1; g.bias_stride = ld; g.relu = 1; g.n_valid = hidden;
+    g.out_hi = a1h; g.out_lo = a1l; g.out_batch_stride = act_bs; g.ld_out = p.K2p;
+    g.outT_hi = a1th; g.outT_lo = a1tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    if (int rc = launch_f16_gemm(xh, xl, Npts, 1, p.K1p, w1h, w1l, p.Nph, p.BNh, C, g, st)) return rc;
+    g.bias = theta + ob2; g.out_hi = a2h; g.out_lo = a2l; g.outT_hi = a2th; g.outT_lo = a2tl;
+    if (int rc = launch_f16_gemm(a1h, a1l, Npts, C, p.K2p, w2h, w2l, p.Nph, p.BNh, C, g, st)) return rc;
+    g = fresh(); g.M = Npts; g.bias = theta + ob3; g.bias_stride = ld; g.n_valid = ncls;
+    g.out_f32 = logits; g.out_batch_stride = (int64_t)Npts * ncls; g.ld_out = ncls;
+    if (int rc = launch_f16_gemm(a2h, a2l, Npts, C, p.K2p, w3h, w3l, p.Npc, p.BNc, C, g, st)) return rc;
+    // ---- loss
+    hmc_f16_loss_kernel<<<C, 256, 0, st>>>(logits, y, Npts, ncls, p, dlh, dll, dlth, dltl, ce);
+    URSA_LAUNCH_CHECK("hmc_f16_loss_kernel");
+    // ---- backward
+    // da2 = (dlo W3) . [a2 > 0]  -> point-major (A of the da1 GEMM) and transposed (A of the dW2 GEMM)
+    g = fresh(); g.M = Npts; g.n_valid = hidden;
+    g.out_hi = d2h; g.out_lo = d2l; g.out_batch_stride = act_bs; g.ld_out = p.K2p;
+    g.outT_hi = d2th; g.outT_lo = d2tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    g.mask_hi = a2h; g.mask_lo = a2l; g.ld_mask = p.K2p; g.mask_batch_stride = act_bs;
+    if (int rc = launch_f16_gemm(dlh, dll, Npts, C, p.K3p, w3th, w3tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // dW3^T[h][k] = sum_n a2T[h][n] dloT[k][n]  -> stored transposed = W3's own [k][h] layout
+    g = fresh(); g.M = hidden; g.n_valid = ncls;
+    g.outT_f32 = grad + oW3; g.outT_batch_stride = ld; g.ld_t = hidden; g.t_valid = ncls;
+    if (int rc = launch_f16_gemm(a2th, a2tl, p.Nph, C, p.Kq, dlth, dltl, p.Npc, p.BNc, C, g, st)) return rc;
+    // dW2[o][i] = sum_n da2T[o][n] a1T[i][n]
+    g = fresh(); g.M = hidden; g.n_valid = hidden;
+    g.out_f32 = grad + oW2; g.out_batch_stride = ld; g.ld_out = hidden;
+    if (int rc = launch_f16_gemm(d2th, d2tl, p.Nph, C, p.Kq, a1th, a1tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // da1 = (da2 W2) . [a1 > 0]  -> only its transposed form is needed
+    g = fresh(); g.M = Npts; g.n_valid = hidden;
+    g.outT_hi = d1th; g.outT_lo = d1tl; g.outT_batch_stride = actT_bs; g.ld_t = p.Kq;
+    g.mask_hi = a1h; g.mask_lo = a1l; g.ld_mask = p.K2p; g.mask_batch_stride = act_bs;
+    if (int rc = launch_f16_gemm(d2h, d2l, Npts, C, p.K2p, w2th, w2tl, p.Nph, p.BNh, C, g, st)) return rc;
+    // dW1[o][k] = sum_n da1T[o][n] XT[k][n]   (XT shared by all chains)
+    g = fresh(); g.M = hidden; g.n_valid = in_dim; g.b_shared = 1;
+    g.out_f32 = grad + oW1; g.out_batch_stride = ld; g.ld_out = in_dim;
+    if (int rc = launch_f16_gemm(d1th, d1tl, p.Nph, C, p.Kq, xth, xtl, p.Npi, p.BNi, C, g, st)) return rc;
+    // bias gradients = row sums of the transposed planes
+    const int gb1 = (C * hidden + 7) / 8, gb3 = (C * ncls + 7) / 8;
+    hmc_f16_bias_kernel<<<gb1, 256, 0, st>>>(d1th, d1tl, p.Nph, p.Kq, hidden, C, grad, ld, ob1);
+    hmc_f16_bias_kernel<<<gb1, 256, 0, st>>>(d2th, d2tl, p.Nph, p.Kq, hidden, C, grad, ld, ob2);
+    hmc_f16_bias_kernel<<<gb3, 256, 0, st>>>(dlth, dltl, p.Npc, p.Kq, ncls, C, grad, ld, ob3);
+    URSA_LAUNCH_CHECK("hmc_f16_bias_kernel");
+    return URSA_OK;
+}

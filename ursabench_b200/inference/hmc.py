@@ -220,17 +220,18 @@ class HMC(_Inference):
 
         return fn
 
-    def _build_grad_fn_mlp_fused(self, arch):
-        """``ursa_hmc_mlp_grad``: forward, loss and backward of all chains as eight hand-written tcgen05 GEMMs whose operands
-        are produced in split form by the previous GEMM's epilogue (csrc/bma_mlp_tc.cu).  Writes straight into the [C, ld]
-        gradient / energy buffers: ``fn(theta, g, ce)``."""
+    def _build_grad_fn_mlp_fused(self, arch, engine="tf32"):
+        """``ursa_hmc_mlp_grad`` / ``ursa_hmc_mlp_grad_f16``: forward, loss and backward of all chains as eight hand-written
+        tcgen05 GEMMs whose operands are produced in split form by the previous GEMM's epilogue (csrc/bma_mlp_tc.cu: 3xTF32,
+        one tile per CTA; csrc/bma_mlp_f16.cu: 2xFP16-split, persistent).  Writes straight into the [C, ld] gradient / energy
+        buffers: ``fn(theta, g, ce)``."""
         _, in_dim, hid, ncls = arch
         x2 = self.x.reshape(self.x.shape[0], -1).contiguous().float()
         y = self.y.long().contiguous()
         ws = [None]
 
         def fn(theta, g, ce):
-            ws[0] = _C.hmc_mlp_grad(theta, x2, y, in_dim, hid, ncls, g, ce, workspace=ws[0])
+            ws[0] = _C.hmc_mlp_grad(theta, x2, y, in_dim, hid, ncls, g, ce, workspace=ws[0], engine=engine)
             if ws[0] is None:
                 raise RuntimeError("ursa_hmc_mlp_grad does not cover this MLP shape")
 
@@ -316,11 +317,16 @@ class HMC(_Inference):
             fused_ok = self.chain_chunk <= 0 and _C.lib().ursa_hmc_mlp_grad_workspace(self.num_chains, self.x.shape[0], arch[1],
                                                                                       arch[2], arch[3]) > 0
             if engine is None:
-                engine = "mlp_tcgen05_fused" if fused_ok else "mlp_gemm"
+                engine = "mlp_tcgen05_fused_f16" if fused_ok else "mlp_gemm"
             if getattr(self, "force_tc_grad", False):
                 engine = "mlp_tcgen05"
-            if engine == "mlp_tcgen05_fused":
-                self._grad_fn = self._build_grad_fn_mlp_fused(arch)      # hand-written tcgen05 forward + backward (default)
+            if engine == "mlp_tcgen05_fused_f16":
+                # the product path: persistent FP16-split GEMMs.  Its range is fp16's: if the gradient at the initial state is
+                # not finite where the 3xTF32 engine's is, this run stays on the 3xTF32 engine
+                self._grad_fn = self._build_grad_fn_mlp_fused(arch, "f16")
+                self._f16_probe = arch
+            elif engine == "mlp_tcgen05_fused":
+                self._grad_fn = self._build_grad_fn_mlp_fused(arch)      # the same dataflow on the 3xTF32 kernel
             elif engine == "mlp_tcgen05":
                 self._grad_fn = self._build_grad_fn_mlp_tc(arch)         # the same GEMMs one by one through ursa_gemm_nt_3xtf32
             else:
@@ -340,6 +346,13 @@ class HMC(_Inference):
             accept = torch.zeros(C, dtype=torch.int32, device=dev)
             n_accept = torch.zeros(C, dtype=torch.int64, device=dev)
             rows = []
+            if self.grad_engine == "mlp_tcgen05_fused_f16":
+                self._grad(theta, g, ce)
+                if not (bool(torch.isfinite(ce).all()) and bool(torch.isfinite(g).all())):
+                    tf32_fn = self._build_grad_fn_mlp_fused(self._f16_probe)
+                    tf32_fn(theta, g, ce)
+                    if bool(torch.isfinite(ce).all()):                # fp16 range, not a diverged chain: use fp32's range
+                        self._grad_fn, self.grad_engine = tf32_fn, "mlp_tcgen05_fused"
 
             def keep_rows():
                 lo = self.bank.count
