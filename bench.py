@@ -840,25 +840,26 @@ def run_extras(dev, rank, world, peak):
     P, E = torch.zeros(N, C_w, device=dev), torch.zeros(N, device=dev)
     wrn_flop = 11_902_350_336                                 # 2*MAC per image and sample (convs + shortcuts + linear)
 
-    def bma_wrn():
-        P.zero_()
-        E.zero_()
-        if ns > 0:
-            ws[0] = _C.bma_wrn_forward(bankw, bufw, ns, xi, 28, 10, C_w, P, E, workspace=ws[0])
-        Pr, Er, n = udist.allreduce_bma(P, E, ns)
-        return _C.bma_metrics(Pr, n, yw)
-    ws[0] = _C.bma_wrn_forward(bankw[:1], bufw[:1], 1, xi[:512], 28, 10, C_w, P[:512], E[:512], workspace=None)   # warm-up
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    wsampler = _ClockSampler(dev.index if dev.index is not None else 0)
-    wsampler.start()
-    ms, _ = _event_time_ms(bma_wrn, 1)
-    wclocks = wsampler.stop()                               # a 5-17 s tensor-core run: the SM clock under its own power draw
-    ms = udist.allreduce_max_scalar(ms, dev)
-    out["bma_wrn28x10_S30_N10k_tcgen05"] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
-                                            "img_samples_per_s": N * S_w / ms * 1e3,
-                                            "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world, "clocks": wclocks}
+    for algo_name, algo in (("tcgen05", _C.ALGO_TCGEN05), ("f16", _C.ALGO_TCGEN05_F16)):
+        def bma_wrn():
+            P.zero_()
+            E.zero_()
+            if ns > 0:
+                ws[0] = _C.bma_wrn_forward(bankw, bufw, ns, xi, 28, 10, C_w, P, E, workspace=ws[0], algo=algo)
+            Pr, Er, n = udist.allreduce_bma(P, E, ns)
+            return _C.bma_metrics(Pr, n, yw)
+        ws[0] = _C.bma_wrn_forward(bankw[:1], bufw[:1], 1, xi[:512], 28, 10, C_w, P[:512], E[:512], workspace=None, algo=algo)   # warm-up
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        wsampler = _ClockSampler(dev.index if dev.index is not None else 0)
+        wsampler.start()
+        ms, _ = _event_time_ms(bma_wrn, 1)
+        wclocks = wsampler.stop()                           # a 5-17 s tensor-core run: the SM clock under its own power draw
+        ms = udist.allreduce_max_scalar(ms, dev)
+        out["bma_wrn28x10_S30_N10k_" + algo_name] = {"ms": ms, "img_per_s_over_S_samples": N / ms * 1e3,
+                                                     "img_samples_per_s": N * S_w / ms * 1e3,
+                                                     "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world, "clocks": wclocks}
     # K3b: BatchNorm re-estimation of one SWAG draw (util.bn_update, once per sample): bounded sample of the 50 000-image pass
     Nbn, Bbn = 2048, 128
     bn_fn = lambda: _C.wrn_bn_update(bankw[0], bufw[0], xi[:Nbn], Bbn, 28, 10, C_w, workspace=ws[0])  # noqa: E731

@@ -51,7 +51,8 @@ def test_wrn_workspace_query_rejects_unsupported_shapes():
     lib = _C.lib()
     assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_TCGEN05) > 0
     assert lib.ursa_bma_wrn_workspace(1, 16, 10, 2, 10, _C.ALGO_TCGEN05) > 0
-    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_FFMA) == 0        # tcgen05 engine only
+    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_TCGEN05_F16) > 0
+    assert lib.ursa_bma_wrn_workspace(1, 16, 28, 10, 100, _C.ALGO_FFMA) == 0        # tcgen05 engines only
     assert lib.ursa_bma_wrn_workspace(1, 16, 27, 10, 100, _C.ALGO_TCGEN05) == 0     # depth != 6n+4
     assert lib.ursa_bma_wrn_workspace(1, 16, 28, 3, 100, _C.ALGO_TCGEN05) == 0      # odd widen factor: widths % 32 != 0
     assert lib.ursa_bma_wrn_workspace(0, 16, 28, 10, 100, _C.ALGO_TCGEN05) == 0
@@ -59,8 +60,9 @@ def test_wrn_workspace_query_rejects_unsupported_shapes():
 
 # ------------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
 @pytest.mark.parametrize("tag", ["wrn10x2", "wrn16x2"])
-def test_k3_wrn_forward_matches_reference_golden(tag):
+def test_k3_wrn_forward_matches_reference_golden(tag, engine):
     from ursabench_b200 import _C
     g = np.load(GOLD)
     ms, depth, widen, C, S = _models(g, tag)
@@ -69,7 +71,7 @@ def test_k3_wrn_forward_matches_reference_golden(tag):
     N = x.shape[0]
     P, E = torch.zeros(N, C, device="cuda"), torch.zeros(N, device="cuda")
     logits = torch.empty(S, N, C, device="cuda")
-    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, logits_out=logits)
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, logits_out=logits, algo=getattr(_C, engine))
     torch.cuda.synchronize()
     ref = g[tag + "/logits"]
     err = np.abs(logits.cpu().numpy() - ref).max()
@@ -79,8 +81,9 @@ def test_k3_wrn_forward_matches_reference_golden(tag):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
 @pytest.mark.parametrize("depth,widen,S,N,Cc", [(10, 10, 2, 9, 100), (16, 4, 2, 6, 10), (10, 6, 1, 515, 10), (10, 2, 3, 1, 10)])
-def test_k3_wrn_forward_vs_torch_fp32(depth, widen, S, N, Cc):
+def test_k3_wrn_forward_vs_torch_fp32(depth, widen, S, N, Cc, engine):
     """Widths with 1 / 2 / 4 output-channel tiles (widen 10: 160 / 320 / 640), identity and transition blocks, an odd image
     count (the 8x8 tiles pair two images), N = 1, and N > 512 (image chunking) against PyTorch fp32 (TF32 off)."""
     from ursabench_b200 import _C
@@ -91,7 +94,7 @@ def test_k3_wrn_forward_vs_torch_fp32(depth, widen, S, N, Cc):
     x = torch.randn(N, 3, 32, 32, device="cuda")
     P, E = torch.zeros(N, Cc, device="cuda"), torch.zeros(N, device="cuda")
     logits = torch.empty(S, N, Cc, device="cuda")
-    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, Cc, P, E, logits_out=logits)
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, Cc, P, E, logits_out=logits, algo=getattr(_C, engine))
     torch.cuda.synchronize()
     mm = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -116,8 +119,18 @@ def test_prediction_routes_wideresnet_through_the_tcgen05_engine():
     loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=4, shuffle=False)
     task = Prediction({"in_distribution_test": loader}, C, torch.device("cuda"), "ALL")
     task.update_statistics(ms, output_performance=False)
-    assert task.last_engine == "fused_wrn"
+    from ursabench_b200 import _C
+    assert task.last_engine == "fused_wrn" and task.last_algo == _C.ALGO_TCGEN05_F16      # the FP16-split engine is the product path
     np.testing.assert_allclose(task.ensemble_proba.cpu().numpy(), g["wrn10x2/ensemble_proba"], atol=1e-5, rtol=0)
+    # an image beyond fp16's range: NaN from the FP16-split engine, so the evaluation is redone on the 3xTF32 engine
+    x2 = x.clone()
+    x2[1] *= 3e6
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x2, y), batch_size=4, shuffle=False)
+    task = Prediction({"in_distribution_test": loader}, C, torch.device("cuda"), "ALL")
+    task.update_statistics(ms, output_performance=False)
+    assert task.last_algo == _C.ALGO_TCGEN05 and bool(torch.isfinite(task.ensemble_proba).all())
+    keep = [i for i in range(x.shape[0]) if i != 1]
+    np.testing.assert_allclose(task.ensemble_proba.cpu().numpy()[keep], g["wrn10x2/ensemble_proba"][keep], atol=1e-5, rtol=0)
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm re-estimation

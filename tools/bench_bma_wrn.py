@@ -1,4 +1,4 @@
-"""WRN BMA forward timing on one GPU: python tools/bench_bma_wrn.py [depth widen C S N] [--ref]
+"""WRN BMA forward timing on one GPU: python tools/bench_bma_wrn.py [depth widen C S N] [--ref] [--f16]
 Prints one JSON line: ms, img*samples/s, fp32-equivalent TFLOP/s (2*MAC of convs + linear), and with --ref the
 per-sample PyTorch fp32 forward (cuDNN, TF32 off = the generic engine this kernel replaces) beside it."""
 import json
@@ -98,18 +98,19 @@ def main():
     torch.manual_seed(0)
     x = torch.randn(N, 3, 32, 32, device="cuda")
     P, E = torch.zeros(N, C, device="cuda"), torch.zeros(N, device="cuda")
-    ws = _C.bma_wrn_forward(bank, bufs, 1, x[:min(N, 64)], depth, widen, C, P[:min(N, 64)], E[:min(N, 64)])   # warm-up
-    ws = _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E)
+    algo = _C.ALGO_TCGEN05_F16 if "--f16" in sys.argv else _C.ALGO_TCGEN05
+    ws = _C.bma_wrn_forward(bank, bufs, 1, x[:min(N, 64)], depth, widen, C, P[:min(N, 64)], E[:min(N, 64)], algo=algo)   # warm-up
+    ws = _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, algo=algo)
     P.zero_(), E.zero_()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, workspace=ws)
+    _C.bma_wrn_forward(bank, bufs, S, x, depth, widen, C, P, E, workspace=ws, algo=algo)
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1)
     fl = wrn_flops(depth, widen) + 2 * 64 * widen * C
-    out = {"depth": depth, "widen": widen, "C": C, "S": S, "N": N, "ms": t, "img_samples_per_s": S * N / t * 1e3,
+    out = {"engine": "f16" if "--f16" in sys.argv else "3xtf32", "depth": depth, "widen": widen, "C": C, "S": S, "N": N, "ms": t, "img_samples_per_s": S * N / t * 1e3,
            "TFLOPs_fp32_equiv": fl * S * N / t / 1e9, "MFLOP_per_img": fl / 1e6}
     if "--ref" in sys.argv:
         torch.backends.cuda.matmul.allow_tf32 = False

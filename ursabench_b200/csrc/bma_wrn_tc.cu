@@ -35,6 +35,7 @@
 //            (bias, residual, BN, split, stores) overlaps the next tile's first segments.
 //   epilogue v = acc + bias (+ residual);  raw fp32 v | split(v) (next block's shortcut input) | split(relu(bn_next(v)))
 //   head     BN + ReLU + 8x8 average pool + linear -> logits;  accumulate (bma_metrics.cu) in sample order
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -49,6 +50,44 @@ constexpr int WRN_MAX_TBUF = 4;                    // TMEM accumulators: min(4, 
 constexpr int WRN_EPI_CHUNKS = 5;                  // 16-column chunks per epilogue thread: bn_tile / 2 <= 80
 constexpr uint32_t WRN_A_BYTES = 128 * 128;        // 128 pixels x 32 channels x fp32, 128-byte swizzle rows
 constexpr int WRN_CHUNK_IMAGES = 512;
+// FP16-split variant (F16 = true, URSA_ALGO_TCGEN05_F16): planes and filters are halves, x = hi + lo' 2^-11 (22 significant bits like
+// the TF32 split); a K block is still 32 channels = a 64-byte swizzle row; per K = 16 step hi*hi -> ACC columns, hi*lo' and lo'*hi ->
+// LO columns of the accumulator (pitch 2 * bn_tile), result = ACC + LO 2^-11 in the epilogue registers.  Half the operand bytes
+// and half the tensor-pipe time per MAC of 3xTF32 (kind::f16 runs at twice the TF32 rate): bn_tile <= 128 so that two
+// [ACC | LO] accumulators rotate.  Range: fp16's (|x| <= 65 504), overflow surfaces as NaN logits.
+constexpr uint32_t WRN_A_BYTES_H = 128 * 64;       // 128 pixels x 32 channels x fp16, 64-byte swizzle rows
+constexpr int WRN_MAX_STAGES_H = 8;
+constexpr float kWrnLoScale = 2048.f, kWrnLoUnscale = 1.f / 2048.f;
+
+__device__ __forceinline__ uint32_t wrn_f16_idesc(int m, int n) {        // D = F32, A = B = F16, K-major both
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <int NCTA>
+__device__ __forceinline__ void wrn_umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (NCTA == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// four floats -> packed hi halves and packed lo' halves (8 bytes each)
+__device__ __forceinline__ void wrn_split_h4(float y0, float y1, float y2, float y3, uint2 &hi, uint2 &lo) {
+    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((y0 - f01.x) * kWrnLoScale, (y1 - f01.y) * kWrnLoScale);
+    const __half2 l23 = __floats2half2_rn((y2 - f23.x) * kWrnLoScale, (y3 - f23.y) * kWrnLoScale);
+    hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+}
 
 struct WrnMaps {
     CUtensorMap a_hi[4], a_lo[4];      // index = h-parity * 2 + w-parity for stride 2; [0] only for stride 1
@@ -72,12 +111,14 @@ struct WrnConvArgs {
 // NCTA = 2: CTA pair (cta_group::2).  The two CTAs of a cluster take adjacent M tiles of the same N tile and run ONE M = 256 MMA:
 // each streams its own A tile and HALF of the B tile from its shared memory (52 KB instead of 72 KB per K block -> a 4-stage
 // ring), the leader (cluster rank 0) issues the MMAs and multicasts its commits; both epilogues release the leader's accumulator.
-template <int NCTA>
+template <int NCTA, bool F16 = false>
 __global__ void __launch_bounds__(WRN_THREADS, 1)
 wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[WRN_MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[WRN_MAX_STAGES];
+    constexpr uint32_t A_BYTES = F16 ? WRN_A_BYTES_H : WRN_A_BYTES;
+    constexpr uint32_t ROW_BYTES = F16 ? 64u : 128u;               // one K block (32 channels) of an operand row
+    __shared__ __align__(8) uint64_t full_bar[WRN_MAX_STAGES_H];
+    __shared__ __align__(8) uint64_t empty_bar[WRN_MAX_STAGES_H];
     __shared__ __align__(8) uint64_t tfull_bar[WRN_MAX_TBUF];
     __shared__ __align__(8) uint64_t tempty_bar[WRN_MAX_TBUF];
     __shared__ uint32_t tmem_base_s;
@@ -87,14 +128,15 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     const int tpi = (a.hout * a.hout) / 128;                 // tiles per image (0 when one tile spans 2 images)
     const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
     const uint32_t b_rows = (uint32_t)a.bn_tile / NCTA;        // rows of the B tile this CTA stages
-    const uint32_t b_bytes = b_rows * 128u;
-    const uint32_t stage_bytes = 2 * WRN_A_BYTES + 2 * b_bytes;
+    const uint32_t b_bytes = b_rows * ROW_BYTES;
+    const uint32_t stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+    const uint32_t acc_pitch = (F16 ? 2u : 1u) * (uint32_t)a.bn_tile;      // TMEM columns per accumulator: [ACC | LO] in FP16 mode
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int kb3 = 9 * a.kchunks, k_blocks = kb3 + a.xchunks;
     // work units: (M tile [pair], N tile), N fastest; unit u -> this CTA's tile (mt, nt)
     const int total_tiles = ((a.m_tiles + NCTA - 1) / NCTA) * a.n_tiles;
     const int first_unit = (int)blockIdx.x / NCTA, unit_stride = (int)gridDim.x / NCTA;
-    const uint32_t ntbuf = 512u / (uint32_t)a.bn_tile < (uint32_t)WRN_MAX_TBUF ? 512u / (uint32_t)a.bn_tile : (uint32_t)WRN_MAX_TBUF;
+    const uint32_t ntbuf = 512u / acc_pitch < (uint32_t)WRN_MAX_TBUF ? 512u / acc_pitch : (uint32_t)WRN_MAX_TBUF;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -150,27 +192,27 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                         }
                         if (NCTA == 2) {
                             tma_load_4d_2cta(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
-                            tma_load_4d_2cta(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                            tma_load_4d_2cta(base + A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
                         } else {
                             tma_load_4d_a(base, &maps.a_hi[mi], cc * 32, cw, ch, n0, fb);
-                            tma_load_4d_a(base + WRN_A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
+                            tma_load_4d_a(base + A_BYTES, &maps.a_lo[mi], cc * 32, cw, ch, n0, fb);
                         }
                     } else {
                         const int cc = kb - kb3;
                         if (NCTA == 2) {
                             tma_load_4d_2cta(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
-                            tma_load_4d_2cta(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                            tma_load_4d_2cta(base + A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
                         } else {
                             tma_load_4d_a(base, &maps.x_hi, cc * 32, 0, h0, n0, fb);
-                            tma_load_4d_a(base + WRN_A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
+                            tma_load_4d_a(base + A_BYTES, &maps.x_lo, cc * 32, 0, h0, n0, fb);
                         }
                     }
                     if (NCTA == 2) {
-                        tma_load_2d_2cta(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, brow, fb);
-                        tma_load_2d_2cta(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
+                        tma_load_2d_2cta(base + 2 * A_BYTES, &maps.b_hi, kb * 32, brow, fb);
+                        tma_load_2d_2cta(base + 2 * A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
                     } else {
-                        tma_load_2d_a(base + 2 * WRN_A_BYTES, &maps.b_hi, kb * 32, brow, fb);
-                        tma_load_2d_a(base + 2 * WRN_A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
+                        tma_load_2d_a(base + 2 * A_BYTES, &maps.b_hi, kb * 32, brow, fb);
+                        tma_load_2d_a(base + 2 * A_BYTES + b_bytes, &maps.b_lo, kb * 32, brow, fb);
                     }
                     if (++st == nstages) { st = 0; ph ^= 1u; }
                 }
@@ -179,23 +221,33 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     } else if (warp == 1) {
         if (cta_rank == 0 && elect_one()) {
             // ===== MMA issuer (the leader CTA of a pair) =====
-            const uint32_t idesc = make_tf32_idesc(128 * NCTA, a.bn_tile);
+            const uint32_t idesc = F16 ? wrn_f16_idesc(128 * NCTA, a.bn_tile) : make_tf32_idesc(128 * NCTA, a.bn_tile);
             uint32_t st = 0, ph = 0, buf = 0, bph = 0;
             const uint32_t nstages = (uint32_t)a.stages;
             for (int t = first_unit; t < total_tiles; t += unit_stride) {
                 for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
                     mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);                   // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.bn_tile;
+                    const uint32_t d_tmem = tmem_base + buf * acc_pitch;
                     const int kb1 = kb0 + len < k_blocks ? kb0 + len : k_blocks;
                     uint32_t acc = 0;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait_a(smem_u32(&full_bar[st]), ph);
                         tc_fence_after();
                         const uint32_t base = smem_base + st * stage_bytes;
-                        const uint64_t d_ahi = make_kmajor_desc<128>(base), d_alo = make_kmajor_desc<128>(base + WRN_A_BYTES);
-                        const uint64_t d_bhi = make_kmajor_desc<128>(base + 2 * WRN_A_BYTES);
-                        const uint64_t d_blo = make_kmajor_desc<128>(base + 2 * WRN_A_BYTES + b_bytes);
+                        const uint64_t d_ahi = make_kmajor_desc<(int)ROW_BYTES>(base), d_alo = make_kmajor_desc<(int)ROW_BYTES>(base + A_BYTES);
+                        const uint64_t d_bhi = make_kmajor_desc<(int)ROW_BYTES>(base + 2 * A_BYTES);
+                        const uint64_t d_blo = make_kmajor_desc<(int)ROW_BYTES>(base + 2 * A_BYTES + b_bytes);
+                        if (F16) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {                                // K = 16 halves = 32 bytes of the 64-byte row
+                                const uint64_t koff = (uint64_t)((k * 32) >> 4);
+                                wrn_umma_f16<NCTA>(d_tmem, d_ahi + koff, d_bhi + koff, idesc, acc);                       // ACC
+                                wrn_umma_f16<NCTA>(d_tmem + (uint32_t)a.bn_tile, d_ahi + koff, d_blo + koff, idesc, acc);  // LO
+                                acc = 1;
+                                wrn_umma_f16<NCTA>(d_tmem + (uint32_t)a.bn_tile, d_alo + koff, d_bhi + koff, idesc, 1);
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t koff = (uint64_t)((k * 32) >> 4);
@@ -211,6 +263,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                                 umma_tf32(d_tmem, d_ahi + koff, d_bhi + koff, idesc, 1);
                             }
                         }
+                        }
                         if (NCTA == 2) umma_commit_2cta(smem_u32(&empty_bar[st]), 3);     // frees the stage in BOTH CTAs
                         else umma_commit(smem_u32(&empty_bar[st]));
                         if (++st == nstages) { st = 0; ph ^= 1u; }
@@ -222,9 +275,12 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             }
         }
     } else {
-        // ===== epilogue: thread = output pixel (TMEM lane) x one half of the tile's channels =====
+        // ===== epilogue: thread = output pixel (TMEM lane) x one half of the tile's channels (3xTF32: a contiguous half, a
+        // multiple of 16 <= 80; FP16-split: the even or the odd 16-column chunks of a tile of <= 128) =====
         const int q = warp & 3, half_id = (warp - 2) >> 2;
-        const int half = a.bn_tile >> 1;                      // channels per thread, a multiple of 16 (<= 80)
+        const int half = a.bn_tile >> 1;
+        auto chunk_col = [&](int j) { return F16 ? (2 * j + half_id) * 16 : half_id * half + j * 16; };   // first column within the tile
+        auto chunk_on = [&](int j) { return F16 ? (2 * j + half_id) * 16 < a.bn_tile : j * 16 < half; };
         const int qi = lane & 3, qb = lane & ~3;
         const int r = q * 32 + qb;                            // first pixel of this lane's quad (4 consecutive pixels of a row)
         const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
@@ -235,8 +291,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             if (tpi > 0) { n0 = mt / tpi; h0 = (mt % tpi) * HT; } else { n0 = mt * 2; h0 = 0; }
             const int n = n0 + nl;
             const bool valid = n < a.n_images;
-            const int cbase = nt * a.bn_tile + half_id * half;
-            const int64_t off = (((int64_t)n * a.hout + (h0 + h)) * a.hout + w) * a.cout + cbase;
+            const int tbase = nt * a.bn_tile;
+            const int64_t off = (((int64_t)n * a.hout + (h0 + h)) * a.hout + w) * a.cout + tbase;
             float accr[WRN_EPI_CHUNKS][16];
 #pragma unroll
             for (int j = 0; j < WRN_EPI_CHUNKS; ++j)
@@ -245,14 +301,23 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
                 mbar_wait_a(smem_u32(&tfull_bar[buf]), bph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)a.bn_tile + (uint32_t)(half_id * half);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_pitch;
 #pragma unroll
                 for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
-                    if (j * 16 < half) {
+                    if (chunk_on(j)) {
                         uint32_t rr[16];
-                        tmem_ld16(taddr + (uint32_t)(j * 16), rr);
+                        if (F16) {
+                            uint32_t rl[16];
+                            tmem_ld16_nowait(taddr + (uint32_t)chunk_col(j), rr);
+                            tmem_ld16_nowait(taddr + (uint32_t)(a.bn_tile + chunk_col(j)), rl);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
+                            for (int e = 0; e < 16; ++e) accr[j][e] += fmaf(__uint_as_float(rl[e]), kWrnLoUnscale, __uint_as_float(rr[e]));
+                        } else {
+                            tmem_ld16(taddr + (uint32_t)chunk_col(j), rr);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -269,7 +334,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             // [4 qi, 4 qi + 4) of the quad's 4 rows, so a quad reads / writes 64 contiguous bytes of one pixel per access.
 #pragma unroll
             for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
-                if (j * 16 >= half) continue;
+                if (!chunk_on(j)) continue;
                 float tr[4][4];
 #pragma unroll
                 for (int rd = 0; rd < 4; ++rd) {
@@ -283,7 +348,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             if (jr == jj) tr[jj][e] = rv;
                     }
                 }
-                const int c0 = j * 16 + 4 * qi;
+                const int c0 = chunk_col(j) + 4 * qi;
+                const int cbase = tbase;
                 float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
                 if (valid) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + cbase + c0));
@@ -307,15 +373,29 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
                         }
                         if (a.outx_hi) {
+                            if (F16) {
+                                uint2 hh, ll;
+                                wrn_split_h4(v.x, v.y, v.z, v.w, hh, ll);
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a.outx_hi) + o) = hh;
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a.outx_lo) + o) = ll;
+                            } else {
                             float4 hv, lv;
                             hv.x = rn_tf32(v.x); hv.y = rn_tf32(v.y); hv.z = rn_tf32(v.z); hv.w = rn_tf32(v.w);
                             lv.x = rn_tf32(v.x - hv.x); lv.y = rn_tf32(v.y - hv.y); lv.z = rn_tf32(v.z - hv.z); lv.w = rn_tf32(v.w - hv.w);
                             *reinterpret_cast<float4 *>(a.outx_hi + o) = hv;
                             *reinterpret_cast<float4 *>(a.outx_lo + o) = lv;
+                            }
                         }
                         if (a.out_hi) {
                             const float y0 = relu_nan(fmaf(a4.x, v.x, s4.x)), y1 = relu_nan(fmaf(a4.y, v.y, s4.y));
                             const float y2 = relu_nan(fmaf(a4.z, v.z, s4.z)), y3 = relu_nan(fmaf(a4.w, v.w, s4.w));
+                            if (F16) {
+                                uint2 hh, ll;
+                                wrn_split_h4(y0, y1, y2, y3, hh, ll);
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a.out_hi) + o) = hh;
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a.out_lo) + o) = ll;
+                                continue;
+                            }
                             float4 hv, lv;
                             hv.x = rn_tf32(y0); hv.y = rn_tf32(y1); hv.z = rn_tf32(y2); hv.w = rn_tf32(y3);
                             lv.x = rn_tf32(y0 - hv.x); lv.y = rn_tf32(y1 - hv.y); lv.z = rn_tf32(y2 - hv.z); lv.w = rn_tf32(y3 - hv.w);
@@ -359,6 +439,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
 
 // ---- pack / fold (per sample) --------------------------------------------------------------------------------------
 // filters [co][ci][taps] (PyTorch) -> K-major rows dst[co][koff + tap * cin_p + ci], ci >= cin zero-filled, TF32 hi / lo
+template <bool F16>
 __global__ void __launch_bounds__(256) wrn_pack_filter_kernel(const float *__restrict__ src, float *__restrict__ dhi,
                                                               float *__restrict__ dlo, int cin, int cin_p, int cout, int taps,
                                                               int ktot, int koff) {
@@ -368,10 +449,16 @@ __global__ void __launch_bounds__(256) wrn_pack_filter_kernel(const float *__res
         const int rem = (int)(i - (int64_t)co * per_row);
         const int tap = rem / cin_p, ci = rem - tap * cin_p;
         const float wv = ci < cin ? __ldg(src + ((int64_t)co * cin + ci) * taps + tap) : 0.f;
-        const float hv = rn_tf32(wv);
         const int64_t d = (int64_t)co * ktot + koff + rem;
-        dhi[d] = hv;
-        dlo[d] = rn_tf32(wv - hv);
+        if (F16) {                                             // the same regions of `packed`, viewed as halves
+            const __half hh = __float2half_rn(wv);
+            reinterpret_cast<__half *>(dhi)[d] = hh;
+            reinterpret_cast<__half *>(dlo)[d] = __float2half_rn((wv - __half2float(hh)) * kWrnLoScale);
+        } else {
+            const float hv = rn_tf32(wv);
+            dhi[d] = hv;
+            dlo[d] = rn_tf32(wv - hv);
+        }
     }
 }
 
@@ -392,6 +479,7 @@ __global__ void wrn_bias_kernel(const float *__restrict__ b0, const float *__res
 
 // ---- stem: R0 = conv3x3(x) + bias (3 -> 16); A = split(relu(bn(R0))), X = split(R0), both padded to 32 channels ------
 // Train mode (bn == null): no A planes; the raw 16-channel output goes to raw16 and its per-batch sums to stats.
+template <bool F16>
 __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__ x, const float *__restrict__ wsrc,
                                                        const float *__restrict__ bsrc, const float *__restrict__ bn,
                                                        float *__restrict__ a_hi, float *__restrict__ a_lo,
@@ -461,6 +549,23 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
                 yh[k] = rn_tf32(y[k]); yl[k] = rn_tf32(y[k] - yh[k]);
                 st1[i + k] += r[k];
                 st2[i + k] = fmaf(r[k], r[k], st2[i + k]);
+            }
+            if (F16) {                                     // eval mode only: A and X planes as halves
+                uint2 hh, ll;
+                const uint2 z2 = make_uint2(0u, 0u);
+                __half *ah = reinterpret_cast<__half *>(a_hi), *al = reinterpret_cast<__half *>(a_lo);
+                __half *xh = reinterpret_cast<__half *>(x_hi), *xl = reinterpret_cast<__half *>(x_lo);
+                wrn_split_h4(y[0], y[1], y[2], y[3], hh, ll);
+                *reinterpret_cast<uint2 *>(ah + off + i) = hh;
+                *reinterpret_cast<uint2 *>(al + off + i) = ll;
+                *reinterpret_cast<uint2 *>(ah + off + 16 + i) = z2;
+                *reinterpret_cast<uint2 *>(al + off + 16 + i) = z2;
+                wrn_split_h4(r[0], r[1], r[2], r[3], hh, ll);
+                *reinterpret_cast<uint2 *>(xh + off + i) = hh;
+                *reinterpret_cast<uint2 *>(xl + off + i) = ll;
+                *reinterpret_cast<uint2 *>(xh + off + 16 + i) = z2;
+                *reinterpret_cast<uint2 *>(xl + off + 16 + i) = z2;
+                continue;
             }
             if (bn) {
                 *reinterpret_cast<float4 *>(a_hi + off + i) = make_float4(yh[0], yh[1], yh[2], yh[3]);
@@ -696,24 +801,29 @@ static WrnChunking wrn_chunking(int64_t N, const WrnPlan &pl) {
 }
 
 // plane [N][H][H][C]: stride-1 map, or the (hp, wp) parity sub-lattice for a stride-2 consumer; box = one 128-pixel tile
-static int wrn_act_map(CUtensorMap *tm, const float *plane, int nc, int H, int C, int hout, int stride, int parity) {
+static int wrn_act_map(CUtensorMap *tm, const float *plane, int nc, int H, int C, int hout, int stride, int parity, bool f16) {
     const int WT = hout, HT = hout >= 16 ? 128 / hout : hout, NT = 128 / (WT * HT);
     const uint32_t box[4] = {32u, (uint32_t)WT, (uint32_t)HT, (uint32_t)NT};
+    const uint64_t es = f16 ? 2 : 4;                           // FP16-split planes: halves, 64-byte swizzle rows
+    const int swz = f16 ? 64 : 128;
     if (stride == 1) {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)nc};
-        const uint64_t st[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
-        return make_tensor_map(tm, plane, 4, dims, st, box, 128);
+        const uint64_t st[3] = {(uint64_t)C * es, (uint64_t)H * C * es, (uint64_t)H * H * C * es};
+        return make_tensor_map_t(tm, plane, 4, dims, st, box, swz, f16 ? 1 : 0);
     }
     const int hp = parity >> 1, wp = parity & 1;
-    const float *base = plane + ((int64_t)hp * H + wp) * C;
+    const char *base = reinterpret_cast<const char *>(plane) + ((int64_t)hp * H + wp) * C * es;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)(H / 2), (uint64_t)(H / 2), (uint64_t)nc};
-    const uint64_t st[3] = {(uint64_t)2 * C * 4, (uint64_t)2 * H * C * 4, (uint64_t)H * H * C * 4};
-    return make_tensor_map(tm, base, 4, dims, st, box, 128);
+    const uint64_t st[3] = {(uint64_t)2 * C * es, (uint64_t)2 * H * C * es, (uint64_t)H * H * C * es};
+    return make_tensor_map_t(tm, base, 4, dims, st, box, swz, f16 ? 1 : 0);
 }
 
-static int wrn_pick_bn_tile(int cout) {
-    for (int nt = 1; nt <= 16; ++nt)
-        if (cout % nt == 0 && cout / nt <= 160 && (cout / nt) % 32 == 0) return cout / nt;    // two 16-column-granular halves
+static int wrn_pick_bn_tile(int cout, bool f16) {
+    for (int nt = 1; nt <= 16; ++nt) {
+        if (cout % nt != 0) continue;
+        const int bn = cout / nt;
+        if (f16 ? (bn <= 128 && bn % 16 == 0) : (bn <= 160 && bn % 32 == 0)) return bn;    // 3xTF32: two 16-column-granular halves
+    }
     return 0;
 }
 
@@ -748,45 +858,48 @@ static bool wrn_pairs_supported() {
 // conv over the X planes [nc][hin][hin][xin_p] into the accumulation
 static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int cin_p, const float *x_hi, const float *x_lo,
                            int xin_p, int cout, int stride, int nc, const float *b_hi, const float *b_lo, int ktot,
-                           WrnConvArgs g, cudaStream_t st) {
+                           WrnConvArgs g, cudaStream_t st, bool f16 = false) {
     const int hout = hin / stride;
     WrnMaps maps;
     const int nmaps = stride == 2 ? 4 : 1;
     for (int i = 0; i < nmaps; ++i) {
-        if (int rc = wrn_act_map(&maps.a_hi[i], a_hi, nc, hin, cin_p, hout, stride, i)) return rc;
-        if (int rc = wrn_act_map(&maps.a_lo[i], a_lo, nc, hin, cin_p, hout, stride, i)) return rc;
+        if (int rc = wrn_act_map(&maps.a_hi[i], a_hi, nc, hin, cin_p, hout, stride, i, f16)) return rc;
+        if (int rc = wrn_act_map(&maps.a_lo[i], a_lo, nc, hin, cin_p, hout, stride, i, f16)) return rc;
     }
     for (int i = nmaps; i < 4; ++i) { maps.a_hi[i] = maps.a_hi[0]; maps.a_lo[i] = maps.a_lo[0]; }
     if (xin_p > 0) {
-        if (int rc = wrn_act_map(&maps.x_hi, x_hi, nc, hin, xin_p, hout, stride, 0)) return rc;
-        if (int rc = wrn_act_map(&maps.x_lo, x_lo, nc, hin, xin_p, hout, stride, 0)) return rc;
+        if (int rc = wrn_act_map(&maps.x_hi, x_hi, nc, hin, xin_p, hout, stride, 0, f16)) return rc;
+        if (int rc = wrn_act_map(&maps.x_lo, x_lo, nc, hin, xin_p, hout, stride, 0, f16)) return rc;
     } else {
         maps.x_hi = maps.a_hi[0];
         maps.x_lo = maps.a_lo[0];
     }
-    const int bn_tile = wrn_pick_bn_tile(cout);
+    const int bn_tile = wrn_pick_bn_tile(cout, f16);
     URSA_REQUIRE(bn_tile > 0, "ursa_bma_wrn_forward: no output-channel tile for cout = %d", cout);
     int ncta = 2;                                                       // CTA pairs (cta_group::2); URSA_WRN_2CTA=0 selects single CTAs
     if (const char *e = getenv("URSA_WRN_2CTA")) ncta = atoi(e) == 0 ? 1 : 2;
     if (ncta == 2 && !wrn_pairs_supported()) ncta = 1;
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)cout};
-        const uint64_t sb[1] = {(uint64_t)ktot * 4};
+        const uint64_t sb[1] = {(uint64_t)ktot * (f16 ? 2 : 4)};
         const uint32_t box[2] = {32u, (uint32_t)(bn_tile / ncta)};
-        if (int rc = make_tensor_map(&maps.b_hi, b_hi, 2, dims, sb, box, 128)) return rc;
-        if (int rc = make_tensor_map(&maps.b_lo, b_lo, 2, dims, sb, box, 128)) return rc;
+        if (int rc = make_tensor_map_t(&maps.b_hi, b_hi, 2, dims, sb, box, f16 ? 64 : 128, f16 ? 1 : 0)) return rc;
+        if (int rc = make_tensor_map_t(&maps.b_lo, b_lo, 2, dims, sb, box, f16 ? 64 : 128, f16 ? 1 : 0)) return rc;
     }
     g.cout = cout; g.bn_tile = bn_tile; g.hout = hout; g.stride = stride; g.n_images = nc;
     g.kchunks = cin_p / 32; g.xchunks = xin_p / 32;
     const int tpi = (hout * hout) / 128;
     g.m_tiles = tpi > 0 ? nc * tpi : (nc + 1) / 2;
     g.n_tiles = cout / bn_tile;
-    const size_t stage_bytes = 2 * (size_t)WRN_A_BYTES + 2 * (size_t)(bn_tile / ncta) * 128;
+    const size_t stage_bytes = f16 ? 2 * (size_t)WRN_A_BYTES_H + 2 * (size_t)(bn_tile / ncta) * 64
+                                   : 2 * (size_t)WRN_A_BYTES + 2 * (size_t)(bn_tile / ncta) * 128;
     int stages = (int)(((size_t)(226 << 10) - 1024) / stage_bytes);
-    if (stages > WRN_MAX_STAGES) stages = WRN_MAX_STAGES;
+    if (stages > (f16 ? WRN_MAX_STAGES_H : WRN_MAX_STAGES)) stages = f16 ? WRN_MAX_STAGES_H : WRN_MAX_STAGES;
     if (const char *e = getenv("URSA_WRN_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
     g.stages = stages;
-    g.seg = WRN_SEG;
+    // FP16-split: a K block is 6 MMAs of ~40-64 clk instead of 12 of 80, and its chains hold 2 (ACC) / 4 (LO) MMAs per block: 16-block
+    // segments keep the drains off the critical path (SEG 4 / 8 / 16 / 32: 231 / 260 / 274 / 277 TFLOP/s) at 3e-6 from fp64
+    g.seg = f16 ? 4 * WRN_SEG : WRN_SEG;
     if (const char *e = getenv("URSA_WRN_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }      // accuracy / speed experiments
     g.seg0 = WRN_SEG0_FACTOR * g.seg;                        // ... but never more than a quarter of the K extent
     if (g.seg0 > (g.kchunks * 9 + g.xchunks) / 4) g.seg0 = (g.kchunks * 9 + g.xchunks) / 4;
@@ -795,7 +908,8 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     if (ncta == 2) {
         const int units = ((g.m_tiles + 1) / 2) * g.n_tiles, pairs = sm_count() / 2;
-        URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (f16) URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * (units < pairs ? units : pairs));
         cfg.blockDim = dim3(WRN_THREADS);
@@ -806,12 +920,19 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        URSA_CUDA(cudaLaunchKernelEx(&cfg, wrn_conv_tc_kernel<2>, maps, g));
+        if (f16) URSA_CUDA(cudaLaunchKernelEx(&cfg, wrn_conv_tc_kernel<2, true>, maps, g));
+        else URSA_CUDA(cudaLaunchKernelEx(&cfg, wrn_conv_tc_kernel<2>, maps, g));
         URSA_LAUNCH_CHECK("wrn_conv_tc_kernel<2>");
         return URSA_OK;
     }
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
+    if (f16) {
+        URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wrn_conv_tc_kernel<1, true><<<grid, WRN_THREADS, smem, st>>>(maps, g);
+        URSA_LAUNCH_CHECK("wrn_conv_tc_kernel<1, f16>");
+        return URSA_OK;
+    }
     URSA_CUDA(cudaFuncSetAttribute(wrn_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wrn_conv_tc_kernel<1><<<grid, WRN_THREADS, smem, st>>>(maps, g);
     URSA_LAUNCH_CHECK("wrn_conv_tc_kernel");
@@ -819,12 +940,13 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
 }
 
 static int wrn_pack_sample(const WrnPlan &pl, const float *row, const float *brow, float *packed, cudaStream_t st,
-                           bool fold_bn = true) {
+                           bool fold_bn = true, bool f16 = false) {
     auto pack = [&](const float *src, float *dhi, float *dlo, int cin, int cin_p, int cout, int taps, int ktot, int koff) {
         const int64_t total = (int64_t)cout * taps * cin_p;
         int64_t blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        wrn_pack_filter_kernel<<<(int)blocks, 256, 0, st>>>(src, dhi, dlo, cin, cin_p, cout, taps, ktot, koff);
+        if (f16) wrn_pack_filter_kernel<true><<<(int)blocks, 256, 0, st>>>(src, dhi, dlo, cin, cin_p, cout, taps, ktot, koff);
+        else wrn_pack_filter_kernel<false><<<(int)blocks, 256, 0, st>>>(src, dhi, dlo, cin, cin_p, cout, taps, ktot, koff);
     };
     for (int g = 0; g < 3; ++g)
         for (int b = 0; b < pl.n; ++b) {
@@ -855,7 +977,7 @@ using namespace ursa;
 
 extern "C" size_t ursa_bma_wrn_workspace(int S, int64_t N, int depth, int widen, int C, int algo) {
     WrnPlan pl;
-    if (S < 1 || N < 1 || algo != URSA_ALGO_TCGEN05 || !wrn_build_plan(depth, widen, C, pl)) return 0;
+    if (S < 1 || N < 1 || (algo != URSA_ALGO_TCGEN05 && algo != URSA_ALGO_TCGEN05_F16) || !wrn_build_plan(depth, widen, C, pl)) return 0;
     return wrn_chunking(N, pl).total;
 }
 
@@ -865,10 +987,11 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
                                     size_t workspace_bytes, int algo, void *stream) {
     URSA_REQUIRE(bank && bufbank && x && proba_sum && entropy_sum && workspace, "ursa_bma_wrn_forward: null pointer");
     URSA_REQUIRE(S >= 1 && N >= 1, "ursa_bma_wrn_forward: bad shape");
-    if (algo != URSA_ALGO_TCGEN05) {
-        set_error("ursa_bma_wrn_forward: unknown algo %d (the WideResNet forward exists on the tcgen05 engine only)", algo);
+    if (algo != URSA_ALGO_TCGEN05 && algo != URSA_ALGO_TCGEN05_F16) {
+        set_error("ursa_bma_wrn_forward: unknown algo %d (the WideResNet forward exists on the tcgen05 engines only)", algo);
         return URSA_ERR_UNSUPPORTED;
     }
+    const bool f16 = algo == URSA_ALGO_TCGEN05_F16;
     static thread_local WrnPlan pl;
     if (!wrn_build_plan(depth, widen, C, pl)) {
         set_error("ursa_bma_wrn_forward: unsupported WRN-%d-%d (depth = 6n+4 with n <= %d, even widen factor 2..16)", depth, widen,
@@ -894,12 +1017,16 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
 
     for (int s = 0; s < S; ++s) {
         const float *row = bank + (int64_t)s * ld_bank, *brow = bufbank + (int64_t)s * ld_buf;
-        if (int rc = wrn_pack_sample(pl, row, brow, packed, st)) return rc;
+        if (int rc = wrn_pack_sample(pl, row, brow, packed, st, true, f16)) return rc;
         for (int64_t i0 = 0; i0 < N; i0 += ck.nc) {
             const int nc = (int)((N - i0 < ck.nc) ? (N - i0) : ck.nc);
             int xi = 0;                                   // X plane pair holding the current block's raw input
-            wrn_stem_kernel<<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, row + pl.conv1_w, row + pl.conv1_b,
-                                                packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi], nullptr, nullptr, 1);
+            if (f16)
+                wrn_stem_kernel<true><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, row + pl.conv1_w, row + pl.conv1_b,
+                                                          packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi], nullptr, nullptr, 1);
+            else
+                wrn_stem_kernel<false><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, row + pl.conv1_w, row + pl.conv1_b,
+                                                           packed + pl.blocks[0][0].p_bn1, A1h, A1l, Xh[xi], Xl[xi], nullptr, nullptr, 1);
             URSA_LAUNCH_CHECK("wrn_stem_kernel");
             float *cur = Ra, *nxt = Rb;
             int hw = 32;
@@ -911,7 +1038,7 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
                     WrnConvArgs c1 = {};
                     c1.bias = packed + B.p_bias1; c1.bn = packed + B.p_bn2; c1.out_hi = A2h; c1.out_lo = A2l;
                     if (int rc = wrn_launch_conv(A1h, A1l, hw, B.cin_p, nullptr, nullptr, 0, B.cout, 1, nc, packed + B.p_w1_hi,
-                                                 packed + B.p_w1_lo, B.k1, c1, st))
+                                                 packed + B.p_w1_lo, B.k1, c1, st, f16))
                         return rc;
                     WrnConvArgs c2 = {};
                     c2.bias = packed + B.p_bias2;
@@ -924,7 +1051,7 @@ extern "C" int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const fl
                         c2.out_raw = nxt;
                     }
                     if (int rc = wrn_launch_conv(A2h, A2l, hw, B.cout, Xh[xi], Xl[xi], B.transition ? B.cin_p : 0, B.cout, B.stride,
-                                                 nc, packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st))
+                                                 nc, packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st, f16))
                         return rc;
                     if (c2.outx_hi) xi ^= 1;
                     if (c2.out_raw) { float *t = cur; cur = nxt; nxt = t; }
@@ -1023,7 +1150,7 @@ extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const f
         int xi = 0;
         float *cur = Ra, *nxt = Rb;
         const WrnBlock &B0 = pl.blocks[0][0];
-        wrn_stem_kernel<<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
+        wrn_stem_kernel<false><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
                                             nullptr, Xh[xi], Xl[xi], cur, stats, batch);
         URSA_LAUNCH_CHECK("wrn_stem_kernel");
         finalize(B0.bn1_w, B0.bn1_b, B0.bn1_buf, 16, 1024, nc, i0);

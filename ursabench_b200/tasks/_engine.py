@@ -222,8 +222,9 @@ class BMAAccumulator:
                 if lib.ursa_bma_preresnet_workspace(1, 1, arch[1], arch[2], algo) > 0:
                     return algo
         elif arch[0] == "wrn" and self.engine != "ffma":
-            if lib.ursa_bma_wrn_workspace(1, 1, arch[1], arch[2], arch[3], _C.ALGO_TCGEN05) > 0:
-                return _C.ALGO_TCGEN05
+            for algo in (_C.ALGO_TCGEN05_F16, _C.ALGO_TCGEN05):
+                if lib.ursa_bma_wrn_workspace(1, 1, arch[1], arch[2], arch[3], algo) > 0:
+                    return algo
         return None
 
     def _accumulate_rows(self, w, b, arch, skeleton, lo=0, hi=None):
@@ -254,7 +255,12 @@ class BMAAccumulator:
                 _, depth, widen, C = arch
                 if C != self.num_classes:
                     raise ValueError("WideResNet class dimension does not match the task")
-                self._ws = _C.bma_wrn_forward(w, b, S, x, depth, widen, C, proba, entropy, algo=algo, workspace=self._ws)
+                if algo == _C.ALGO_TCGEN05_F16:       # fp16's range: scratch-and-commit like the other FP16-split engines
+                    sp, se = self._scratch()
+                    self._ws = _C.bma_wrn_forward(w, b, S, x, depth, widen, C, sp[lo:hi], se[lo:hi], algo=algo, workspace=self._ws)
+                    self._pending.append(("wrn", w, b, S, depth, widen, C, lo, hi))
+                else:
+                    self._ws = _C.bma_wrn_forward(w, b, S, x, depth, widen, C, proba, entropy, algo=algo, workspace=self._ws)
                 self._ws_key = None
                 self.last_engine = "fused_wrn"
             else:
@@ -315,7 +321,12 @@ class BMAAccumulator:
             return
         ws = None
         for job in pending:
-            if job[0] == "mlp":
+            if job[0] == "wrn":
+                _, w, b, S, depth, widen, C, lo, hi = job
+                self.last_algo = _C.ALGO_TCGEN05
+                ws = _C.bma_wrn_forward(w, b, S, self._x[lo:hi], depth, widen, C, self._proba[lo:hi], self._entropy[lo:hi],
+                                        algo=_C.ALGO_TCGEN05, workspace=ws)
+            elif job[0] == "mlp":
                 _, w, S, in_dim, hidden, C, lo, hi = job
                 self.last_algo = _C.ALGO_TCGEN05
                 ws = _C.bma_mlp_forward(w, S, self._x.view(self._n, -1)[lo:hi], in_dim, hidden, C, self._proba[lo:hi],
