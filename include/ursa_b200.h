@@ -198,7 +198,8 @@ int ursa_bma_metrics(const float *proba_sum, int64_t N, int C, float num_samples
 #define URSA_ALGO_FLAG_WS_KEPT 0x100 /* OR-ed into `algo` of ursa_bma_preresnet_forward: the workspace is the one the caller's PREVIOUS
                                       * call of this entry used, with the same min(S, 8), N, depth and C, and nothing else has written
                                       * to it since -- the FP16-split engine then skips re-zeroing the pad positions of its plane images */
-#define URSA_ALGO_TCGEN05_F16 4     /* MLP only: persistent 2xFP16-split GEMM kernel (csrc/bma_mlp_f16.cu) */
+#define URSA_ALGO_TCGEN05_F16 4     /* MLP: persistent 2xFP16-split GEMM kernel (csrc/bma_mlp_f16.cu); WideResNet: the FP16-split
+                                     * instantiation of the conv kernel.  fp16's range: overflow surfaces as NaN logits */
 #define URSA_ALGO_TCGEN05_FUSED_F16 3 /* PreResNet only: stage-fused kernel on 2xFP16-split operands (22 significant bits, fp32
                                        * accumulate), MMA / epilogue wavefront per 128-position tile.  Activations above ~1e6
                                        * overflow FP16 and surface as NaN logits (never as finite wrong values). */
@@ -264,9 +265,10 @@ int ursa_bma_preresnet_forward(const float *bank, int64_t ld_bank, const float *
  *     models/wideresnet.py:78-120 -- BASELINE.json configs[2] is WRN-28-10 with C = 100).
  *     depth = 6n+4 (n <= 8), widen even in [2, 16].  bank / bufbank / x as for the PreResNet entry point.
  *     One posterior sample at a time over chunks of images; every 3x3 conv (and the 1x1 shortcut convs,
- *     folded into conv2's K loop) runs as a persistent 3xTF32 tcgen05 implicit GEMM; the head kernel (BN + ReLU +
- *     pool + linear) ends in the softmax-average / entropy epilogue.  algo must be
- *     URSA_ALGO_TCGEN05; the workspace query returns 0 for an unsupported shape.
+ *     folded into conv2's K loop) runs as a persistent tcgen05 implicit GEMM; the head kernel (BN + ReLU +
+ *     pool + linear) ends in the softmax-average / entropy epilogue.  algo: URSA_ALGO_TCGEN05_F16 (2xFP16-split
+ *     operands, the product path: 1.3x the 3xTF32 engine and closer to an fp64 forward; fp16's range) or
+ *     URSA_ALGO_TCGEN05 (3xTF32, fp32's range); the workspace query returns 0 for an unsupported shape.
  * ---------------------------------------------------------------------- */
 size_t ursa_bma_wrn_workspace(int S, int64_t N, int depth, int widen, int C, int algo);
 int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const float *bufbank, int64_t ld_buf,
