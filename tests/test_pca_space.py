@@ -47,6 +47,18 @@ def test_pca_space_on_device_matches_reference_golden(tag):
     many = model(torch.from_numpy(np.stack([g[tag + "/t"], 2 * g[tag + "/t"]])).cuda())     # batched proposals, one pass
     np.testing.assert_allclose(many[0].cpu().numpy(), g[tag + "/projected"], atol=2e-5, rtol=2e-5)
     np.testing.assert_allclose((many[1] - model.mean).cpu().numpy(), 2 * (g[tag + "/projected"] - g[tag + "/mean"]), atol=4e-5, rtol=4e-5)
+    # the reference's state_dict keys / shapes, and its differentiable expression when t requires grad (projection_model.py:13-14)
+    sd = model.state_dict()
+    assert set(sd) == {"mean", "cov_factor"} and tuple(sd["cov_factor"].shape) == tuple(ref.shape)
+    t = torch.from_numpy(g[tag + "/t"]).cuda().requires_grad_(True)
+    out_g = model(t)
+    np.testing.assert_allclose(out_g.detach().cpu().numpy(), g[tag + "/projected"], atol=2e-5, rtol=2e-5)
+    out_g.sum().backward()
+    np.testing.assert_allclose(t.grad.cpu().numpy(), ref.sum(1), atol=1e-4, rtol=1e-4)
+    # buffers changed in place (load_state_dict): the padded copies the kernel reads follow
+    model.load_state_dict({"mean": sd["mean"] * 0 + 1.0, "cov_factor": sd["cov_factor"]})
+    out2 = model(torch.from_numpy(g[tag + "/t"]).cuda())
+    np.testing.assert_allclose(out2.cpu().numpy(), g[tag + "/projected"] - g[tag + "/mean"] + 1.0, atol=4e-5, rtol=4e-5)
 
 
 @pytest.mark.gpu
