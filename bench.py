@@ -862,13 +862,15 @@ def run_extras(dev, rank, world, peak):
                                                      "TFLOPs": wrn_flop * N * S_w / ms / 1e9, "n_gpus": world, "clocks": wclocks}
     # K3b: BatchNorm re-estimation of one SWAG draw (util.bn_update, once per sample): bounded sample of the 50 000-image pass
     Nbn, Bbn = 2048, 128
-    bn_fn = lambda: _C.wrn_bn_update(bankw[0], bufw[0], xi[:Nbn], Bbn, 28, 10, C_w, workspace=ws[0])  # noqa: E731
-    ws[0] = None
-    ws[0] = bn_fn()
-    torch.cuda.synchronize()
-    ms, _ = _event_time_ms(bn_fn, 2)
-    out["k3b_bn_update_wrn28x10_N2048_b128"] = {"ms": ms, "img_per_s": Nbn / ms * 1e3, "TFLOPs": wrn_flop * Nbn / ms / 1e9,
-                                                "full_pass_50k_images_s": ms * 50_000 / Nbn / 1e3}
+    for algo_name, algo in (("", _C.ALGO_TCGEN05), ("_f16", _C.ALGO_TCGEN05_F16)):
+        bn_fn = lambda: _C.wrn_bn_update(bankw[0], bufw[0], xi[:Nbn], Bbn, 28, 10, C_w, workspace=ws[0], algo=algo)  # noqa: E731
+        ws[0] = None
+        ws[0] = bn_fn()
+        torch.cuda.synchronize()
+        ms, _ = _event_time_ms(bn_fn, 2)
+        out["k3b_bn_update_wrn28x10_N2048_b128" + algo_name] = {"ms": ms, "img_per_s": Nbn / ms * 1e3,
+                                                                "TFLOPs": wrn_flop * Nbn / ms / 1e9,
+                                                                "full_pass_50k_images_s": ms * 50_000 / Nbn / 1e3}
     if rank == 0:
         worker = m.to(dev).eval()
         mm_tf32 = torch.backends.cuda.matmul.allow_tf32

@@ -287,6 +287,11 @@ int ursa_bma_wrn_forward(const float *bank, int64_t ld_bank, const float *bufban
 size_t ursa_wrn_bn_update_workspace(int64_t N, int batch, int depth, int widen, int C);
 int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch,
                        int depth, int widen, int C, void *workspace, size_t workspace_bytes, void *stream);
+/* the same with the engine chosen by the caller: URSA_ALGO_TCGEN05 (3xTF32, = ursa_wrn_bn_update) or URSA_ALGO_TCGEN05_F16
+ * (2xFP16-split conv kernel: faster and closer to an fp64 pass; activations beyond fp16's range make the statistics
+ * non-finite -- callers then repeat the pass on URSA_ALGO_TCGEN05) */
+int ursa_wrn_bn_update_algo(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch,
+                            int depth, int widen, int C, void *workspace, size_t workspace_bytes, int algo, void *stream);
 
 /* The same for PreResNets (the north-star model), SAMPLE-BATCHED: S posterior samples (rows of bank / bufbank) take the
  * train-mode pass together, 8 per launch.  Layer by layer on the 3xTF32 tcgen05 conv kernel with a statistics epilogue

@@ -143,8 +143,9 @@ def _flat_buffers_any(m):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
 @pytest.mark.parametrize("depth,widen,N,batch", [(10, 2, 300, 128), (16, 4, 70, 32), (10, 10, 40, 16), (10, 2, 1030, 256)])
-def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
+def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch, engine):
     """ursa_wrn_bn_update (train-mode pass on the tcgen05 conv kernel, fp64 batch sums) against util.bn_update's PyTorch pass
     (reference util.py:212-247): ragged last batch, several chunks (N > 512), identity and transition blocks."""
     from ursabench_b200 import _C
@@ -169,7 +170,7 @@ def test_wrn_bn_update_matches_torch_train_mode(depth, widen, N, batch):
         torch.backends.cuda.matmul.allow_tf32 = mm
     ref = _flat_buffers(m)
     buf = torch.full_like(ref, float("nan"))                       # the kernel must overwrite every statistic
-    ws = _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, 10)
+    ws = _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, 10, algo=getattr(_C, engine))
     torch.cuda.synchronize()
     assert ws is not None
     assert torch.isfinite(buf).all()
@@ -270,7 +271,8 @@ def test_bn_update_port_reproduces_the_reference_cpu():
 
 
 @pytest.mark.gpu
-def test_wrn_bn_update_matches_reference_golden():
+@pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
+def test_wrn_bn_update_matches_reference_golden(engine):
     """ursa_wrn_bn_update against the same golden: means within 2e-5 of the layer's standard deviation, variances within 5e-5
     relative (the tensor core's systematic ~1e-6 offset, see the fp64-bracket test above)."""
     from ursabench_b200 import _C
@@ -278,7 +280,7 @@ def test_wrn_bn_update_matches_reference_golden():
     row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cuda().contiguous()
     ref = torch.from_numpy(g["buffers"]).cuda()
     buf = torch.full_like(ref, float("nan"))
-    assert _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, C) is not None
+    assert _C.wrn_bn_update(row, buf, x.cuda(), batch, depth, widen, C, algo=getattr(_C, engine)) is not None
     off = 0
     for mod in m.modules():
         if isinstance(mod, torch.nn.BatchNorm2d):

@@ -61,12 +61,13 @@ def bench_bn(depth, widen, C, N, batch=128):
     buf = torch.zeros(nbuf, device="cuda")
     torch.manual_seed(0)
     x = torch.randn(N, 3, 32, 32, device="cuda")
-    ws = _C.wrn_bn_update(row, buf, x[:batch * 2], batch, depth, widen, C)
-    ws = _C.wrn_bn_update(row, buf, x, batch, depth, widen, C)
+    algo = _C.ALGO_TCGEN05_F16 if "--f16" in sys.argv else _C.ALGO_TCGEN05
+    ws = _C.wrn_bn_update(row, buf, x[:batch * 2], batch, depth, widen, C, algo=algo)
+    ws = _C.wrn_bn_update(row, buf, x, batch, depth, widen, C, algo=algo)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _C.wrn_bn_update(row, buf, x, batch, depth, widen, C, workspace=ws)
+    _C.wrn_bn_update(row, buf, x, batch, depth, widen, C, workspace=ws, algo=algo)
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ursa_swag_gram": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "ursa_wrn_bn_update_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "ursa_wrn_bn_update": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "ursa_wrn_bn_update_algo": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp]),
     "ursa_preresnet_bn_update_workspace": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "ursa_preresnet_bn_update": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ursa_hmc_momentum": (_i32, [_vp, _vp, _i64, _f32, _u64, _u64, _u64, _vp]),
@@ -338,9 +339,10 @@ def bma_wrn_forward(bank, bufbank, S, x, depth, widen, C, proba_sum, entropy_sum
 
 
 @_on_device
-def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
+def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None, algo=ALGO_TCGEN05):
     """Re-estimate the BatchNorm running statistics of ONE WideResNet sample with a train-mode pass over ``x`` (batches of
-    ``batch`` images); ``buf_row`` [nb] is overwritten.  Returns the workspace (None if the shape is not covered)."""
+    ``batch`` images); ``buf_row`` [nb] is overwritten.  ``algo``: ALGO_TCGEN05 (3xTF32) or ALGO_TCGEN05_F16.  Returns the
+    workspace (None if the shape is not covered)."""
     _dev_f32(bank_row, "bank_row"), _dev_f32(buf_row, "buf_row"), _dev_f32(x, "x")
     N = x.shape[0]
     need = lib().ursa_wrn_bn_update_workspace(N, batch, depth, widen, C)
@@ -348,8 +350,8 @@ def wrn_bn_update(bank_row, buf_row, x, batch, depth, widen, C, workspace=None):
         return None
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
-    rc = lib().ursa_wrn_bn_update(_ptr(bank_row), _ptr(buf_row), _ptr(x), N, batch, depth, widen, C, _ptr(workspace),
-                                  workspace.numel() * workspace.element_size(), _stream(x))
+    rc = lib().ursa_wrn_bn_update_algo(_ptr(bank_row), _ptr(buf_row), _ptr(x), N, batch, depth, widen, C, _ptr(workspace),
+                                       workspace.numel() * workspace.element_size(), algo, _stream(x))
     _check(rc, "ursa_wrn_bn_update")
     return workspace
 

@@ -542,7 +542,9 @@ static TcChunking tc_chunking(int S, int64_t N, const NetPlan &pl, bool fused = 
         const int v = e ? atoi(e) : 0;
         return v >= 64 && v <= 16384 ? v : 0;
     }();
-    const int ci = chunk_images ? chunk_images : (fused ? kFusedChunkImages : kTcChunkImages);
+    // fused engines: a launch holds up to 8 x 2 500 (sample, image) pairs whatever the split -- fewer samples, more images
+    // (S = 1: the whole 10 000-image test set in one launch chain; matters for the small shares of an 8-rank evaluation)
+    const int ci = chunk_images ? chunk_images : (fused ? kFusedChunkImages * (kTcChunkSamples / c.sc) : kTcChunkImages);
     c.nc = (int)(N < ci ? N : ci);
     const size_t pairs = (size_t)c.sc * c.nc;
     c.raw_bytes = pairs * 16 * 32 * 32 * sizeof(float);               // largest activation: 64 KB per pair

@@ -550,16 +550,20 @@ __global__ void __launch_bounds__(256) wrn_stem_kernel(const float *__restrict__
                 st1[i + k] += r[k];
                 st2[i + k] = fmaf(r[k], r[k], st2[i + k]);
             }
-            if (F16) {                                     // eval mode only: A and X planes as halves
+            if (F16) {                                     // A and X planes as halves
                 uint2 hh, ll;
                 const uint2 z2 = make_uint2(0u, 0u);
                 __half *ah = reinterpret_cast<__half *>(a_hi), *al = reinterpret_cast<__half *>(a_lo);
                 __half *xh = reinterpret_cast<__half *>(x_hi), *xl = reinterpret_cast<__half *>(x_lo);
-                wrn_split_h4(y[0], y[1], y[2], y[3], hh, ll);
-                *reinterpret_cast<uint2 *>(ah + off + i) = hh;
-                *reinterpret_cast<uint2 *>(al + off + i) = ll;
-                *reinterpret_cast<uint2 *>(ah + off + 16 + i) = z2;
-                *reinterpret_cast<uint2 *>(al + off + 16 + i) = z2;
+                if (bn) {
+                    wrn_split_h4(y[0], y[1], y[2], y[3], hh, ll);
+                    *reinterpret_cast<uint2 *>(ah + off + i) = hh;
+                    *reinterpret_cast<uint2 *>(al + off + i) = ll;
+                    *reinterpret_cast<uint2 *>(ah + off + 16 + i) = z2;
+                    *reinterpret_cast<uint2 *>(al + off + 16 + i) = z2;
+                } else {
+                    *reinterpret_cast<float4 *>(raw16 + (off >> 1) + i) = make_float4(r[0], r[1], r[2], r[3]);
+                }
                 wrn_split_h4(r[0], r[1], r[2], r[3], hh, ll);
                 *reinterpret_cast<uint2 *>(xh + off + i) = hh;
                 *reinterpret_cast<uint2 *>(xl + off + i) = ll;
@@ -689,6 +693,7 @@ __global__ void wrn_bn_finalize_kernel(double *__restrict__ stats, const float *
 }
 
 // raw [P][hw][C] -> A planes split(relu(a_j v + b_j)) [P][hw][c_pad] (channels >= C zero) and, optionally, X planes split(v)
+template <bool F16>
 __global__ void __launch_bounds__(256) wrn_bn_apply_kernel(const float *__restrict__ raw, const float *__restrict__ ab, int C,
                                                            int c_pad, int hw, int batch, int64_t total4, float *__restrict__ a_hi,
                                                            float *__restrict__ a_lo, float *__restrict__ x_hi,
@@ -699,6 +704,24 @@ __global__ void __launch_bounds__(256) wrn_bn_apply_kernel(const float *__restri
         const int64_t px = i / cp4;
         const int j = (int)(px / hw) / batch;
         float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), lv = hv, xh = hv, xl = hv;
+        if (F16) {                                             // the same planes as halves
+            uint2 yh2 = make_uint2(0u, 0u), yl2 = yh2, xh2 = yh2, xl2 = yh2;
+            if (c < C) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(raw + px * C + c));
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ab + (int64_t)j * 2 * C + c));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(ab + (int64_t)j * 2 * C + C + c));
+                wrn_split_h4(relu_nan(fmaf(a4.x, v.x, b4.x)), relu_nan(fmaf(a4.y, v.y, b4.y)), relu_nan(fmaf(a4.z, v.z, b4.z)),
+                             relu_nan(fmaf(a4.w, v.w, b4.w)), yh2, yl2);
+                wrn_split_h4(v.x, v.y, v.z, v.w, xh2, xl2);
+            }
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a_hi) + px * c_pad + c) = yh2;
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a_lo) + px * c_pad + c) = yl2;
+            if (x_hi) {
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(x_hi) + px * c_pad + c) = xh2;
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(x_lo) + px * c_pad + c) = xl2;
+            }
+            continue;
+        }
         if (c < C) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(raw + px * C + c));
             const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ab + (int64_t)j * 2 * C + c));
@@ -1106,8 +1129,8 @@ extern "C" size_t ursa_wrn_bn_update_workspace(int64_t N, int batch, int depth, 
     return L.total;
 }
 
-extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch, int depth,
-                                  int widen, int C, void *workspace, size_t workspace_bytes, void *stream) {
+static int wrn_bn_update_impl(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch, int depth,
+                              int widen, int C, void *workspace, size_t workspace_bytes, void *stream, bool f16) {
     URSA_REQUIRE(bank_row && buf_row && x && workspace, "ursa_wrn_bn_update: null pointer");
     static thread_local WrnPlan pl;
     WrnTrainLayout L;
@@ -1133,7 +1156,7 @@ extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const f
     float *ab = reinterpret_cast<float *>(tail + L.packed_bytes + L.stats_bytes);
     const int n = pl.n;
 
-    if (int rc = wrn_pack_sample(pl, bank_row, buf_row, packed, st, false)) return rc;
+    if (int rc = wrn_pack_sample(pl, bank_row, buf_row, packed, st, false, f16)) return rc;
     URSA_CUDA(cudaMemsetAsync(stats, 0, L.stats_bytes, st));
     auto finalize = [&](int64_t gw, int64_t gb, int64_t bufo, int Cc, int hw, int nc, int64_t n_before) {
         wrn_bn_finalize_kernel<<<(Cc + 127) / 128, 128, 0, st>>>(stats, bank_row + gw, bank_row + gb, Cc, hw, nc, batch, n_before,
@@ -1143,15 +1166,20 @@ extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const f
         const int64_t total4 = (int64_t)nc * hw * (c_pad / 4);
         int64_t blocks = (total4 + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        wrn_bn_apply_kernel<<<(int)blocks, 256, 0, st>>>(raw, ab, Cc, c_pad, hw, batch, total4, ah, al, xh, xl);
+        if (f16) wrn_bn_apply_kernel<true><<<(int)blocks, 256, 0, st>>>(raw, ab, Cc, c_pad, hw, batch, total4, ah, al, xh, xl);
+        else wrn_bn_apply_kernel<false><<<(int)blocks, 256, 0, st>>>(raw, ab, Cc, c_pad, hw, batch, total4, ah, al, xh, xl);
     };
     for (int64_t i0 = 0; i0 < N; i0 += L.nc) {
         const int nc = (int)((N - i0 < L.nc) ? (N - i0) : L.nc);
         int xi = 0;
         float *cur = Ra, *nxt = Rb;
         const WrnBlock &B0 = pl.blocks[0][0];
-        wrn_stem_kernel<false><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
-                                            nullptr, Xh[xi], Xl[xi], cur, stats, batch);
+        if (f16)
+            wrn_stem_kernel<true><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
+                                                      nullptr, Xh[xi], Xl[xi], cur, stats, batch);
+        else
+            wrn_stem_kernel<false><<<nc, 256, 0, st>>>(x + i0 * 3 * 32 * 32, bank_row + pl.conv1_w, bank_row + pl.conv1_b, nullptr, nullptr,
+                                                       nullptr, Xh[xi], Xl[xi], cur, stats, batch);
         URSA_LAUNCH_CHECK("wrn_stem_kernel");
         finalize(B0.bn1_w, B0.bn1_b, B0.bn1_buf, 16, 1024, nc, i0);
         apply(cur, 16, 32, 1024, nc, A1h, A1l, nullptr, nullptr);
@@ -1164,14 +1192,14 @@ extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const f
                 WrnConvArgs c1 = {};
                 c1.bias = packed + B.p_bias1; c1.out_raw = T; c1.stats = stats; c1.batch = batch;
                 if (int rc = wrn_launch_conv(A1h, A1l, hw, B.cin_p, nullptr, nullptr, 0, B.cout, 1, nc, packed + B.p_w1_hi,
-                                             packed + B.p_w1_lo, B.k1, c1, st))
+                                             packed + B.p_w1_lo, B.k1, c1, st, f16))
                     return rc;
                 finalize(B.bn2_w, B.bn2_b, B.bn2_buf, B.cout, hw * hw, nc, i0);
                 apply(T, B.cout, B.cout, hw * hw, nc, A2h, A2l, nullptr, nullptr);
                 WrnConvArgs c2 = {};
                 c2.bias = packed + B.p_bias2; c2.res = B.transition ? nullptr : cur; c2.out_raw = nxt; c2.stats = stats; c2.batch = batch;
                 if (int rc = wrn_launch_conv(A2h, A2l, hw, B.cout, Xh[xi], Xl[xi], B.transition ? B.cin_p : 0, B.cout, B.stride, nc,
-                                             packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st))
+                                             packed + B.p_w2_hi, packed + B.p_w2_lo, B.k2, c2, st, f16))
                     return rc;
                 hw /= B.stride;
                 if (NB) {
@@ -1187,4 +1215,16 @@ extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const f
         URSA_LAUNCH_CHECK("wrn train-mode kernels");
     }
     return URSA_OK;
+}
+
+extern "C" int ursa_wrn_bn_update(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch, int depth,
+                                  int widen, int C, void *workspace, size_t workspace_bytes, void *stream) {
+    return wrn_bn_update_impl(bank_row, buf_row, x, N, batch, depth, widen, C, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int ursa_wrn_bn_update_algo(const float *bank_row, float *buf_row, const float *x, int64_t N, int batch, int depth,
+                                       int widen, int C, void *workspace, size_t workspace_bytes, int algo, void *stream) {
+    URSA_REQUIRE(algo == URSA_ALGO_TCGEN05 || algo == URSA_ALGO_TCGEN05_F16, "ursa_wrn_bn_update_algo: algo must be URSA_ALGO_TCGEN05 or URSA_ALGO_TCGEN05_F16");
+    return wrn_bn_update_impl(bank_row, buf_row, x, N, batch, depth, widen, C, workspace, workspace_bytes, stream,
+                              algo == URSA_ALGO_TCGEN05_F16);
 }
