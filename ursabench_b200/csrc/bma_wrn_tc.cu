@@ -52,9 +52,8 @@ constexpr uint32_t WRN_A_BYTES = 128 * 128;        // 128 pixels x 32 channels x
 constexpr int WRN_CHUNK_IMAGES = 512;
 // FP16-split variant (F16 = true, URSA_ALGO_TCGEN05_F16): planes and filters are halves, x = hi + lo' 2^-11 (22 significant bits like
 // the TF32 split); a K block is still 32 channels = a 64-byte swizzle row; per K = 16 step hi*hi -> ACC columns, hi*lo' and lo'*hi ->
-// LO columns of the accumulator (pitch 2 * bn_tile), result = ACC + LO 2^-11 in the epilogue registers.  Half the operand bytes
-// and half the tensor-pipe time per MAC of 3xTF32 (kind::f16 runs at twice the TF32 rate): bn_tile <= 128 so that two
-// [ACC | LO] accumulators rotate.  Range: fp16's (|x| <= 65 504), overflow surfaces as NaN logits.
+// the LO accumulator, result = ACC + LO 2^-11 in the epilogue registers.  Half the operand bytes and half the tensor-pipe time per
+// MAC of 3xTF32 (kind::f16 runs at twice the TF32 rate).  Range: fp16's (|x| <= 65 504), overflow surfaces as NaN logits.
 constexpr uint32_t WRN_A_BYTES_H = 128 * 64;       // 128 pixels x 32 channels x fp16, 64-byte swizzle rows
 constexpr int WRN_MAX_STAGES_H = 8;
 constexpr float kWrnLoScale = 2048.f, kWrnLoUnscale = 1.f / 2048.f;
@@ -121,6 +120,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     __shared__ __align__(8) uint64_t empty_bar[WRN_MAX_STAGES_H];
     __shared__ __align__(8) uint64_t tfull_bar[WRN_MAX_TBUF];
     __shared__ __align__(8) uint64_t tempty_bar[WRN_MAX_TBUF];
+    __shared__ __align__(8) uint64_t lo_empty_bar;                 // FP16-split: the tile's LO accumulator has been drained
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,13 +130,18 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
     const uint32_t b_rows = (uint32_t)a.bn_tile / NCTA;        // rows of the B tile this CTA stages
     const uint32_t b_bytes = b_rows * ROW_BYTES;
     const uint32_t stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-    const uint32_t acc_pitch = (F16 ? 2u : 1u) * (uint32_t)a.bn_tile;      // TMEM columns per accumulator: [ACC | LO] in FP16 mode
+    // FP16-split TMEM layout: two rotating ACC accumulators at columns [0, bn) and [bn, 2 bn), ONE LO accumulator at [2 bn, 3 bn).
+    // LO holds the 2^-11-scaled cross terms: the truncation bias of its chain enters the result 2^-11 times smaller, so it is one
+    // chain per tile (no two-level accumulation) and is drained once, after the tile's last ACC segment -- which is what lets
+    // bn_tile stay at 160 (3 x 160 = 480 of the 512 columns) instead of 80 and halves the activation re-reads of stages 1 and 2.
+    const uint32_t acc_pitch = (uint32_t)a.bn_tile;
+    const uint32_t lo_col = 2u * (uint32_t)a.bn_tile;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int kb3 = 9 * a.kchunks, k_blocks = kb3 + a.xchunks;
     // work units: (M tile [pair], N tile), N fastest; unit u -> this CTA's tile (mt, nt)
     const int total_tiles = ((a.m_tiles + NCTA - 1) / NCTA) * a.n_tiles;
     const int first_unit = (int)blockIdx.x / NCTA, unit_stride = (int)gridDim.x / NCTA;
-    const uint32_t ntbuf = 512u / acc_pitch < (uint32_t)WRN_MAX_TBUF ? 512u / acc_pitch : (uint32_t)WRN_MAX_TBUF;
+    const uint32_t ntbuf = F16 ? 2u : (512u / acc_pitch < (uint32_t)WRN_MAX_TBUF ? 512u / acc_pitch : (uint32_t)WRN_MAX_TBUF);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -147,6 +152,7 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], NCTA * (WRN_THREADS - 64) / 32);   // one arrival per epilogue warp (of both CTAs)
         }
+        mbar_init(&lo_empty_bar, NCTA * (WRN_THREADS - 64) / 32);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -222,9 +228,14 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         if (cta_rank == 0 && elect_one()) {
             // ===== MMA issuer (the leader CTA of a pair) =====
             const uint32_t idesc = F16 ? wrn_f16_idesc(128 * NCTA, a.bn_tile) : make_tf32_idesc(128 * NCTA, a.bn_tile);
-            uint32_t st = 0, ph = 0, buf = 0, bph = 0;
+            uint32_t st = 0, ph = 0, buf = 0, bph = 0, lph = 0;
             const uint32_t nstages = (uint32_t)a.stages;
             for (int t = first_unit; t < total_tiles; t += unit_stride) {
+                uint32_t lo_acc = 0;
+                if (F16) {                                                               // the previous tile's LO has been drained
+                    mbar_wait_a(smem_u32(&lo_empty_bar), lph ^ 1u);
+                    lph ^= 1u;
+                }
                 for (int kb0 = 0, len = a.seg0; kb0 < k_blocks; kb0 += len, len = a.seg) {
                     mbar_wait_a(smem_u32(&tempty_bar[buf]), bph ^ 1u);                   // epilogue has drained this accumulator
                     tc_fence_after();
@@ -243,9 +254,10 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                             for (int k = 0; k < 2; ++k) {                                // K = 16 halves = 32 bytes of the 64-byte row
                                 const uint64_t koff = (uint64_t)((k * 32) >> 4);
                                 wrn_umma_f16<NCTA>(d_tmem, d_ahi + koff, d_bhi + koff, idesc, acc);                       // ACC
-                                wrn_umma_f16<NCTA>(d_tmem + (uint32_t)a.bn_tile, d_ahi + koff, d_blo + koff, idesc, acc);  // LO
+                                wrn_umma_f16<NCTA>(tmem_base + lo_col, d_ahi + koff, d_blo + koff, idesc, lo_acc);       // LO
                                 acc = 1;
-                                wrn_umma_f16<NCTA>(d_tmem + (uint32_t)a.bn_tile, d_alo + koff, d_bhi + koff, idesc, 1);
+                                lo_acc = 1;
+                                wrn_umma_f16<NCTA>(tmem_base + lo_col, d_alo + koff, d_bhi + koff, idesc, 1);
                             }
                         } else {
 #pragma unroll
@@ -279,8 +291,8 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
         // multiple of 16 <= 80; FP16-split: the even or the odd 16-column chunks of a tile of <= 128) =====
         const int q = warp & 3, half_id = (warp - 2) >> 2;
         const int half = a.bn_tile >> 1;
-        auto chunk_col = [&](int j) { return F16 ? (2 * j + half_id) * 16 : half_id * half + j * 16; };   // first column within the tile
-        auto chunk_on = [&](int j) { return F16 ? (2 * j + half_id) * 16 < a.bn_tile : j * 16 < half; };
+        auto chunk_col = [&](int j) { return half_id * half + j * 16; };   // first column within the tile
+        auto chunk_on = [&](int j) { return j * 16 < half; };
         const int qi = lane & 3, qb = lane & ~3;
         const int r = q * 32 + qb;                            // first pixel of this lane's quad (4 consecutive pixels of a row)
         const int w = r % WT, h = (r / WT) % HT, nl = r / (WT * HT);
@@ -306,18 +318,9 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                 for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
                     if (chunk_on(j)) {
                         uint32_t rr[16];
-                        if (F16) {
-                            uint32_t rl[16];
-                            tmem_ld16_nowait(taddr + (uint32_t)chunk_col(j), rr);
-                            tmem_ld16_nowait(taddr + (uint32_t)(a.bn_tile + chunk_col(j)), rl);
-                            tmem_wait_ld();
+                        tmem_ld16(taddr + (uint32_t)chunk_col(j), rr);
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) accr[j][e] += fmaf(__uint_as_float(rl[e]), kWrnLoUnscale, __uint_as_float(rr[e]));
-                        } else {
-                            tmem_ld16(taddr + (uint32_t)chunk_col(j), rr);
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
-                        }
+                        for (int e = 0; e < 16; ++e) accr[j][e] += __uint_as_float(rr[e]);
                     }
                 }
                 tc_fence_before();
@@ -327,6 +330,25 @@ wrn_conv_tc_kernel(const __grid_constant__ WrnMaps maps, const WrnConvArgs a) {
                     else mbar_arrive(&tempty_bar[buf]);
                 }
                 if (++buf == ntbuf) { buf = 0; bph ^= 1u; }
+            }
+            if (F16) {
+                // the commit of the tile's last segment also covers every LO MMA: add the cross terms and free the LO accumulator
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + lo_col;
+#pragma unroll
+                for (int j = 0; j < WRN_EPI_CHUNKS; ++j) {
+                    if (chunk_on(j)) {
+                        uint32_t rl[16];
+                        tmem_ld16(taddr + (uint32_t)chunk_col(j), rl);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) accr[j][e] = fmaf(__uint_as_float(rl[e]), kWrnLoUnscale, accr[j][e]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&lo_empty_bar), 0));
+                    else mbar_arrive(&lo_empty_bar);
+                }
             }
             // The TMEM layout gives a thread one pixel (row) x 16 columns: stored as is, every warp-level access touches 32
             // different 128-byte lines (32 L1 tag cycles each -- measured: the epilogue then takes ~3/4 of a tile's MMA time and
@@ -845,7 +867,8 @@ static int wrn_pick_bn_tile(int cout, bool f16) {
     for (int nt = 1; nt <= 16; ++nt) {
         if (cout % nt != 0) continue;
         const int bn = cout / nt;
-        if (f16 ? (bn <= 128 && bn % 16 == 0) : (bn <= 160 && bn % 32 == 0)) return bn;    // 3xTF32: two 16-column-granular halves
+        (void)f16;                                             // both engines: <= 160 columns (FP16-split: 3 x 160 TMEM columns)
+        if (bn <= 160 && bn % 32 == 0) return bn;              // two 16-column-granular halves
     }
     return 0;
 }
@@ -920,9 +943,10 @@ static int wrn_launch_conv(const float *a_hi, const float *a_lo, int hin, int ci
     if (stages > (f16 ? WRN_MAX_STAGES_H : WRN_MAX_STAGES)) stages = f16 ? WRN_MAX_STAGES_H : WRN_MAX_STAGES;
     if (const char *e = getenv("URSA_WRN_STAGES")) { const int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
     g.stages = stages;
-    // FP16-split: a K block is 6 MMAs of ~40-64 clk instead of 12 of 80, and its chains hold 2 (ACC) / 4 (LO) MMAs per block: 16-block
-    // segments keep the drains off the critical path (SEG 4 / 8 / 16 / 32: 231 / 260 / 274 / 277 TFLOP/s) at 3e-6 from fp64
-    g.seg = f16 ? 4 * WRN_SEG : WRN_SEG;
+    // FP16-split: a K block is 6 MMAs of 80 clk instead of 12, and the ACC chain holds 2 MMAs per block: 24-block segments keep the
+    // drains off the critical path.  WRN-28-10, 160-column tiles, SEG 8 / 16 / 24 / 32 / 48: 308 / 332 / 352 / 358 / 364 TFLOP/s at
+    // 3.1 / 3.2 / 2.7 / 3.7 / 7.1 e-6 from an fp64 forward (PyTorch fp32: 4.0e-6)
+    g.seg = f16 ? 6 * WRN_SEG : WRN_SEG;
     if (const char *e = getenv("URSA_WRN_SEG")) { const int v = atoi(e); if (v >= 1) g.seg = v; }      // accuracy / speed experiments
     g.seg0 = WRN_SEG0_FACTOR * g.seg;                        // ... but never more than a quarter of the K extent
     if (g.seg0 > (g.kchunks * 9 + g.xchunks) / 4) g.seg0 = (g.kchunks * 9 + g.xchunks) / 4;
