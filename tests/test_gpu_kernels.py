@@ -373,6 +373,29 @@ def test_k3_preresnet_forward_vs_torch_fp32(C, depth, S, N, Cc, algo):
     assert (P.double() / S - pbar).abs().max().item() < 1e-5
 
 
+def test_k3_preresnet_workspace_kept_flag(C):
+    """URSA_ALGO_FLAG_WS_KEPT: a second call on the caller's untouched workspace skips re-zeroing the plane-image padding and returns
+    the same bits; without the flag a scribbled workspace is re-initialised by the call itself."""
+    from ursabench_b200.models import PreResNet
+    torch.manual_seed(11)
+    ms = [PreResNet(num_classes=10, depth=8).eval() for _ in range(3)]
+    bank = torch.stack([torch.cat([p.detach().reshape(-1) for p in m.parameters()]) for m in ms]).cuda()
+    bufs = torch.stack([torch.cat([b.detach().reshape(-1) for b in m.buffers() if b.dtype == torch.float32]) for m in ms]).cuda()
+    x = torch.randn(77, 3, 32, 32, device="cuda")
+    outs = []
+    ws = None
+    for step in range(3):
+        P, E = torch.zeros(77, 10, device="cuda"), torch.zeros(77, device="cuda")
+        if step == 2:
+            ws.fill_(float("nan"))                                        # somebody else used the memory: no flag
+        algo = C.ALGO_TCGEN05_FUSED_F16 | (C.ALGO_FLAG_WS_KEPT if step == 1 else 0)
+        ws = C.bma_preresnet_forward(bank, bufs, 3, x, 8, 10, P, E, algo=algo, workspace=ws)
+        outs.append((P.clone(), E.clone()))
+    assert torch.isfinite(outs[0][0]).all()
+    for P, E in outs[1:]:
+        assert torch.equal(P, outs[0][0]) and torch.equal(E, outs[0][1])
+
+
 # ----------------------------------------------------------------------------- K3 forward, MLP on tcgen05 (3xTF32, 2xFP16-split)
 @pytest.mark.parametrize("engine", ["ALGO_TCGEN05", "ALGO_TCGEN05_F16"])
 @pytest.mark.parametrize("name,S", [("mlp", 5), ("mlp_c100", 3)])
