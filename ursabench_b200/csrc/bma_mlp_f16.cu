@@ -291,6 +291,29 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
 }
 
+// zero columns [c0, c0 + nq * 8) of a half plane [rows][pitch] (pad columns no tile writes): one 16-byte store per thread
+__global__ void __launch_bounds__(256) zero_cols_h_kernel(__half *__restrict__ p, int64_t rows, int pitch, int c0, int nq) {
+    const int64_t total = rows * nq;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / nq;
+        const int q = (int)(i - r * nq);
+        *reinterpret_cast<uint4 *>(p + r * pitch + c0 + q * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+static int zero_cols_h(__half *p, int64_t rows, int pitch, int c0, int c1, cudaStream_t st) {
+    if (c1 <= c0 || rows <= 0) return URSA_OK;
+    if ((c0 & 7) || ((c1 - c0) & 7) || (pitch & 7)) {                    // not 16-byte granular: whole plane
+        URSA_CUDA(cudaMemsetAsync(p, 0, (size_t)rows * pitch * sizeof(__half), st));
+        return URSA_OK;
+    }
+    const int nq = (c1 - c0) / 8;
+    int64_t blocks = (rows * nq + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    zero_cols_h_kernel<<<(int)blocks, 256, 0, st>>>(p, rows, pitch, c0, nq);
+    URSA_LAUNCH_CHECK("zero_cols_h_kernel");
+    return URSA_OK;
+}
+
 // fp32 [rows, cols] (ld, per-batch stride) -> zero-padded hi / lo' half planes [batch][rows_p][cols_p]
 __global__ void __launch_bounds__(256) split_f16_kernel(const float *__restrict__ src, int64_t ld_src, int64_t src_batch_stride,
                                                         int rows, int cols, __half *__restrict__ hi, __half *__restrict__ lo,
@@ -430,8 +453,9 @@ int mlp_forward_f16(const float *bank, int64_t ld_bank, int S, const float *x, i
         return URSA_OK;
     };
     if (int rc = split(x, in_dim, 0, (int)N, in_dim, x_hi, x_lo, (int)N, p.K1p, 1)) return rc;
-    // hidden-activation padding columns (hidden..K2p) are never written by a tile: zero them once
-    URSA_CUDA(cudaMemsetAsync(h1_hi, 0, 4 * (size_t)p.sc * p.h_plane * sizeof(__half), st));
+    // hidden-activation padding columns (Np1..K2p) are never written by a tile: zero those columns of the four planes (a strided
+    // memset: 1/9 of the planes at hidden = 400)
+    if (int rc = zero_cols_h(h1_hi, 4 * (int64_t)p.sc * N, p.K2p, p.Np1, p.K2p, st)) return rc;
 
     for (int s0 = 0; s0 < S; s0 += p.sc) {
         const int nb = (S - s0 < p.sc) ? (S - s0) : p.sc;
@@ -650,9 +674,8 @@ extern "C" int ursa_hmc_mlp_grad_f16(const float *theta, int64_t ld, int C, cons
                   ob3 = oW3 + (int64_t)ncls * hidden;
 
     // pads: K2p - Nph columns of the point-major activations (the N tiles cover the rest), the class pads of dlo / dloT
-    if (p.Nph < p.K2p) {
-        URSA_CUDA(cudaMemsetAsync(a1h, 0, (size_t)((char *)a1th - (char *)a1h), st));
-    }
+    for (__half *pl : {a1h, a1l, a2h, a2l, d2h, d2l})
+        if (int rc = zero_cols_h(pl, (int64_t)C * Npts, p.K2p, p.Nph, p.K2p, st)) return rc;
     URSA_CUDA(cudaMemsetAsync(dlh, 0, (size_t)((char *)logits - (char *)dlh), st));
     hmc_f16_xprep_kernel<<<148 * 4, 256, 0, st>>>(x, Npts, in_dim, p, xh, xl, xth, xtl);
     URSA_LAUNCH_CHECK("hmc_f16_xprep_kernel");
