@@ -266,13 +266,19 @@ mlp_f16_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 if (tlive) {
                     // transposed copy: lanes are consecutive rows, so every store of a warp is one contiguous segment
                     if (thi != nullptr) {
+                        // a lane pair owns rows (r, r + 1) x columns (2 i, 2 i + 1): the even lane stores column 2 i of both rows,
+                        // the odd lane column 2 i + 1 -- 4-byte stores, 128 contiguous bytes per warp and column pair (tlive is
+                        // warp-uniform: a warp's 32 rows start on a multiple of 32 and ld_t is a multiple of 64)
+                        const bool odd = lane & 1;
+                        __half *th2 = thi - (odd ? 1 : 0), *tl2 = tlo - (odd ? 1 : 0);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const __half2 hh = *reinterpret_cast<const __half2 *>(&h[i]), ll = *reinterpret_cast<const __half2 *>(&l[i]);
-                            thi[(int64_t)(col0 + 2 * i) * a.ld_t] = __low2half(hh);
-                            thi[(int64_t)(col0 + 2 * i + 1) * a.ld_t] = __high2half(hh);
-                            tlo[(int64_t)(col0 + 2 * i) * a.ld_t] = __low2half(ll);
-                            tlo[(int64_t)(col0 + 2 * i + 1) * a.ld_t] = __high2half(ll);
+                            const uint32_t ph = __shfl_xor_sync(0xffffffffu, h[i], 1), pl = __shfl_xor_sync(0xffffffffu, l[i], 1);
+                            const uint32_t oh = odd ? __byte_perm(ph, h[i], 0x7632) : __byte_perm(h[i], ph, 0x5410);
+                            const uint32_t ol = odd ? __byte_perm(pl, l[i], 0x7632) : __byte_perm(l[i], pl, 0x5410);
+                            const int64_t co = (int64_t)(col0 + 2 * i + (odd ? 1 : 0)) * a.ld_t;
+                            *reinterpret_cast<uint32_t *>(th2 + co) = oh;
+                            *reinterpret_cast<uint32_t *>(tl2 + co) = ol;
                         }
                     } else if (live) {
 #pragma unroll
