@@ -3,10 +3,11 @@
 //  variance  reference inference/swa.py:106-108                                 12 B/param
 //  draw      reference inference/swag.py:85-97 (formula; see header)            (K + 2 + S) * 4 B/param
 //
-// The draw stages [K x 1024-column] tiles of the deviation ring in shared memory with the TMA engine
-// (cp.async.bulk + mbarrier, double buffered) and contracts them with z2 [S, K] on the warp-level tensor-core MMA
-// (3xTF32), so the ring is read from HBM exactly once for all S draws.  z1 comes from Philox in-register (or from
-// memory in parity mode).
+//  gram      reference inference/subspaces.py:116-131 (first half of the PCA fit) K * 4 B/param, one pass
+//
+// The draw stages [K x 512-column] tiles of the deviation ring in shared memory with the TMA engine
+// (cp.async.bulk + mbarrier, double buffered) and contracts them with z2 [S, K] on tcgen05 (3xTF32, accumulators in TMEM),
+// so the ring is read from HBM exactly once per 30 draws.  z1 comes from Philox in-register (or from memory in parity mode).
 #include "async.cuh"
 #include "common.cuh"
 #include "tc_common.cuh"

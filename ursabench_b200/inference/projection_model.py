@@ -2,7 +2,7 @@
 
 The reference evaluates this with a dense ``[D, r] @ [r]`` product on the host for every proposal of the subspace
 samplers; here it is one launch of the K2b kernel (``ursa_swag_draw`` with z2 = t, var = 0): the ``[r, D]`` factor is
-staged tile by tile by the TMA engine and contracted on the warp-level tensor-core MMA.
+staged tile by tile by the TMA engine and contracted on tcgen05 (3xTF32, fp32 accumulate in TMEM).
 """
 import torch
 

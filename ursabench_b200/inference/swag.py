@@ -88,7 +88,7 @@ class SWAG(SWA):
 
     # -- K2b -----------------------------------------------------------------------------------------------------
     def _draw_into_bank(self, num, full_cov):
-        """Draw ``num`` weight vectors into fresh bank rows with ONE ``ursa_swag_draw`` call (one pass over the ring per 32 draws)."""
+        """Draw ``num`` weight vectors into fresh bank rows with ONE ``ursa_swag_draw`` call (one pass over the ring per 30 draws)."""
         if full_cov and self.reference_compat:
             # reference :90 dereferences self.swag_model.subspace, which does not exist (Q7)
             raise AttributeError("'%s' object has no attribute 'subspace'" % type(self.swag_model).__name__)
