@@ -174,21 +174,10 @@ __device__ __forceinline__ void emit_draws(const DrawArgs &a, int64_t c, float m
     }
 }
 
-// K = 0 (diagonal draw): nothing to stage or contract -- thread = column, 8 B read and 4 S bytes written per column
-template <bool EXTZ>
-__global__ void __launch_bounds__(kDrawThreads, 2) swag_draw_diag_kernel(const DrawArgs a) {
-    const int64_t stride = (int64_t)gridDim.x * kDrawThreads;
-    int64_t c = (int64_t)blockIdx.x * kDrawThreads + threadIdx.x;
-    float m_next = 0.f, v_next = 0.f;
-    if (c < a.D) { m_next = __ldg(a.mean + c); v_next = __ldg(a.var + c); }
-    for (; c < a.D; c += stride) {
-        const float m = m_next, sd = sqrtf(v_next);                                        // swag.py:88 var.sqrt()
-        if (c + stride < a.D) { m_next = __ldg(a.mean + c + stride); v_next = __ldg(a.var + c + stride); }   // one column ahead
-        uint32_t none[kDrawN];
-        emit_draws<false, EXTZ>(a, c, m, sd, none);
-    }
-}
-
+// K = 0 (diagonal draw) runs through the same kernel: the producer stages only the mean / var rows, no MMA is issued (the
+// commit then arrives at once) and the Gaussians skip the low-rank term.  A stand-alone thread-per-column kernel with global loads
+// was slower (1.80 vs 1.65 ms at S = 30, D = 36.5 M): its loads queued behind the 30 stores per column in the LSU (ncu:
+// long_scoreboard 5.1, lg_throttle 2.3 warp-cycles per issued instruction).
 template <bool EXTZ>
 __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const DrawArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -206,8 +195,8 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
 
     if (!producer) {
         // B operand: z2 / rank_div (swag.py:95), split hi + lo; element (s, k) at chunk (k / 4) * kBPlane + s * 16 + (k % 4) * 4
-        const float inv_div = 1.0f / a.rank_div;
-        for (int e = tid; e < kDrawN * kKP; e += kDrawThreads) {
+        const float inv_div = K > 0 ? 1.0f / a.rank_div : 0.f;
+        for (int e = tid; e < (K > 0 ? kDrawN * kKP : 0); e += kDrawThreads) {
             const int s = e & (kDrawN - 1), k = e / kDrawN;
             const float z = (s < S && k < K) ? __ldg(a.z2 + (int64_t)s * K + k) * inv_div : 0.f;
             const uint32_t h = __float_as_uint(z) & 0xFFFFE000u;
@@ -280,7 +269,8 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
                         }
                     }
                 }
-                umma_commit(smem_u32(&mma_bar[i & 1]));
+                if (K > 0) umma_commit(smem_u32(&mma_bar[i & 1]));
+                else mbar_arrive(&mma_bar[i & 1]);                               // diagonal draw: nothing to wait for
                 if (i + 2 < n_my) issue(i + 2);
             }
         }
@@ -329,17 +319,19 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
             // TMEM lane = row of the 128-column accumulator tile = 32 (warp % 4) + lane; tile warp / 4 at columns 32 (warp / 4)
             const uint32_t taddr = tmem + (uint32_t)(i & 1) * (kTmemCols / 2) + (uint32_t)(warp >> 2) * kDrawN +
                                    ((uint32_t)((warp & 3) * 32) << 16);
+            const int64_t c = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols + tid;
             uint32_t lr[kDrawN];
-            {
+            if (K > 0) {
                 uint32_t r0[16], r1[16];
                 tmem_ld16_nowait(taddr, r0);
                 tmem_ld16_nowait(taddr + 16, r1);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) { lr[e] = r0[e]; lr[16 + e] = r1[e]; }
+                if (c < a.D) emit_draws<true, EXTZ>(a, c, m, sd, lr);
+            } else {
+                if (c < a.D) emit_draws<false, EXTZ>(a, c, m, sd, lr);
             }
-            const int64_t c = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols + tid;
-            if (c < a.D) emit_draws<true, EXTZ>(a, c, m, sd, lr);
         }
         tc_fence_before();
     }
@@ -590,12 +582,6 @@ static int ew_grid(int64_t work_items) {
 template <bool EXTZ>
 static int launch_draw(const DrawArgs &a, cudaStream_t st) {
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
-    if (a.K == 0) {
-        const int64_t cap = (int64_t)sm_count() * 2;
-        swag_draw_diag_kernel<EXTZ><<<(int)(ntiles < cap ? ntiles : cap), kDrawThreads, 0, st>>>(a);
-        URSA_LAUNCH_CHECK("swag_draw_diag_kernel");
-        return URSA_OK;
-    }
     const size_t smem = kDrawSmem + 1024;                                      // + slack for the 1 KB alignment
     URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<EXTZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
