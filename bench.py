@@ -686,6 +686,12 @@ def run_extras(dev, rank, world, peak):
     ms, _ = _event_time_ms(fn, 10)
     out["k2_draw_S30_K20_wrn28x10"] = {"ms": ms, "GBps": (K + 2 + S) * 4 * D / ms / 1e6,
                                        "frac": (K + 2 + S) * 4 * D / ms / 1e6 / peak, "us_per_draw": ms * 1e3 / S}
+    fn = lambda: _C.swag_draw(bank, mean, var, D, seed=5, step=1)  # noqa: E731     (SWAG-Diag: no low-rank term)
+    for _ in range(3):
+        fn()
+    ms, _ = _event_time_ms(fn, 10)
+    out["k2_draw_S30_diag_wrn28x10"] = {"ms": ms, "GBps": (2 + S) * 4 * D / ms / 1e6, "frac": (2 + S) * 4 * D / ms / 1e6 / peak,
+                                        "us_per_draw": ms * 1e3 / S}
     fn = lambda: _C.swag_gram(ring, D)  # noqa: E731
     for _ in range(3):
         fn()
