@@ -178,7 +178,7 @@ __device__ __forceinline__ void emit_draws(const DrawArgs &a, int64_t c, float m
 // commit then arrives at once) and the Gaussians skip the low-rank term.  A stand-alone thread-per-column kernel with global loads
 // was slower (1.80 vs 1.65 ms at S = 30, D = 36.5 M): its loads queued behind the 30 stores per column in the LSU (ncu:
 // long_scoreboard 5.1, lg_throttle 2.3 warp-cycles per issued instruction).
-template <bool EXTZ>
+template <bool EXTZ, bool RING>
 __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const DrawArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int MROW = kKP;                                                   // row index of the mean (var = MROW + 1)
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool producer = warp == kDrawThreads / 32;
-    const int K = a.K, S = a.S;
+    const int K = RING ? a.K : 0, S = a.S;                                      // RING = false: the diagonal draw (K = 0)
     const int KS = (K + 7) >> 3, KC = 2 * KS;                                   // 8-k MMA steps / 4-k chunks in use
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t a_hi = sbase + kAOff, a_lo = a_hi + kABytes, b_hi = sbase + kBOff, b_lo = b_hi + kBBytes;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
                         }
                     }
                 }
-                if (K > 0) umma_commit(smem_u32(&mma_bar[i & 1]));
+                if (RING) umma_commit(smem_u32(&mma_bar[i & 1]));
                 else mbar_arrive(&mma_bar[i & 1]);                               // diagonal draw: nothing to wait for
                 if (i + 2 < n_my) issue(i + 2);
             }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kDrawThreads + 32, 1) swag_draw_kernel(const D
                                    ((uint32_t)((warp & 3) * 32) << 16);
             const int64_t c = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kTileCols + tid;
             uint32_t lr[kDrawN];
-            if (K > 0) {
+            if (RING) {
                 uint32_t r0[16], r1[16];
                 tmem_ld16_nowait(taddr, r0);
                 tmem_ld16_nowait(taddr + 16, r1);
@@ -579,13 +579,13 @@ static int ew_grid(int64_t work_items) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-template <bool EXTZ>
+template <bool EXTZ, bool RING>
 static int launch_draw(const DrawArgs &a, cudaStream_t st) {
     const int64_t ntiles = (a.D + kTileCols - 1) / kTileCols;
     const size_t smem = kDrawSmem + 1024;                                      // + slack for the 1 KB alignment
-    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<EXTZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    URSA_CUDA(cudaFuncSetAttribute(swag_draw_kernel<EXTZ, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    swag_draw_kernel<EXTZ><<<grid, kDrawThreads + 32, smem, st>>>(a);
+    swag_draw_kernel<EXTZ, RING><<<grid, kDrawThreads + 32, smem, st>>>(a);
     URSA_LAUNCH_CHECK("swag_draw_kernel");
     return URSA_OK;
 }
@@ -642,7 +642,8 @@ extern "C" int ursa_swag_draw(float *out, int64_t ld_out, const float *mean, con
         a.rank_div = rank_div;
         a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         a.step = step;
-        const int rc = z1 ? launch_draw<true>(a, st) : launch_draw<false>(a, st);
+        const int rc = K > 0 ? (z1 ? launch_draw<true, true>(a, st) : launch_draw<false, true>(a, st))
+                             : (z1 ? launch_draw<true, false>(a, st) : launch_draw<false, false>(a, st));
         if (rc) return rc;
     }
     return URSA_OK;
