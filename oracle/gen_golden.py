@@ -472,8 +472,31 @@ def gen_pca_space(R):
         t = torch.from_numpy(rng.randn(space.shape[0]).astype(np.float32))
         out[tag + "/mean"], out[tag + "/t"] = mean.numpy(), t.numpy()
         out[tag + "/projected"] = SubspaceModel(mean, space)(t).numpy().copy()
+    # pca_rank = 'mle' (subspaces.py:123-153): the live reference's branch around the restated scikit-learn <= 0.22
+    # ``_assess_dimension_`` (oracle/stubs.py binds oracle/restate.py::assess_dimension_sklearn022 in its place).  Three
+    # spectra: a clear 3-direction signal in noise, a full ring with a 5-direction signal, pure noise.
+    for tag, D, max_rank, ncollect, nsig, seed in (("mle3", 2000, 10, 10, 3, 2), ("mle5", 1500, 12, 17, 5, 3), ("mle0", 900, 8, 8, 0, 4)):
+        rng = np.random.RandomState(seed)
+        sp = R["subspaces"].PCASpace(num_parameters=D, pca_rank="mle", max_rank=max_rank)
+        basis = rng.randn(max(nsig, 1), D).astype(np.float32)
+        coef = rng.randn(ncollect, max(nsig, 1)).astype(np.float32) * (np.linspace(6.0, 3.0, max(nsig, 1))[None, :] if nsig else 0.0)
+        vecs = (coef @ basis + 0.3 * rng.randn(ncollect, D)).astype(np.float32)
+        for v in vecs:
+            sp.collect_vector(torch.from_numpy(v))
+        np.random.seed(seed)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints the chosen rank
+            space = sp.get_space()
+        out[tag + "/vecs"] = vecs
+        out[tag + "/cfg"] = np.array([D, max_rank, ncollect])
+        out[tag + "/ring"] = sp.cov_mat_sqrt.numpy().copy()
+        out[tag + "/rank"] = sp.rank.numpy().copy()
+        out[tag + "/space"] = space.numpy().copy()
+        out[tag + "/ll"] = np.asarray(sp.ll, dtype=np.float64)
+        out[tag + "/corrected_ll"] = np.asarray(sp.corrected_ll, dtype=np.float64)
+        out[tag + "/chosen"] = np.array([int(sp.pca_rank)])
     np.savez_compressed(os.path.join(OUT, "pca_space.npz"), **out)
-    print("pca_space.npz", {k: out[k].shape for k in out if k.endswith("space")})
+    print("pca_space.npz", {k: out[k].shape for k in out if k.endswith("space")}, {k: out[k] for k in out if k.endswith("chosen")})
 
 
 def gen_bn_update(R):

@@ -454,6 +454,68 @@ def pca_space(ring_rows, rank, pca_rank):
     return (sv[:k, None] * Vt[:k]).astype(np.float32)                                 # :156
 
 
+# --------------------------------------------------------------------------
+# SURVEY 8(f).3  PCASpace.get_space, pca_rank = 'mle'        inference/subspaces.py:123-153
+# The rank selection calls ``sklearn.decomposition.pca._assess_dimension_`` (subspaces.py:13,143-146), a private function of a
+# third-party dependency that is absent here: the four-argument form (spectrum, rank, n_samples, n_features) exists in
+# scikit-learn <= 0.22.x (the reference pins no version; 0.23 renamed it to ``_assess_dimension(spectrum, rank, n_samples)``
+# and 0.24 removed the ``sklearn.decomposition.pca`` module).  Its published algorithm is the Laplace-approximated evidence of
+# Minka, "Automatic choice of dimensionality for PCA" (NIPS 2000), eq. 30, restated below term by term.  Pinned in
+# tests/test_pca_space.py against the installed scikit-learn's three-argument ``_assess_dimension`` (same formula with
+# n_features = len(spectrum), which is exactly how the reference calls it: n_features = min(shape) = len(eigs); the <= 0.22
+# exponent of the 2 pi term is (m + rank + 1) / 2, the later one (m + rank) / 2 -- a constant over ranks).
+# --------------------------------------------------------------------------
+def assess_dimension_sklearn022(spectrum, rank, n_samples, n_features):
+    """log p(data | rank) of Minka's PCA model for a spectrum of covariance eigenvalues (descending)."""
+    spectrum = np.asarray(spectrum, dtype=np.float64)
+    if rank > len(spectrum):
+        raise ValueError("The tested rank cannot exceed the rank of the dataset")
+    pu = -rank * math.log(2.0)                                              # p(U): area of the Stiefel manifold
+    for i in range(rank):
+        pu += math.lgamma((n_features - i) / 2.0) - math.log(math.pi) * (n_features - i) / 2.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pl = -float(np.sum(np.log(spectrum[:rank]))) * n_samples / 2.0      # retained eigenvalues
+    if rank == n_features:
+        pv, v = 0.0, 1.0
+    else:
+        v = float(np.sum(spectrum[rank:])) / (n_features - rank)            # ML noise variance
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pv = -float(np.log(v)) * n_samples * (n_features - rank) / 2.0    # numpy's log: v = 0 gives +inf, not an error
+    m = n_features * rank - rank * (rank + 1.0) / 2.0                       # degrees of freedom of U
+    pp = math.log(2.0 * math.pi) * (m + rank + 1.0) / 2.0
+    pa = 0.0                                                                # log |A_Z|, the Hessian determinant
+    spectrum_ = spectrum.copy()
+    spectrum_[rank:n_features] = v
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(rank):
+            for j in range(i + 1, len(spectrum)):
+                pa += float(np.log((spectrum[i] - spectrum[j]) * (1.0 / spectrum_[j] - 1.0 / spectrum_[i]))) + math.log(n_samples)
+    return pu + pl + pv + pp - pa / 2.0 - rank * math.log(n_samples) / 2.0
+
+
+def pca_mle_rank(eigs, n_rows, n_cols):
+    """The reference's post-selection (subspaces.py:133-151): eigs = s**2 of the [n_rows, n_cols] matrix A; returns
+    (ll, corrected_ll, chosen rank = nanargmax(corrected_ll)).  Candidate ranks are 0 .. len(eigs) - 1."""
+    eigs = np.asarray(eigs, dtype=np.float64)
+    ll = np.zeros(len(eigs))
+    correction = np.zeros(len(eigs))
+    for rank in range(len(eigs)):
+        m = n_cols * rank - rank * (rank + 1) / 2.0                          # :139
+        correction[rank] = 0.5 * m * np.log(n_rows)                          # :140
+        ll[rank] = assess_dimension_sklearn022(eigs, rank, n_samples=max(n_rows, n_cols), n_features=min(n_rows, n_cols))
+    corrected = ll - correction
+    return ll, corrected, int(np.nanargmax(corrected))
+
+
+def pca_space_mle(ring_rows, rank):
+    """get_space of PCASpace(pca_rank='mle') (subspaces.py:123-153): full-rank SVD, Minka's criterion, first k components."""
+    full = pca_space(ring_rows, rank, rank).astype(np.float64)               # s[:, None] * Vt, all r components
+    A = _f32(ring_rows)
+    eigs = np.sum(full * full, axis=1)                                       # s**2
+    ll, corrected, k = pca_mle_rank(eigs, A.shape[0], A.shape[1])
+    return full[:k].astype(np.float32), k, ll, corrected
+
+
 def subspace_project(mean, cov_factor, t):
     """mean + cov_factor^T t (projection_model.py:14)."""
     return (_f32(mean).astype(np.float64) + _f32(cov_factor).astype(np.float64).T @ _f32(t).astype(np.float64)).astype(np.float32)

@@ -78,7 +78,11 @@ def install(root=None):
         if name not in sys.modules:
             _module(name, **attrs)
     if "sklearn.decomposition.pca" not in sys.modules:
-        _module("sklearn.decomposition.pca", _assess_dimension_=lambda *a, **k: 0.0)
+        # scikit-learn <= 0.22's private four-argument function, absent from the installed release: the restatement of its
+        # published algorithm (oracle/restate.py::assess_dimension_sklearn022) stands in, so the reference's own 'mle'
+        # branch (subspaces.py:133-153) runs around it.
+        from . import restate as _restate
+        _module("sklearn.decomposition.pca", _assess_dimension_=_restate.assess_dimension_sklearn022)
     if "wandb" not in sys.modules:
         try:
             import wandb  # noqa: F401

@@ -26,6 +26,81 @@ def test_oracle_pca_space_matches_reference_golden(tag):
     np.testing.assert_allclose(proj, g[tag + "/projected"], atol=1e-5, rtol=1e-5)
 
 
+MLE_TAGS = ["mle3", "mle5", "mle0"]
+
+
+def test_restated_assess_dimension_matches_installed_sklearn():
+    """Pin of oracle/restate.py::assess_dimension_sklearn022 (the <= 0.22 four-argument function the reference imports): the
+    installed scikit-learn's three-argument ``_assess_dimension`` is the same formula with n_features = len(spectrum), up to
+    one rank-independent constant."""
+    _pca = pytest.importorskip("sklearn.decomposition._pca")
+    rng = np.random.RandomState(0)
+    for n in (4, 9, 20):
+        spectrum = np.sort(rng.gamma(2.0, 1.0, n))[::-1].copy()
+        for n_samples in (n, 50, 36546980):
+            for rank in range(1, n):
+                want = _pca._assess_dimension(spectrum, rank, n_samples)
+                got = R.assess_dimension_sklearn022(spectrum, rank, n_samples, n)
+                # 0.23 changed the prior-volume exponent from (m + rank + 1) / 2 to (m + rank) / 2: a rank-independent
+                # constant, log(2 pi) / 2, which no argmax over ranks sees
+                assert got - 0.5 * np.log(2.0 * np.pi) == pytest.approx(want, rel=1e-12, abs=1e-9), (n, n_samples, rank)
+
+
+@pytest.mark.parametrize("tag", MLE_TAGS)
+def test_oracle_and_host_mle_rank_match_reference_golden(tag):
+    """pca_rank='mle' (subspaces.py:123-153): golden = the live reference's branch; the oracle restatement and the product's
+    host-side criterion (PCASpace.minka_log_evidence, no device work) both reproduce its evidence curve and chosen rank."""
+    from ursabench_b200.inference.subspaces import PCASpace
+    g = np.load(GOLD)
+    D, max_rank, ncollect = (int(v) for v in g[tag + "/cfg"])
+    rank = int(g[tag + "/rank"][0])
+    space, k, ll, corrected = R.pca_space_mle(g[tag + "/ring"], rank)
+    assert k == int(g[tag + "/chosen"][0]) and space.shape == g[tag + "/space"].shape == (k, D)
+    np.testing.assert_allclose(ll, g[tag + "/ll"], rtol=1e-4)                    # the reference's spectrum is float32
+    np.testing.assert_allclose(corrected, g[tag + "/corrected_ll"], rtol=1e-4)
+    if k:
+        np.testing.assert_allclose(space, g[tag + "/space"], atol=2e-5 * np.abs(g[tag + "/space"]).max(), rtol=1e-4)
+    A = g[tag + "/ring"].astype(np.float64) / max(1, rank - 1) ** 0.5
+    eigs = np.linalg.svd(A, compute_uv=False) ** 2
+    host = PCASpace.minka_log_evidence(eigs, n_samples=max(A.shape), n_features=min(A.shape)).numpy()
+    np.testing.assert_allclose(host, ll, rtol=1e-7)            # eigenvalues from two SVD routes
+    np.testing.assert_allclose(host, g[tag + "/ll"], rtol=1e-4)
+
+
+def test_host_mle_evidence_degenerate_spectrum_is_nan_not_an_error():
+    """Equal or zero eigenvalues put a non-positive number under a logarithm: the reference gets NaN / -inf there and
+    nanargmax skips it (subspaces.py:151)."""
+    from ursabench_b200.inference.subspaces import PCASpace
+    eigs = np.array([4.0, 4.0, 1.0, 0.0])
+    host = PCASpace.minka_log_evidence(eigs, n_samples=100, n_features=4).numpy()
+    with np.errstate(all="ignore"):
+        want = np.array([R.assess_dimension_sklearn022(eigs, k, 100, 4) for k in range(4)])
+    assert np.isfinite(host[0]) and host[0] == pytest.approx(want[0], rel=1e-12)
+    assert np.array_equal(np.isnan(host), np.isnan(want))
+    assert np.array_equal(np.isposinf(host), np.isposinf(want)) and np.array_equal(np.isneginf(host), np.isneginf(want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", MLE_TAGS)
+def test_pca_space_mle_on_device_matches_reference_golden(tag, capsys):
+    from ursabench_b200.inference import PCASpace
+    g = np.load(GOLD)
+    D, max_rank, ncollect = (int(v) for v in g[tag + "/cfg"])
+    sp = PCASpace(num_parameters=D, pca_rank="mle", max_rank=max_rank, device="cuda")
+    for v in g[tag + "/vecs"]:
+        sp.collect_vector(torch.from_numpy(v).cuda())
+    space = sp.get_space()
+    ref = g[tag + "/space"]
+    assert "PCA Rank is" in capsys.readouterr().out                                          # reference :152
+    assert sp.pca_rank == int(g[tag + "/chosen"][0]) and tuple(space.shape) == ref.shape and space.is_cuda
+    np.testing.assert_allclose(sp.ll, g[tag + "/ll"], rtol=1e-4)
+    np.testing.assert_allclose(sp.corrected_ll, g[tag + "/corrected_ll"], rtol=1e-4)
+    if ref.shape[0]:
+        np.testing.assert_allclose(space.cpu().numpy(), ref, atol=5e-5 * np.abs(ref).max(), rtol=1e-3)
+    again = sp.get_space()                                # pca_rank is now the chosen integer (reference :151): integer branch
+    assert again.shape[0] == max(1, ref.shape[0])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["wrap", "short"])
 def test_pca_space_on_device_matches_reference_golden(tag):

@@ -5,9 +5,12 @@ matrix with ``torch.cat`` on every collect (:85-89); here the ring is one preall
 buffer and the K2a kernel writes the new row in place (slot = collects mod max_rank).  ``cov_mat_sqrt`` presents the
 rows oldest-first like the reference.  ``PCASpace.get_space`` runs on the device: Gram matrix of the ring
 in one streaming pass (``ursa_swag_gram``), eigen-decomposition of the K x K matrix in fp64, components s V^T = U^T A by
-one K2b-shaped pass (``ursa_swag_draw`` with z2 = U^T, var = 0).  FreqDir / Random spaces and the ``'mle'`` rank selection
-(Minka's criterion through a private sklearn function) are out of scope.
+one K2b-shaped pass (``ursa_swag_draw`` with z2 = U^T, var = 0).  ``pca_rank='mle'`` (Minka's criterion, which the reference
+reaches through a private scikit-learn <= 0.22 function) is evaluated on the <= 24 eigenvalues on the host in fp64.  FreqDir /
+Random spaces are out of scope.
 """
+import math
+
 import torch
 
 from .. import _C
@@ -112,14 +115,70 @@ class PCASpace(CovarianceSpace):
         sgn[sgn == 0] = 1.0
         return lam.sqrt(), U * sgn[None, :], rows
 
+    @staticmethod
+    def minka_log_evidence(eigs, n_samples, n_features):
+        """Laplace-approximated log evidence of the PCA model for every candidate rank 0 .. len(eigs) - 1 (Minka, "Automatic
+        choice of dimensionality for PCA", 2000, eq. 30) as the reference evaluates it through scikit-learn <= 0.22's
+        ``_assess_dimension_(spectrum, rank, n_samples, n_features)`` (subspaces.py:13,143-146).  ``eigs``: descending
+        covariance eigenvalues, fp64 on the host -- at most ``DRAW_MAX_K`` numbers, the ring itself never leaves the device.
+        A non-positive argument of a logarithm gives NaN / -inf like the reference's; the caller's nanargmax skips it."""
+        lam = torch.as_tensor(eigs, dtype=torch.float64)
+        r = lam.numel()
+        logn = math.log(n_samples)
+        out = torch.full((r,), float("nan"), dtype=torch.float64)
+        half_dims = (n_features - torch.arange(r, dtype=torch.float64)) / 2.0
+        stiefel = torch.lgamma(half_dims) - math.log(math.pi) * half_dims                 # one term per retained direction
+        for k in range(r):
+            kept, rest = lam[:k], lam[k:]
+            if k == n_features:
+                noise, log_noise_term = 1.0, 0.0
+            else:
+                noise = rest.sum() / (n_features - k)                                     # ML noise variance
+                log_noise_term = float(-torch.log(noise) * n_samples * (n_features - k) / 2.0)
+            dof = n_features * k - k * (k + 1.0) / 2.0
+            smoothed = lam.clone()
+            smoothed[k:n_features] = noise
+            # log |A_Z|: pairs (i < j), i among the retained directions
+            gap = kept[:, None] - lam[None, :]
+            inv_gap = 1.0 / smoothed[None, :] - 1.0 / smoothed[:k, None]
+            pair = torch.triu(torch.ones(k, r, dtype=torch.bool), diagonal=1)
+            hess = (torch.log((gap * inv_gap)[pair]) + logn).sum() if k else torch.zeros((), dtype=torch.float64)
+            out[k] = (-k * math.log(2.0) + float(stiefel[:k].sum())
+                      - float(torch.log(kept).sum()) * n_samples / 2.0
+                      + log_noise_term
+                      + math.log(2.0 * math.pi) * (dof + k + 1.0) / 2.0
+                      - float(hess) / 2.0
+                      - k * logn / 2.0)
+        return out
+
+    def select_mle_rank(self, s):
+        """Post-selection of the reference's ``'mle'`` branch (subspaces.py:133-151): evidence of every rank 0 .. r - 1 minus
+        the 0.5 m log(rows) correction, rank = nanargmax.  Sets ``ll``, ``corrected_ll`` and -- like the reference -- overwrites
+        ``pca_rank`` with the chosen integer, so later calls take the integer branch."""
+        r, D = int(s.numel()), self.num_parameters
+        ll = self.minka_log_evidence(s.double() ** 2, n_samples=max(r, D), n_features=min(r, D))
+        ranks = torch.arange(r, dtype=torch.float64)
+        correction = 0.5 * (D * ranks - ranks * (ranks + 1) / 2.0) * math.log(r)          # reference :139-140
+        corrected = ll - correction
+        if bool(torch.isnan(corrected).all()):
+            raise ValueError("All-NaN slice encountered")                                # numpy.nanargmax's error
+        k = int(torch.where(torch.isnan(corrected), torch.full_like(corrected, -float("inf")), corrected).argmax())
+        self.ll, self.corrected_ll = ll.numpy(), corrected.numpy()
+        self.pca_rank = k
+        print("PCA Rank is: ", k)                                                         # reference :152
+        return k
+
     def get_space(self):
-        if self.pca_rank == "mle":
-            raise NotImplementedError("PCASpace(pca_rank='mle'): Minka's rank selection (sklearn's private "
-                                      "_assess_dimension_) is outside this engine's hot path")
         s, U, rows = self.decompose()
         rank = int(self.rank.item())
-        k = max(1, min(int(self.pca_rank), rank))                                         # reference :128
         D = self.num_parameters
+        if self.pca_rank == "mle":
+            k = self.select_mle_rank(s[:max(1, rank)])                                    # reference :123-126: all components
+            if k == 0:                                                                    # s[:0, None] * Vt[:0]
+                self.singular_values = s[:0]
+                return torch.empty(0, D, dtype=torch.float32, device=self.device)
+        else:
+            k = max(1, min(int(self.pca_rank), rank))                                     # reference :128
         zeros = torch.zeros(self.ld, dtype=torch.float32, device=self.device)
         out = torch.empty(k, self.ld, dtype=torch.float32, device=self.device)
         z2 = U[:, :k].t().contiguous().to(device=self.device, dtype=torch.float32)        # s V^T = U^T A
