@@ -116,3 +116,52 @@ def test_csghmc_class_samples_the_gaussian_target():
     # samples come from the low-lr tail of each cycle, where the discretisation bias vanishes but the chain has had
     # ~350 noisy epochs to equilibrate; allow 6 % on the covariance scale
     _check(_stack(out), mean, cov1, n_eff=CHAINS, disc=0.06)
+
+
+def test_swag_low_rank_draws_follow_the_documented_gaussian_law():
+    """Row a7, low-rank branch (swag.py:88-97): the reference's own branch raises, so no golden can pin it; the
+    formula is pinned to the restatement elsewhere (test_k2_draw_matches_oracle) and the LAW is checked here.  12 000 draws
+    of the production path (30 draws per launch, Philox z1 generated in the kernel, z2 from torch's device generator the
+    way ``SWAG._draw_into_bank`` does) must have mean = SWA mean and covariance diag(var) + R^T R / (max_rank - 1) within
+    6 standard errors per entry, and draws of the same launch must be uncorrelated."""
+    from ursabench_b200 import _C
+    D, K, S, LAUNCHES, max_rank = 301, 6, 30, 400, 20                     # D: two column tiles + a ragged tail, ld = 304
+    rng = np.random.RandomState(3)
+    ld = (D + 3) // 4 * 4
+    mean = rng.randn(D)
+    var = 0.05 + rng.rand(D)
+    ring = rng.randn(K, D) * np.linspace(3.0, 0.5, K)[:, None]
+
+    def padded(a):
+        t = torch.zeros(a.shape[:-1] + (ld,), device=DEV)
+        t[..., :D] = torch.from_numpy(a).float().to(DEV)
+        return t
+
+    mean_d, var_d, ring_d = padded(mean), padded(var), padded(ring)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(1234)
+    out = torch.empty(LAUNCHES, S, ld, device=DEV)
+    for step in range(LAUNCHES):
+        z2 = torch.randn(S, K, device=DEV, generator=gen)
+        _C.swag_draw(out[step], mean_d, var_d, D, ring=ring_d, z2=z2, rank_div=float((max_rank - 1) ** 0.5), seed=77, step=step)
+    x = out[..., :D].double().cpu().numpy()                               # [LAUNCHES, S, D]
+    mean32, var32, ring32 = (t[..., :D].double().cpu().numpy() for t in (mean_d, var_d, ring_d))
+    cov = np.diag(var32) + ring32.T @ ring32 / (max_rank - 1)
+    flat = x.reshape(-1, D)
+    n = flat.shape[0]
+    se_mean = np.sqrt(np.diag(cov) / n)
+    assert np.all(np.abs(flat.mean(0) - mean32) <= 6 * se_mean), np.abs((flat.mean(0) - mean32) / se_mean).max()
+    emp = np.cov(flat.T)
+    se_cov = np.sqrt((np.outer(np.diag(cov), np.diag(cov)) + cov ** 2) / n)
+    z = np.abs(emp - cov) / se_cov
+    assert z.max() <= 6.0, (z.max(), np.unravel_index(z.argmax(), z.shape))
+    # not a diagonal law passing by accident: the low-rank part carries real correlations
+    corr = cov / np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+    assert np.abs(corr - np.eye(D)).max() > 0.3
+    # draws s != s' of one launch share the ring pass and the Philox blocks (six normals per block): they must still be
+    # independent.  Standardised residuals of draw 0 vs draw 1, and of two draws served by the SAME Philox block (0 and 5)
+    res = (x - mean32) / np.sqrt(np.diag(cov))
+    for a, b in ((0, 1), (0, 5), (6, 29)):
+        per_launch = (res[:, a, :] * res[:, b, :]).mean(1)                # one number per launch, iid over launches, mean 0
+        t = per_launch.mean() / (per_launch.std(ddof=1) / np.sqrt(LAUNCHES))
+        assert abs(t) <= 5.0, (a, b, t)
