@@ -8,6 +8,7 @@ forward otherwise) and accumulates  sum_s softmax_s  and  sum_s entropy(smooth(s
 ``ursa_bma_accumulate``; the tasks derive their own statistics from those two accumulators.
 """
 import copy
+import os
 import weakref
 
 import torch
@@ -18,6 +19,7 @@ from ..flat import FlatParams
 
 _LOGIT_CHUNK_BYTES = 256 << 20
 _PACK_BATCH = 8            # = the conv forwards' sample chunk
+_PACK_SPLIT_MIN = int(os.environ.get("URSA_PACK_SPLIT_MIN", "4"))    # lists longer than this are packed in overlapped sub-batches
 
 
 _ARCH_CACHE = weakref.WeakKeyDictionary()
@@ -191,10 +193,16 @@ class BMAAccumulator:
             # one H2D per sample instead of 2 per batch -- in sub-batches, so that packing sub-batch i + 1 on the host
             # (a Python walk over ~100 tensors per module) overlaps the forward of sub-batch i on the device
             # The first sub-batch is small: nothing runs on the device while it is being packed.
-            step = _PACK_BATCH if len(plain) > 2 * _PACK_BATCH else len(plain)
+            # (≈ 1 ms of host time per PreResNet-20 module: a rank's 12-sample share of an 8-rank evaluation packed in one go
+            # left the device idle for a fifth of the call.)
+            # An MLP module packs in microseconds and its whole evaluation is a few ms: only long lists are split there.
+            split_min = _PACK_SPLIT_MIN if arch[0] != "mlp" else 2 * _PACK_BATCH
+            step = _PACK_BATCH if len(plain) > split_min else len(plain)
             s0 = 0
             while s0 < len(plain):
-                n = min(2, step) if s0 == 0 and len(plain) > step else step
+                n = 2 if s0 == 0 and len(plain) > split_min else step
+                if len(plain) - (s0 + n) == 1 and n > 2:    # no one-module tail: leave two for the last launch chain
+                    n -= 1
                 bank = SampleBank.from_modules(plain[s0:s0 + n], self.device)
                 self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
                 self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
