@@ -604,6 +604,33 @@ def test_prediction_pair_shards_sum_to_the_unsharded_result(U):
     assert torch.equal(oi_a, oi_b)
 
 
+def test_host_module_lists_are_packed_in_overlapped_sub_batches(U, monkeypatch):
+    """A list of 5+ conv-net modules goes down as sub-batches (2 first, then up to 8, never a one-module tail) so that packing
+    overlaps the device; the result must not depend on the split, on whole lists or on a rank's partial image range."""
+    from ursabench_b200.tasks import _engine
+    ms, loaders = _preresnet8_ensemble(U, n_models=11, n=150)
+    sizes = []
+    orig = _engine.SampleBank.from_modules
+    monkeypatch.setattr(_engine.SampleBank, "from_modules", classmethod(lambda cls, models, device: (sizes.append(len(models)), orig(models, device))[1]))
+    split = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    split.update_statistics(ms, output_performance=False)
+    assert sizes == [2, 7, 2] and split.last_engine == "fused_preresnet"
+    del sizes[:]
+    part = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    part.accumulate(ms, [(i, 32, 128) for i in range(5)])
+    assert sizes == [2, 3]
+    monkeypatch.setattr(_engine, "_PACK_SPLIT_MIN", 99)
+    del sizes[:]
+    whole = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    whole.update_statistics(ms, output_performance=False)
+    assert sizes == [11]
+    assert float((split._proba - whole._proba).abs().max()) <= 2e-6
+    assert float((split._entropy - whole._entropy).abs().max()) <= 2e-5
+    whole5 = U.tasks.Prediction(loaders, 10, DEV, ["error_rate"])
+    whole5.accumulate(ms, [(i, 32, 128) for i in range(5)])
+    assert float((part._proba - whole5._proba).abs().max()) <= 2e-6 and float(part._proba[:32].abs().max()) == 0.0
+
+
 def test_tensor_shaped_loader_fast_path_equals_iteration(U):
     """A sequential DataLoader over a TensorDataset is ingested without re-collating; a shuffled-off custom dataset is
     iterated -- both must give the same resident inputs and targets."""

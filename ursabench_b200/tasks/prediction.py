@@ -35,7 +35,7 @@ class Prediction(_Task, BMAAccumulator):
         super().__init__(dataloader, num_classes, device)
         self.data_loader = dataloader["in_distribution_test"]
         self._setup(self.data_loader, num_classes, device, engine)   # engine='generic' forces the per-sample PyTorch forward
-        self._y = self.targets.to(self.device).long().contiguous()
+        self._y = self._y_dev.long().contiguous()                    # uploaded by _setup, ahead of the images
         self.distributed = distributed
         self.replicated_samples = bool(replicated_samples)
         self.num_samples_collected = 0
