@@ -658,7 +658,7 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[CTC_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[CTC_MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar, sc_full_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float bn_s[128];
 
@@ -675,13 +675,37 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     const uint32_t tmem_cols = (a.has_sc ? 4 : 2) * a.cout;     // [ACC | LO | SC_ACC | SC_LO]: 64 .. 256 columns
     const int n_kb = a.has_sc ? 10 : 9;
 
+    // K blocks in ISSUE order: the shortcut block first (its accumulators are drained by the epilogue warps while the nine
+    // taps are still streaming in), then taps 0 .. 8
+    const int pass_in = s * a.n_groups_in + n0 / a.g_in, g0 = n0 % a.g_in;
+    auto issue_loads = [&](int k) {
+        const int st = k % a.stages;
+        const uint32_t fb = smem_u32(&full_bar[st]);
+        mbar_expect_tx_a(fb, stage_bytes);
+        const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
+        const int tap = k - a.has_sc;
+        if (tap < 0) {                                               // shortcut: pixels (2 oh, 2 ow) of the raw rows
+            tma_load_5d_a(base, &maps.r, 0, 0, h0, g0, pass_in, fb);
+            tma_load_3d_a(base + A_BYTES, &maps.bsc, 0, 0, s, fb);
+            return;
+        }
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const int mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);          // parity of (kh - 1, kw - 1)
+        tma_load_5d_a(base, &maps.a[mi], 0, (kw - 1) >> 1, h0 + ((kh - 1) >> 1), g0, pass_in, fb);
+        tma_load_3d_a(base + A_BYTES, &maps.b, tap * 2 * CIN, 0, s, fb);
+    };
+    const int n_early = a.stages < n_kb ? a.stages : n_kb;
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(&tmem_full_bar, 1);
+        mbar_init(&sc_full_bar, 1);
         fence_barrier_init();
+        // a CTA lives for one tile: the first round of loads leaves before the CTA-wide sync (TMEM allocation, BatchNorm
+        // constants) instead of after it -- the stages are empty by construction
+        for (int k = 0; k < n_early; ++k) issue_loads(k);
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
     if (warp >= 2) {
@@ -695,46 +719,35 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
 
     if (warp == 0) {
         if (elect_one()) {
-            const int pass_in = s * a.n_groups_in + n0 / a.g_in, g0 = n0 % a.g_in;
-            for (int tap = 0; tap < n_kb; ++tap) {
-                const int st = tap % a.stages;
-                const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
-                const int kh = tap / 3, kw = tap - kh * 3;
-                mbar_wait_a(smem_u32(&empty_bar[st]), ph ^ 1u);
-                const uint32_t fb = smem_u32(&full_bar[st]);
-                mbar_expect_tx_a(fb, stage_bytes);
-                const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
-                if (tap == 9) {                                          // shortcut: pixels (2 oh, 2 ow) of the raw rows
-                    tma_load_5d_a(base, &maps.r, 0, 0, h0, g0, pass_in, fb);
-                    tma_load_3d_a(base + A_BYTES, &maps.bsc, 0, 0, s, fb);
-                    continue;
-                }
-                const int mi = ((kh + 1) & 1) * 2 + ((kw + 1) & 1);      // parity of (kh - 1, kw - 1)
-                tma_load_5d_a(base, &maps.a[mi], 0, (kw - 1) >> 1, h0 + ((kh - 1) >> 1), g0, pass_in, fb);
-                tma_load_3d_a(base + A_BYTES, &maps.b, tap * 2 * CIN, 0, s, fb);
+            for (int k = n_early; k < n_kb; ++k) {
+                const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
+                mbar_wait_a(smem_u32(&empty_bar[k % a.stages]), ph ^ 1u);
+                issue_loads(k);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = make_f16_idesc(128, a.cout);
             // a row = [hi(16 ch) | lo'(16 ch)] per 16-channel group: hi of K step ks at 64 ks bytes, lo' 32 bytes further
-            for (int tap = 0; tap < n_kb; ++tap) {
-                const int st = tap % a.stages;
-                const uint32_t ph = (uint32_t)(tap / a.stages) & 1u;
+            for (int k = 0; k < n_kb; ++k) {
+                const int st = k % a.stages;
+                const uint32_t ph = (uint32_t)(k / a.stages) & 1u;
+                const int tap = k - a.has_sc;
                 mbar_wait_a(smem_u32(&full_bar[st]), ph);
                 tc_fence_after();
                 const uint32_t base = smem_base + (uint32_t)st * stage_bytes;
                 const uint64_t d_a = make_kmajor_desc<ROW_BYTES>(base), d_b = make_kmajor_desc<ROW_BYTES>(base + A_BYTES);
-                const uint32_t d0 = tmem_base + (tap == 9 ? 2 * a.cout : 0);      // shortcut block: its own accumulators
-                const int first = tap == 9 ? 9 : 0;
+                const uint32_t d0 = tmem_base + (tap < 0 ? 2 * a.cout : 0);       // shortcut block: its own accumulators
 #pragma unroll
                 for (int ks = 0; ks < CIN / 16; ++ks) {
                     const uint64_t kh = (uint64_t)(4 * ks), kl = kh + 2;          // 16-byte descriptor units
-                    umma_f16(d0, d_a + kh, d_b + kh, idesc, (tap != first) || ks != 0);
-                    umma_f16(d0 + a.cout, d_a + kh, d_b + kl, idesc, (tap != first) || ks != 0);
+                    const uint32_t acc = (tap > 0 || ks != 0) ? 1u : 0u;          // first MMA of the shortcut block / of tap 0
+                    umma_f16(d0, d_a + kh, d_b + kh, idesc, acc);
+                    umma_f16(d0 + a.cout, d_a + kh, d_b + kl, idesc, acc);
                     umma_f16(d0 + a.cout, d_a + kl, d_b + kh, idesc, 1);
                 }
                 umma_commit(smem_u32(&empty_bar[st]));
+                if (tap < 0) umma_commit(smem_u32(&sc_full_bar));
             }
             umma_commit(smem_u32(&tmem_full_bar));
         }
@@ -750,9 +763,29 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
             pi_px = a.pi_out + ((int64_t)s * a.pi_ngroups + grp) * a.pi_pass_bytes +
                     (int64_t)((g * (a.hout + 1) + (h0 + h)) * a.pi_pitch + w) * 16;
         }
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (a.has_sc) {                                              // drained while the nine taps are still in flight
+            mbar_wait_a(smem_u32(&sc_full_bar), 0);
+            tc_fence_after();
+            float *rp = a.rs_out + ((((int64_t)s * a.n_images + n) * a.hout + (h0 + h)) * a.hout + w) * a.cout;
+            for (int c0 = 0; c0 < a.cout; c0 += 16) {
+                uint32_t ra[16], rl[16];
+                tmem_ld<16>(tl + (uint32_t)(2 * a.cout + c0), ra);
+                tmem_ld<16>(tl + (uint32_t)(3 * a.cout + c0), rl);
+                tmem_ld_wait();
+                if (!valid) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)                   // operand rows were R / 16
+                        v[e] = fmaf(__uint_as_float(rl[i + e]), kLoUnscale, __uint_as_float(ra[i + e])) * kActUp;
+                    *reinterpret_cast<float4 *>(rp + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
         mbar_wait_a(smem_u32(&tmem_full_bar), 0);
         tc_fence_after();
-        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int c0 = 0; c0 < a.cout; c0 += 16) {
             uint32_t ra[16], rl[16];
             tmem_ld<16>(tl + (uint32_t)c0, ra);
@@ -774,24 +807,6 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
                 const int64_t pl = (int64_t)((c0 + i) >> 3) * a.pi_img_pos * 16;
                 *reinterpret_cast<uint4 *>(pi_px + pl) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 *reinterpret_cast<uint4 *>(pi_px + (int64_t)a.pi_nplanes * a.pi_img_pos * 16 + pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-        }
-        if (a.has_sc) {
-            float *rp = a.rs_out + ((((int64_t)s * a.n_images + n) * a.hout + (h0 + h)) * a.hout + w) * a.cout;
-            for (int c0 = 0; c0 < a.cout; c0 += 16) {
-                uint32_t ra[16], rl[16];
-                tmem_ld<16>(tl + (uint32_t)(2 * a.cout + c0), ra);
-                tmem_ld<16>(tl + (uint32_t)(3 * a.cout + c0), rl);
-                tmem_ld_wait();
-                if (!valid) continue;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)                   // operand rows were R / 16
-                        v[e] = fmaf(__uint_as_float(rl[i + e]), kLoUnscale, __uint_as_float(ra[i + e])) * kActUp;
-                    *reinterpret_cast<float4 *>(rp + c0 + i) = make_float4(v[0], v[1], v[2], v[3]);
-                }
             }
         }
         tc_fence_before();
