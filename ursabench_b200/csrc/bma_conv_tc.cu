@@ -818,6 +818,11 @@ conv3x3s2_f16_kernel(const __grid_constant__ ConvS2Maps maps, const ConvS2Args a
     }
 }
 
+// Negative result (round 2): a persistent form of this kernel (one CTA per SM walking the (sample, tile) grid, the TMA producer
+// 16 / 8 K blocks ahead across tile boundaries, 4 / 2 tiles' accumulators in the 512 TMEM columns, epilogue of tile i under the
+// loads of tiles i + 1 ..) was parity-green and SLOWER: 612 vs 595 us per launch.  The one-tile CTAs' idle phases are therefore
+// not what holds the kernel at ~4.3 TB/s of DRAM traffic; four co-resident CTAs already overlap them.
+
 // a_rows: the producer stage's TMA-stored rows (stage geometry CIN: H = hin, pitch, positions per pass, images per pass)
 template <int CIN>
 static int launch_conv_s2_f16(const void *a_rows, const void *r_rows, int hin, int pitch_in, int img_pos_in, int g_in, int sc,
