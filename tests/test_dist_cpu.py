@@ -42,6 +42,26 @@ def test_shard_pairs_covers_the_grid_once_and_balances():
     assert udist.shard_pairs(0, 10, 0, 2) == [] and udist.shard_pairs(4, 0, 1, 2) == []
 
 
+def test_pack_plan_covers_the_list_with_a_small_first_sub_batch(monkeypatch):
+    """Host modules handed to a task are packed / uploaded in sub-batches that overlap the device (tasks/_engine.py):
+    every module exactly once and in order, 2 first when the list is split, at most 8 per sub-batch, no one-module tail."""
+    from ursabench_b200.tasks import _engine
+    for family in ("preresnet", "wrn", "mlp"):
+        for n in range(0, 70):
+            plan = _engine.pack_plan(n, family)
+            assert sum(plan) == n and all(k >= 1 for k in plan)
+            if len(plan) > 1:
+                assert plan[0] == 2 and max(plan) <= 8 and plan[-1] >= 2
+            else:
+                assert n <= (4 if family != "mlp" else 16)
+    assert _engine.pack_plan(12, "preresnet") == [2, 8, 2]          # a rank's share of S = 100 on 8 ranks
+    assert _engine.pack_plan(11, "preresnet") == [2, 7, 2]
+    assert _engine.pack_plan(12, "mlp") == [12]
+    monkeypatch.setattr(_engine, "_PACK_SPLIT_MIN", 0)              # a silly knob value must not loop
+    assert _engine.pack_plan(1, "wrn") == [1] and _engine.pack_plan(2, "wrn") == [2] and _engine.pack_plan(3, "wrn") == [3]
+    assert _engine.pack_plan(4, "wrn") == [2, 2]
+
+
 def test_chain_elem_offsets_disjoint_and_aligned():
     D = 272_282
     offs = [udist.chain_elem_offset(c, D) for c in range(8)]

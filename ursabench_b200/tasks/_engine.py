@@ -22,6 +22,24 @@ _PACK_BATCH = 8            # = the conv forwards' sample chunk
 _PACK_SPLIT_MIN = int(os.environ.get("URSA_PACK_SPLIT_MIN", "4"))    # lists longer than this are packed in overlapped sub-batches
 
 
+def pack_plan(n_modules, family):
+    """Sizes of the sub-batches a list of ``n_modules`` host modules is packed and uploaded in: 2 first (nothing runs on the
+    device while the first sub-batch is being packed), then ``_PACK_BATCH`` at a time, never a one-module tail (its launch chain
+    costs more than its packing hides).  An MLP module packs in microseconds and a whole MLP evaluation takes a few ms, so
+    only long MLP lists are split."""
+    split_min = _PACK_SPLIT_MIN if family != "mlp" else 2 * _PACK_BATCH
+    if n_modules <= max(split_min, 3):
+        return [n_modules] if n_modules else []
+    plan, left = [2], n_modules - 2
+    while left:
+        n = min(_PACK_BATCH, left)
+        if left - n == 1 and n > 2:
+            n -= 1
+        plan.append(n)
+        left -= n
+    return plan
+
+
 _ARCH_CACHE = weakref.WeakKeyDictionary()
 
 
@@ -198,14 +216,8 @@ class BMAAccumulator:
             # The first sub-batch is small: nothing runs on the device while it is being packed.
             # (≈ 1 ms of host time per PreResNet-20 module: a rank's 12-sample share of an 8-rank evaluation packed in one go
             # left the device idle for a fifth of the call.)
-            # An MLP module packs in microseconds and its whole evaluation is a few ms: only long lists are split there.
-            split_min = _PACK_SPLIT_MIN if arch[0] != "mlp" else 2 * _PACK_BATCH
-            step = _PACK_BATCH if len(plain) > split_min else len(plain)
             s0 = 0
-            while s0 < len(plain):
-                n = 2 if s0 == 0 and len(plain) > split_min else step
-                if len(plain) - (s0 + n) == 1 and n > 2:    # no one-module tail: leave two for the last launch chain
-                    n -= 1
+            for n in pack_plan(len(plain), arch[0]):
                 bank = SampleBank.from_modules(plain[s0:s0 + n], self.device)
                 self.h2d_sample_bytes += bank.count * (bank.ld + bank.ldb) * 4
                 self._accumulate_rows(bank.w[:bank.count], bank.b[:bank.count], arch, None, lo, hi)
