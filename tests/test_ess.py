@@ -49,6 +49,10 @@ def test_log_pdf_of_subspace_points_matches_reference():
     inf.subspace = U.inference.SubspaceModel(torch.from_numpy(g["logpdf/mean"]).to(dev), torch.from_numpy(g["logpdf/factor"]).to(dev))
     got = np.array([inf._oracle(t) for t in g["logpdf/t"]])
     np.testing.assert_allclose(got, g["logpdf/value"], rtol=2e-5, atol=2e-5)
+    # the free function under the reference's name and signature (util.py:260-274) gives the same numbers
+    model = U.models.MLP(16, 20, 3).to(dev)
+    free = np.array([U.util.log_pdf(t, inf.subspace, model, loader, U.util.cross_entropy, 7.0, dev) for t in g["logpdf/t"]])
+    np.testing.assert_allclose(free, g["logpdf/value"], rtol=2e-5, atol=2e-5)
     # the projection really went through the flat buffer the model's parameters are views of
     w = torch.from_numpy(g["logpdf/mean"] + g["logpdf/factor"].T @ g["logpdf/t"][-1].astype(np.float32)).float()
     now = torch.cat([p.detach().reshape(-1) for p in inf.model.parameters()]).cpu()
@@ -82,3 +86,29 @@ def test_pca_subspace_sampler_end_to_end(capsys):
     inf.update_hyp(dict(hyp, num_samples=2))
     assert inf.subspace is None and inf.current_theta is None
     assert len(inf.sample()) == 2
+
+
+def test_util_exports_the_reference_helpers_of_the_path():
+    """``from ursabench_b200 import util`` must offer what the reference's samplers import from its util on this path
+    (util.py:110-123, 185-199, 260-354)."""
+    import ursabench_b200 as U
+    from ursabench_b200.inference import pca_subspace
+    for name in ("flatten", "set_weights", "unflatten_like", "check_bn", "reset_bn", "bn_update", "central_smoothing",
+                 "compute_predictive_entropy", "cross_entropy", "log_pdf", "elliptical_slice", "convert_sample_to_net",
+                 "get_loss_criterion", "reset_model", "adjust_learning_rate"):
+        assert callable(getattr(U.util, name)), name
+    assert pca_subspace.elliptical_slice is U.util.elliptical_slice
+    m = U.models.MLP(8, 20, 3)
+    n_par = sum(p.numel() for p in m.parameters())
+    v = torch.arange(n_par, dtype=torch.float32)
+    net = U.util.convert_sample_to_net(v, m)
+    assert net is not m and torch.equal(torch.cat([p.reshape(-1) for p in net.parameters()]), v)
+    assert not torch.equal(torch.cat([p.detach().reshape(-1) for p in m.parameters()]), v)          # the original is untouched
+    with pytest.raises(ValueError):
+        U.util.convert_sample_to_net(v[:-1].clone(), m)
+    bn = torch.nn.BatchNorm1d(4)
+    bn.running_mean.fill_(3.0), bn.running_var.fill_(5.0)
+    torch.nn.Sequential(bn).apply(U.util.reset_bn)
+    assert float(bn.running_mean.abs().max()) == 0.0 and float((bn.running_var - 1).abs().max()) == 0.0
+    loss, out, extra = U.util.cross_entropy(torch.nn.Linear(5, 3), torch.zeros(2, 5), torch.tensor([0, 2]))
+    assert out.shape == (2, 3) and extra == {} and loss.ndim == 0

@@ -10,8 +10,6 @@ traffic but the final scalar.  The slice-sampling logic itself (bracket, shrinka
 ``util.elliptical_slice`` statement by statement so that, given the same ``np.random`` state and log-density values, the
 chain is the reference's chain (tests/golden/ess.npz).
 """
-import math
-
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -19,48 +17,12 @@ import torch.nn.functional as F
 from .. import _C
 from ..bank import SampleBank
 from ..flat import FlatParams
-from ..util import bn_update, check_bn, get_loss_criterion, reset_model
+from ..util import bn_update, check_bn, elliptical_slice, get_loss_criterion, reset_model
 from .inference_base import _Inference, require_cuda
 from .projection_model import SubspaceModel
 from .swa import SWA
 
 __all__ = ["PCASubspaceSampler", "elliptical_slice"]
-
-
-def elliptical_slice(initial_theta, prior, lnpdf, cur_lnpdf=None, angle_range=None, subspace=None, **kwargs):
-    """Markov-chain update for a density with a Gaussian prior factored out (Murray, Adams & MacKay 2010); argument
-    meaning, RNG call order and return value of reference util.py:287-354."""
-    D = len(initial_theta)
-    if cur_lnpdf is None:
-        cur_lnpdf = lnpdf(initial_theta, subspace, **kwargs)
-    if len(prior.shape) == 1:                                  # a sample from the prior
-        nu = prior
-    else:                                                      # chol(Sigma)
-        if not prior.shape[0] == D or not prior.shape[1] == D:
-            raise IOError("Prior must be given by a D-element sample or DxD chol(Sigma)")
-        nu = np.dot(prior, np.random.normal(size=D))
-    hh = math.log(np.random.uniform()) + cur_lnpdf             # slice threshold
-    if angle_range is None or angle_range == 0.:
-        phi = np.random.uniform() * 2. * math.pi               # whole ellipse, both bracket edges at the first proposal
-        phi_min = phi - 2. * math.pi
-        phi_max = phi
-    else:
-        phi_min = -angle_range * np.random.uniform()
-        phi_max = phi_min + angle_range
-        phi = np.random.uniform() * (phi_max - phi_min) + phi_min
-    while True:
-        xx_prop = initial_theta * math.cos(phi) + nu * math.sin(phi)
-        cur_lnpdf = lnpdf(xx_prop, subspace, **kwargs)
-        if cur_lnpdf > hh:
-            break
-        if phi > 0:
-            phi_max = phi
-        elif phi < 0:
-            phi_min = phi
-        else:
-            raise RuntimeError("BUG DETECTED: Shrunk to current position and still not acceptable.")
-        phi = np.random.uniform() * (phi_max - phi_min) + phi_min
-    return (xx_prop, cur_lnpdf)
 
 
 class PCASubspaceSampler(_Inference):
