@@ -17,7 +17,8 @@ import torch.nn.functional as F
 from .. import _C
 from ..bank import SampleBank
 from ..flat import FlatParams
-from ..util import bn_update, check_bn, elliptical_slice, get_loss_criterion, reset_model
+from ..ess import elliptical_slice
+from ..util import bn_update, check_bn, get_loss_criterion, reset_model
 from .inference_base import _Inference, require_cuda
 from .projection_model import SubspaceModel
 from .swa import SWA
