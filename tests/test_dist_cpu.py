@@ -48,6 +48,36 @@ def test_shard_pairs_covers_the_grid_once_and_balances():
     assert udist.shard_pairs(0, 10, 0, 2) == [] and udist.shard_pairs(4, 0, 1, 2) == []
 
 
+def test_shard_pairs_properties_random_shapes():
+    """Property check over random (S, N, world, quantum): the shares tile the grid exactly once, in sample-major order
+    across ranks, and stay within one block + two snapped blocks per end of the ideal share."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=150, deadline=None)
+    @hyp.given(S=st.integers(1, 40), N=st.integers(1, 20_000), world=st.integers(1, 16), quantum=st.sampled_from([16, 64, 100]))
+    def check(S, N, world, quantum):
+        flat = []
+        sizes = []
+        for r in range(world):
+            sh = udist.shard_pairs(S, N, r, world, quantum=quantum)
+            sizes.append(sum(hi - lo for _, lo, hi in sh))
+            for s, lo, hi in sh:
+                assert 0 <= lo < hi <= N
+                flat.append((s, lo, hi))
+        # sample-major, contiguous, nothing twice, nothing missing
+        pos = 0
+        for s, lo, hi in flat:
+            assert s * N + lo == pos, (S, N, world, quantum, flat)
+            pos = s * N + hi
+        assert pos == S * N
+        if S % world:
+            assert max(sizes) - min(sizes) <= 6 * quantum, (S, N, world, quantum, sizes)
+        else:
+            assert max(sizes) == min(sizes) == (S // world) * N
+    check()
+
+
 def test_pack_plan_covers_the_list_with_a_small_first_sub_batch(monkeypatch):
     """Host modules handed to a task are packed / uploaded in sub-batches that overlap the device (tasks/_engine.py):
     every module exactly once and in order, 2 first when the list is split, at most 8 per sub-batch, no one-module tail."""
